@@ -1,0 +1,195 @@
+"""CPU restatement (NumPy/SciPy) of monocle3's preprocess_cds PCA hot path.
+
+TEST INFRASTRUCTURE ONLY (oracle/): the parity checker for tests/ and the CPU
+baseline for bench.py.  The product package (monocle3_b200/) never imports it.
+
+Each function cites the reference lines it follows (paths under /root/reference).
+Third-party arithmetic (irlba, Matrix, DelayedMatrixStats, base-R RNG) is
+restated in irlba_ref.py / r_rng.py.  Parity is pinned by the reference's own
+golden values -- tests/test_oracle_golden.py.
+
+Conventions: `counts` is a scipy.sparse.csc_matrix, genes x cells (the
+`dgCMatrix` of counts(cds), R/cell_data_set.R:117,123).
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import irlba_ref
+from .r_rng import RRandom
+
+
+def r_mean(x):
+    """R's mean() for doubles (summary.c): long-double sum, then one refinement pass."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    xl = x.astype(np.longdouble)
+    s = np.cumsum(xl)[-1] / n  # sequential accumulation in long double
+    t = np.cumsum(xl - s)[-1] / n
+    return np.float64(s + t)
+
+
+def estimate_sf_sparse(counts, round_exprs=True, method="mean-geometric-mean-total"):
+    """R/utils.R:54-70.  Returns (size_factors, cell_total)."""
+    x = counts.data
+    if round_exprs:
+        x = np.round(x)  # R's round() is half-to-even on .5 for doubles, like np.round
+    c = sp.csc_matrix((x, counts.indices, counts.indptr), shape=counts.shape)
+    cell_total = np.asarray(c.sum(axis=0)).ravel()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if method == "mean-geometric-mean-total":
+            sfs = cell_total / np.exp(r_mean(np.log(cell_total)))
+        elif method == "mean-geometric-mean-log-total":
+            sfs = np.log(cell_total) / np.exp(r_mean(np.log(np.log(cell_total))))
+        else:
+            raise ValueError("method")
+    sfs = np.where(np.isnan(sfs), 1.0, sfs)  # R/utils.R:68
+    return sfs, cell_total
+
+
+def estimate_size_factors(counts, round_exprs=True, method="mean-geometric-mean-total"):
+    """R/utils.R:26-50: returns None (cds unchanged + warning) if any cell has zero reads."""
+    raw_tot = np.asarray(counts.sum(axis=0)).ravel()
+    if np.any(raw_tot == 0):
+        return None
+    return estimate_sf_sparse(counts, round_exprs, method)[0]
+
+
+def normalize_expr_data(counts, sf, norm_method="log", pseudo_count=None):
+    """R/preprocess_cds.R:253-286.  Returns FM as csc (sparse path) or ndarray (dense path)."""
+    if pseudo_count is None:
+        pseudo_count = 1 if norm_method == "log" else 0
+    FM = counts.copy().astype(np.float64)
+    if norm_method == "log":
+        FM.data = FM.data / np.repeat(sf, np.diff(FM.indptr))  # t(t(FM)/sf)  :272
+        if pseudo_count != 1:
+            D = FM.toarray() + pseudo_count  # :274-276 (densifies)
+            return np.log2(D)
+        FM.data = np.log2(FM.data + 1)  # :278
+        return FM
+    if norm_method == "size_only":
+        FM.data = FM.data / np.repeat(sf, np.diff(FM.indptr))  # :282
+        if pseudo_count != 0:
+            return FM.toarray() + pseudo_count  # :283 (densifies)
+        return FM
+    if norm_method == "none":
+        return FM
+    raise ValueError("norm_method must be one of 'log', 'size_only' or 'none'")
+
+
+def normalized_counts(counts, sf, norm_method="log", pseudocount=1):
+    """R/utils.R:477-509 (sparse branch). NOTE log10, not log2."""
+    nm = counts.copy().astype(np.float64)
+    if norm_method == "binary":
+        nm.data = (nm.data > 0).astype(np.float64)
+        nm.eliminate_zeros()
+        return nm
+    nm.data = nm.data / np.repeat(sf, np.diff(nm.indptr))  # :493
+    if norm_method == "log":
+        if pseudocount != 1:
+            raise ValueError("Pseudocount must equal 1 with sparse expression matrices")
+        nm.data = np.log10(nm.data + pseudocount)  # :496
+    elif norm_method != "size_only":
+        raise ValueError("norm_method")
+    return nm
+
+
+def select_and_filter_genes(FM, use_genes_idx=None):
+    """R/preprocess_cds.R:117-122. Returns (FM', kept_original_gene_indices)."""
+    idx = np.arange(FM.shape[0]) if use_genes_idx is None else np.asarray(use_genes_idx)
+    if use_genes_idx is not None:
+        FM = FM[idx, :] if not sp.issparse(FM) else FM.tocsr()[idx, :].tocsc()
+    rs = np.asarray(FM.sum(axis=1)).ravel()
+    keep = np.isfinite(rs) & (rs != 0)
+    FM = FM[keep, :] if not sp.issparse(FM) else FM.tocsr()[keep, :].tocsc()
+    return FM, idx[keep]
+
+
+def gene_moments(At):
+    """R/utils.R:383,389: colMeans2 / sqrt(colVars) of the cells x genes matrix (n-1 denominator)."""
+    C = At.shape[0]
+    if sp.issparse(At):
+        A = At.tocsc()
+        mean = np.asarray(A.sum(axis=0)).ravel() / C
+        nnz = np.diff(A.indptr)
+        dev = A.data - np.repeat(mean, nnz)
+        ss = np.zeros(A.shape[1])
+        np.add.at(ss, np.repeat(np.arange(A.shape[1]), nnz), dev * dev)
+        ss += (C - nnz) * mean * mean
+    else:
+        mean = At.mean(axis=0)
+        ss = ((At - mean) ** 2).sum(axis=0)
+    return mean, np.sqrt(ss / (C - 1))
+
+
+def sparse_prcomp_irlba(At, n, center=True, scale=False, v0=None, **irlba_args):
+    """R/utils.R:365-430 with logical center/scale. (monocle3 always passes center == scale.)"""
+    C, G = At.shape
+    cen = sc = None
+    if center:
+        cen, sd = gene_moments(At)
+        if scale:
+            sc = sd
+    elif scale:
+        # R/utils.R:396-400: no centering -> root-mean-square scaling
+        sq = At.multiply(At) if sp.issparse(At) else At * At
+        sc = np.sqrt(np.asarray(sq.sum(axis=0)).ravel() / max(1, C - 1))
+    if v0 is None:
+        v0 = RRandom(2016).rnorm(G)  # set.seed(2016) at R/preprocess_cds.R:110, rnorm(n) inside irlba
+    s = irlba_ref.irlba(At, n, v0, center=cen, scale=sc, **irlba_args)
+    if s.err not in (0, -2):
+        raise RuntimeError("irlba error %d" % s.err)
+    ans = dict(sdev=s.d / np.sqrt(max(1, C - 1)),  # :418
+               rotation=s.v,  # :419
+               center=cen, svd_scale=sc,
+               x=s.u * s.d[None, :],  # sweep(u,2,d,'*')  :425
+               d=s.d, u=s.u, iter=s.iter, mprod=s.mprod, err=s.err)
+    return ans
+
+
+def preprocess_cds(counts, sf, num_dim=50, norm_method="log", use_genes_idx=None,
+                   pseudo_count=None, scaling=True, v0=None, **irlba_args):
+    """PCA branch of R/preprocess_cds.R:62-248.  Returns the model dict + embedding.
+
+    use_genes_idx: integer row indices (R passes names; translation is host glue).
+    """
+    FM = normalize_expr_data(counts, sf, norm_method, pseudo_count)  # :111
+    if FM.shape[0] == 0:
+        raise ValueError("all rows have standard deviation zero")
+    FM, kept = select_and_filter_genes(FM, use_genes_idx)  # :117-122
+    At = FM.T
+    if sp.issparse(At):
+        At = At.tocsc()
+    n = min(num_dim, min(FM.shape) - 1)  # :140
+    res = sparse_prcomp_irlba(At, n, center=scaling, scale=scaling, v0=v0, **irlba_args)
+    sdev = res["sdev"]
+    return dict(PCA=res["x"], svd_v=res["rotation"], svd_sdev=sdev,
+                svd_center=res["center"], svd_scale=res["svd_scale"],
+                prop_var_expl=sdev ** 2 / np.sum(sdev ** 2),  # :158-160
+                kept_genes=kept, num_dim=num_dim, norm_method=norm_method,
+                pseudo_count=pseudo_count, d=res["d"], u=res["u"],
+                iter=res["iter"], mprod=res["mprod"], err=res["err"])
+
+
+def preprocess_transform(counts, sf, model, gene_index_in_model):
+    """PCA branch of R/projection.R:102-149.
+
+    gene_index_in_model[g] = row of model['svd_v'] for query gene g, or -1 if the
+    query gene is not in the model (R does this by rowname intersect, :121-122).
+    """
+    FM = normalize_expr_data(counts, sf, model["norm_method"], model.get("pseudo_count"))
+    rs = np.asarray(FM.sum(axis=1)).ravel()
+    keep = np.isfinite(rs) & (rs != 0)  # :117-118
+    gidx = np.asarray(gene_index_in_model)
+    # R: intersect(rownames(rotation), rownames(FM)) keeps the MODEL's order (:121)
+    q_rows = np.nonzero(keep & (gidx >= 0))[0]
+    order = np.argsort(gidx[q_rows], kind="stable")
+    q_rows = q_rows[order]
+    m_rows = gidx[q_rows]
+    X = FM.tocsr()[q_rows, :].T if sp.issparse(FM) else FM[q_rows, :].T  # cells x genes
+    V = model["svd_v"][m_rows, :]
+    if model["svd_center"] is not None:
+        c = model["svd_center"][m_rows]
+        s = model["svd_scale"][m_rows]
+        Xd = (np.asarray(X.todense()) if sp.issparse(X) else X)
+        return ((Xd - c[None, :]) / s[None, :]) @ V  # :141-148, densified like DelayedArray does
+    return np.asarray(X @ V)
