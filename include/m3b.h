@@ -1,0 +1,201 @@
+/*
+ * m3b.h -- C ABI of the B200-native preprocess_cds PCA path (monocle3 drop-in).
+ *
+ * This is the whole boundary between the reference's R code and the CUDA
+ * (sm_100a) implementation.  Plain C types only: no R, Rcpp or torch types.
+ * The reference has no native entry point for this path; what each function
+ * replaces is the R-level call into a third-party package that the reference
+ * makes today (paths relative to the monocle3 source tree):
+ *
+ *   m3b_cell_totals / m3b_size_factors ... estimate_sf_sparse: round() + Matrix::colSums
+ *                                          R/utils.R:54-70 (called from R/utils.R:26-50)
+ *   m3b_normalize / m3b_export_values .... normalize_expr_data R/preprocess_cds.R:253-286,
+ *                                          normalized_counts R/utils.R:477-509
+ *   m3b_select_genes ..................... FM[use_genes,], Matrix::rowSums zero-gene filter,
+ *                                          Matrix::t(FM)  R/preprocess_cds.R:117-122,139
+ *   m3b_gene_moments ..................... DelayedMatrixStats::colMeans2 / colVars
+ *                                          R/utils.R:383,389
+ *   m3b_pca_irlba ........................ irlba::irlba(A=t(FM), nv, center, scale) and the
+ *                                          post-processing R/utils.R:417-428
+ *   m3b_project .......................... preprocess_transform's delayed (x-c)/s %*% V,
+ *                                          R/projection.R:135-148, R/utils.R:823-849
+ *
+ * The registration pattern a maintainer mirrors is src/RcppExports.cpp:15-47
+ * (see INTEGRATION.md for the Rcpp stubs).
+ *
+ * Conventions
+ *   - G = genes (rows of counts(cds)), C = cells (columns).  The input is the
+ *     dgCMatrix of counts(cds): CSC, cell-major, 0-based int32 row indices,
+ *     f64 values (R/cell_data_set.R:117,123).  Because a dgCMatrix cannot hold
+ *     more than 2^31-1 non-zeros, matrices are appended as cell-range chunks.
+ *   - Dense matrices are column-major (R layout) with an explicit leading
+ *     dimension where noted.
+ *   - All host pointers are caller-owned and borrowed only for the duration of
+ *     the call.  Device memory is owned by the context / matrix handles.
+ *   - Every function returns an int status: 0 on success, a negative M3B_E_*
+ *     code otherwise; m3b_last_error() gives the message.  Nothing throws,
+ *     exits or longjmps across this boundary.  M3B_W_NOT_CONVERGED (-2) mirrors
+ *     irlba's "did not converge" warning: results are still written.
+ *   - One context drives one GPU.  Multi-GPU runs use one context per process
+ *     (or thread), each owning a contiguous cell range, joined by
+ *     m3b_comm_init(); gene-space results are replicated, cell-space results
+ *     stay sharded.
+ *   - There is no CPU fallback: if no CUDA device is usable, m3b_create fails.
+ */
+#ifndef M3B_H
+#define M3B_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3B_ABI_VERSION 1
+
+/* status codes (negative = error; the first five mirror irlba's C path) */
+#define M3B_OK                0
+#define M3B_E_DIMS           -1  /* invalid dimensions / arguments                  */
+#define M3B_W_NOT_CONVERGED  -2  /* maxit reached; outputs written (irlba warning)  */
+#define M3B_E_NOMEM          -3  /* host or device allocation failed                */
+#define M3B_E_NULLSPACE      -4  /* start vector in the null space of A             */
+#define M3B_E_LINDEP         -5  /* linear dependency / invariant subspace hit      */
+#define M3B_E_CUDA           -10 /* CUDA runtime failure (message has the details)  */
+#define M3B_E_NCCL           -11 /* NCCL failure                                    */
+#define M3B_E_STATE          -12 /* call sequence violated (e.g. normalize missing) */
+#define M3B_E_NODEVICE       -13 /* no usable sm_100 device: there is no fallback   */
+#define M3B_E_ABORTED        -14 /* should_abort callback asked to stop             */
+
+/* norm_method codes for m3b_normalize */
+#define M3B_NORM_LOG2       0 /* log2(x/sf + pc)   preprocess_cds norm_method="log"        */
+#define M3B_NORM_SIZE_ONLY  1 /* x/sf + pc         norm_method="size_only"                 */
+#define M3B_NORM_NONE       2 /* x                 norm_method="none"                      */
+#define M3B_NORM_LOG10      3 /* log10(x/sf + 1)   normalized_counts(norm_method="log")    */
+#define M3B_NORM_BINARY     4 /* (x > 0) + 0       normalized_counts(norm_method="binary") */
+
+/* size-factor methods (R/utils.R:60-66) */
+#define M3B_SF_MEAN_GEOMETRIC_MEAN_TOTAL      0
+#define M3B_SF_MEAN_GEOMETRIC_MEAN_LOG_TOTAL  1
+
+typedef struct m3b_ctx m3b_ctx;
+typedef struct m3b_mat m3b_mat;
+
+/* Optional callbacks.  small_svd lets the R shim supply R's own LAPACK dgesdd
+ * for the (work x work) bidiagonal matrix so signs match the reference bit for
+ * bit; the built-in default is a one-sided Jacobi SVD.  All matrices are
+ * column-major n x n: on entry B; on exit U (n x n), s (n, descending),
+ * Vt (n x n, rows are right singular vectors).  Return 0 on success. */
+typedef int (*m3b_small_svd_fn)(int n, const double* B, double* U, double* s, double* Vt, void* user);
+/* Polled once per restart (irlba polls R_CheckUserInterrupt after each product). */
+typedef int (*m3b_should_abort_fn)(void* user);
+
+/* ---- library / context ------------------------------------------------ */
+int         m3b_abi_version(void);
+const char* m3b_status_string(int status);
+int         m3b_device_count(void);
+
+int         m3b_create(int device, int flags, m3b_ctx** out);
+void        m3b_destroy(m3b_ctx* ctx);
+const char* m3b_last_error(const m3b_ctx* ctx);
+int         m3b_set_small_svd(m3b_ctx* ctx, m3b_small_svd_fn fn, void* user);
+int         m3b_set_should_abort(m3b_ctx* ctx, m3b_should_abort_fn fn, void* user);
+
+/* ---- multi-GPU plumbing (one context per rank) ------------------------ */
+#define M3B_COMM_ID_BYTES 128
+int m3b_comm_unique_id(m3b_ctx* ctx, char id[M3B_COMM_ID_BYTES]);              /* rank 0 */
+int m3b_comm_init(m3b_ctx* ctx, int rank, int world, const char id[M3B_COMM_ID_BYTES]);
+int m3b_comm_world(const m3b_ctx* ctx);                                        /* 1 if unsharded */
+
+/* ---- sparse ingest (K0) ------------------------------------------------ */
+/* n_cells_local cells will be appended to this context; n_cells_total is the
+ * cell count over all ranks (== n_cells_local when unsharded). */
+int  m3b_matrix_begin(m3b_ctx* ctx, int32_t n_genes, int64_t n_cells_local,
+                      int64_t n_cells_total, int64_t nnz_hint, m3b_mat** out);
+/* p: chunk-local column pointers (n_cells_chunk+1, p[0]==0); i: row indices; x: values */
+int  m3b_matrix_append_csc(m3b_mat* mat, int64_t n_cells_chunk, const int32_t* p,
+                           const int32_t* i, const double* x);
+int  m3b_matrix_end(m3b_mat* mat);
+void m3b_matrix_free(m3b_mat* mat);
+int  m3b_matrix_dims(const m3b_mat* mat, int32_t* n_genes, int64_t* n_cells_local,
+                     int64_t* n_cells_total, int64_t* nnz_local);
+
+/* ---- size factors (K1) -------------------------------------------------- */
+/* Per-cell sums of (optionally rounded) counts for the local cells. Exact. */
+int m3b_cell_totals(m3b_mat* mat, int round_exprs, double* cell_total /* n_cells_local */);
+/* Host-only finish, given the totals of ALL cells in cell order (R/utils.R:61-68):
+ * long-double two-pass mean like R's mean(); NA -> 1.  any_zero reports the
+ * zero-read-cell guard of R/utils.R:32-39 (sf is still written). */
+int m3b_size_factors_from_totals(const double* cell_total, int64_t n_cells, int method,
+                                 double* sf /* n_cells */, int* any_zero);
+/* Convenience for the unsharded case: totals + finish. */
+int m3b_size_factors(m3b_mat* mat, int round_exprs, int method, double* cell_total,
+                     double* sf, int* any_zero);
+
+/* ---- normalisation (K2) ------------------------------------------------- */
+/* sf: size factors of the local cells (ignored for NONE/BINARY).  pseudo_count
+ * follows normalize_expr_data: LOG2 with pc != 1 and SIZE_ONLY with pc != 0 are
+ * the reference's dense paths; here the matrix stays sparse and the constant
+ * f(0) is carried implicitly through every later step. */
+int m3b_normalize(m3b_mat* mat, const double* sf, int norm_method, double pseudo_count);
+/* Normalised stored values in the input's CSC order (normalized_counts()@x). */
+int m3b_export_values(m3b_mat* mat, double* y /* nnz_local */);
+
+/* ---- gene selection, zero-gene filter, dual-layout build (K0) ---------- */
+/* gene_order: optional list of n_sel gene indices (use_genes, in that order);
+ * NULL = all genes.  keep[n_sel] receives the zero/non-finite row-sum filter
+ * (1 = kept), n_kept the number of kept genes G'.  Collective across ranks. */
+int m3b_select_genes(m3b_mat* mat, const int32_t* gene_order, int32_t n_sel,
+                     uint8_t* keep, int32_t* n_kept);
+/* Exact per-selected-gene bookkeeping after m3b_select_genes (local shard). */
+int m3b_gene_nnz(m3b_mat* mat, int64_t* nnz_per_sel_gene /* n_sel */);
+
+/* ---- gene moments (K3) -------------------------------------------------- */
+int m3b_gene_moments(m3b_mat* mat, double* center /* G' */, double* scale /* G' */);
+
+/* ---- IRLBA PCA (K4-K9) -------------------------------------------------- */
+/* nv: number of PCs; work: Lanczos subspace (0 => nv+7); v0: start vector (G').
+ * center/scale: 0/1 flags (preprocess_cds passes scaling for both).
+ * Outputs: d[nv]; V (G' x nv, ld G'); X = U*diag(d) for the local cells
+ * (n_cells_local x nv, leading dimension ldx >= n_cells_local); center_out /
+ * scale_out (G', nullable).  Collective across ranks. */
+int m3b_pca_irlba(m3b_mat* mat, int nv, int work, int maxit, double tol, double svtol,
+                  const double* v0, int center, int scale,
+                  double* d, double* V, double* X, int64_t ldx,
+                  double* center_out, double* scale_out, int* iter, int* mprod);
+/* As above but leaves X on the device and returns timings only (bench). */
+int m3b_pca_irlba_device(m3b_mat* mat, int nv, int work, int maxit, double tol, double svtol,
+                         const double* v0, int center, int scale,
+                         double* d, int* iter, int* mprod);
+
+/* ---- projection of query cells (K10) ------------------------------------ */
+/* Call after m3b_normalize + m3b_select_genes on the QUERY matrix.
+ * model_row[G'_q]: for each kept query gene, its row in the model's V (>= 0).
+ * V: n_model x nv (ld n_model); center/scale: n_model or NULL (scaling=FALSE).
+ * Y: n_cells_local x nv, leading dimension ldy. */
+int m3b_project(m3b_mat* query, const int32_t* model_row, int32_t n_model,
+                const double* V, const double* center, const double* scale, int nv,
+                double* Y, int64_t ldy);
+
+/* ---- instrumentation ----------------------------------------------------- */
+typedef struct m3b_stats {
+  int64_t kernel_launches;     /* CUDA kernels launched by this context so far     */
+  int64_t spmv_cells_out;      /* K4 launches                                      */
+  int64_t spmv_genes_out;      /* K5 launches                                      */
+  double  spmv_cells_out_ms;   /* summed CUDA-event time of K4 (when timing is on) */
+  double  spmv_genes_out_ms;   /* summed CUDA-event time of K5                     */
+  double  irlba_ms;            /* device time of the last m3b_pca_irlba            */
+  double  prepare_ms;          /* normalize+select+moments device time             */
+  int64_t spmv_bytes_cells_out;/* algorithmic bytes of one K4 launch               */
+  int64_t spmv_bytes_genes_out;/* algorithmic bytes of one K5 launch               */
+  int64_t h2d_bytes;           /* host->device bytes copied so far                 */
+  int64_t d2h_bytes;           /* device->host bytes copied so far                 */
+} m3b_stats;
+int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);
+int m3b_reset_stats(m3b_ctx* ctx);
+/* flags for m3b_create */
+#define M3B_FLAG_TIME_SPMV 1  /* bracket every SpMV launch with CUDA events */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3B_H */

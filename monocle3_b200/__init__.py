@@ -1,0 +1,13 @@
+"""monocle3_b200 -- B200-native preprocess_cds PCA path (drop-in for monocle3's
+estimate_size_factors / normalized_counts / preprocess_cds / preprocess_transform).
+
+Importing the package does not load the CUDA library; the first call that needs
+the device does (and raises if libm3b.so is not built or no B200 is visible --
+there is no CPU fallback)."""
+from .api import (CellDataSet, estimate_size_factors, get_context, load_a549, new_cell_data_set,  # noqa: F401
+                  normalized_counts, preprocess_cds, preprocess_transform, set_context, set_size_factors,
+                  size_factors)
+
+__all__ = ["CellDataSet", "estimate_size_factors", "get_context", "load_a549", "new_cell_data_set",
+           "normalized_counts", "preprocess_cds", "preprocess_transform", "set_context", "set_size_factors",
+           "size_factors"]

@@ -1,0 +1,260 @@
+"""Host-side mirror of the reference's R interface for the preprocess_cds PCA path.
+
+R is not available in this image, so the part of the path that stays in R in the
+real drop-in (argument checks, set.seed(2016)+rnorm, name->index translation,
+dimnames, model-slot assembly) is written here in Python with the same function
+names, argument meaning and error behaviour as the reference:
+
+  estimate_size_factors   R/utils.R:26-50
+  size_factors            R/methods-cell_data_set.R:36-41
+  normalized_counts       R/utils.R:477-509
+  preprocess_cds          R/preprocess_cds.R:62-248   (PCA branch)
+  preprocess_transform    R/projection.R:72-155       (PCA branch)
+  new_cell_data_set       R/cell_data_set.R:67-137
+  load_a549               R/io.R:10-26 (reads the committed fixture)
+
+All arithmetic goes through the C ABI (engine.py -> libm3b.so); nothing here
+computes on the CPU beyond O(genes) bookkeeping.
+"""
+import os
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as L
+from . import engine
+from .r_rng import rnorm_after_seed
+
+_default_ctx = None
+
+
+def get_context(device=None):
+    """Process-wide default context (one process drives one GPU)."""
+    global _default_ctx
+    if _default_ctx is None:
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        _default_ctx = engine.Context(device=device, small_svd=os.environ.get("M3B_SMALL_SVD", "lapack"))
+    return _default_ctx
+
+
+def set_context(ctx):
+    global _default_ctx
+    _default_ctx = ctx
+
+
+class CellDataSet:
+    """Minimal stand-in for the S4 `cell_data_set` (R/cell_data_set.R:28-34): the slots
+    this path reads and writes.  `counts` is genes x cells CSC (the dgCMatrix).
+
+    For a cell-sharded run `counts` holds this rank's contiguous cell range and
+    `shard = (rank, world, n_cells_total, allgather)`, where allgather(np.ndarray)
+    returns the concatenation over ranks in rank order (see dist.py)."""
+
+    def __init__(self, counts, gene_names=None, cell_names=None, shard=None):
+        if not sp.isspmatrix_csc(counts):
+            counts = sp.csc_matrix(counts)  # methods::as(expression_data, "dgCMatrix")
+        self.counts = counts
+        G, C = counts.shape
+        self.gene_names = np.asarray(gene_names if gene_names is not None else [str(i) for i in range(G)])
+        self.cell_names = np.asarray(cell_names if cell_names is not None else [str(i) for i in range(C)])
+        if len(self.gene_names) != G or len(self.cell_names) != C:
+            raise ValueError("dimnames do not match the expression matrix")
+        self.col_data = {}           # colData(cds): 'Size_Factor'
+        self.reduced_dims = {}       # reducedDims(cds)
+        self.reduce_dim_aux = {}     # cds@reduce_dim_aux
+        self.shard = shard
+        self._dev = None             # DeviceMatrix cache (counts resident in HBM)
+
+    @property
+    def n_cells_total(self):
+        return self.shard[2] if self.shard else self.counts.shape[1]
+
+    def device_matrix(self, ctx=None):
+        ctx = ctx or get_context()
+        if self._dev is None or self._dev.ctx is not ctx or self._dev.h is None:
+            self._dev = engine.DeviceMatrix.from_csc(ctx, self.counts, self.n_cells_total)
+        return self._dev
+
+
+def size_factors(cds):
+    """R/methods-cell_data_set.R:36-41."""
+    return cds.col_data.get("Size_Factor")
+
+
+def set_size_factors(cds, value):
+    cds.col_data["Size_Factor"] = None if value is None else np.asarray(value, dtype=np.float64)
+    return cds
+
+
+def new_cell_data_set(expression_data, cell_names=None, gene_names=None, shard=None):
+    """R/cell_data_set.R:67-137: coerce to dgCMatrix, then estimate_size_factors (:135)."""
+    cds = CellDataSet(expression_data, gene_names, cell_names, shard)
+    return estimate_size_factors(cds)
+
+
+def load_a549():
+    """R/io.R:10-26, from the committed copy of inst/extdata/small_a549_dex_*.rda."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "a549.npz")
+    z = np.load(path, allow_pickle=False)
+    dim = tuple(int(v) for v in z["dim"])
+    m = sp.csc_matrix((z["x"], z["i"], z["p"]), shape=dim)
+    return new_cell_data_set(m, cell_names=z["cells"], gene_names=z["genes"])
+
+
+_SF_METHODS = {"mean-geometric-mean-total": L.SF_TOTAL, "mean-geometric-mean-log-total": L.SF_LOG_TOTAL}
+
+
+def estimate_size_factors(cds, round_exprs=True, method="mean-geometric-mean-total"):
+    """R/utils.R:26-50.  Totals come from the device (K1); the geometric mean is finished
+    on the host in long double like R's mean()."""
+    if method not in _SF_METHODS:
+        raise ValueError("'arg' should be one of 'mean-geometric-mean-total', 'mean-geometric-mean-log-total'")
+    dev = cds.device_matrix()
+    raw = dev.cell_totals(round_exprs=False)
+    if cds.shard:
+        raw = cds.shard[3](raw)
+    if np.any(raw == 0):  # R/utils.R:32-39
+        warnings.warn("Your CDS object contains cells with zero reads. This causes size factor calculation to "
+                      "fail. Please remove the zero read cells using cds <- cds[,Matrix::colSums(exprs(cds)) != 0] "
+                      "and then run cds <- estimate_size_factors(cds)")
+        return cds
+    tot = dev.cell_totals(round_exprs=True) if round_exprs else None
+    if tot is None:
+        tot_all = raw
+    else:
+        tot_all = cds.shard[3](tot) if cds.shard else tot
+    sf_all, _ = engine.size_factors_from_totals(tot_all, _SF_METHODS[method])
+    if cds.shard:
+        rank = cds.shard[0]
+        counts_per_rank = cds.shard[3](np.array([cds.counts.shape[1]], dtype=np.float64)).astype(np.int64)
+        off = int(counts_per_rank[:rank].sum())
+        sf = sf_all[off:off + cds.counts.shape[1]]
+    else:
+        sf = sf_all
+    return set_size_factors(cds, sf)
+
+
+def normalized_counts(cds, norm_method="log", pseudocount=1):
+    """R/utils.R:477-509 (sparse branch): returns a CSC with the input's pattern."""
+    if norm_method not in ("log", "binary", "size_only"):
+        raise ValueError("'arg' should be one of 'log', 'binary', 'size_only'")
+    dev = cds.device_matrix()
+    if norm_method == "binary":
+        dev.normalize(None, L.NORM_BINARY, 0.0)
+    else:
+        if norm_method == "log" and pseudocount != 1:
+            raise ValueError("Pseudocount must equal 1 with sparse expression matrices")
+        dev.normalize(size_factors(cds), L.NORM_LOG10 if norm_method == "log" else L.NORM_SIZE_ONLY,
+                      1.0 if norm_method == "log" else 0.0)
+    y = dev.export_values()
+    out = sp.csc_matrix((y, cds.counts.indices.copy(), cds.counts.indptr.copy()), shape=cds.counts.shape)
+    if norm_method == "binary":
+        out.eliminate_zeros()
+    return out
+
+
+_NORM = {"log": L.NORM_LOG2, "size_only": L.NORM_SIZE_ONLY, "none": L.NORM_NONE}
+
+
+def _normalize_on_device(cds, norm_method, pseudo_count):
+    """normalize_expr_data (R/preprocess_cds.R:253-286) -- result stays on the device."""
+    if pseudo_count is None:
+        pseudo_count = 1 if norm_method == "log" else 0
+    dev = cds.device_matrix()
+    dev.normalize(size_factors(cds) if norm_method != "none" else None, _NORM[norm_method],
+                  float(pseudo_count) if norm_method != "none" else 0.0)
+    return dev
+
+
+def preprocess_cds(cds, method="PCA", num_dim=50, norm_method="log", use_genes=None, pseudo_count=None,
+                   scaling=True, verbose=False, build_nn_index=False, nn_control=None, _irlba_args=None):
+    """R/preprocess_cds.R:62-248, PCA branch."""
+    if method not in ("PCA", "LSI"):
+        raise ValueError("method must be one of 'PCA' or 'LSI'")
+    if norm_method not in _NORM:
+        raise ValueError("norm_method must be one of 'log', 'size_only' or 'none'")
+    if not (isinstance(num_dim, (int, np.integer)) and num_dim > 0):
+        raise ValueError("num_dim is not a count (a single positive integer)")
+    if method == "LSI":
+        raise NotImplementedError("the LSI branch is outside this build's scope (SURVEY.md section 8f)")
+    if build_nn_index:
+        raise NotImplementedError("nearest-neighbour indices are outside this build's scope (SURVEY.md section 8f)")
+    gene_order = None
+    if use_genes is not None:
+        use_genes = list(use_genes)
+        lut = {g: k for k, g in enumerate(cds.gene_names)}
+        if not all(isinstance(g, str) for g in use_genes) or not all(g in lut for g in use_genes):
+            raise ValueError("use_genes must be NULL, or all must be present in the row.names of rowData(cds)")
+        gene_order = np.array([lut[g] for g in use_genes], dtype=np.int32)
+    if size_factors(cds) is None:
+        raise ValueError("You must call estimate_size_factors before calling preprocess_cds.")
+    if np.any(np.isnan(size_factors(cds))):
+        raise ValueError("One or more cells has a size factor of NA.")
+
+    dev = _normalize_on_device(cds, norm_method, pseudo_count)  # :111
+    if cds.counts.shape[0] == 0:
+        raise ValueError("all rows have standard deviation zero")
+    keep = dev.select_genes(gene_order)  # :117-122 + Matrix::t
+    sel = np.arange(cds.counts.shape[0]) if gene_order is None else gene_order
+    kept_idx = sel[keep]
+    if verbose:
+        print("Remove noise by PCA ...")
+    n = min(num_dim, min(len(kept_idx), cds.n_cells_total) - 1)  # :140
+    # set.seed(2016) (:110); irlba draws rnorm(ncol(A)) for its start vector
+    v0 = rnorm_after_seed(2016, len(kept_idx))
+    res = dev.pca_irlba(n, v0, center=scaling, scale=scaling, **(_irlba_args or {}))
+    if res["status"] == L.M3B_W_NOT_CONVERGED:
+        warnings.warn("did not converge--results might be invalid!; try increasing work or maxit")
+    C_tot = cds.n_cells_total
+    sdev = res["d"] / np.sqrt(max(1, C_tot - 1))  # R/utils.R:418
+    cds.reduced_dims["PCA"] = res["x"]            # rows = colnames(cds), cols = PC1..
+    cds.reduced_dims_dimnames = {"PCA": (cds.cell_names, ["PC%d" % (k + 1) for k in range(n)])}
+    cds.reduce_dim_aux["PCA"] = {"model": {
+        "num_dim": num_dim, "norm_method": norm_method, "use_genes": use_genes, "pseudo_count": pseudo_count,
+        "svd_v": res["v"], "svd_v_rownames": cds.gene_names[kept_idx],
+        "svd_sdev": sdev, "svd_center": res["center"], "svd_scale": res["scale"],
+        "prop_var_expl": sdev ** 2 / np.sum(sdev ** 2),  # :158-160
+    }, "irlba": {"iter": res["iter"], "mprod": res["mprod"], "d": res["d"]}}
+    return cds
+
+
+def preprocess_transform(cds, reduction_method="PCA", block_size=None, cores=1):
+    """R/projection.R:72-155, PCA branch.  block_size / cores are accepted for signature
+    compatibility; the projection is a single sparse product on the device (K10)."""
+    if reduction_method not in ("PCA", "LSI"):
+        raise ValueError("reduction_method must be 'PCA' or 'LSI'")
+    if size_factors(cds) is None:
+        raise ValueError("You must call estimate_size_factors before calling preprocess_cds.")
+    if np.any(np.isnan(size_factors(cds))):
+        raise ValueError("One or more cells has a size factor of NA.")
+    if cds.reduce_dim_aux.get(reduction_method) is None:
+        raise ValueError("Reduction method '%s' is not in the model object." % reduction_method)
+    if reduction_method == "LSI":
+        raise NotImplementedError("the LSI branch is outside this build's scope (SURVEY.md section 8f)")
+    model = cds.reduce_dim_aux["PCA"]["model"]
+    dev = _normalize_on_device(cds, model["norm_method"], model["pseudo_count"])  # :109
+    if cds.counts.shape[0] == 0:
+        raise ValueError("all rows have standard deviation zero")
+    keep = dev.select_genes(None)  # :117-118
+    kept_names = cds.gene_names[keep]
+    lut = {g: k for k, g in enumerate(model["svd_v_rownames"])}
+    # intersect(rownames(rotation), rownames(FM)) is in the MODEL's order (:121-122); every kept
+    # query gene must be in the model, otherwise FM[intersect_genes,] would silently drop rows --
+    # R stops when match() yields NA.
+    model_row = np.array([lut.get(g, -1) for g in kept_names], dtype=np.int32)
+    n_common = int(np.sum(model_row >= 0))
+    if len(kept_names) and n_common / len(kept_names) < 0.5:  # :128-130
+        warnings.warn("fewer than half the genes in the subject matrix are also in the reference matrix: "
+                      "are the matrices prepared using the same gene set?")
+    if np.any(model_row < 0):
+        # genes of the query that the model does not know are dropped by the intersect (:121,133)
+        qidx = np.nonzero(keep)[0][model_row >= 0]
+        keep2 = dev.select_genes(qidx.astype(np.int32))
+        if not np.all(keep2):
+            raise RuntimeError("internal: filter changed between passes")
+        model_row = model_row[model_row >= 0]
+    Y = dev.project(model_row, model["svd_v"], model["svd_center"], model["svd_scale"])
+    cds.reduced_dims["PCA"] = Y
+    return cds

@@ -1,0 +1,118 @@
+// K11: NCCL plumbing for the cell-sharded run (one context per rank).
+//
+// The reference has no distributed backend at all; the
+// collectives exist only because cells are sharded across GPUs: one sum-allreduce
+// of the gene-length partial A^T w per Lanczos step, one of the j+1 Gram-Schmidt
+// coefficients and one of {||w||^2, sum w}; plus the moment / row-sum reductions
+// during preparation.  NCCL is resolved with dlopen at first use so that a host
+// process which already carries NCCL (torch) shares that copy.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "m3b_internal.h"
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api(m3b_ctx* ctx) {
+  static NcclApi api;
+  static bool tried = false;
+  if (api.handle) return &api;
+  if (tried) return nullptr;
+  tried = true;
+  const char* cands[4] = {getenv("M3B_NCCL_LIB"), "libnccl.so.2", "libnccl.so", nullptr};
+  // prefer a copy that is already mapped into the process
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  for (int k = 0; !h && k < 3; ++k)
+    if (cands[k]) h = dlopen(cands[k], RTLD_NOW | RTLD_LOCAL);
+  if (!h) {
+    m3b_set_error(ctx, "cannot load NCCL: %s", dlerror());
+    return nullptr;
+  }
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
+    m3b_set_error(ctx, "NCCL library lacks required symbols");
+    return nullptr;
+  }
+  api.handle = h;
+  return &api;
+}
+
+#define NK(ctx, api, call)                                                              \
+  do {                                                                                  \
+    ncclResult_t r__ = (call);                                                          \
+    if (r__ != ncclSuccess) {                                                           \
+      m3b_set_error((ctx), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,                \
+                    (api)->GetErrorString(r__));                                        \
+      return M3B_E_NCCL;                                                                \
+    }                                                                                   \
+  } while (0)
+
+int comm_get_unique_id(m3b_ctx* ctx, char* id) {
+  NcclApi* api = nccl_api(ctx);
+  if (!api) return M3B_E_NCCL;
+  static_assert(sizeof(ncclUniqueId) == M3B_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId uid;
+  NK(ctx, api, api->GetUniqueId(&uid));
+  memcpy(id, &uid, sizeof(uid));
+  return M3B_OK;
+}
+
+int comm_init(m3b_ctx* ctx, int rank, int world, const char* id) {
+  if (world < 1 || rank < 0 || rank >= world) {
+    m3b_set_error(ctx, "m3b_comm_init: bad rank/world %d/%d", rank, world);
+    return M3B_E_DIMS;
+  }
+  comm_destroy(ctx);
+  ctx->comm.rank = rank;
+  ctx->comm.world = world;
+  if (world == 1) return M3B_OK;
+  NcclApi* api = nccl_api(ctx);
+  if (!api) return M3B_E_NCCL;
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  ncclComm_t c;
+  CK(ctx, cudaSetDevice(ctx->device));
+  NK(ctx, api, api->CommInitRank(&c, world, uid, rank));
+  ctx->comm.comm = (void*)c;
+  return M3B_OK;
+}
+
+void comm_destroy(m3b_ctx* ctx) {
+  if (ctx->comm.comm) {
+    NcclApi* api = nccl_api(ctx);
+    if (api) api->CommDestroy((ncclComm_t)ctx->comm.comm);
+    ctx->comm.comm = nullptr;
+  }
+  ctx->comm.world = 1;
+  ctx->comm.rank = 0;
+}
+
+int comm_allreduce_f64(m3b_ctx* ctx, double* dev, size_t n) {
+  if (ctx->comm.world == 1 || n == 0) return M3B_OK;
+  NcclApi* api = nccl_api(ctx);
+  if (!api) return M3B_E_NCCL;
+  NK(ctx, api, api->AllReduce(dev, dev, n, ncclDouble, ncclSum, (ncclComm_t)ctx->comm.comm, ctx->stream));
+  return M3B_OK;
+}
+
+int comm_allreduce_i64(m3b_ctx* ctx, long long* dev, size_t n) {
+  if (ctx->comm.world == 1 || n == 0) return M3B_OK;
+  NcclApi* api = nccl_api(ctx);
+  if (!api) return M3B_E_NCCL;
+  NK(ctx, api, api->AllReduce(dev, dev, n, ncclInt64, ncclSum, (ncclComm_t)ctx->comm.comm, ctx->stream));
+  return M3B_OK;
+}

@@ -1,0 +1,867 @@
+// K3 (gene moments), K6/K7 (orthogonalisation, norms), K9 (restart GEMMs) and the
+// IRLBA driver that strings them together with K4/K5 (spmv.cu) and K8 (small_svd.cu).
+//
+// Replaces irlba::irlba(A=t(FM), nv, center, scale) and the post-processing of
+// sparse_prcomp_irlba (R/utils.R:383-428).  The iteration is irlba's fast C path
+// step for step: single-vector implicitly restarted
+// Lanczos bidiagonalisation, work = nv+7, one classical Gram-Schmidt pass per
+// vector, thick restart on the Ritz vectors, irlba's convergence test.
+//
+// Everything between two restarts is queued on one stream without host
+// synchronisation: all scalars (S, R_F, beta, sum(w)) live in device memory and
+// every reduction is a fixed-order two-stage reduction (bit-reproducible).  The
+// host reads back two ints per restart ({k, converged}).
+//
+// Operator (m = local cells, n = kept genes):
+//   Ax(x):  xs = x / s;  w = A' xs - (ce . xs)
+//   Atw(w): f = (A'^T w) / s - sum(w) * ce / s
+// where A' is the stored sparse matrix, s the gene sd (or 1), and ce the
+// effective centre = mean(A') when scaling, -f0 on the reference's dense
+// pseudo-count paths without scaling, 0 otherwise (DESIGN.md "implicit constant").
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "m3b_internal.h"
+
+int launch_jacobi_svd(m3b_ctx* ctx, int n, const double* B, double* U, double* s, double* V, double* scratch, int* info);
+
+#define NT 256
+#define MAX_PART 592  // upper bound on per-kernel partial counts (4 * 148)
+
+// scalar slots in the device scalar buffer
+enum { SC_S = 0, SC_RF = 1, SC_SUMW = 2, SC_NRM2 = 3, SC_SUM = 4, SC_COUNT = 8 };
+// control block (ints)
+enum { CT_K = 0, CT_CONV = 1, CT_FLAG = 2, CT_SWEEPS = 3, CT_COUNT = 8 };
+
+// --------------------------------------------------------------------------
+// deterministic block reduction (fixed tree): result valid in thread 0
+// --------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh /* >= 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) r += sh[w];
+  }
+  __syncthreads();
+  return r;
+}
+
+// sum of a short partial array, identical in every block that calls it (broadcast via smem)
+__device__ __forceinline__ double block_sum_partials(const double* __restrict__ p, int np, double* sh) {
+  double v = 0.0;
+  for (int k = threadIdx.x; k < np; k += blockDim.x) v += p[k];
+  double r = block_sum(v, sh);
+  __shared__ double bc;
+  if (threadIdx.x == 0) bc = r;
+  __syncthreads();
+  return bc;
+}
+
+// --------------------------------------------------------------------------
+// gene-side vector kernels
+// --------------------------------------------------------------------------
+// xs = v / s ; pb[block] = partial dot(xs, ce)
+__global__ void __launch_bounds__(NT) k_make_xs(const double* __restrict__ v, const double* __restrict__ s,
+                                                const double* __restrict__ ce, int n, double* __restrict__ xs,
+                                                double* __restrict__ pb) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+    double x = v[g];
+    if (s) x = x / s[g];
+    xs[g] = x;
+    if (ce) acc += x * ce[g];
+  }
+  double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) pb[blockIdx.x] = r;
+}
+
+// w[r] = sum(partials of row r) - beta - R_F * wprev[r]      (K4 epilogue)
+__global__ void __launch_bounds__(NT) k_combine_A(const double* __restrict__ partial, const int* __restrict__ rip,
+                                                  long long rows, int n_tiles, const double* __restrict__ pb, int npb,
+                                                  const double* __restrict__ wprev, const double* __restrict__ scal,
+                                                  double* __restrict__ w) {
+  __shared__ double sh[32];
+  const double beta = pb ? block_sum_partials(pb, npb, sh) : 0.0;
+  const double rf = wprev ? scal[SC_RF] : 0.0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int* p = rip + (long long)t * (rows + 1) + r;
+      const int b = p[0], e = p[1];
+      for (int k = b; k < e; ++k) acc += partial[k];
+    }
+    acc -= beta;
+    if (wprev) acc -= rf * wprev[r];
+    w[r] = acc;
+  }
+}
+
+// Fraw[g] = sum(partials of row g)                           (K5 combine, local shard)
+// F[g] = Fraw[g]/s - (sumw*ce)/s - S*vj[g]                   (fix-ups, after the allreduce)
+__global__ void __launch_bounds__(NT) k_fix_F(const double* __restrict__ Fraw, const double* __restrict__ s,
+                                              const double* __restrict__ ce, const double* __restrict__ vj,
+                                              const double* __restrict__ scal, int n, double* __restrict__ F) {
+  const double sumw = scal[SC_SUMW], S = scal[SC_S];
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+    double f = Fraw[g];
+    if (s) f = f / s[g];
+    if (ce) {
+      double c = sumw * ce[g];
+      if (s) c = c / s[g];
+      f = f - c;
+    }
+    f = f - S * vj[g];
+    F[g] = f;
+  }
+}
+
+// --------------------------------------------------------------------------
+// K6: tall-skinny orthogonalisation  y -= X (X^T y), one classical GS pass
+// --------------------------------------------------------------------------
+// part[blk*ncols + c] = sum over the block's rows of X[r,c]*y[r]
+__global__ void __launch_bounds__(NT) k_dots(const double* __restrict__ X, long long ld, long long rows, int ncols,
+                                             const double* __restrict__ y, int chunk, double* __restrict__ part) {
+  extern __shared__ double ys[];  // chunk doubles
+  const long long r0 = (long long)blockIdx.x * chunk;
+  const int len = (int)min((long long)chunk, rows - r0);
+  for (int k = threadIdx.x; k < len; k += blockDim.x) ys[k] = y[r0 + k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < ncols; c += nwarps) {
+    const double* xc = X + (long long)c * ld + r0;
+    double a0 = 0.0, a1 = 0.0;
+    int k = lane;
+    for (; k + 32 < len; k += 64) {
+      a0 += xc[k] * ys[k];
+      a1 += xc[k + 32] * ys[k + 32];
+    }
+    if (k < len) a0 += xc[k] * ys[k];
+    double a = a0 + a1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) part[(long long)blockIdx.x * ncols + c] = a;
+  }
+}
+
+// t[c] = sum_b part[b*ncols + c] (fixed order)
+__global__ void k_reduce_dots(const double* __restrict__ part, int nblk, int ncols, double* __restrict__ t) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  double a = 0.0;
+  for (int b = 0; b < nblk; ++b) a += part[(long long)b * ncols + c];
+  t[c] = a;
+}
+
+// y[r] -= sum_c X[r,c]*t[c];  pn[blk] = partial ||y||^2, ps[blk] = partial sum(y)
+__global__ void __launch_bounds__(NT) k_apply_orth(const double* __restrict__ X, long long ld, long long rows, int ncols,
+                                                   const double* __restrict__ t, double* __restrict__ y,
+                                                   double* __restrict__ pn, double* __restrict__ ps) {
+  extern __shared__ double ts[];  // ncols
+  __shared__ double sh[32];
+  for (int k = threadIdx.x; k < ncols; k += blockDim.x) ts[k] = t[k];
+  __syncthreads();
+  double n2 = 0.0, sm = 0.0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    double a0 = 0.0, a1 = 0.0;
+    const double* xr = X + r;
+    int c = 0;
+    for (; c + 1 < ncols; c += 2) {
+      a0 += xr[(long long)c * ld] * ts[c];
+      a1 += xr[(long long)(c + 1) * ld] * ts[c + 1];
+    }
+    if (c < ncols) a0 += xr[(long long)c * ld] * ts[c];
+    double v = y[r] - (a0 + a1);
+    y[r] = v;
+    n2 += v * v;
+    sm += v;
+  }
+  double r1 = block_sum(n2, sh);
+  double r2 = block_sum(sm, sh);
+  if (threadIdx.x == 0) {
+    pn[blockIdx.x] = r1;
+    ps[blockIdx.x] = r2;
+  }
+}
+
+// plain norm/sum partials of a vector (first Lanczos vector: no orthogonalisation)
+__global__ void __launch_bounds__(NT) k_norm_partials(const double* __restrict__ y, long long rows,
+                                                      double* __restrict__ pn, double* __restrict__ ps) {
+  __shared__ double sh[32];
+  double n2 = 0.0, sm = 0.0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    double v = y[r];
+    n2 += v * v;
+    sm += v;
+  }
+  double r1 = block_sum(n2, sh);
+  double r2 = block_sum(sm, sh);
+  if (threadIdx.x == 0) {
+    pn[blockIdx.x] = r1;
+    ps[blockIdx.x] = r2;
+  }
+}
+
+// buf2 = {sum pn, sum ps}   (single block; the allreduce of the W side rides on buf2)
+__global__ void __launch_bounds__(NT) k_reduce2(const double* __restrict__ pn, const double* __restrict__ ps, int np,
+                                                double* __restrict__ buf2) {
+  __shared__ double sh[32];
+  double a = 0.0, b = 0.0;
+  for (int k = threadIdx.x; k < np; k += blockDim.x) {
+    a += pn[k];
+    b += ps[k];
+  }
+  double r1 = block_sum(a, sh);
+  double r2 = block_sum(b, sh);
+  if (threadIdx.x == 0) {
+    buf2[0] = r1;
+    buf2[1] = r2;
+  }
+}
+
+// W side: S = sqrt(buf2[0]); w *= 1/S; scal[S], scal[SUMW] = buf2[1]/S
+__global__ void __launch_bounds__(NT) k_scale_w(double* __restrict__ w, long long rows, const double* __restrict__ buf2,
+                                                double* __restrict__ scal, int* __restrict__ ctl, double eps,
+                                                int first) {
+  const double S = sqrt(buf2[0]);
+  const double SS = 1.0 / S;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+    w[r] *= SS;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[SC_S] = S;
+    scal[SC_SUMW] = buf2[1] * SS;
+    if (!(S >= eps)) ctl[CT_FLAG] |= first ? 1 : 2;  // 1: start vector in null space, 2: breakdown
+  }
+}
+
+// V side: R_F = ||F|| from pn; vnext = F * (1/R_F); xs = vnext / s; pb = partial dot(xs, ce);
+// B[j,j] = S, B[j,j+1] = R_F
+__global__ void __launch_bounds__(NT) k_finish_F(const double* __restrict__ F, const double* __restrict__ pn, int np,
+                                                 const double* __restrict__ s, const double* __restrict__ ce, int n,
+                                                 double* __restrict__ vnext, double* __restrict__ xs,
+                                                 double* __restrict__ pb, double* __restrict__ Bm, int work, int j,
+                                                 double* __restrict__ scal, int* __restrict__ ctl, double eps) {
+  __shared__ double sh[32];
+  const double rf = sqrt(block_sum_partials(pn, np, sh));
+  const double R = 1.0 / rf;
+  double acc = 0.0;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+    double v = F[g] * R;
+    vnext[g] = v;
+    double x = s ? v / s[g] : v;
+    xs[g] = x;
+    if (ce) acc += x * ce[g];
+  }
+  double r = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    pb[blockIdx.x] = r;
+    if (blockIdx.x == 0) {
+      scal[SC_RF] = rf;
+      Bm[(long long)j * work + j] = scal[SC_S];
+      Bm[(long long)(j + 1) * work + j] = rf;
+      if (!(rf >= eps)) ctl[CT_FLAG] |= 2;
+    }
+  }
+}
+
+// end of a Lanczos cycle: B[j,j] = S; R_F = ||F||; F *= 1/R_F  (F becomes the restart vector)
+__global__ void __launch_bounds__(NT) k_finish_last(double* __restrict__ F, const double* __restrict__ pn, int np, int n,
+                                                    double* __restrict__ Bm, int work, int j, double* __restrict__ scal,
+                                                    double eps) {
+  __shared__ double sh[32];
+  const double rf = sqrt(block_sum_partials(pn, np, sh));
+  const double R = 1.0 / rf;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) F[g] *= R;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[SC_RF] = (rf < eps) ? 0.0 : rf;
+    Bm[(long long)j * work + j] = scal[SC_S];
+  }
+}
+
+// --------------------------------------------------------------------------
+// restart logic on the device (irlb.c after dgesdd + convtests), one thread block
+//   BU (work x work), BS, res, svratio; k, converged -> ctl
+//   new B: diag(BS[:k]) + column k = res[:k]
+// --------------------------------------------------------------------------
+__global__ void k_restart_logic(int work, int nu, double tol, double svtol, const double* __restrict__ BU,
+                                const double* __restrict__ BS, double* __restrict__ svratio, double* __restrict__ res,
+                                double* __restrict__ Bm, const double* __restrict__ scal, int* __restrict__ ctl) {
+  __shared__ int s_len;
+  __shared__ int s_k;
+  const double rf = scal[SC_RF];
+  const double S = scal[SC_S];
+  if (threadIdx.x == 0) s_len = 0;
+  __syncthreads();
+  double smax = 0.0;
+  for (int i = 0; i < work; ++i) smax = fmax(smax, BS[i]);
+  for (int i = threadIdx.x; i < work; i += blockDim.x) {
+    double sr = fabs(svratio[i] - BS[i]) / BS[i];
+    double r = rf * BU[(long long)i * work + (work - 1)];  // last ROW of BU
+    res[i] = r;
+    svratio[i] = sr;
+    if (fabs(r) < tol * smax && sr < svtol) atomicAdd(&s_len, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int k = ctl[CT_K];
+    int len = s_len;
+    int conv = (len >= nu || S == 0.0) ? 1 : 0;
+    if (!conv) {
+      if (k < nu + len) k = nu + len;
+      if (k > work - 3) k = work - 3;
+      if (k < 1) k = 1;
+    }
+    ctl[CT_K] = k;
+    ctl[CT_CONV] = conv;
+    s_k = k;
+  }
+  __syncthreads();
+  if (ctl[CT_CONV]) return;
+  const int k = s_k;
+  for (int i = threadIdx.x; i < work; i += blockDim.x) svratio[i] = BS[i];
+  for (int e = threadIdx.x; e < work * work; e += blockDim.x) Bm[e] = 0.0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    Bm[(long long)i * work + i] = BS[i];
+    Bm[(long long)k * work + i] = res[i];
+  }
+}
+
+// Q[:, c] = BU[:, c] * BS[c]  (final embedding X = W * BU[:, :nu] * diag(d))
+__global__ void k_scale_cols(const double* __restrict__ BU, const double* __restrict__ BS, int work, int nu,
+                             double* __restrict__ Q) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < work * nu) Q[e] = BU[e] * BS[e / work];
+}
+
+// transpose a small matrix (host-callback path hands Vt)
+__global__ void k_transpose_small(const double* __restrict__ in, int n, double* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n * n) {
+    int r = e % n, c = e / n;
+    out[(long long)r * n + c] = in[(long long)c * n + r];
+  }
+}
+
+// --------------------------------------------------------------------------
+// K9: in-place tall-skinny GEMM  X[:, :kout] = X[:, :kin] * Q   (Q: kin x kout, ld kin)
+// A block owns RB rows: it first stages its whole row block in shared memory
+// (so the update can be done in place), then sweeps Q in column chunks.  Each
+// thread accumulates RPT rows x 13 columns in registers; Q reads are warp
+// broadcasts.
+// --------------------------------------------------------------------------
+#define GEMM_CT 13
+template <int RPT>
+__global__ void __launch_bounds__(256, 1)
+k_restart_gemm(double* __restrict__ X, long long ld, long long rows, int kin, int kout, const double* __restrict__ Q,
+               int qc) {
+  extern __shared__ double smg[];
+  const int RB = 64 * RPT;
+  double* Xs = smg;                     // [kin][RB]
+  double* Qs = smg + (size_t)kin * RB;  // [qc][kin]  (column chunk of Q)
+  const long long r0 = (long long)blockIdx.x * RB;
+  const int nr = (int)min((long long)RB, rows - r0);
+  for (int e = threadIdx.x; e < kin * RB; e += blockDim.x) {
+    int c = e / RB, r = e % RB;
+    Xs[e] = (r < nr) ? X[(long long)c * ld + r0 + r] : 0.0;
+  }
+  const int rl = threadIdx.x & 63;  // row lane
+  const int cg = threadIdx.x >> 6;  // column group 0..3
+  for (int c0 = 0; c0 < kout; c0 += qc) {
+    const int nc = min(qc, kout - c0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nc * kin; e += blockDim.x) Qs[e] = Q[(long long)c0 * kin + e];
+    __syncthreads();
+    // this thread's columns inside the chunk: cg, cg+4, cg+8, ...  in passes of GEMM_CT
+    for (int cb = cg; cb < nc; cb += 4 * GEMM_CT) {
+      double acc[RPT][GEMM_CT];
+#pragma unroll
+      for (int a = 0; a < RPT; ++a)
+#pragma unroll
+        for (int b = 0; b < GEMM_CT; ++b) acc[a][b] = 0.0;
+      for (int kk = 0; kk < kin; ++kk) {
+        double xv[RPT];
+#pragma unroll
+        for (int a = 0; a < RPT; ++a) xv[a] = Xs[kk * RB + rl + 64 * a];
+#pragma unroll
+        for (int b = 0; b < GEMM_CT; ++b) {
+          const int c = cb + 4 * b;
+          const double q = (c < nc) ? Qs[c * kin + kk] : 0.0;
+#pragma unroll
+          for (int a = 0; a < RPT; ++a) acc[a][b] += xv[a] * q;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < GEMM_CT; ++b) {
+        const int c = cb + 4 * b;
+        if (c < nc) {
+#pragma unroll
+          for (int a = 0; a < RPT; ++a) {
+            const int r = rl + 64 * a;
+            if (r < nr) X[(long long)(c0 + c) * ld + r0 + r] = acc[a][b];
+          }
+        }
+      }
+    }
+  }
+}
+
+// ==========================================================================
+// host driver
+// ==========================================================================
+struct Irlba {
+  m3b_ctx* ctx;
+  m3b_mat* m;
+  int n, work, nu;
+  long long mrows;
+  double *V = nullptr, *W = nullptr, *F = nullptr, *Fraw = nullptr, *xs = nullptr;
+  double *s = nullptr, *ce = nullptr;  // nullable
+  double *part = nullptr, *t = nullptr, *pn = nullptr, *ps = nullptr, *pb = nullptr, *buf2 = nullptr;
+  double *scal = nullptr, *Bm = nullptr, *BU = nullptr, *BV = nullptr, *BS = nullptr, *svr = nullptr, *res = nullptr;
+  double *Q = nullptr, *svd_scratch = nullptr;
+  int* ctl = nullptr;
+  int nb_n, nb_m;        // blocks of the vector kernels (gene side / cell side)
+  int chunk_n, chunk_m;  // rows per block of k_dots
+  int nblk_n, nblk_m;
+  double eps;
+  std::vector<void*> owned;
+
+  template <typename T>
+  int alloc(T** p, size_t cnt) {
+    RET(dev_alloc(ctx, p, cnt));
+    owned.push_back(*p);
+    return M3B_OK;
+  }
+  void release() {
+    for (void* p : owned) dev_free(p);
+    owned.clear();
+  }
+
+  static int pick_chunk(long long rows, int sms) {
+    long long c = (rows + 2LL * sms - 1) / (2LL * sms);
+    c = (c + 31) & ~31LL;
+    c = std::max<long long>(256, std::min<long long>(c, 4096));
+    return (int)c;
+  }
+
+  int orthog(double* X, long long ld, long long rows, int ncols, double* y, int chunk, int nblk, int nb, bool allreduce) {
+    if (ncols > 0) {
+      k_dots<<<nblk, NT, chunk * sizeof(double), ctx->stream>>>(X, ld, rows, ncols, y, chunk, part);
+      k_reduce_dots<<<(ncols + 127) / 128, 128, 0, ctx->stream>>>(part, nblk, ncols, t);
+      count_launch(ctx, 2);
+      if (allreduce) RET(comm_allreduce_f64(ctx, t, ncols));
+    }
+    k_apply_orth<<<nb, NT, std::max(ncols, 1) * sizeof(double), ctx->stream>>>(X, ld, rows, ncols, t, y, pn, ps);
+    count_launch(ctx);
+    CK(ctx, cudaGetLastError());
+    return M3B_OK;
+  }
+
+  // W[:, jw] = Ax(V[:, jv]) given xs/pb already prepared; optional "- R_F * W[:, jw-1]"
+  int product_A(int jw, bool sub_prev) {
+    cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
+    const bool timing = (ctx->flags & M3B_FLAG_TIME_SPMV) != 0;
+    if (timing) cudaEventRecord(e0, ctx->stream);
+    RET(launch_tile_stream(ctx, m->A, OP_DOT, xs));
+    if (timing) {
+      cudaEventRecord(e1, ctx->stream);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      ctx->stats.spmv_cells_out_ms += ms;
+    }
+    ctx->stats.spmv_cells_out++;
+    double* w = W + (long long)jw * mrows;
+    if (mrows) {
+      k_combine_A<<<nb_m, NT, 0, ctx->stream>>>(m->A.partial, m->A.row_item_ptr, mrows, m->A.n_tiles, ce ? pb : nullptr,
+                                                nb_n, sub_prev ? (w - mrows) : nullptr, scal, w);
+      count_launch(ctx);
+    }
+    CK(ctx, cudaGetLastError());
+    return M3B_OK;
+  }
+
+  // F = Atw(W[:, j]) - S * V[:, j]
+  int product_B(int j) {
+    const bool timing = (ctx->flags & M3B_FLAG_TIME_SPMV) != 0;
+    if (timing) cudaEventRecord(ctx->ev0, ctx->stream);
+    RET(launch_tile_stream(ctx, m->B, OP_DOT, W + (long long)j * mrows));
+    if (timing) {
+      cudaEventRecord(ctx->ev1, ctx->stream);
+      cudaEventSynchronize(ctx->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      ctx->stats.spmv_genes_out_ms += ms;
+    }
+    ctx->stats.spmv_genes_out++;
+    RET(launch_combine_rows(ctx, m->B, Fraw));
+    RET(comm_allreduce_f64(ctx, Fraw, n));
+    k_fix_F<<<nb_n, NT, 0, ctx->stream>>>(Fraw, s, ce, V + (long long)j * n, scal, n, F);
+    count_launch(ctx);
+    CK(ctx, cudaGetLastError());
+    return M3B_OK;
+  }
+
+  // normalise W[:, jw] using pn/ps partials (cell side): S, sum(w)
+  int finish_w(int jw, bool first) {
+    k_reduce2<<<1, NT, 0, ctx->stream>>>(pn, ps, nb_m, buf2);
+    count_launch(ctx);
+    RET(comm_allreduce_f64(ctx, buf2, 2));
+    k_scale_w<<<nb_m, NT, 0, ctx->stream>>>(W + (long long)jw * mrows, mrows, buf2, scal, ctl, eps, first ? 1 : 0);
+    count_launch(ctx);
+    CK(ctx, cudaGetLastError());
+    return M3B_OK;
+  }
+
+  int gemm_inplace(double* X, long long ld, long long rows, int kin, int kout, const double* Qd) {
+    if (rows == 0 || kout == 0) return M3B_OK;
+    const size_t budget = 220 * 1024;
+    int rpt = (kin <= 110) ? 2 : 1;
+    size_t xs_bytes = (size_t)kin * 64 * rpt * sizeof(double);
+    if (xs_bytes + (size_t)kin * 4 * sizeof(double) > budget) {
+      m3b_set_error(ctx, "restart GEMM: work=%d too large for the shared-memory tiling", kin);
+      return M3B_E_DIMS;
+    }
+    int qc = (int)((budget - xs_bytes) / ((size_t)kin * sizeof(double)));
+    qc = std::min(qc, kout);
+    if (qc >= 4) qc &= ~3;
+    size_t smem = xs_bytes + (size_t)qc * kin * sizeof(double);
+    const int RB = 64 * rpt;
+    unsigned grid = (unsigned)((rows + RB - 1) / RB);
+    if (rpt == 2) {
+      CK(ctx, cudaFuncSetAttribute(k_restart_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+      k_restart_gemm<2><<<grid, 256, smem, ctx->stream>>>(X, ld, rows, kin, kout, Qd, qc);
+    } else {
+      CK(ctx, cudaFuncSetAttribute(k_restart_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+      k_restart_gemm<1><<<grid, 256, smem, ctx->stream>>>(X, ld, rows, kin, kout, Qd, qc);
+    }
+    count_launch(ctx);
+    CK(ctx, cudaGetLastError());
+    return M3B_OK;
+  }
+};
+
+// --------------------------------------------------------------------------
+// K3: gene moments on layout B (R/utils.R:383,389).  Two passes, fp64:
+//   mean_g = sum_c y / C ;  var_g = (sum_nz (y-mean)^2 + (C - nnz_g) mean^2) / (C-1)
+// Pad entries are stored zeros, so pass 2 counts them as zeros: the closed-form
+// term uses the padded run length instead of nnz_g.  Sharded: both sums are
+// allreduced.  `center` holds the mean of the implicit dense matrix (mean + f0).
+// --------------------------------------------------------------------------
+__global__ void k_mean_from_sum(const double* __restrict__ sum, int n, double invC, double f0, double* __restrict__ mean_sparse,
+                                double* __restrict__ center) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) {
+    double mu = sum[g] * invC;
+    mean_sparse[g] = mu;
+    center[g] = mu + f0;
+  }
+}
+__global__ void k_ss_local(double* __restrict__ ss, const double* __restrict__ mean_sparse,
+                           const long long* __restrict__ padlen, long long c_local, int n) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) {
+    double mu = mean_sparse[g];
+    ss[g] += (double)(c_local - padlen[g]) * mu * mu;
+  }
+}
+__global__ void k_sd_from_ss(const double* __restrict__ ss, int n, double denom, double* __restrict__ sd) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) sd[g] = sqrt(ss[g] / denom);
+}
+
+int compute_moments(m3b_mat* m) {
+  m3b_ctx* ctx = m->ctx;
+  if (m->moments_done) return M3B_OK;
+  const int n = m->n_kept;
+  dev_free(m->center);
+  dev_free(m->scale);
+  dev_free(m->mean_sparse);
+  RET(dev_alloc(ctx, &m->center, (size_t)std::max(n, 1)));
+  RET(dev_alloc(ctx, &m->scale, (size_t)std::max(n, 1)));
+  RET(dev_alloc(ctx, &m->mean_sparse, (size_t)std::max(n, 1)));
+  double* tmp = nullptr;
+  RET(dev_alloc(ctx, &tmp, (size_t)std::max(n, 1)));
+  if (n) {
+    const int nb = (n + 255) / 256;
+    RET(launch_tile_stream(ctx, m->B, OP_SUM, nullptr));
+    RET(launch_combine_rows(ctx, m->B, tmp));
+    RET(comm_allreduce_f64(ctx, tmp, n));
+    k_mean_from_sum<<<nb, 256, 0, ctx->stream>>>(tmp, n, 1.0 / (double)m->n_cells_total, m->f0, m->mean_sparse, m->center);
+    RET(launch_tile_stream(ctx, m->B, OP_SQDEV, m->mean_sparse));
+    RET(launch_combine_rows(ctx, m->B, tmp));
+    k_ss_local<<<nb, 256, 0, ctx->stream>>>(tmp, m->mean_sparse, m->kept_padlen, m->n_cells, n);
+    RET(comm_allreduce_f64(ctx, tmp, n));
+    k_sd_from_ss<<<nb, 256, 0, ctx->stream>>>(tmp, n, (double)(m->n_cells_total - 1), m->scale);
+    count_launch(ctx, 3);
+    CK(ctx, cudaGetLastError());
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  dev_free(tmp);
+  m->moments_done = true;
+  return M3B_OK;
+}
+
+__global__ void k_fill(double* p, int n, double v) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) p[g] = v;
+}
+
+int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol, const double* v0, int center,
+              int scale, double* d_out, double* V_out, double* X_out, long long ldx, double* center_out,
+              double* scale_out, int* iter_out, int* mprod_out, bool copy_x) {
+  m3b_ctx* ctx = m->ctx;
+  const int n = m->n_kept;
+  const long long mloc = m->n_cells, mtot = m->n_cells_total;
+  const long long minmn = std::min<long long>(mtot, n);
+  if (nv <= 0 || nv >= minmn) {
+    m3b_set_error(ctx, "max(nu, nv) must be strictly less than min(nrow(A), ncol(A)) (nv=%d, min dim=%lld)", nv, minmn);
+    return M3B_E_DIMS;
+  }
+  if (work <= 0) work = nv + 7;
+  if (work <= nv) work = nv + 1;
+  if (work > minmn) work = (int)minmn;
+  if (work < 4 || n < 4 || mtot < 4) {
+    m3b_set_error(ctx, "irlba needs work, genes and cells >= 4 (work=%d, genes=%d, cells=%lld)", work, n, mtot);
+    return M3B_E_DIMS;
+  }
+  if (copy_x && X_out && ldx < mloc) {
+    m3b_set_error(ctx, "ldx (%lld) < local cells (%lld)", ldx, mloc);
+    return M3B_E_DIMS;
+  }
+  if (svtol <= 0) svtol = tol;
+  const bool use_scale = scale != 0;
+  const bool use_center = center != 0;
+  if (use_scale || use_center) RET(compute_moments(m));
+
+  Irlba I;
+  I.ctx = ctx;
+  I.m = m;
+  I.n = n;
+  I.work = work;
+  I.nu = nv;
+  I.mrows = mloc;
+  I.eps = 2.220446049250313e-16;
+  I.nb_n = std::max(1, std::min((n + NT - 1) / NT, 64));
+  I.nb_m = (int)std::max<long long>(1, std::min<long long>((mloc + NT - 1) / NT, MAX_PART));
+  I.chunk_n = Irlba::pick_chunk(n, ctx->sm_count);
+  I.chunk_m = Irlba::pick_chunk(mloc, ctx->sm_count);
+  I.nblk_n = std::max(1, (n + I.chunk_n - 1) / I.chunk_n);
+  I.nblk_m = (int)std::max<long long>(1, (mloc + I.chunk_m - 1) / I.chunk_m);
+  int status = M3B_OK;
+  cudaEvent_t evA = nullptr, evB = nullptr;
+#define IR(expr)               \
+  do {                         \
+    status = (expr);           \
+    if (status != M3B_OK) goto done; \
+  } while (0)
+#define ICK(call)                                                                               \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      m3b_set_error(ctx, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      status = (e__ == cudaErrorMemoryAllocation) ? M3B_E_NOMEM : M3B_E_CUDA;                   \
+      goto done;                                                                                \
+    }                                                                                           \
+  } while (0)
+  {
+    std::vector<double> hv(n);
+    std::vector<double> hB((size_t)work * work), hU((size_t)work * work), hS(work), hVt((size_t)work * work);
+    int hctl[CT_COUNT];
+    int it = 0, mprod = 0, k = 0;
+    bool converged = false;
+    const size_t part_sz = (size_t)std::max(I.nblk_n, I.nblk_m) * work;
+    IR(I.alloc(&I.V, (size_t)n * work));
+    IR(I.alloc(&I.W, (size_t)std::max<long long>(mloc, 1) * work));
+    IR(I.alloc(&I.F, (size_t)n));
+    IR(I.alloc(&I.Fraw, (size_t)n + 2));
+    IR(I.alloc(&I.xs, (size_t)n));
+    IR(I.alloc(&I.part, part_sz));
+    IR(I.alloc(&I.t, (size_t)work));
+    IR(I.alloc(&I.pn, (size_t)MAX_PART));
+    IR(I.alloc(&I.ps, (size_t)MAX_PART));
+    IR(I.alloc(&I.pb, (size_t)64));
+    IR(I.alloc(&I.buf2, (size_t)4));
+    IR(I.alloc(&I.scal, (size_t)SC_COUNT));
+    IR(I.alloc(&I.Bm, (size_t)work * work));
+    IR(I.alloc(&I.BU, (size_t)work * work));
+    IR(I.alloc(&I.BV, (size_t)work * work));
+    IR(I.alloc(&I.BS, (size_t)work));
+    IR(I.alloc(&I.svr, (size_t)work));
+    IR(I.alloc(&I.res, (size_t)work));
+    IR(I.alloc(&I.Q, (size_t)work * work));
+    IR(I.alloc(&I.svd_scratch, (size_t)2 * work * work));
+    IR(I.alloc(&I.ctl, (size_t)CT_COUNT));
+    ICK(cudaMemsetAsync(I.Bm, 0, (size_t)work * work * sizeof(double), ctx->stream));
+    ICK(cudaMemsetAsync(I.svr, 0, work * sizeof(double), ctx->stream));
+    ICK(cudaMemsetAsync(I.scal, 0, SC_COUNT * sizeof(double), ctx->stream));
+    ICK(cudaMemsetAsync(I.ctl, 0, CT_COUNT * sizeof(int), ctx->stream));
+    ICK(cudaMemsetAsync(I.pb, 0, 64 * sizeof(double), ctx->stream));
+    // operator vectors
+    I.s = use_scale ? m->scale : nullptr;
+    if (use_center) {
+      I.ce = m->mean_sparse;  // mean(D) - f0 = mean of the stored sparse part
+    } else if (m->f0 != 0.0) {
+      IR(I.alloc(&I.ce, (size_t)n));
+      k_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(I.ce, n, -m->f0);
+      count_launch(ctx);
+    } else {
+      I.ce = nullptr;
+    }
+    // start vector: V[:,0] = v0 / ||v0||   (irlb.c: dnrm2 + dscal)
+    {
+      long double nn = 0;
+      for (int g = 0; g < n; ++g) nn += (long double)v0[g] * v0[g];
+      double dn = std::sqrt((double)nn);
+      if (!(dn >= I.eps)) {
+        m3b_set_error(ctx, "start vector has zero norm");
+        status = M3B_E_DIMS;
+        goto done;
+      }
+      double inv = 1.0 / dn;
+      for (int g = 0; g < n; ++g) hv[g] = v0[g] * inv;
+      ICK(cudaMemcpyAsync(I.V, hv.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      ctx->stats.h2d_bytes += n * 8;
+    }
+    ICK(cudaEventCreate(&evA));
+    ICK(cudaEventCreate(&evB));
+    ICK(cudaEventRecord(evA, ctx->stream));
+
+    while (it < maxit) {
+      int j = (it == 0) ? 0 : k;
+      // W[:,j] = Ax(V[:,j])
+      k_make_xs<<<I.nb_n, NT, 0, ctx->stream>>>(I.V + (long long)j * n, I.s, I.ce, n, I.xs, I.pb);
+      count_launch(ctx);
+      IR(I.product_A(j, false));
+      mprod++;
+      if (it > 0) {
+        IR(I.orthog(I.W, mloc, mloc, j, I.W + (long long)j * mloc, I.chunk_m, I.nblk_m, I.nb_m, true));
+      } else {
+        k_norm_partials<<<I.nb_m, NT, 0, ctx->stream>>>(I.W + (long long)j * mloc, mloc, I.pn, I.ps);
+        count_launch(ctx);
+      }
+      IR(I.finish_w(j, it == 0 && j == 0));
+      // Lanczos process
+      while (j < work) {
+        IR(I.product_B(j));
+        mprod++;
+        IR(I.orthog(I.V, n, n, j + 1, I.F, I.chunk_n, I.nblk_n, I.nb_n, false));
+        if (j + 1 < work) {
+          k_finish_F<<<I.nb_n, NT, 0, ctx->stream>>>(I.F, I.pn, I.nb_n, I.s, I.ce, n, I.V + (long long)(j + 1) * n, I.xs,
+                                                     I.pb, I.Bm, work, j, I.scal, I.ctl, I.eps);
+          count_launch(ctx);
+          IR(I.product_A(j + 1, true));
+          mprod++;
+          IR(I.orthog(I.W, mloc, mloc, j + 1, I.W + (long long)(j + 1) * mloc, I.chunk_m, I.nblk_m, I.nb_m, true));
+          IR(I.finish_w(j + 1, false));
+        } else {
+          k_finish_last<<<I.nb_n, NT, 0, ctx->stream>>>(I.F, I.pn, I.nb_n, n, I.Bm, work, j, I.scal, I.eps);
+          count_launch(ctx);
+        }
+        j++;
+      }
+      ICK(cudaGetLastError());
+      // small SVD of B
+      if (ctx->small_svd) {
+        ICK(cudaMemcpyAsync(hB.data(), I.Bm, hB.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ICK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->small_svd(work, hB.data(), hU.data(), hS.data(), hVt.data(), ctx->small_svd_user) != 0) {
+          m3b_set_error(ctx, "small_svd callback failed");
+          status = M3B_E_STATE;
+          goto done;
+        }
+        ICK(cudaMemcpyAsync(I.BU, hU.data(), hU.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ICK(cudaMemcpyAsync(I.BS, hS.data(), hS.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ICK(cudaMemcpyAsync(I.Q, hVt.data(), hVt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        k_transpose_small<<<(work * work + 255) / 256, 256, 0, ctx->stream>>>(I.Q, work, I.BV);
+        count_launch(ctx);
+      } else {
+        IR(launch_jacobi_svd(ctx, work, I.Bm, I.BU, I.BS, I.BV, I.svd_scratch, I.ctl + CT_SWEEPS));
+      }
+      k_restart_logic<<<1, 128, 0, ctx->stream>>>(work, nv, tol, svtol, I.BU, I.BS, I.svr, I.res, I.Bm, I.scal, I.ctl);
+      count_launch(ctx);
+      ICK(cudaMemcpyAsync(hctl, I.ctl, sizeof(hctl), cudaMemcpyDeviceToHost, ctx->stream));
+      ICK(cudaStreamSynchronize(ctx->stream));
+      ctx->stats.d2h_bytes += sizeof(hctl);
+      if (hctl[CT_FLAG] & 1) {
+        m3b_set_error(ctx, "starting vector near the null space");
+        status = M3B_E_NULLSPACE;
+        goto done;
+      }
+      if (hctl[CT_FLAG] & 2) {
+        m3b_set_error(ctx, "linear dependency encountered (invariant subspace) at restart %d", it);
+        status = M3B_E_LINDEP;
+        goto done;
+      }
+      k = hctl[CT_K];
+      if (hctl[CT_CONV]) {
+        converged = true;
+        it++;
+        break;
+      }
+      if (ctx->should_abort && ctx->should_abort(ctx->should_abort_user)) {
+        m3b_set_error(ctx, "aborted by caller");
+        status = M3B_E_ABORTED;
+        goto done;
+      }
+      // thick restart: V[:, :k] = V BV[:, :k]; V[:,k] = F; W[:, :k] = W BU[:, :k]
+      IR(I.gemm_inplace(I.V, n, n, work, k, I.BV));
+      ICK(cudaMemcpyAsync(I.V + (long long)k * n, I.F, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      IR(I.gemm_inplace(I.W, mloc, mloc, work, k, I.BU));
+      it++;
+    }
+    // results: d = BS[:nu]; U*diag(d) = W (BU[:, :nu] diag(d)); V = V BV[:, :nu]
+    k_scale_cols<<<(work * nv + 255) / 256, 256, 0, ctx->stream>>>(I.BU, I.BS, work, nv, I.Q);
+    count_launch(ctx);
+    IR(I.gemm_inplace(I.W, mloc, mloc, work, nv, I.Q));
+    IR(I.gemm_inplace(I.V, n, n, work, nv, I.BV));
+    ICK(cudaEventRecord(evB, ctx->stream));
+    ICK(cudaMemcpyAsync(d_out, I.BS, nv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (V_out) ICK(cudaMemcpyAsync(V_out, I.V, (size_t)n * nv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (copy_x && X_out) {
+      ICK(cudaMemcpy2DAsync(X_out, ldx * sizeof(double), I.W, mloc * sizeof(double), mloc * sizeof(double), nv,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->stats.d2h_bytes += mloc * nv * 8;
+    }
+    if (center_out && use_center)
+      ICK(cudaMemcpyAsync(center_out, m->center, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (scale_out && use_scale)
+      ICK(cudaMemcpyAsync(scale_out, m->scale, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ICK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += nv * 8 + (V_out ? (long long)n * nv * 8 : 0);
+    {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, evA, evB);
+      ctx->stats.irlba_ms = ms;
+    }
+    // keep the embedding on the device for callers that want it there
+    dev_free(m->Xdev);
+    m->Xdev = nullptr;
+    if (!copy_x) {
+      // hand W's first nv columns over without a copy: steal the buffer
+      for (auto& p : I.owned)
+        if (p == I.W) p = nullptr;
+      m->Xdev = I.W;
+      m->Xdev_nv = nv;
+    }
+    if (iter_out) *iter_out = it;
+    if (mprod_out) *mprod_out = mprod;
+    status = converged ? M3B_OK : M3B_W_NOT_CONVERGED;
+    if (!converged) m3b_set_error(ctx, "did not converge--results might be invalid!; try increasing work or maxit");
+  }
+done:
+  if (evA) cudaEventDestroy(evA);
+  if (evB) cudaEventDestroy(evB);
+  cudaStreamSynchronize(ctx->stream);
+  I.release();
+  return status;
+#undef IR
+#undef ICK
+}

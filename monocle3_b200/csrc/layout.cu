@@ -1,0 +1,642 @@
+// K0 (ingest + dual tiled layout build), K1 (cell totals), K2 (fused normalise+log).
+//
+// Replaces, for dgCMatrix input: round()+Matrix::colSums (R/utils.R:57-61),
+// t(t(FM)/sf) + log2(FM@x+1) (R/preprocess_cds.R:272-283), FM[use_genes,],
+// Matrix::rowSums filter (R/preprocess_cds.R:117-122) and the Matrix::t()
+// materialisation handed to irlba (R/preprocess_cds.R:139).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "m3b_internal.h"
+
+template <typename T>
+int dev_alloc(m3b_ctx* ctx, T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CK(ctx, cudaMalloc((void**)p, n * sizeof(T)));
+  return M3B_OK;
+}
+template int dev_alloc<double>(m3b_ctx*, double**, size_t);
+template int dev_alloc<int>(m3b_ctx*, int**, size_t);
+template int dev_alloc<long long>(m3b_ctx*, long long**, size_t);
+template int dev_alloc<ItemDesc>(m3b_ctx*, ItemDesc**, size_t);
+template int dev_alloc<int4>(m3b_ctx*, int4**, size_t);
+template int dev_alloc<unsigned int>(m3b_ctx*, unsigned int**, size_t);
+template int dev_alloc<unsigned char>(m3b_ctx*, unsigned char**, size_t);
+
+void dev_free(void* p) {
+  if (p) cudaFree(p);
+}
+
+void TiledLayout::free_all() {
+  dev_free(idx);
+  dev_free(val);
+  dev_free(items);
+  dev_free(units);
+  dev_free(row_item_ptr);
+  dev_free(partial);
+  *this = TiledLayout();
+}
+
+// ---------------------------------------------------------------------------
+// streaming loads: the CSC arrays are read exactly once per pass, so keep them
+// out of L1 (ld.global.nc.L1::no_allocate) and leave L1/L2 to the gathers.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// ingest helpers
+// ---------------------------------------------------------------------------
+__global__ void k_offset_colptr(const int* __restrict__ p_chunk, long long n, long long base,
+                                long long* __restrict__ p_out) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k < n) p_out[k] = base + (long long)p_chunk[k];
+}
+
+int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* i, const double* x) {
+  m3b_ctx* ctx = m->ctx;
+  if (m->ended) {
+    m3b_set_error(ctx, "m3b_matrix_append_csc after m3b_matrix_end");
+    return M3B_E_STATE;
+  }
+  if (n_cells_chunk < 0 || m->cells_appended + n_cells_chunk > m->n_cells || p[0] != 0) {
+    m3b_set_error(ctx, "append: chunk of %lld cells does not fit (have %lld of %lld) or p[0] != 0",
+                  n_cells_chunk, m->cells_appended, m->n_cells);
+    return M3B_E_DIMS;
+  }
+  long long nnz_chunk = p[n_cells_chunk];
+  if (nnz_chunk < 0) {
+    m3b_set_error(ctx, "append: negative nnz");
+    return M3B_E_DIMS;
+  }
+  if (m->nnz + nnz_chunk > m->nnz_cap) {  // grow
+    long long cap = std::max(m->nnz + nnz_chunk, (long long)(m->nnz_cap * 1.5) + 1024);
+    int* ni;
+    double* nx;
+    RET(dev_alloc(ctx, &ni, (size_t)cap));
+    RET(dev_alloc(ctx, &nx, (size_t)cap));
+    if (m->nnz) {
+      CK(ctx, cudaMemcpyAsync(ni, m->i, m->nnz * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+      CK(ctx, cudaMemcpyAsync(nx, m->x, m->nnz * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    dev_free(m->i);
+    dev_free(m->x);
+    m->i = ni;
+    m->x = nx;
+    m->nnz_cap = cap;
+  }
+  int* d_pchunk;
+  RET(dev_alloc(ctx, &d_pchunk, (size_t)n_cells_chunk + 1));
+  CK(ctx, cudaMemcpyAsync(d_pchunk, p, (n_cells_chunk + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(m->i + m->nnz, i, nnz_chunk * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(m->x + m->nnz, x, nnz_chunk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  long long n = n_cells_chunk + 1;
+  k_offset_colptr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_pchunk, n, m->nnz, m->p + m->cells_appended);
+  count_launch(ctx);
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  dev_free(d_pchunk);
+  ctx->stats.h2d_bytes += (n_cells_chunk + 1) * 4 + nnz_chunk * 12;
+  m->nnz += nnz_chunk;
+  m->cells_appended += n_cells_chunk;
+  return M3B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K1: per-cell totals.  One warp per cell (column of the CSC): coalesced 8-byte
+// loads, fixed-order shuffle reduction.  Sums of integers < 2^53 are exact in
+// fp64 regardless of order, so the totals are bit-identical to colSums().
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_totals(const long long* __restrict__ p, const double* __restrict__ x,
+                                                     long long n_cells, int round_exprs, double* __restrict__ tot) {
+  const int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    double acc = 0.0;
+    for (long long k = lo + lane; k < hi; k += 32) {
+      double v = ld_stream_f64(x + k);
+      acc += round_exprs ? rint(v) : v;  // R's round(): IEC 60559 half-to-even
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) tot[c] = acc;
+  }
+}
+
+int k1_cell_totals(m3b_mat* m, int round_exprs, double* d_tot) {
+  m3b_ctx* ctx = m->ctx;
+  if (m->n_cells == 0) return M3B_OK;
+  int blocks = (int)std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8);
+  k_cell_totals<<<blocks, 256, 0, ctx->stream>>>(m->p, m->x, m->n_cells, round_exprs, d_tot);
+  count_launch(ctx);
+  CK(ctx, cudaGetLastError());
+  return M3B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K2: fused size-factor divide + log.  y = f(x / sf_c) - f(0); f(0) is non-zero
+// only on the reference's dense paths (pseudo_count != 1 for log, != 0 for
+// size_only, R/preprocess_cds.R:274-276,283) and is carried as m->f0.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__ p, const double* __restrict__ x,
+                                                   const double* __restrict__ sf, long long n_cells, int method,
+                                                   double pc, double f0, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    const double s = (method == M3B_NORM_NONE || method == M3B_NORM_BINARY) ? 1.0 : sf[c];
+    for (long long k = lo + lane; k < hi; k += 32) {
+      double v = ld_stream_f64(x + k);
+      double r;
+      switch (method) {
+        case M3B_NORM_LOG2: r = log2(v / s + pc) - f0; break;
+        case M3B_NORM_LOG10: r = log10(v / s + pc); break;
+        case M3B_NORM_SIZE_ONLY: r = v / s; break;  // + pc is the implicit constant f0
+        case M3B_NORM_BINARY: r = (v > 0.0) ? 1.0 : 0.0; break;
+        default: r = v; break;
+      }
+      y[k] = r;
+    }
+  }
+}
+
+int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc) {
+  m3b_ctx* ctx = m->ctx;
+  if (!m->y) RET(dev_alloc(ctx, &m->y, (size_t)std::max<long long>(m->nnz, 1)));
+  double f0 = 0.0;
+  if (method == M3B_NORM_LOG2) f0 = (pc == 1.0) ? 0.0 : std::log2(pc);
+  if (method == M3B_NORM_SIZE_ONLY) f0 = pc;
+  if (method == M3B_NORM_LOG10) f0 = 0.0;
+  m->f0 = f0;
+  if (m->n_cells) {
+    int blocks = (int)std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8);
+    k_normalize<<<blocks, 256, 0, ctx->stream>>>(m->p, m->x, d_sf, m->n_cells, method, pc, f0, m->y);
+    count_launch(ctx);
+    CK(ctx, cudaGetLastError());
+  }
+  return M3B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-side construction of the item / unit / row-pointer tables from the
+// per-(tile,row) entry counts.  cnt[t*rows_in + r] = true entries of input row r
+// in tile t; row_map (nullable) maps input rows to output rows (-1 = dropped).
+// base_out[t*rows_in + r] = entry offset of the run (only meaningful for runs
+// that get storage; storage is laid out for ALL input rows so that a later
+// re-map needs no data movement).
+// ---------------------------------------------------------------------------
+struct HostTables {
+  std::vector<long long> base;
+  std::vector<ItemDesc> items;
+  std::vector<int> row_item_ptr;
+  std::vector<int4> units;
+  long long n_entries = 0, nnz = 0;
+};
+
+static inline long long pad4(long long n) { return (n + 3) & ~3LL; }
+
+static void compute_bases(const std::vector<int>& cnt, int n_tiles, long long rows_in, HostTables& T) {
+  T.base.resize((size_t)n_tiles * rows_in);
+  long long off = 0;
+  for (size_t k = 0; k < T.base.size(); ++k) {
+    T.base[k] = off;
+    off += pad4(cnt[k]);
+  }
+  T.n_entries = off;
+}
+
+static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows_in, const int* row_map,
+                        long long rows_out, int sm_count, HostTables& T) {
+  T.items.clear();
+  T.units.clear();
+  T.row_item_ptr.assign((size_t)n_tiles * (rows_out + 1), 0);
+  T.nnz = 0;
+  // per-tile: rows are visited in OUTPUT-row order so that row_item_ptr is monotone
+  std::vector<long long> in_of_out;
+  if (row_map) {
+    in_of_out.assign(rows_out, -1);
+    for (long long r = 0; r < rows_in; ++r)
+      if (row_map[r] >= 0) in_of_out[row_map[r]] = r;
+  }
+  long long total_len = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    int* rip = &T.row_item_ptr[(size_t)t * (rows_out + 1)];
+    for (long long ro = 0; ro < rows_out; ++ro) {
+      rip[ro] = (int)T.items.size();
+      long long ri = row_map ? in_of_out[ro] : ro;
+      if (ri < 0) continue;
+      long long c = cnt[(size_t)t * rows_in + ri];
+      if (c == 0) continue;
+      T.nnz += c;
+      long long len = pad4(c), start = T.base[(size_t)t * rows_in + ri];
+      total_len += len;
+      while (len > 0) {
+        int l = (int)std::min<long long>(len, M3B_ITEM_MAX);
+        T.items.push_back(ItemDesc{start, l, (int)ro});
+        start += l;
+        len -= l;
+      }
+    }
+    rip[rows_out] = (int)T.items.size();
+  }
+  // work units: contiguous item ranges inside one tile, ~equal entry counts
+  long long target = std::max<long long>(total_len / ((long long)sm_count * 8), 8192);
+  for (int t = 0; t < n_tiles; ++t) {
+    const int* rip = &T.row_item_ptr[(size_t)t * (rows_out + 1)];
+    int ib = rip[0], ie = rip[rows_out];
+    int cur = ib;
+    long long acc = 0;
+    for (int it = ib; it < ie; ++it) {
+      acc += T.items[it].len + 64;  // +64: per-item overhead so that many tiny rows also get split
+      if (acc >= target) {
+        T.units.push_back(make_int4(t, cur, it + 1, 0));
+        cur = it + 1;
+        acc = 0;
+      }
+    }
+    if (cur < ie) T.units.push_back(make_int4(t, cur, ie, 0));
+  }
+}
+
+static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T) {
+  dev_free(L.items);
+  dev_free(L.units);
+  dev_free(L.row_item_ptr);
+  dev_free(L.partial);
+  L.items = nullptr;
+  L.units = nullptr;
+  L.row_item_ptr = nullptr;
+  L.partial = nullptr;
+  L.n_items = (long long)T.items.size();
+  L.n_units = (int)T.units.size();
+  L.nnz = T.nnz;
+  RET(dev_alloc(ctx, &L.items, T.items.size()));
+  RET(dev_alloc(ctx, &L.units, T.units.size()));
+  RET(dev_alloc(ctx, &L.row_item_ptr, T.row_item_ptr.size()));
+  RET(dev_alloc(ctx, &L.partial, T.items.size()));
+  if (!T.items.empty())
+    CK(ctx, cudaMemcpyAsync(L.items, T.items.data(), T.items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, ctx->stream));
+  if (!T.units.empty())
+    CK(ctx, cudaMemcpyAsync(L.units, T.units.data(), T.units.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(L.row_item_ptr, T.row_item_ptr.data(), T.row_item_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return M3B_OK;
+}
+
+static void choose_tiling(long long cols, int* tile_w, int* n_tiles) {
+  if (cols <= 0) {
+    *tile_w = 32;
+    *n_tiles = 1;
+    return;
+  }
+  int nt = (int)((cols + M3B_TILE_W_MAX - 1) / M3B_TILE_W_MAX);
+  long long tw = (cols + nt - 1) / nt;
+  tw = (tw + 31) & ~31LL;
+  if (tw > M3B_TILE_W_MAX) tw = M3B_TILE_W_MAX;
+  *tile_w = (int)tw;
+  *n_tiles = (int)((cols + tw - 1) / tw);
+}
+
+// ---------------------------------------------------------------------------
+// Layout B (gene-major, tiled along cells): stable counting-sort transpose.
+// A CHUNK is a run of consecutive cells of one tile owned by ONE warp, which
+// walks its cells in order; within a cell the row indices are distinct, so the
+// per-(chunk,row) cursor hands out slots in cell order => the transpose is
+// deterministic and every gene row is sorted by cell.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count_B(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                 const int* __restrict__ sel_of_gene, int n_sel, int tile_w,
+                                                 int chunks_per_tile, int cells_per_chunk, long long n_cells,
+                                                 long long n_chunks, int* __restrict__ H) {
+  const int lane = threadIdx.x & 31;
+  long long chunk = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (chunk >= n_chunks) return;
+  long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
+  long long c0 = t * tile_w + s * cells_per_chunk;
+  long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
+  int* Hc = H + chunk * n_sel;
+  for (long long c = c0; c < c1; ++c) {
+    const long long lo = p[c], hi = p[c + 1];
+    for (long long k = lo + lane; k < hi; k += 32) {
+      int r = sel_of_gene[ld_stream_s32(gi + k)];
+      if (r >= 0) atomicAdd(Hc + r, 1);
+    }
+  }
+}
+
+// exclusive scan over the chunks of a tile, per selected row; cnt = tile total
+__global__ void k_scan_chunks(int* __restrict__ H, int n_sel, int chunks_per_tile, int n_tiles, int* __restrict__ cnt) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= (long long)n_tiles * n_sel) return;
+  long long t = k / n_sel, r = k % n_sel;
+  int run = 0;
+  for (int s = 0; s < chunks_per_tile; ++s) {
+    int* h = H + ((t * chunks_per_tile + s) * (long long)n_sel + r);
+    int v = *h;
+    *h = run;
+    run += v;
+  }
+  cnt[k] = run;
+}
+
+__global__ void k_fill_pads(const int* __restrict__ cnt, const long long* __restrict__ base, long long n_runs,
+                            int* __restrict__ idx, double* __restrict__ val) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n_runs) return;
+  int c = cnt[k];
+  long long b = base[k];
+  for (int e = c; e < ((c + 3) & ~3); ++e) {
+    idx[b + e] = 0;
+    val[b + e] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_B(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                   const double* __restrict__ y, const int* __restrict__ sel_of_gene,
+                                                   int n_sel, int tile_w, int chunks_per_tile, int cells_per_chunk,
+                                                   long long n_cells, long long n_chunks, int* __restrict__ H,
+                                                   const long long* __restrict__ base, int* __restrict__ idx,
+                                                   double* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  long long chunk = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (chunk >= n_chunks) return;
+  long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
+  long long c0 = t * tile_w + s * cells_per_chunk;
+  long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
+  int* Hc = H + chunk * n_sel;
+  const long long* bt = base + t * n_sel;
+  for (long long c = c0; c < c1; ++c) {
+    const long long lo = p[c], hi = p[c + 1];
+    const int local = (int)(c - t * tile_w);
+    for (long long k = lo + lane; k < hi; k += 32) {
+      int r = sel_of_gene[ld_stream_s32(gi + k)];
+      if (r >= 0) {
+        int pos = atomicAdd(Hc + r, 1);
+        long long dst = bt[r] + pos;
+        idx[dst] = local;
+        val[dst] = ld_stream_f64(y + k);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// host copies kept for the re-map after the zero-gene filter
+struct BBuild {
+  std::vector<int> cnt;
+  HostTables T;
+};
+void m3b_mat_set_bbuild(m3b_mat* m, void* p) {
+  delete (BBuild*)m->b_host_tables;
+  m->b_host_tables = p;
+}
+
+int build_layout_B(m3b_mat* m) {
+  m3b_ctx* ctx = m->ctx;
+  TiledLayout& L = m->B;
+  L.free_all();
+  const int n_sel = m->n_sel;
+  L.rows = n_sel;
+  L.cols = m->n_cells;
+  choose_tiling(L.cols, &L.tile_w, &L.n_tiles);
+  const int n_tiles = L.n_tiles;
+  int cpt = (int)std::max<long long>(1, std::min<long long>((4096 + n_tiles - 1) / n_tiles, (L.tile_w + 7) / 8));
+  // bound the cursor table to ~1.5 GB
+  while (cpt > 1 && (double)n_tiles * cpt * std::max(n_sel, 1) * 4.0 > 1.5e9) cpt = (cpt + 1) / 2;
+  const int cells_per_chunk = (L.tile_w + cpt - 1) / cpt;
+  const long long n_chunks = (long long)n_tiles * cpt;
+  int* H = nullptr;
+  int* d_cnt = nullptr;
+  long long* d_base = nullptr;
+  RET(dev_alloc(ctx, &H, (size_t)n_chunks * std::max(n_sel, 1)));
+  RET(dev_alloc(ctx, &d_cnt, (size_t)n_tiles * std::max(n_sel, 1)));
+  CK(ctx, cudaMemsetAsync(H, 0, (size_t)n_chunks * std::max(n_sel, 1) * sizeof(int), ctx->stream));
+  const unsigned blocks = (unsigned)((n_chunks * 32 + 255) / 256);
+  if (m->n_cells && n_sel) {
+    k_count_B<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->sel_of_gene, n_sel, L.tile_w, cpt, cells_per_chunk,
+                                               m->n_cells, n_chunks, H);
+    count_launch(ctx);
+  }
+  long long n_runs = (long long)n_tiles * n_sel;
+  if (n_runs) {
+    k_scan_chunks<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(H, n_sel, cpt, n_tiles, d_cnt);
+    count_launch(ctx);
+  }
+  CK(ctx, cudaGetLastError());
+  std::vector<int> cnt((size_t)n_runs);
+  if (n_runs) CK(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  HostTables T;
+  compute_bases(cnt, n_tiles, n_sel, T);
+  build_items(cnt, n_tiles, n_sel, nullptr, n_sel, ctx->sm_count, T);
+  L.n_entries = T.n_entries;
+  RET(dev_alloc(ctx, &L.idx, (size_t)T.n_entries));
+  RET(dev_alloc(ctx, &L.val, (size_t)T.n_entries));
+  RET(dev_alloc(ctx, &d_base, (size_t)std::max<long long>(n_runs, 1)));
+  if (n_runs) {
+    CK(ctx, cudaMemcpyAsync(d_base, T.base.data(), n_runs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    k_fill_pads<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(d_cnt, d_base, n_runs, L.idx, L.val);
+    count_launch(ctx);
+    if (m->n_cells) {
+      k_scatter_B<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->sel_of_gene, n_sel, L.tile_w, cpt,
+                                                   cells_per_chunk, m->n_cells, n_chunks, H, d_base, L.idx, L.val);
+      count_launch(ctx);
+    }
+  }
+  CK(ctx, cudaGetLastError());
+  RET(upload_tables(ctx, L, T));
+  // exact nnz per selected gene (local shard)
+  std::vector<long long> nnz_sel(n_sel, 0);
+  for (int t = 0; t < n_tiles; ++t)
+    for (int r = 0; r < n_sel; ++r) nnz_sel[r] += cnt[(size_t)t * n_sel + r];
+  dev_free(m->sel_nnz);
+  RET(dev_alloc(ctx, &m->sel_nnz, (size_t)std::max(n_sel, 1)));
+  if (n_sel) CK(ctx, cudaMemcpyAsync(m->sel_nnz, nnz_sel.data(), n_sel * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  // stash the host tables for the re-map (kept in the matrix via a heap object)
+  BBuild* bb = new BBuild();
+  bb->cnt.swap(cnt);
+  bb->T.base.swap(T.base);
+  bb->T.n_entries = T.n_entries;
+  m3b_mat_set_bbuild(m, bb);
+  dev_free(H);
+  dev_free(d_cnt);
+  dev_free(d_base);
+  return M3B_OK;
+}
+
+// After the keep mask is known: re-map B's items to kept rows (no data movement).
+int finish_selection(m3b_mat* m, unsigned char* keep_host) {
+  m3b_ctx* ctx = m->ctx;
+  BBuild* bb = (BBuild*)m->b_host_tables;
+  if (!bb) {
+    m3b_set_error(ctx, "internal: layout B tables missing");
+    return M3B_E_STATE;
+  }
+  const int n_sel = m->n_sel;
+  std::vector<int> kept_of_sel(n_sel);
+  int nk = 0;
+  for (int s = 0; s < n_sel; ++s) kept_of_sel[s] = keep_host[s] ? nk++ : -1;
+  m->n_kept = nk;
+  HostTables T;
+  T.base = bb->T.base;
+  build_items(bb->cnt, m->B.n_tiles, n_sel, kept_of_sel.data(), nk, ctx->sm_count, T);
+  m->B.rows = nk;
+  RET(upload_tables(ctx, m->B, T));
+  dev_free(m->kept_of_sel);
+  RET(dev_alloc(ctx, &m->kept_of_sel, (size_t)std::max(n_sel, 1)));
+  if (n_sel) CK(ctx, cudaMemcpyAsync(m->kept_of_sel, kept_of_sel.data(), n_sel * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  // per-kept-gene nnz
+  std::vector<long long> nnzk(std::max(nk, 1), 0), padk(std::max(nk, 1), 0);
+  for (int t = 0; t < m->B.n_tiles; ++t)
+    for (int s = 0; s < n_sel; ++s)
+      if (kept_of_sel[s] >= 0) {
+        nnzk[kept_of_sel[s]] += bb->cnt[(size_t)t * n_sel + s];
+        padk[kept_of_sel[s]] += pad4(bb->cnt[(size_t)t * n_sel + s]);
+      }
+  dev_free(m->kept_nnz);
+  dev_free(m->kept_padlen);
+  RET(dev_alloc(ctx, &m->kept_nnz, (size_t)std::max(nk, 1)));
+  RET(dev_alloc(ctx, &m->kept_padlen, (size_t)std::max(nk, 1)));
+  CK(ctx, cudaMemcpyAsync(m->kept_nnz, nnzk.data(), std::max(nk, 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(m->kept_padlen, padk.data(), std::max(nk, 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  m3b_mat_set_bbuild(m, nullptr);
+  return M3B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Layout A (cell-major, tiled along kept genes): same order as the input, so a
+// warp-per-cell stable compaction (ballot/popc) is enough.
+// ---------------------------------------------------------------------------
+__global__ void k_compose_maps(const int* __restrict__ sel_of_gene, const int* __restrict__ kept_of_sel, int n_genes,
+                               int* __restrict__ kept_of_gene) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_genes) {
+    int s = sel_of_gene[g];
+    kept_of_gene[g] = (s >= 0) ? kept_of_sel[s] : -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_count_A(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                 const int* __restrict__ kept_of_gene, long long n_cells, int tile_w,
+                                                 int n_tiles, int* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    for (int t = 0; t < n_tiles; ++t) {
+      int n = 0;
+      for (long long k = lo + lane; k < hi; k += 32) {
+        int g = kept_of_gene[ld_stream_s32(gi + k)];
+        n += (g >= 0 && g / tile_w == t) ? 1 : 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+      if (lane == 0) cnt[(long long)t * n_cells + c] = n;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_A(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                   const double* __restrict__ y, const int* __restrict__ kept_of_gene,
+                                                   long long n_cells, int tile_w, int n_tiles,
+                                                   const long long* __restrict__ base, int* __restrict__ idx,
+                                                   double* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    for (int t = 0; t < n_tiles; ++t) {
+      long long dst0 = base[(long long)t * n_cells + c];
+      int run = 0;
+      for (long long k0 = lo; k0 < hi; k0 += 32) {
+        long long k = k0 + lane;
+        int g = -1;
+        double v = 0.0;
+        if (k < hi) {
+          g = kept_of_gene[ld_stream_s32(gi + k)];
+          if (g >= 0 && g / tile_w == t) v = ld_stream_f64(y + k);
+          else g = -1;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, g >= 0);
+        if (g >= 0) {
+          long long dst = dst0 + run + __popc(m & lt);
+          idx[dst] = g - t * tile_w;
+          val[dst] = v;
+        }
+        run += __popc(m);
+      }
+      // pads
+      int padded = (run + 3) & ~3;
+      if (lane < padded - run) {
+        idx[dst0 + run + lane] = 0;
+        val[dst0 + run + lane] = 0.0;
+      }
+    }
+  }
+}
+
+int build_layout_A(m3b_mat* m) {
+  m3b_ctx* ctx = m->ctx;
+  TiledLayout& L = m->A;
+  L.free_all();
+  L.rows = m->n_cells;
+  L.cols = m->n_kept;
+  choose_tiling(L.cols, &L.tile_w, &L.n_tiles);
+  dev_free(m->kept_of_gene);
+  RET(dev_alloc(ctx, &m->kept_of_gene, (size_t)std::max(m->n_genes, 1)));
+  if (m->n_genes) {
+    k_compose_maps<<<(m->n_genes + 255) / 256, 256, 0, ctx->stream>>>(m->sel_of_gene, m->kept_of_sel, m->n_genes, m->kept_of_gene);
+    count_launch(ctx);
+  }
+  const long long n_runs = (long long)L.n_tiles * L.rows;
+  int* d_cnt = nullptr;
+  long long* d_base = nullptr;
+  RET(dev_alloc(ctx, &d_cnt, (size_t)std::max<long long>(n_runs, 1)));
+  int blocks = (int)std::max<long long>(1, std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8));
+  if (m->n_cells) {
+    k_count_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, d_cnt);
+    count_launch(ctx);
+  }
+  CK(ctx, cudaGetLastError());
+  std::vector<int> cnt((size_t)n_runs);
+  if (n_runs) CK(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  HostTables T;
+  compute_bases(cnt, L.n_tiles, L.rows, T);
+  build_items(cnt, L.n_tiles, L.rows, nullptr, L.rows, ctx->sm_count, T);
+  L.n_entries = T.n_entries;
+  RET(dev_alloc(ctx, &L.idx, (size_t)T.n_entries));
+  RET(dev_alloc(ctx, &L.val, (size_t)T.n_entries));
+  RET(dev_alloc(ctx, &d_base, (size_t)std::max<long long>(n_runs, 1)));
+  if (n_runs) {
+    CK(ctx, cudaMemcpyAsync(d_base, T.base.data(), n_runs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    k_scatter_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles,
+                                                 d_base, L.idx, L.val);
+    count_launch(ctx);
+  }
+  CK(ctx, cudaGetLastError());
+  RET(upload_tables(ctx, L, T));
+  dev_free(d_cnt);
+  dev_free(d_base);
+  return M3B_OK;
+}

@@ -1,0 +1,178 @@
+// Internal declarations shared by the translation units of libm3b.so.
+// Nothing here is part of the ABI (include/m3b.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/m3b.h"
+
+// ---------------------------------------------------------------------------
+// error plumbing: every CUDA call goes through CK(); the first failure is
+// recorded in the context and turned into a status code at the ABI.
+// ---------------------------------------------------------------------------
+struct m3b_ctx;
+void m3b_set_error(m3b_ctx* ctx, const char* fmt, ...);
+
+#define CK(ctx, call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      m3b_set_error((ctx), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,                \
+                    cudaGetErrorString(e__));                                           \
+      return (e__ == cudaErrorMemoryAllocation) ? M3B_E_NOMEM : M3B_E_CUDA;             \
+    }                                                                                   \
+  } while (0)
+
+#define RET(expr)                  \
+  do {                             \
+    int s__ = (expr);              \
+    if (s__ != M3B_OK) return s__; \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// NCCL (loaded with dlopen so that a host process that already carries its own
+// NCCL, e.g. torch, shares that copy instead of clashing with a second one)
+// ---------------------------------------------------------------------------
+struct NcclApi;
+struct Comm {
+  int rank = 0, world = 1;
+  void* comm = nullptr;  // ncclComm_t
+};
+int comm_get_unique_id(m3b_ctx* ctx, char* id);
+int comm_init(m3b_ctx* ctx, int rank, int world, const char* id);
+void comm_destroy(m3b_ctx* ctx);
+// in-place sum-allreduce of n doubles / int64 on the context stream (no-op if world==1)
+int comm_allreduce_f64(m3b_ctx* ctx, double* dev, size_t n);
+int comm_allreduce_i64(m3b_ctx* ctx, long long* dev, size_t n);
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct m3b_ctx {
+  int device = 0;
+  int flags = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  Comm comm;
+  m3b_small_svd_fn small_svd = nullptr;
+  void* small_svd_user = nullptr;
+  m3b_should_abort_fn should_abort = nullptr;
+  void* should_abort_user = nullptr;
+  m3b_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // scratch events
+  unsigned int* sched = nullptr;             // [2] dynamic unit counter + done counter (zeroed)
+};
+
+// ---------------------------------------------------------------------------
+// tiled row-major sparse layout: the single storage format behind both
+// Lanczos products (see DESIGN.md "Data layout in HBM").
+//   rows x cols matrix; the gathered (cols) dimension is cut into tiles of
+//   tile_w columns so that the dense operand of one tile fits in shared memory;
+//   inside a tile the non-zeros are stored row by row, every run padded to a
+//   multiple of 4 entries (pad entries: idx 0, val 0.0).  An ITEM is one run (or
+//   a <= M3B_ITEM_MAX slice of a long run): the unit of work of one warp.
+// ---------------------------------------------------------------------------
+#define M3B_TILE_W_MAX 28672  // 224 KB of doubles in shared memory
+#define M3B_ITEM_MAX 2048     // entries per item (multiple of 128)
+
+struct ItemDesc {  // 16 bytes, loaded with one 128-bit load
+  long long start;  // entry offset into idx/val (multiple of 4)
+  int len;          // padded entries (multiple of 4)
+  int row;          // output row
+};
+
+struct TiledLayout {
+  long long rows = 0, cols = 0;
+  int tile_w = 0, n_tiles = 0;
+  long long n_entries = 0;  // padded entries allocated
+  long long nnz = 0;        // true stored entries referenced by items
+  int* idx = nullptr;       // tile-local column index
+  double* val = nullptr;
+  long long n_items = 0;
+  ItemDesc* items = nullptr;
+  int n_units = 0;
+  int4* units = nullptr;       // {tile, item_begin, item_end, 0}
+  int* row_item_ptr = nullptr; // [n_tiles][rows+1] item ranges per (tile,row)
+  double* partial = nullptr;   // [n_items]
+  void free_all();
+};
+
+// the matrix handle
+struct m3b_mat {
+  m3b_ctx* ctx = nullptr;
+  int n_genes = 0;
+  long long n_cells = 0;        // local
+  long long n_cells_total = 0;  // over all ranks
+  // raw CSC (cell-major) as appended
+  long long nnz = 0, nnz_cap = 0, cells_appended = 0;
+  long long* p = nullptr;  // [n_cells+1]
+  int* i = nullptr;        // [nnz]
+  double* x = nullptr;     // [nnz] raw counts
+  double* y = nullptr;     // [nnz] normalised values (after m3b_normalize)
+  bool ended = false, normalized = false, selected = false, moments_done = false;
+  int norm_method = -1;
+  double pseudo_count = 0, f0 = 0;  // f0 = implicit value of the non-stored entries
+  // gene selection
+  int n_sel = 0, n_kept = 0;
+  int* sel_of_gene = nullptr;   // [n_genes] -> selected position or -1
+  int* kept_of_sel = nullptr;   // [n_sel]   -> kept index or -1
+  int* kept_of_gene = nullptr;  // [n_genes] -> kept index or -1
+  long long* sel_nnz = nullptr; // [n_sel] exact local nnz per selected gene
+  double* rowsum = nullptr;     // [n_sel] global row sums (incl. f0 term)
+  long long* kept_nnz = nullptr;// [n_kept] local nnz
+  long long* kept_padlen = nullptr;  // [n_kept] local padded run length (>= nnz)
+  double* mean_sparse = nullptr;     // [n_kept] mean of the stored sparse part (center - f0)
+  void* b_host_tables = nullptr;  // host copy of B's run counts between build and re-map
+  TiledLayout A;  // rows = local cells, cols = kept genes   (cells-out product, K4)
+  TiledLayout B;  // rows = kept genes,  cols = local cells  (genes-out product, K5)
+  double* center = nullptr;  // [n_kept] mean of the (implicit-dense) matrix
+  double* scale = nullptr;   // [n_kept] sd
+  // embedding left on the device by the last PCA (n_cells x nv, ld n_cells)
+  double* Xdev = nullptr;
+  int Xdev_nv = 0;
+};
+
+// ---------------------------------------------------------------------------
+// kernels / device-side building blocks (implemented in the .cu files)
+// ---------------------------------------------------------------------------
+template <typename T>
+int dev_alloc(m3b_ctx* ctx, T** p, size_t n);
+void dev_free(void* p);
+
+// layout.cu
+int k1_cell_totals(m3b_mat* m, int round_exprs, double* d_tot);
+int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc);
+int build_layout_B(m3b_mat* m);
+int finish_selection(m3b_mat* m, unsigned char* keep_host);
+int build_layout_A(m3b_mat* m);
+void m3b_mat_set_bbuild(m3b_mat* m, void* p);
+int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* i, const double* x);
+
+// spmv.cu
+enum StreamOp { OP_DOT = 0, OP_SUM = 1, OP_SQDEV = 2 };
+// partial[item] = sum over the item's entries of op(val, x[idx]); x is the dense operand
+// (length L.cols) for OP_DOT, ignored for OP_SUM, the per-row mean for OP_SQDEV.
+int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double* x);
+// out[row] = sum of the row's partials (fixed order: tile, then segment)
+int launch_combine_rows(m3b_ctx* ctx, const TiledLayout& L, double* out);
+long long spmv_algorithmic_bytes(const TiledLayout& L);
+
+// irlba.cu
+int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol, const double* v0,
+              int center, int scale, double* d, double* V, double* X, long long ldx,
+              double* center_out, double* scale_out, int* iter, int* mprod, bool copy_x);
+int compute_moments(m3b_mat* m);
+
+// project.cu
+int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, const double* center,
+                const double* scale, int nv, double* Y, long long ldy);
+
+// small_svd.cpp
+int jacobi_svd(int n, const double* B, double* U, double* s, double* Vt);
+
+static inline void count_launch(m3b_ctx* ctx, int n = 1) { ctx->stats.kernel_launches += n; }

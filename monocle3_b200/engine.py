@@ -1,0 +1,235 @@
+"""Thin object wrappers over the C ABI (include/m3b.h): Context and DeviceMatrix.
+
+No arithmetic happens here -- only marshaling of NumPy buffers to the extern "C"
+entry points, exactly what the Rcpp layer does in the R package.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+def lapack_small_svd():
+    """small_svd callback backed by NumPy's LAPACK gesdd -- the stand-in for R's
+    own LAPACK that the R shim passes for sign fidelity with stock monocle3."""
+    def cb(n, Bp, Up, sp, Vtp, _user):
+        try:
+            B = np.ctypeslib.as_array(Bp, shape=(n * n,)).reshape(n, n).T  # column-major -> B
+            U, s, Vt = np.linalg.svd(B)
+            np.ctypeslib.as_array(Up, shape=(n * n,))[:] = np.asfortranarray(U).ravel(order="F")
+            np.ctypeslib.as_array(sp, shape=(n,))[:] = s
+            np.ctypeslib.as_array(Vtp, shape=(n * n,))[:] = np.asfortranarray(Vt).ravel(order="F")
+            return 0
+        except Exception:  # never let an exception cross the C boundary
+            return 1
+    return L.SMALL_SVD_FN(cb)
+
+
+class Context:
+    """One GPU (m3b_ctx). `small_svd`: 'device' (Jacobi kernel) or 'lapack' (host callback)."""
+
+    def __init__(self, device=0, flags=0, small_svd="device"):
+        self.lib = L.load()
+        h = C.c_void_p()
+        st = self.lib.m3b_create(int(device), int(flags), C.byref(h))
+        if st != L.M3B_OK:
+            raise L.M3BError(st, self.lib.m3b_status_string(st).decode())
+        self.h = h
+        self.device = device
+        self._cb = None
+        self.rank, self.world = 0, 1
+        self.set_small_svd(small_svd)
+
+    def set_small_svd(self, mode):
+        if mode == "lapack":
+            self._cb = lapack_small_svd()
+            self.check(self.lib.m3b_set_small_svd(self.h, self._cb, None))
+        elif mode == "device":
+            self._cb = None
+            self.check(self.lib.m3b_set_small_svd(self.h, C.cast(None, L.SMALL_SVD_FN), None))
+        else:
+            raise ValueError("small_svd must be 'device' or 'lapack'")
+        self.small_svd = mode
+
+    def check(self, st, allow=()):
+        if st != L.M3B_OK and st not in allow:
+            raise L.M3BError(st, self.lib.m3b_last_error(self.h).decode() or self.lib.m3b_status_string(st).decode())
+        return st
+
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(L.COMM_ID_BYTES)
+        self.check(self.lib.m3b_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def comm_init(self, rank, world, uid):
+        self.check(self.lib.m3b_comm_init(self.h, int(rank), int(world), uid))
+        self.rank, self.world = rank, world
+
+    def stats(self):
+        s = L.Stats()
+        self.check(self.lib.m3b_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in L.Stats._fields_}
+
+    def reset_stats(self):
+        self.check(self.lib.m3b_reset_stats(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.m3b_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceMatrix:
+    """The counts matrix (local cell shard) resident on the GPU (m3b_mat)."""
+
+    def __init__(self, ctx, n_genes, n_cells_local, n_cells_total=None, nnz_hint=0):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.n_genes = int(n_genes)
+        self.n_cells = int(n_cells_local)
+        self.n_cells_total = int(n_cells_total if n_cells_total is not None else n_cells_local)
+        h = C.c_void_p()
+        ctx.check(self.lib.m3b_matrix_begin(ctx.h, self.n_genes, self.n_cells, self.n_cells_total, int(nnz_hint), C.byref(h)))
+        self.h = h
+        self.nnz = 0
+        self.n_sel = self.n_kept = None
+
+    @classmethod
+    def from_csc(cls, ctx, counts, n_cells_total=None, chunk_cells=None):
+        """counts: scipy.sparse.csc_matrix genes x (local) cells.  Appended in cell-range
+        chunks whose nnz fits int32 (the dgCMatrix limit)."""
+        G, Cn = counts.shape
+        m = cls(ctx, G, Cn, n_cells_total, counts.nnz)
+        indptr = np.asarray(counts.indptr)
+        indices = np.ascontiguousarray(counts.indices, dtype=np.int32)
+        data = np.ascontiguousarray(counts.data, dtype=np.float64)
+        lo = 0
+        limit = 2 ** 31 - 1
+        while lo < Cn:
+            hi = Cn if chunk_cells is None else min(Cn, lo + chunk_cells)
+            while int(indptr[hi]) - int(indptr[lo]) > limit:
+                hi = lo + max(1, (hi - lo) // 2)
+            m.append_csc(indptr[lo:hi + 1] - indptr[lo], indices[indptr[lo]:indptr[hi]], data[indptr[lo]:indptr[hi]])
+            lo = hi
+        if Cn == 0:
+            pass
+        m.end()
+        return m
+
+    def append_csc(self, p, i, x):
+        p = np.ascontiguousarray(p, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.ctx.check(self.lib.m3b_matrix_append_csc(self.h, len(p) - 1, _ip(p), _ip(i), _dp(x)))
+        self.nnz += len(x)
+
+    def end(self):
+        self.ctx.check(self.lib.m3b_matrix_end(self.h))
+
+    def cell_totals(self, round_exprs=True):
+        out = np.empty(max(self.n_cells, 1), dtype=np.float64)
+        self.ctx.check(self.lib.m3b_cell_totals(self.h, int(bool(round_exprs)), _dp(out)))
+        return out[:self.n_cells]
+
+    def normalize(self, sf, norm_method, pseudo_count):
+        sf_a = None if sf is None else np.ascontiguousarray(sf, dtype=np.float64)
+        self.ctx.check(self.lib.m3b_normalize(self.h, _dp(sf_a), int(norm_method), float(pseudo_count)))
+
+    def export_values(self):
+        y = np.empty(max(self.nnz, 1), dtype=np.float64)
+        self.ctx.check(self.lib.m3b_export_values(self.h, _dp(y)))
+        return y[:self.nnz]
+
+    def select_genes(self, gene_order=None):
+        if gene_order is None:
+            n_sel, go = self.n_genes, None
+        else:
+            go = np.ascontiguousarray(gene_order, dtype=np.int32)
+            n_sel = len(go)
+        keep = np.zeros(max(n_sel, 1), dtype=np.uint8)
+        nk = C.c_int32()
+        self.ctx.check(self.lib.m3b_select_genes(self.h, _ip(go), n_sel, keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nk)))
+        self.n_sel, self.n_kept = n_sel, nk.value
+        return keep[:n_sel].astype(bool)
+
+    def gene_nnz(self):
+        out = np.zeros(max(self.n_sel, 1), dtype=np.int64)
+        self.ctx.check(self.lib.m3b_gene_nnz(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out[:self.n_sel]
+
+    def gene_moments(self):
+        c = np.empty(max(self.n_kept, 1))
+        s = np.empty(max(self.n_kept, 1))
+        self.ctx.check(self.lib.m3b_gene_moments(self.h, _dp(c), _dp(s)))
+        return c[:self.n_kept], s[:self.n_kept]
+
+    def pca_irlba(self, nv, v0, center=True, scale=True, work=0, maxit=1000, tol=1e-5, svtol=None, want_x=True):
+        """Returns dict(d, v, x, center, scale, iter, mprod, status)."""
+        n = self.n_kept
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        if len(v0) != n:
+            raise ValueError("start vector length %d != kept genes %d" % (len(v0), n))
+        d = np.empty(nv)
+        it, mp = C.c_int(), C.c_int()
+        svt = tol if svtol is None else svtol
+        if want_x:
+            V = np.empty((n, nv), order="F")
+            X = np.empty((self.n_cells, nv), order="F")
+            cen = np.empty(n) if center else None
+            sc = np.empty(n) if scale else None
+            st = self.lib.m3b_pca_irlba(self.h, nv, work, maxit, tol, svt, _dp(v0), int(center), int(scale), _dp(d), _dp(V),
+                                        _dp(X), max(self.n_cells, 1), _dp(cen), _dp(sc), C.byref(it), C.byref(mp))
+        else:
+            V = X = cen = sc = None
+            st = self.lib.m3b_pca_irlba_device(self.h, nv, work, maxit, tol, svt, _dp(v0), int(center), int(scale), _dp(d),
+                                               C.byref(it), C.byref(mp))
+        self.ctx.check(st, allow=(L.M3B_W_NOT_CONVERGED,))
+        return dict(d=d, v=V, x=X, center=cen, scale=sc, iter=it.value, mprod=mp.value, status=st)
+
+    def project(self, model_row, V, center, scale):
+        V = np.asfortranarray(V, dtype=np.float64)
+        n_model, nv = V.shape
+        mr = np.ascontiguousarray(model_row, dtype=np.int32)
+        Y = np.empty((self.n_cells, nv), order="F")
+        c = None if center is None else np.ascontiguousarray(center, dtype=np.float64)
+        s = None if scale is None else np.ascontiguousarray(scale, dtype=np.float64)
+        self.ctx.check(self.lib.m3b_project(self.h, _ip(mr), n_model, _dp(V), _dp(c), _dp(s), nv, _dp(Y), max(self.n_cells, 1)))
+        return Y
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.lib.m3b_matrix_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def size_factors_from_totals(cell_total, method=L.SF_TOTAL):
+    """Host-side finish of estimate_sf_sparse (R/utils.R:61-68) through the ABI."""
+    lib = L.load()
+    tot = np.ascontiguousarray(cell_total, dtype=np.float64)
+    sf = np.empty(max(len(tot), 1))
+    az = C.c_int()
+    st = lib.m3b_size_factors_from_totals(_dp(tot), len(tot), int(method), _dp(sf), C.byref(az))
+    if st != L.M3B_OK:
+        raise L.M3BError(st, lib.m3b_status_string(st).decode())
+    return sf[:len(tot)], bool(az.value)

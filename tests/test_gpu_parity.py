@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path (through the C ABI / Python host mirror) against the
+oracle on the committed fixtures.  Bars (BASELINE.json north_star): size factors and nnz
+bookkeeping exact; singular values 1e-6 relative; sign-aligned loadings / embeddings
+subspace angle < 1e-4 rad; iter/mprod equal to the oracle's."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import monocle3_ref as ref
+from tests.parity import column_angles, subspace_angle, sv_rel_err
+
+pytestmark = pytest.mark.gpu
+
+SV_TOL = 1e-6      # relative, north_star
+ANGLE_TOL = 1e-4   # rad, north_star
+
+
+@pytest.fixture(scope="module")
+def m3():
+    import monocle3_b200 as m
+    from monocle3_b200 import engine
+    m.set_context(engine.Context(device=0, small_svd="device"))
+    return m
+
+
+def _cds(m3, counts, extra=None):
+    genes = extra["genes"] if extra and "genes" in extra else None
+    cells = extra["cells"] if extra and "cells" in extra else None
+    return m3.new_cell_data_set(counts, cell_names=cells, gene_names=genes)
+
+
+@pytest.mark.parametrize("name", ["a549", "worm_l2", "worm_embryo"])
+def test_size_factors_exact(m3, request, name):
+    counts, extra = request.getfixturevalue(name)
+    cds = _cds(m3, counts, extra)
+    sf_o, tot_o = ref.estimate_sf_sparse(counts)
+    dev = cds.device_matrix()
+    assert np.array_equal(dev.cell_totals(True), tot_o)  # exact integer sums
+    assert np.array_equal(m3.size_factors(cds), sf_o)     # host finish in long double like R
+    for method in ("mean-geometric-mean-log-total",):
+        cds2 = m3.estimate_size_factors(_cds(m3, counts, extra), method=method)
+        np.testing.assert_allclose(m3.size_factors(cds2), ref.estimate_sf_sparse(counts, method=method)[0], rtol=1e-15)
+
+
+def test_size_factors_rounding_and_zero_cell(m3, a549):
+    counts, _ = a549
+    c = counts.copy().astype(np.float64)
+    c.data = c.data + 0.5  # exercises round-half-even
+    cds = _cds(m3, c)
+    assert np.array_equal(cds.device_matrix().cell_totals(True), ref.estimate_sf_sparse(c)[1])
+    lil = counts.tolil()
+    lil[:, 3] = 0
+    with pytest.warns(UserWarning, match="zero reads"):
+        cds0 = _cds(m3, lil.tocsc())
+    assert m3.size_factors(cds0) is None  # cds returned unchanged (R/utils.R:32-39)
+
+
+@pytest.mark.parametrize("nm", ["log", "size_only", "binary"])
+def test_normalized_counts(m3, a549, nm):
+    counts, extra = a549
+    cds = _cds(m3, counts, extra)
+    got = m3.normalized_counts(cds, norm_method=nm)
+    exp = ref.normalized_counts(counts, m3.size_factors(cds), norm_method=nm)
+    assert np.array_equal(got.indptr, exp.indptr) and np.array_equal(got.indices, exp.indices)
+    np.testing.assert_allclose(got.data, exp.data, rtol=4e-16, atol=0)  # <= 2 ulp (CUDA log10 vs libm)
+    with pytest.raises(ValueError, match="Pseudocount"):
+        m3.normalized_counts(cds, pseudocount=2)
+
+
+@pytest.mark.parametrize("name", ["a549", "worm_l2"])
+def test_filter_nnz_moments(m3, request, name):
+    from monocle3_b200 import _lib as L
+    counts, extra = request.getfixturevalue(name)
+    cds = _cds(m3, counts, extra)
+    sf = m3.size_factors(cds)
+    dev = cds.device_matrix()
+    dev.normalize(sf, L.NORM_LOG2, 1.0)
+    y = dev.export_values()
+    FM = ref.normalize_expr_data(counts, sf, "log")
+    np.testing.assert_allclose(y, FM.data, rtol=4e-16)
+    keep = dev.select_genes(None)
+    FMf, kept = ref.select_and_filter_genes(FM)
+    assert np.array_equal(np.nonzero(keep)[0], kept)
+    assert np.array_equal(dev.gene_nnz(), np.diff(counts.tocsr().indptr))  # exact bookkeeping
+    c, s = dev.gene_moments()
+    co, so = ref.gene_moments(FMf.T.tocsc())
+    np.testing.assert_allclose(c, co, rtol=1e-13)
+    np.testing.assert_allclose(s, so, rtol=1e-12)
+
+
+def _check_pca(m3, counts, extra, num_dim, svd_mode="device", **kw):
+    from monocle3_b200 import engine
+    m3.set_context(engine.Context(device=0, small_svd=svd_mode))
+    cds = _cds(m3, counts, extra)
+    cds = m3.preprocess_cds(cds, num_dim=num_dim, **kw)
+    okw = dict(kw)
+    if "use_genes" in okw:
+        lut = {g: k for k, g in enumerate(cds.gene_names)}
+        okw["use_genes_idx"] = np.array([lut[g] for g in okw.pop("use_genes")])
+    o = ref.preprocess_cds(counts, m3.size_factors(cds), num_dim=num_dim, **okw)
+    model = cds.reduce_dim_aux["PCA"]["model"]
+    ir = cds.reduce_dim_aux["PCA"]["irlba"]
+    assert (ir["iter"], ir["mprod"]) == (o["iter"], o["mprod"])
+    assert sv_rel_err(ir["d"], o["d"]) < SV_TOL
+    assert subspace_angle(model["svd_v"], o["svd_v"]) < ANGLE_TOL
+    assert subspace_angle(cds.reduced_dims["PCA"], o["PCA"]) < ANGLE_TOL
+    assert column_angles(model["svd_v"], o["svd_v"]).max() < ANGLE_TOL
+    assert column_angles(cds.reduced_dims["PCA"], o["PCA"]).max() < ANGLE_TOL
+    np.testing.assert_allclose(model["svd_sdev"], o["svd_sdev"], rtol=SV_TOL)
+    np.testing.assert_allclose(model["prop_var_expl"], o["prop_var_expl"], rtol=1e-5)
+    if o["svd_center"] is not None:
+        np.testing.assert_allclose(model["svd_center"], o["svd_center"], rtol=1e-13)
+        np.testing.assert_allclose(model["svd_scale"], o["svd_scale"], rtol=1e-12)
+    return cds, o
+
+
+@pytest.mark.parametrize("svd_mode", ["device", "lapack"])
+@pytest.mark.parametrize("num_dim", [20, 50])
+def test_pca_a549(m3, a549, num_dim, svd_mode):
+    counts, extra = a549
+    cds, o = _check_pca(m3, counts, extra, num_dim, svd_mode)
+    if svd_mode == "lapack":  # sign fidelity: the reference's own goldens, signs included
+        assert cds.reduced_dims["PCA"][0, 0] == pytest.approx(2.4207391, abs=1e-5)  # test-preprocessing.R:11
+        assert cds.reduced_dims["PCA"][1, 0] == pytest.approx(1.982232, abs=1e-5)  # :75
+        np.testing.assert_allclose(cds.reduced_dims["PCA"], o["PCA"], atol=1e-8)
+
+
+def test_pca_a549_model_slots(m3, a549):
+    counts, extra = a549
+    cds, _ = _check_pca(m3, counts, extra, 20, "lapack")
+    model = cds.reduce_dim_aux["PCA"]["model"]
+    # tests/testthat/test-preprocessing.R:45-51
+    assert model["num_dim"] == 20 and model["norm_method"] == "log"
+    assert model["svd_v"][0, 0] == pytest.approx(0.1362, abs=1e-3)
+    assert model["svd_sdev"][0] == pytest.approx(2.67, abs=1e-2)
+    assert model["svd_center"][0] == pytest.approx(2.22475, abs=1e-4)
+    assert model["svd_scale"][0] == pytest.approx(0.9393, abs=1e-3)
+    assert model["prop_var_expl"][0] == pytest.approx(0.1493, abs=1e-3)
+    assert cds.reduced_dims["PCA"].shape == (500, 20)
+    assert cds.reduced_dims_dimnames["PCA"][0][0] == "E11_A01_RT_467"  # test-reduce_dimension.R:53
+
+
+@pytest.mark.parametrize("kw,golden,pos", [
+    (dict(norm_method="size_only"), 2.222207, (0, 0)),                                   # test-preprocessing.R:22
+    (dict(norm_method="none"), -2.42836, (0, 0)),                                        # :34
+    (dict(norm_method="size_only", pseudo_count=1.4, scaling=False), -24.30544, (0, 0)),  # :69 (dense path)
+])
+def test_pca_a549_variants(m3, a549, kw, golden, pos):
+    counts, extra = a549
+    cds, _ = _check_pca(m3, counts, extra, 20, "lapack", **kw)
+    assert cds.reduced_dims["PCA"][pos] == pytest.approx(golden, abs=1e-5)
+
+
+def test_pca_a549_use_genes(m3, a549):
+    counts, extra = a549
+    cds, _ = _check_pca(m3, counts, extra, 20, "lapack", use_genes=list(extra["genes"][:100]))
+    assert cds.reduced_dims["PCA"][1, 0] == pytest.approx(-0.5347819, abs=1e-5)  # test-preprocessing.R:82
+
+
+def test_pca_log_pseudocount_dense_paths(m3, a549):
+    counts, extra = a549
+    _check_pca(m3, counts, extra, 10, "device", norm_method="log", pseudo_count=2.0)
+    _check_pca(m3, counts, extra, 10, "device", norm_method="log", pseudo_count=0.5, scaling=False)
+    _check_pca(m3, counts, extra, 10, "device", norm_method="log", scaling=False)
+
+
+@pytest.mark.parametrize("name,num_dim", [("worm_l2", 50), ("worm_embryo", 50)])
+def test_pca_worm(m3, request, name, num_dim):
+    counts, extra = request.getfixturevalue(name)
+    _check_pca(m3, counts, extra, num_dim, "device")
+
+
+def test_transform_equals_embedding(m3, a549):
+    """tests/testthat/test-projection.R:14-30: preprocess_transform of the same cells
+    reproduces preprocess_cds's embedding."""
+    counts, extra = a549
+    cds, o = _check_pca(m3, counts, extra, 50, "lapack")
+    cds2 = _cds(m3, counts, extra)
+    cds2.reduce_dim_aux = {"PCA": cds.reduce_dim_aux["PCA"]}  # load_transform_models
+    cds2 = m3.preprocess_transform(cds2)
+    a, b = cds.reduced_dims["PCA"], cds2.reduced_dims["PCA"]
+    for (i, j) in ((0, 0), (1, 0), (0, 1)):
+        assert a[i, j] == pytest.approx(b[i, j], abs=1e-6)
+    assert np.abs(a - b).max() < 1e-9
+    assert b[0, 0] == pytest.approx(2.420739, abs=1e-5)  # test-io.R:267
+
+
+def test_transform_query_subset_and_gene_mismatch(m3, worm_l2):
+    counts, extra = worm_l2
+    ref_counts = counts[:, :3000]
+    q_counts = counts[:, 3000:]
+    cds = _cds(m3, ref_counts)
+    cds = m3.preprocess_cds(cds, num_dim=30)
+    model = cds.reduce_dim_aux["PCA"]["model"]
+    q = _cds(m3, q_counts)
+    q.reduce_dim_aux = {"PCA": cds.reduce_dim_aux["PCA"]}
+    q = m3.preprocess_transform(q)
+    # oracle projection with the SAME model (so only the projection arithmetic is compared)
+    lut = {g: k for k, g in enumerate(model["svd_v_rownames"])}
+    gidx = np.array([lut.get(g, -1) for g in q.gene_names])
+    yo = ref.preprocess_transform(q_counts, m3.size_factors(q), model, gidx)
+    np.testing.assert_allclose(q.reduced_dims["PCA"], yo, atol=1e-9, rtol=1e-9)
+
+
+def test_errors(m3, a549):
+    from monocle3_b200 import _lib as L
+    counts, extra = a549
+    cds = _cds(m3, counts, extra)
+    with pytest.raises(ValueError, match="norm_method"):
+        m3.preprocess_cds(cds, norm_method="bogus")
+    with pytest.raises(ValueError, match="use_genes"):
+        m3.preprocess_cds(cds, use_genes=["not-a-gene"])
+    with pytest.raises(L.M3BError) as ei:  # nv >= min(dim): irlba's own error
+        cds.device_matrix().normalize(m3.size_factors(cds), L.NORM_LOG2, 1.0)
+        cds.device_matrix().select_genes(None)
+        cds.device_matrix().pca_irlba(400, np.ones(179))
+    assert ei.value.status == L.M3B_E_DIMS
+    with pytest.raises(L.M3BError) as ei:  # call-order violation
+        from monocle3_b200 import engine
+        d = engine.DeviceMatrix.from_csc(m3.get_context(), counts)
+        d.select_genes(None)
+    assert ei.value.status == L.M3B_E_STATE
+
+
+def test_ragged_and_empty_inputs(m3):
+    """Empty cells are rejected by the zero-read guard; empty genes are filtered; chunked
+    append with ragged chunks gives the same result as one chunk."""
+    from monocle3_b200 import engine, _lib as L
+    rng = np.random.default_rng(0)
+    G, C = 300, 700
+    dense = rng.poisson(0.3, size=(G, C)).astype(np.float64)
+    dense[5, :] = 0
+    dense[17, :] = 0
+    dense[:, dense.sum(axis=0) == 0] = 1
+    counts = sp.csc_matrix(dense)
+    ctx = m3.get_context()
+    one = engine.DeviceMatrix.from_csc(ctx, counts)
+    rag = engine.DeviceMatrix(ctx, G, C, C, 0)  # nnz_hint 0 forces the grow path
+    cuts = [0, 1, 2, 130, 131, 699, 700]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        p = counts.indptr[a:b + 1] - counts.indptr[a]
+        rag.append_csc(p, counts.indices[counts.indptr[a]:counts.indptr[b]], counts.data[counts.indptr[a]:counts.indptr[b]])
+    rag.end()
+    assert np.array_equal(one.cell_totals(), rag.cell_totals())
+    sf = ref.estimate_sf_sparse(counts)[0]
+    for d in (one, rag):
+        d.normalize(sf, L.NORM_LOG2, 1.0)
+    k1, k2 = one.select_genes(None), rag.select_genes(None)
+    assert np.array_equal(k1, k2) and not k1[5] and not k1[17] and k1.sum() == G - 2
+    v0 = np.linspace(-1, 1, int(k1.sum()))
+    r1 = one.pca_irlba(10, v0)
+    r2 = rag.pca_irlba(10, v0)
+    assert np.array_equal(r1["d"], r2["d"]) and np.array_equal(r1["x"], r2["x"])  # bit-reproducible
+    o = ref.preprocess_cds(counts, sf, num_dim=10, v0=v0)
+    assert sv_rel_err(r1["d"], o["d"]) < SV_TOL and subspace_angle(r1["x"], o["PCA"]) < ANGLE_TOL
