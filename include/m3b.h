@@ -192,8 +192,14 @@ typedef struct m3b_stats {
 } m3b_stats;
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);
 int m3b_reset_stats(m3b_ctx* ctx);
-/* flags for m3b_create */
-#define M3B_FLAG_TIME_SPMV 1  /* bracket every SpMV launch with CUDA events */
+/* flags for m3b_create / m3b_set_flags */
+#define M3B_FLAG_TIME_SPMV 1  /* bracket every SpMV launch with CUDA events (read back after the run) */
+int m3b_set_flags(m3b_ctx* ctx, int flags);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of this
+ * library is launched on): start records an event, stop records a second one,
+ * synchronises and returns the elapsed device time in milliseconds. */
+int m3b_timer_start(m3b_ctx* ctx);
+int m3b_timer_stop(m3b_ctx* ctx, double* elapsed_ms);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,9 @@ SIGNATURES = {
     "m3b_project": (C.c_int, [_P, _ip, C.c_int32, _dp, _dp, _dp, C.c_int, _dp, C.c_int64]),
     "m3b_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "m3b_reset_stats": (C.c_int, [_P]),
+    "m3b_set_flags": (C.c_int, [_P, C.c_int]),
+    "m3b_timer_start": (C.c_int, [_P]),
+    "m3b_timer_stop": (C.c_int, [_P, _dp]),
 }
 
 _lib = None

@@ -19,6 +19,35 @@ void m3b_set_error(m3b_ctx* ctx, const char* fmt, ...) {
   ctx->err = buf;
 }
 
+void spmv_timer_begin(m3b_ctx* ctx, int kind) {
+  if (!(ctx->flags & M3B_FLAG_TIME_SPMV)) return;
+  if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+    for (int k = 0; k < 512; ++k) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      ctx->ev_pool.push_back(e);
+    }
+  }
+  ctx->ev_kind.push_back(kind);
+  cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream);
+}
+void spmv_timer_end(m3b_ctx* ctx) {
+  if (!(ctx->flags & M3B_FLAG_TIME_SPMV)) return;
+  if (ctx->ev_used & 1) cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream);
+}
+void spmv_timer_collect(m3b_ctx* ctx) {
+  if (!(ctx->flags & M3B_FLAG_TIME_SPMV)) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (size_t k = 0; k + 1 < ctx->ev_used; k += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]) != cudaSuccess) continue;
+    if (ctx->ev_kind[k / 2] == 0) ctx->stats.spmv_cells_out_ms += ms;
+    else ctx->stats.spmv_genes_out_ms += ms;
+  }
+  ctx->ev_used = 0;
+  ctx->ev_kind.clear();
+}
+
 extern "C" {
 
 int m3b_abi_version(void) { return M3B_ABI_VERSION; }
@@ -88,6 +117,7 @@ void m3b_destroy(m3b_ctx* ctx) {
   if (ctx->sched) cudaFree(ctx->sched);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -461,6 +491,30 @@ int m3b_project(m3b_mat* q, const int32_t* model_row, int32_t n_model, const dou
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out) {
   if (!ctx || !out) return M3B_E_DIMS;
   *out = ctx->stats;
+  return M3B_OK;
+}
+
+int m3b_set_flags(m3b_ctx* ctx, int flags) {
+  if (!ctx) return M3B_E_DIMS;
+  ctx->flags = flags;
+  return M3B_OK;
+}
+
+int m3b_timer_start(m3b_ctx* ctx) {
+  if (!ctx) return M3B_E_DIMS;
+  cudaSetDevice(ctx->device);
+  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return M3B_OK;
+}
+
+int m3b_timer_stop(m3b_ctx* ctx, double* elapsed_ms) {
+  if (!ctx || !elapsed_ms) return M3B_E_DIMS;
+  cudaSetDevice(ctx->device);
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *elapsed_ms = ms;
   return M3B_OK;
 }
 

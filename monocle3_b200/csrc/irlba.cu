@@ -466,17 +466,9 @@ struct Irlba {
 
   // W[:, jw] = Ax(V[:, jv]) given xs/pb already prepared; optional "- R_F * W[:, jw-1]"
   int product_A(int jw, bool sub_prev) {
-    cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
-    const bool timing = (ctx->flags & M3B_FLAG_TIME_SPMV) != 0;
-    if (timing) cudaEventRecord(e0, ctx->stream);
+    spmv_timer_begin(ctx, 0);
     RET(launch_tile_stream(ctx, m->A, OP_DOT, xs));
-    if (timing) {
-      cudaEventRecord(e1, ctx->stream);
-      cudaEventSynchronize(e1);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, e0, e1);
-      ctx->stats.spmv_cells_out_ms += ms;
-    }
+    spmv_timer_end(ctx);
     ctx->stats.spmv_cells_out++;
     double* w = W + (long long)jw * mrows;
     if (mrows) {
@@ -490,16 +482,9 @@ struct Irlba {
 
   // F = Atw(W[:, j]) - S * V[:, j]
   int product_B(int j) {
-    const bool timing = (ctx->flags & M3B_FLAG_TIME_SPMV) != 0;
-    if (timing) cudaEventRecord(ctx->ev0, ctx->stream);
+    spmv_timer_begin(ctx, 1);
     RET(launch_tile_stream(ctx, m->B, OP_DOT, W + (long long)j * mrows));
-    if (timing) {
-      cudaEventRecord(ctx->ev1, ctx->stream);
-      cudaEventSynchronize(ctx->ev1);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-      ctx->stats.spmv_genes_out_ms += ms;
-    }
+    spmv_timer_end(ctx);
     ctx->stats.spmv_genes_out++;
     RET(launch_combine_rows(ctx, m->B, Fraw));
     RET(comm_allreduce_f64(ctx, Fraw, n));
@@ -835,6 +820,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     if (scale_out && use_scale)
       ICK(cudaMemcpyAsync(scale_out, m->scale, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ICK(cudaStreamSynchronize(ctx->stream));
+    spmv_timer_collect(ctx);
     ctx->stats.d2h_bytes += nv * 8 + (V_out ? (long long)n * nv * 8 : 0);
     {
       float ms = 0;

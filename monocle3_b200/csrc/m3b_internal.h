@@ -65,6 +65,10 @@ struct m3b_ctx {
   void* should_abort_user = nullptr;
   m3b_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // scratch events
+  // M3B_FLAG_TIME_SPMV: event pairs recorded around every SpMV launch, read back after the run
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_kind;  // 0 = cells-out (K4), 1 = genes-out (K5)
+  size_t ev_used = 0;
   unsigned int* sched = nullptr;             // [2] dynamic unit counter + done counter (zeroed)
 };
 
@@ -176,3 +180,7 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
 int jacobi_svd(int n, const double* B, double* U, double* s, double* Vt);
 
 static inline void count_launch(m3b_ctx* ctx, int n = 1) { ctx->stats.kernel_launches += n; }
+// event-pool helpers (api.cu)
+void spmv_timer_begin(m3b_ctx* ctx, int kind);
+void spmv_timer_end(m3b_ctx* ctx);
+void spmv_timer_collect(m3b_ctx* ctx);

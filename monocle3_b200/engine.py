@@ -79,6 +79,17 @@ class Context:
         self.check(self.lib.m3b_get_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in L.Stats._fields_}
 
+    def set_flags(self, flags):
+        self.check(self.lib.m3b_set_flags(self.h, int(flags)))
+
+    def timer_start(self):
+        self.check(self.lib.m3b_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self.check(self.lib.m3b_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def reset_stats(self):
         self.check(self.lib.m3b_reset_stats(self.h))
 
