@@ -51,56 +51,56 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (pynvml) in a
+    background thread.  (Polling the nvidia-smi binary instead perturbs the run: it re-enumerates
+    the devices on every sample and stalled this launch-heavy step by ~40%.)"""
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index, period=0.25):
+        self.idx, self.period = gpu_index, period
+        self.samples, self.stop_flag, self.thread, self.err = [], threading.Event(), None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+        except Exception as e:  # pragma: no cover
+            self.err = "nvml unavailable: %s" % e
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((sm, mx, rs, pw))
+            except Exception as e:  # pragma: no cover
+                self.err = str(e)
+                break
+            self.stop_flag.wait(self.period)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(pw)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in self.samples))
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])),
+                "sm_max_mhz": float(max(s[1] for s in self.samples)), "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(s[3] for s in self.samples), "source": "nvml"}
 
 
 def pinned(a):
@@ -233,12 +233,22 @@ def main():
     dev = cds.device_matrix()
     sf = m3.size_factors(cds)
 
+    wall = {}
+
     def device_step():
+        t0 = time.perf_counter()
         dev.normalize(sf, L.NORM_LOG2, 1.0)
+        t1 = time.perf_counter()
         dev.select_genes(None)
+        t2 = time.perf_counter()
         v0 = rnorm_after_seed(2016, dev.n_kept)
         nv = min(args.num_dim, min(dev.n_kept, C_total) - 1)
-        return dev.pca_irlba(nv, v0, center=True, scale=True, want_x=False)
+        t3 = time.perf_counter()
+        r = dev.pca_irlba(nv, v0, center=True, scale=True, want_x=False)
+        t4 = time.perf_counter()
+        wall.update(normalize_ms=1e3 * (t1 - t0), select_genes_ms=1e3 * (t2 - t1), rnorm_ms=1e3 * (t3 - t2),
+                    pca_irlba_call_ms=1e3 * (t4 - t3))
+        return r
 
     for _ in range(args.warmup):
         res = device_step()
@@ -288,7 +298,13 @@ def main():
                               "avg_us": 1e3 * sti["spmv_cells_out_ms"] / max(1, nA)},
                 "genes_out": {"gbs": nB * sti["spmv_bytes_genes_out"] / max(sti["spmv_genes_out_ms"], 1e-9) / 1e6,
                               "avg_us": 1e3 * sti["spmv_genes_out_ms"] / max(1, nB)},
-                "spmv_share_of_irlba": spmv_ms / max(sti["irlba_ms"], 1e-9)}
+                "spmv_share_of_irlba": spmv_ms / max(sti["irlba_ms"], 1e-9),
+                "irlba_phase_ms": dict(zip(["spmv_cells_out", "spmv_genes_out", "orthog", "small_svd", "restart_gemm",
+                                            "vector_epilogues", "allreduce"], [round(v, 3) for v in sti["phase_ms"][:7]])),
+                "irlba_ms": sti["irlba_ms"], "svd_sweeps": sti["svd_sweeps"],
+                "host_wall_ms": {k: round(v, 2) for k, v in wall.items()},
+                "irlba_host_ms": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in sti["host_ms"]])),
+                "irlba_host_ms_untimed_step": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in st["host_ms"]]))}
 
     # ---- end-to-end arm: public API from pinned host buffers ----
     def e2e_step():

@@ -189,6 +189,15 @@ typedef struct m3b_stats {
   int64_t spmv_bytes_genes_out;/* algorithmic bytes of one K5 launch               */
   int64_t h2d_bytes;           /* host->device bytes copied so far                 */
   int64_t d2h_bytes;           /* device->host bytes copied so far                 */
+  /* with M3B_FLAG_TIME_SPMV: summed CUDA-event time of the IRLBA phases of the last run:
+   * [0] K4 SpMV cells-out  [1] K5 SpMV genes-out  [2] K6 orthogonalisation (dots+apply)
+   * [3] K8 small SVD + restart logic  [4] K9 restart GEMMs  [5] vector epilogues / combines
+   * [6] allreduces  [7] reserved */
+  double  phase_ms[8];
+  int64_t svd_sweeps;          /* Jacobi sweeps summed over the restarts of the last run */
+  /* host wall clock of the last m3b_pca_irlba: [0] setup+allocation [1] Lanczos loop
+   * [2] final GEMMs + result copies [3] release */
+  double  host_ms[4];
 } m3b_stats;
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);
 int m3b_reset_stats(m3b_ctx* ctx);

@@ -36,7 +36,8 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("spmv_cells_out", C.c_int64), ("spmv_genes_out", C.c_int64),
                 ("spmv_cells_out_ms", C.c_double), ("spmv_genes_out_ms", C.c_double), ("irlba_ms", C.c_double),
                 ("prepare_ms", C.c_double), ("spmv_bytes_cells_out", C.c_int64), ("spmv_bytes_genes_out", C.c_int64),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("phase_ms", C.c_double * 8),
+                ("svd_sweeps", C.c_int64), ("host_ms", C.c_double * 4)]
 
 
 # name -> (restype, argtypes); every symbol include/m3b.h declares

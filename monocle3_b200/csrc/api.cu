@@ -41,8 +41,10 @@ void spmv_timer_collect(m3b_ctx* ctx) {
   for (size_t k = 0; k + 1 < ctx->ev_used; k += 2) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]) != cudaSuccess) continue;
-    if (ctx->ev_kind[k / 2] == 0) ctx->stats.spmv_cells_out_ms += ms;
-    else ctx->stats.spmv_genes_out_ms += ms;
+    const int kind = ctx->ev_kind[k / 2];
+    if (kind == 0) ctx->stats.spmv_cells_out_ms += ms;
+    if (kind == 1) ctx->stats.spmv_genes_out_ms += ms;
+    if (kind >= 0 && kind < 8) ctx->stats.phase_ms[kind] += ms;
   }
   ctx->ev_used = 0;
   ctx->ev_kind.clear();
@@ -102,6 +104,10 @@ int m3b_create(int device, int flags, m3b_ctx** out) {
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaMalloc((void**)&ctx->sched, 4 * sizeof(unsigned int)) != cudaSuccess ||
       cudaMemset(ctx->sched, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
+    m3b_destroy(ctx);
+    return M3B_E_CUDA;
+  }
+  if (spmv_init(ctx) != M3B_OK || svd_init(ctx) != M3B_OK || irlba_init(ctx) != M3B_OK) {
     m3b_destroy(ctx);
     return M3B_E_CUDA;
   }

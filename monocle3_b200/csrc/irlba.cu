@@ -20,6 +20,7 @@
 // pseudo-count paths without scaling, 0 otherwise (DESIGN.md "implicit constant").
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -127,6 +128,8 @@ __global__ void __launch_bounds__(NT) k_fix_F(const double* __restrict__ Fraw, c
 // K6: tall-skinny orthogonalisation  y -= X (X^T y), one classical GS pass
 // --------------------------------------------------------------------------
 // part[blk*ncols + c] = sum over the block's rows of X[r,c]*y[r]
+// A block owns `chunk` rows (y chunk staged in shared memory); a warp takes 4 columns at a
+// time so that every lane keeps 4 independent load streams in flight.
 __global__ void __launch_bounds__(NT) k_dots(const double* __restrict__ X, long long ld, long long rows, int ncols,
                                              const double* __restrict__ y, int chunk, double* __restrict__ part) {
   extern __shared__ double ys[];  // chunk doubles
@@ -135,53 +138,87 @@ __global__ void __launch_bounds__(NT) k_dots(const double* __restrict__ X, long 
   for (int k = threadIdx.x; k < len; k += blockDim.x) ys[k] = y[r0 + k];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int c = warp; c < ncols; c += nwarps) {
-    const double* xc = X + (long long)c * ld + r0;
-    double a0 = 0.0, a1 = 0.0;
-    int k = lane;
-    for (; k + 32 < len; k += 64) {
-      a0 += xc[k] * ys[k];
-      a1 += xc[k + 32] * ys[k + 32];
+  for (int c0 = warp * 4; c0 < ncols; c0 += nwarps * 4) {
+    const int nc = min(4, ncols - c0);
+    const double* x0 = X + (long long)c0 * ld + r0;
+    const double* x1 = x0 + (nc > 1 ? ld : 0);
+    const double* x2 = x0 + (nc > 2 ? 2 * ld : 0);
+    const double* x3 = x0 + (nc > 3 ? 3 * ld : 0);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int k = lane; k < len; k += 32) {
+      const double yv = ys[k];
+      a0 += x0[k] * yv;
+      a1 += x1[k] * yv;
+      a2 += x2[k] * yv;
+      a3 += x3[k] * yv;
     }
-    if (k < len) a0 += xc[k] * ys[k];
-    double a = a0 + a1;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) part[(long long)blockIdx.x * ncols + c] = a;
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (lane == 0) {
+      double* pp = part + (long long)blockIdx.x * ncols + c0;
+      pp[0] = a0;
+      if (nc > 1) pp[1] = a1;
+      if (nc > 2) pp[2] = a2;
+      if (nc > 3) pp[3] = a3;
+    }
   }
 }
 
-// t[c] = sum_b part[b*ncols + c] (fixed order)
-__global__ void k_reduce_dots(const double* __restrict__ part, int nblk, int ncols, double* __restrict__ t) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+// t[c] = sum_b part[b*ncols + c]: one warp per column, lanes stride over the blocks, fixed tree
+__global__ void __launch_bounds__(NT) k_reduce_dots(const double* __restrict__ part, int nblk, int ncols,
+                                                    double* __restrict__ t) {
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= ncols) return;
   double a = 0.0;
-  for (int b = 0; b < nblk; ++b) a += part[(long long)b * ncols + c];
-  t[c] = a;
+  for (int b = lane; b < nblk; b += 32) a += part[(long long)b * ncols + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) t[c] = a;
 }
 
 // y[r] -= sum_c X[r,c]*t[c];  pn[blk] = partial ||y||^2, ps[blk] = partial sum(y)
+// Block = 64 rows x 4 column groups: each thread sums its quarter of the columns with four
+// independent accumulators (16 loads in flight per row), the groups are added in a fixed
+// order through shared memory.
 __global__ void __launch_bounds__(NT) k_apply_orth(const double* __restrict__ X, long long ld, long long rows, int ncols,
                                                    const double* __restrict__ t, double* __restrict__ y,
                                                    double* __restrict__ pn, double* __restrict__ ps) {
   extern __shared__ double ts[];  // ncols
+  __shared__ double red[4][64];
   __shared__ double sh[32];
   for (int k = threadIdx.x; k < ncols; k += blockDim.x) ts[k] = t[k];
   __syncthreads();
+  const int rl = threadIdx.x & 63, cg = threadIdx.x >> 6;
   double n2 = 0.0, sm = 0.0;
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
-    double a0 = 0.0, a1 = 0.0;
-    const double* xr = X + r;
-    int c = 0;
-    for (; c + 1 < ncols; c += 2) {
-      a0 += xr[(long long)c * ld] * ts[c];
-      a1 += xr[(long long)(c + 1) * ld] * ts[c + 1];
+  for (long long rb = blockIdx.x; rb * 64 < rows; rb += gridDim.x) {
+    const long long r = rb * 64 + rl;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (r < rows) {
+      const double* xr = X + r;
+      int c = cg;
+      for (; c + 12 < ncols; c += 16) {
+        a0 += xr[(long long)c * ld] * ts[c];
+        a1 += xr[(long long)(c + 4) * ld] * ts[c + 4];
+        a2 += xr[(long long)(c + 8) * ld] * ts[c + 8];
+        a3 += xr[(long long)(c + 12) * ld] * ts[c + 12];
+      }
+      for (; c < ncols; c += 4) a0 += xr[(long long)c * ld] * ts[c];
     }
-    if (c < ncols) a0 += xr[(long long)c * ld] * ts[c];
-    double v = y[r] - (a0 + a1);
-    y[r] = v;
-    n2 += v * v;
-    sm += v;
+    red[cg][rl] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (cg == 0 && r < rows) {
+      const double v = y[r] - (((red[0][rl] + red[1][rl]) + red[2][rl]) + red[3][rl]);
+      y[r] = v;
+      n2 += v * v;
+      sm += v;
+    }
+    __syncthreads();
   }
   double r1 = block_sum(n2, sh);
   double r2 = block_sum(sm, sh);
@@ -352,65 +389,128 @@ __global__ void k_transpose_small(const double* __restrict__ in, int n, double* 
 
 // --------------------------------------------------------------------------
 // K9: in-place tall-skinny GEMM  X[:, :kout] = X[:, :kin] * Q   (Q: kin x kout, ld kin)
-// A block owns RB rows: it first stages its whole row block in shared memory
-// (so the update can be done in place), then sweeps Q in column chunks.  Each
-// thread accumulates RPT rows x 13 columns in registers; Q reads are warp
-// broadcasts.
+//
+// Persistent CTAs (one per SM, 256 threads).  Q is staged once per CTA in shared memory as
+// Qs[col][kinp]; the CTA then walks 64-row blocks of X, each staged TRANSPOSED as Xs[row][kinp]
+// with 8-byte cp.async (double-buffered: block i+1 lands while block i is multiplied), so the
+// update can be done in place (a block's rows are fully in shared memory before its outputs
+// are written).  kinp is padded so that kinp % 4 == 2: the 16-byte shared loads of two
+// consecutive k for 8 different rows then hit 8 different bank groups.  Thread = 2 rows x 13
+// columns of accumulators; per two k-steps it issues 2 + 13 LDS.128 and 52 DFMA.
+// (First cut, profiles/: 4.3 instructions per DFMA, fp64 pipe 25% busy, 2.2 waves of 1-CTA/SM
+// blocks.)
 // --------------------------------------------------------------------------
 #define GEMM_CT 13
-template <int RPT>
-__global__ void __launch_bounds__(256, 1)
-k_restart_gemm(double* __restrict__ X, long long ld, long long rows, int kin, int kout, const double* __restrict__ Q,
-               int qc) {
-  extern __shared__ double smg[];
-  const int RB = 64 * RPT;
-  double* Xs = smg;                     // [kin][RB]
-  double* Qs = smg + (size_t)kin * RB;  // [qc][kin]  (column chunk of Q)
-  const long long r0 = (long long)blockIdx.x * RB;
-  const int nr = (int)min((long long)RB, rows - r0);
-  for (int e = threadIdx.x; e < kin * RB; e += blockDim.x) {
-    int c = e / RB, r = e % RB;
-    Xs[e] = (r < nr) ? X[(long long)c * ld + r0 + r] : 0.0;
+#define GEMM_RB 64
+#define GEMM_CPP (8 * GEMM_CT)  // columns per pass = 104
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ void gemm_stage_rows(double* Xs, const double* X, long long ld, long long rows, long long r0,
+                                                int kin, int kinp) {
+  // Xs[r][k] = X[r0 + r, k]; global reads coalesced along r
+  const int total = kin * GEMM_RB;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = e / GEMM_RB, r = e % GEMM_RB;
+    if (r0 + r < rows) cp_async8(Xs + r * kinp + c, X + (long long)c * ld + r0 + r);
   }
-  const int rl = threadIdx.x & 63;  // row lane
-  const int cg = threadIdx.x >> 6;  // column group 0..3
-  for (int c0 = 0; c0 < kout; c0 += qc) {
-    const int nc = min(qc, kout - c0);
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_restart_gemm(double* __restrict__ X, long long ld, long long rows, int kin, int kinp, int kout,
+               const double* __restrict__ Q, int nbuf) {
+  extern __shared__ double smg[];
+  double* Qs = smg;                               // [GEMM_CPP][kinp]
+  double* Xs0 = smg + (size_t)GEMM_CPP * kinp;    // [GEMM_RB][kinp] x nbuf
+  const int rl = threadIdx.x & 31;                // rows rl, rl + 32
+  const int cg = threadIdx.x >> 5;                // column group 0..7
+  const long long nblk = (rows + GEMM_RB - 1) / GEMM_RB;
+  const int npass = (kout + GEMM_CPP - 1) / GEMM_CPP;
+  // zero the k padding once (never written by the staging)
+  for (int e = threadIdx.x; e < (GEMM_CPP + nbuf * GEMM_RB) * (kinp - kin); e += blockDim.x) {
+    const int row = e / (kinp - kin), k = kin + e % (kinp - kin);
+    smg[(size_t)row * kinp + k] = 0.0;
+  }
+  auto stage_q = [&](int pass) {
+    const int c0 = pass * GEMM_CPP;
+    for (int e = threadIdx.x; e < GEMM_CPP * kin; e += blockDim.x) {
+      const int c = e / kin, k = e % kin;
+      Qs[c * kinp + k] = (c0 + c < kout) ? Q[(long long)(c0 + c) * kin + k] : 0.0;
+    }
+  };
+  if (npass == 1) stage_q(0);
+  long long blk = blockIdx.x;
+  int buf = 0;
+  if (blk < nblk) gemm_stage_rows(Xs0, X, ld, rows, blk * GEMM_RB, kin, kinp);
+  cp_async_commit();
+  for (; blk < nblk; blk += gridDim.x) {
+    const long long nxt = blk + gridDim.x;
+    double* Xs = Xs0 + (size_t)buf * GEMM_RB * kinp;
+    if (nbuf == 2) {
+      if (nxt < nblk) gemm_stage_rows(Xs0 + (size_t)(buf ^ 1) * GEMM_RB * kinp, X, ld, rows, nxt * GEMM_RB, kin, kinp);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    for (int e = threadIdx.x; e < nc * kin; e += blockDim.x) Qs[e] = Q[(long long)c0 * kin + e];
-    __syncthreads();
-    // this thread's columns inside the chunk: cg, cg+4, cg+8, ...  in passes of GEMM_CT
-    for (int cb = cg; cb < nc; cb += 4 * GEMM_CT) {
-      double acc[RPT][GEMM_CT];
+    const long long r0 = blk * GEMM_RB;
+    for (int pass = 0; pass < npass; ++pass) {
+      if (npass > 1) {
+        __syncthreads();
+        stage_q(pass);
+        __syncthreads();
+      }
+      double acc0[GEMM_CT], acc1[GEMM_CT];
 #pragma unroll
-      for (int a = 0; a < RPT; ++a)
-#pragma unroll
-        for (int b = 0; b < GEMM_CT; ++b) acc[a][b] = 0.0;
-      for (int kk = 0; kk < kin; ++kk) {
-        double xv[RPT];
-#pragma unroll
-        for (int a = 0; a < RPT; ++a) xv[a] = Xs[kk * RB + rl + 64 * a];
+      for (int b = 0; b < GEMM_CT; ++b) acc0[b] = acc1[b] = 0.0;
+      const double2* x0 = reinterpret_cast<const double2*>(Xs + (size_t)rl * kinp);
+      const double2* x1 = reinterpret_cast<const double2*>(Xs + (size_t)(rl + 32) * kinp);
+      const double2* qb = reinterpret_cast<const double2*>(Qs + (size_t)cg * kinp);
+      const int kq = kinp >> 1;  // double2 per row
+#pragma unroll 2
+      for (int k2 = 0; k2 < kq; ++k2) {
+        const double2 a = x0[k2], c = x1[k2];
 #pragma unroll
         for (int b = 0; b < GEMM_CT; ++b) {
-          const int c = cb + 4 * b;
-          const double q = (c < nc) ? Qs[c * kin + kk] : 0.0;
-#pragma unroll
-          for (int a = 0; a < RPT; ++a) acc[a][b] += xv[a] * q;
+          const double2 q = qb[(size_t)b * 8 * kq + k2];  // column cg + 8 b
+          acc0[b] += a.x * q.x;
+          acc0[b] += a.y * q.y;
+          acc1[b] += c.x * q.x;
+          acc1[b] += c.y * q.y;
         }
       }
+      const int cbase = pass * GEMM_CPP + cg;
 #pragma unroll
       for (int b = 0; b < GEMM_CT; ++b) {
-        const int c = cb + 4 * b;
-        if (c < nc) {
-#pragma unroll
-          for (int a = 0; a < RPT; ++a) {
-            const int r = rl + 64 * a;
-            if (r < nr) X[(long long)(c0 + c) * ld + r0 + r] = acc[a][b];
-          }
+        const int c = cbase + 8 * b;
+        if (c < kout) {
+          if (r0 + rl < rows) X[(long long)c * ld + r0 + rl] = acc0[b];
+          if (r0 + rl + 32 < rows) X[(long long)c * ld + r0 + rl + 32] = acc1[b];
         }
       }
     }
+    __syncthreads();  // everyone is done with Xs[buf] before it is refilled
+    if (nbuf == 1 && nxt < nblk) {
+      gemm_stage_rows(Xs0, X, ld, rows, nxt * GEMM_RB, kin, kinp);
+      cp_async_commit();
+    }
+    if (nbuf == 2) buf ^= 1;
   }
+  cp_async_wait<0>();
+}
+
+int irlba_init(m3b_ctx* ctx) {
+  CK(ctx, cudaFuncSetAttribute(k_restart_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  return M3B_OK;
 }
 
 // ==========================================================================
@@ -428,6 +528,7 @@ struct Irlba {
   double *Q = nullptr, *svd_scratch = nullptr;
   int* ctl = nullptr;
   int nb_n, nb_m;        // blocks of the vector kernels (gene side / cell side)
+  int nbo_n, nbo_m;      // blocks of k_apply_orth (= number of pn/ps partials it writes)
   int chunk_n, chunk_m;  // rows per block of k_dots
   int nblk_n, nblk_m;
   double eps;
@@ -452,14 +553,16 @@ struct Irlba {
   }
 
   int orthog(double* X, long long ld, long long rows, int ncols, double* y, int chunk, int nblk, int nb, bool allreduce) {
+    spmv_timer_begin(ctx, 2);
     if (ncols > 0) {
       k_dots<<<nblk, NT, chunk * sizeof(double), ctx->stream>>>(X, ld, rows, ncols, y, chunk, part);
-      k_reduce_dots<<<(ncols + 127) / 128, 128, 0, ctx->stream>>>(part, nblk, ncols, t);
+      k_reduce_dots<<<(ncols * 32 + NT - 1) / NT, NT, 0, ctx->stream>>>(part, nblk, ncols, t);
       count_launch(ctx, 2);
       if (allreduce) RET(comm_allreduce_f64(ctx, t, ncols));
     }
     k_apply_orth<<<nb, NT, std::max(ncols, 1) * sizeof(double), ctx->stream>>>(X, ld, rows, ncols, t, y, pn, ps);
     count_launch(ctx);
+    spmv_timer_end(ctx);
     CK(ctx, cudaGetLastError());
     return M3B_OK;
   }
@@ -471,11 +574,13 @@ struct Irlba {
     spmv_timer_end(ctx);
     ctx->stats.spmv_cells_out++;
     double* w = W + (long long)jw * mrows;
+    spmv_timer_begin(ctx, 5);
     if (mrows) {
       k_combine_A<<<nb_m, NT, 0, ctx->stream>>>(m->A.partial, m->A.row_item_ptr, mrows, m->A.n_tiles, ce ? pb : nullptr,
                                                 nb_n, sub_prev ? (w - mrows) : nullptr, scal, w);
       count_launch(ctx);
     }
+    spmv_timer_end(ctx);
     CK(ctx, cudaGetLastError());
     return M3B_OK;
   }
@@ -486,47 +591,53 @@ struct Irlba {
     RET(launch_tile_stream(ctx, m->B, OP_DOT, W + (long long)j * mrows));
     spmv_timer_end(ctx);
     ctx->stats.spmv_genes_out++;
+    spmv_timer_begin(ctx, 5);
     RET(launch_combine_rows(ctx, m->B, Fraw));
-    RET(comm_allreduce_f64(ctx, Fraw, n));
+    spmv_timer_end(ctx);
+    if (ctx->comm.world > 1) {
+      spmv_timer_begin(ctx, 6);
+      RET(comm_allreduce_f64(ctx, Fraw, n));
+      spmv_timer_end(ctx);
+    }
+    spmv_timer_begin(ctx, 5);
     k_fix_F<<<nb_n, NT, 0, ctx->stream>>>(Fraw, s, ce, V + (long long)j * n, scal, n, F);
     count_launch(ctx);
+    spmv_timer_end(ctx);
     CK(ctx, cudaGetLastError());
     return M3B_OK;
   }
 
   // normalise W[:, jw] using pn/ps partials (cell side): S, sum(w)
-  int finish_w(int jw, bool first) {
-    k_reduce2<<<1, NT, 0, ctx->stream>>>(pn, ps, nb_m, buf2);
+  int finish_w(int jw, bool first, int np) {
+    spmv_timer_begin(ctx, 5);
+    k_reduce2<<<1, NT, 0, ctx->stream>>>(pn, ps, np, buf2);
     count_launch(ctx);
     RET(comm_allreduce_f64(ctx, buf2, 2));
     k_scale_w<<<nb_m, NT, 0, ctx->stream>>>(W + (long long)jw * mrows, mrows, buf2, scal, ctl, eps, first ? 1 : 0);
     count_launch(ctx);
+    spmv_timer_end(ctx);
     CK(ctx, cudaGetLastError());
     return M3B_OK;
   }
 
   int gemm_inplace(double* X, long long ld, long long rows, int kin, int kout, const double* Qd) {
     if (rows == 0 || kout == 0) return M3B_OK;
-    const size_t budget = 220 * 1024;
-    int rpt = (kin <= 110) ? 2 : 1;
-    size_t xs_bytes = (size_t)kin * 64 * rpt * sizeof(double);
-    if (xs_bytes + (size_t)kin * 4 * sizeof(double) > budget) {
-      m3b_set_error(ctx, "restart GEMM: work=%d too large for the shared-memory tiling", kin);
+    const size_t budget = 224 * 1024;
+    int kinp = kin + 1;
+    while ((kinp & 3) != 2) ++kinp;  // kinp % 4 == 2: conflict-free 16-byte row loads
+    int nbuf = 2;
+    size_t smem = (size_t)(GEMM_CPP + nbuf * GEMM_RB) * kinp * sizeof(double);
+    if (smem > budget) {
+      nbuf = 1;
+      smem = (size_t)(GEMM_CPP + GEMM_RB) * kinp * sizeof(double);
+    }
+    if (smem > budget) {
+      m3b_set_error(ctx, "restart GEMM: work=%d too large for the shared-memory tiling (max ~165)", kin);
       return M3B_E_DIMS;
     }
-    int qc = (int)((budget - xs_bytes) / ((size_t)kin * sizeof(double)));
-    qc = std::min(qc, kout);
-    if (qc >= 4) qc &= ~3;
-    size_t smem = xs_bytes + (size_t)qc * kin * sizeof(double);
-    const int RB = 64 * rpt;
-    unsigned grid = (unsigned)((rows + RB - 1) / RB);
-    if (rpt == 2) {
-      CK(ctx, cudaFuncSetAttribute(k_restart_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-      k_restart_gemm<2><<<grid, 256, smem, ctx->stream>>>(X, ld, rows, kin, kout, Qd, qc);
-    } else {
-      CK(ctx, cudaFuncSetAttribute(k_restart_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-      k_restart_gemm<1><<<grid, 256, smem, ctx->stream>>>(X, ld, rows, kin, kout, Qd, qc);
-    }
+    const long long nblk = (rows + GEMM_RB - 1) / GEMM_RB;
+    const unsigned grid = (unsigned)std::min<long long>(nblk, ctx->sm_count);
+    k_restart_gemm<<<grid, 256, smem, ctx->stream>>>(X, ld, rows, kin, kinp, kout, Qd, nbuf);
     count_launch(ctx);
     CK(ctx, cudaGetLastError());
     return M3B_OK;
@@ -636,12 +747,17 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
   I.eps = 2.220446049250313e-16;
   I.nb_n = std::max(1, std::min((n + NT - 1) / NT, 64));
   I.nb_m = (int)std::max<long long>(1, std::min<long long>((mloc + NT - 1) / NT, MAX_PART));
+  I.nbo_n = std::max(1, std::min((n + 63) / 64, MAX_PART));
+  I.nbo_m = (int)std::max<long long>(1, std::min<long long>((mloc + 63) / 64, MAX_PART));
   I.chunk_n = Irlba::pick_chunk(n, ctx->sm_count);
   I.chunk_m = Irlba::pick_chunk(mloc, ctx->sm_count);
   I.nblk_n = std::max(1, (n + I.chunk_n - 1) / I.chunk_n);
   I.nblk_m = (int)std::max<long long>(1, (mloc + I.chunk_m - 1) / I.chunk_m);
   int status = M3B_OK;
   cudaEvent_t evA = nullptr, evB = nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_enter = now();
+  double t_loop0 = 0, t_loop1 = 0, t_fin = 0;
 #define IR(expr)               \
   do {                         \
     status = (expr);           \
@@ -718,6 +834,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     ICK(cudaEventCreate(&evA));
     ICK(cudaEventCreate(&evB));
     ICK(cudaEventRecord(evA, ctx->stream));
+    t_loop0 = now();
 
     while (it < maxit) {
       int j = (it == 0) ? 0 : k;
@@ -727,33 +844,34 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       IR(I.product_A(j, false));
       mprod++;
       if (it > 0) {
-        IR(I.orthog(I.W, mloc, mloc, j, I.W + (long long)j * mloc, I.chunk_m, I.nblk_m, I.nb_m, true));
+        IR(I.orthog(I.W, mloc, mloc, j, I.W + (long long)j * mloc, I.chunk_m, I.nblk_m, I.nbo_m, true));
       } else {
         k_norm_partials<<<I.nb_m, NT, 0, ctx->stream>>>(I.W + (long long)j * mloc, mloc, I.pn, I.ps);
         count_launch(ctx);
       }
-      IR(I.finish_w(j, it == 0 && j == 0));
+      IR(I.finish_w(j, it == 0 && j == 0, it > 0 ? I.nbo_m : I.nb_m));
       // Lanczos process
       while (j < work) {
         IR(I.product_B(j));
         mprod++;
-        IR(I.orthog(I.V, n, n, j + 1, I.F, I.chunk_n, I.nblk_n, I.nb_n, false));
+        IR(I.orthog(I.V, n, n, j + 1, I.F, I.chunk_n, I.nblk_n, I.nbo_n, false));
         if (j + 1 < work) {
-          k_finish_F<<<I.nb_n, NT, 0, ctx->stream>>>(I.F, I.pn, I.nb_n, I.s, I.ce, n, I.V + (long long)(j + 1) * n, I.xs,
+          k_finish_F<<<I.nb_n, NT, 0, ctx->stream>>>(I.F, I.pn, I.nbo_n, I.s, I.ce, n, I.V + (long long)(j + 1) * n, I.xs,
                                                      I.pb, I.Bm, work, j, I.scal, I.ctl, I.eps);
           count_launch(ctx);
           IR(I.product_A(j + 1, true));
           mprod++;
-          IR(I.orthog(I.W, mloc, mloc, j + 1, I.W + (long long)(j + 1) * mloc, I.chunk_m, I.nblk_m, I.nb_m, true));
-          IR(I.finish_w(j + 1, false));
+          IR(I.orthog(I.W, mloc, mloc, j + 1, I.W + (long long)(j + 1) * mloc, I.chunk_m, I.nblk_m, I.nbo_m, true));
+          IR(I.finish_w(j + 1, false, I.nbo_m));
         } else {
-          k_finish_last<<<I.nb_n, NT, 0, ctx->stream>>>(I.F, I.pn, I.nb_n, n, I.Bm, work, j, I.scal, I.eps);
+          k_finish_last<<<I.nb_n, NT, 0, ctx->stream>>>(I.F, I.pn, I.nbo_n, n, I.Bm, work, j, I.scal, I.eps);
           count_launch(ctx);
         }
         j++;
       }
       ICK(cudaGetLastError());
       // small SVD of B
+      spmv_timer_begin(ctx, 3);
       if (ctx->small_svd) {
         ICK(cudaMemcpyAsync(hB.data(), I.Bm, hB.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         ICK(cudaStreamSynchronize(ctx->stream));
@@ -772,6 +890,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       }
       k_restart_logic<<<1, 128, 0, ctx->stream>>>(work, nv, tol, svtol, I.BU, I.BS, I.svr, I.res, I.Bm, I.scal, I.ctl);
       count_launch(ctx);
+      spmv_timer_end(ctx);
       ICK(cudaMemcpyAsync(hctl, I.ctl, sizeof(hctl), cudaMemcpyDeviceToHost, ctx->stream));
       ICK(cudaStreamSynchronize(ctx->stream));
       ctx->stats.d2h_bytes += sizeof(hctl);
@@ -786,6 +905,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         goto done;
       }
       k = hctl[CT_K];
+      ctx->stats.svd_sweeps += hctl[CT_SWEEPS];
       if (hctl[CT_CONV]) {
         converged = true;
         it++;
@@ -797,11 +917,14 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         goto done;
       }
       // thick restart: V[:, :k] = V BV[:, :k]; V[:,k] = F; W[:, :k] = W BU[:, :k]
+      spmv_timer_begin(ctx, 4);
       IR(I.gemm_inplace(I.V, n, n, work, k, I.BV));
       ICK(cudaMemcpyAsync(I.V + (long long)k * n, I.F, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       IR(I.gemm_inplace(I.W, mloc, mloc, work, k, I.BU));
+      spmv_timer_end(ctx);
       it++;
     }
+    t_loop1 = now();
     // results: d = BS[:nu]; U*diag(d) = W (BU[:, :nu] diag(d)); V = V BV[:, :nu]
     k_scale_cols<<<(work * nv + 255) / 256, 256, 0, ctx->stream>>>(I.BU, I.BS, work, nv, I.Q);
     count_launch(ctx);
@@ -837,6 +960,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       m->Xdev = I.W;
       m->Xdev_nv = nv;
     }
+    t_fin = now();
     if (iter_out) *iter_out = it;
     if (mprod_out) *mprod_out = mprod;
     status = converged ? M3B_OK : M3B_W_NOT_CONVERGED;
@@ -847,6 +971,10 @@ done:
   if (evB) cudaEventDestroy(evB);
   cudaStreamSynchronize(ctx->stream);
   I.release();
+  ctx->stats.host_ms[0] = t_loop0 - t_enter;  // moments + allocation + setup
+  ctx->stats.host_ms[1] = t_loop1 - t_loop0;  // Lanczos loop (host wall clock)
+  ctx->stats.host_ms[2] = t_fin - t_loop1;    // final GEMMs + copies
+  ctx->stats.host_ms[3] = now() - t_fin;      // release
   return status;
 #undef IR
 #undef ICK

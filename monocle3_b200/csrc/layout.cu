@@ -22,6 +22,7 @@ template int dev_alloc<int>(m3b_ctx*, int**, size_t);
 template int dev_alloc<long long>(m3b_ctx*, long long**, size_t);
 template int dev_alloc<ItemDesc>(m3b_ctx*, ItemDesc**, size_t);
 template int dev_alloc<int4>(m3b_ctx*, int4**, size_t);
+template int dev_alloc<int2>(m3b_ctx*, int2**, size_t);
 template int dev_alloc<unsigned int>(m3b_ctx*, unsigned int**, size_t);
 template int dev_alloc<unsigned char>(m3b_ctx*, unsigned char**, size_t);
 
@@ -33,7 +34,10 @@ void TiledLayout::free_all() {
   dev_free(idx);
   dev_free(val);
   dev_free(items);
-  dev_free(units);
+  dev_free(chunks);
+  dev_free(tile_chunk_ptr);
+  dev_free(cta_tile);
+  dev_free(counters);
   dev_free(row_item_ptr);
   dev_free(partial);
   *this = TiledLayout();
@@ -204,7 +208,8 @@ struct HostTables {
   std::vector<long long> base;
   std::vector<ItemDesc> items;
   std::vector<int> row_item_ptr;
-  std::vector<int4> units;
+  std::vector<int2> chunks;
+  std::vector<int> tile_chunk_ptr, cta_tile;
   long long n_entries = 0, nnz = 0;
 };
 
@@ -223,7 +228,8 @@ static void compute_bases(const std::vector<int>& cnt, int n_tiles, long long ro
 static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows_in, const int* row_map,
                         long long rows_out, int sm_count, HostTables& T) {
   T.items.clear();
-  T.units.clear();
+  T.chunks.clear();
+  T.tile_chunk_ptr.assign(n_tiles + 1, 0);
   T.row_item_ptr.assign((size_t)n_tiles * (rows_out + 1), 0);
   T.nnz = 0;
   // per-tile: rows are visited in OUTPUT-row order so that row_item_ptr is monotone
@@ -233,9 +239,21 @@ static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows
     for (long long r = 0; r < rows_in; ++r)
       if (row_map[r] >= 0) in_of_out[row_map[r]] = r;
   }
-  long long total_len = 0;
+  std::vector<long long> tile_len(n_tiles, 0);
+  for (int t = 0; t < n_tiles; ++t)
+    for (long long ro = 0; ro < rows_out; ++ro) {
+      long long ri = row_map ? in_of_out[ro] : ro;
+      if (ri >= 0) tile_len[t] += pad4(cnt[(size_t)t * rows_in + ri]);
+    }
   for (int t = 0; t < n_tiles; ++t) {
     int* rip = &T.row_item_ptr[(size_t)t * (rows_out + 1)];
+    // the last ~20% of a tile's entries are cut into short items/chunks so that the
+    // warps of a launch run dry together (tail = one short chunk, not one long one)
+    const long long tail_from = tile_len[t] - tile_len[t] / 5;
+    long long seen = 0;
+    T.tile_chunk_ptr[t] = (int)T.chunks.size();
+    int chunk_begin = (int)T.items.size();
+    long long chunk_acc = 0;
     for (long long ro = 0; ro < rows_out; ++ro) {
       rip[ro] = (int)T.items.size();
       long long ri = row_map ? in_of_out[ro] : ro;
@@ -244,55 +262,77 @@ static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows
       if (c == 0) continue;
       T.nnz += c;
       long long len = pad4(c), start = T.base[(size_t)t * rows_in + ri];
-      total_len += len;
       while (len > 0) {
-        int l = (int)std::min<long long>(len, M3B_ITEM_MAX);
+        const int lim = (seen >= tail_from) ? M3B_ITEM_TAIL : M3B_ITEM_MAX;
+        int l = (int)std::min<long long>(len, lim);
         T.items.push_back(ItemDesc{start, l, (int)ro});
         start += l;
         len -= l;
+        seen += l;
+        chunk_acc += l + 32;  // +32: per-item overhead, so that runs of tiny rows are split too
+        if (chunk_acc >= lim) {
+          T.chunks.push_back(make_int2(chunk_begin, (int)T.items.size()));
+          chunk_begin = (int)T.items.size();
+          chunk_acc = 0;
+        }
       }
     }
+    if (chunk_begin < (int)T.items.size()) T.chunks.push_back(make_int2(chunk_begin, (int)T.items.size()));
     rip[rows_out] = (int)T.items.size();
   }
-  // work units: contiguous item ranges inside one tile, ~equal entry counts
-  long long target = std::max<long long>(total_len / ((long long)sm_count * 8), 8192);
-  for (int t = 0; t < n_tiles; ++t) {
-    const int* rip = &T.row_item_ptr[(size_t)t * (rows_out + 1)];
-    int ib = rip[0], ie = rip[rows_out];
-    int cur = ib;
+  T.tile_chunk_ptr[n_tiles] = (int)T.chunks.size();
+  // CTA -> starting tile, proportional to the tiles' entry counts (every non-empty tile gets >= 1)
+  T.cta_tile.assign(sm_count, 0);
+  long long total = 0;
+  for (int t = 0; t < n_tiles; ++t) total += tile_len[t];
+  if (total > 0) {
     long long acc = 0;
-    for (int it = ib; it < ie; ++it) {
-      acc += T.items[it].len + 64;  // +64: per-item overhead so that many tiny rows also get split
-      if (acc >= target) {
-        T.units.push_back(make_int4(t, cur, it + 1, 0));
-        cur = it + 1;
-        acc = 0;
-      }
+    int b = 0;
+    for (int t = 0; t < n_tiles && b < sm_count; ++t) {
+      acc += tile_len[t];
+      int upto = (int)((double)acc / (double)total * sm_count + 0.5);
+      if (tile_len[t] > 0 && upto <= b) upto = b + 1;
+      upto = std::min(upto, sm_count);
+      for (; b < upto; ++b) T.cta_tile[b] = t;
     }
-    if (cur < ie) T.units.push_back(make_int4(t, cur, ie, 0));
+    for (; b < sm_count; ++b) T.cta_tile[b] = n_tiles - 1;
   }
 }
 
 static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T) {
   dev_free(L.items);
-  dev_free(L.units);
+  dev_free(L.chunks);
+  dev_free(L.tile_chunk_ptr);
+  dev_free(L.cta_tile);
+  dev_free(L.counters);
   dev_free(L.row_item_ptr);
   dev_free(L.partial);
   L.items = nullptr;
-  L.units = nullptr;
+  L.chunks = nullptr;
+  L.tile_chunk_ptr = nullptr;
+  L.cta_tile = nullptr;
+  L.counters = nullptr;
   L.row_item_ptr = nullptr;
   L.partial = nullptr;
   L.n_items = (long long)T.items.size();
-  L.n_units = (int)T.units.size();
+  L.n_chunks = (int)T.chunks.size();
+  L.n_cta = (int)T.cta_tile.size();
   L.nnz = T.nnz;
   RET(dev_alloc(ctx, &L.items, T.items.size()));
-  RET(dev_alloc(ctx, &L.units, T.units.size()));
+  RET(dev_alloc(ctx, &L.chunks, T.chunks.size()));
+  RET(dev_alloc(ctx, &L.tile_chunk_ptr, T.tile_chunk_ptr.size()));
+  RET(dev_alloc(ctx, &L.cta_tile, T.cta_tile.size()));
+  RET(dev_alloc(ctx, &L.counters, (size_t)L.n_tiles + 1));
   RET(dev_alloc(ctx, &L.row_item_ptr, T.row_item_ptr.size()));
   RET(dev_alloc(ctx, &L.partial, T.items.size()));
   if (!T.items.empty())
     CK(ctx, cudaMemcpyAsync(L.items, T.items.data(), T.items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, ctx->stream));
-  if (!T.units.empty())
-    CK(ctx, cudaMemcpyAsync(L.units, T.units.data(), T.units.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  if (!T.chunks.empty())
+    CK(ctx, cudaMemcpyAsync(L.chunks, T.chunks.data(), T.chunks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(L.tile_chunk_ptr, T.tile_chunk_ptr.data(), T.tile_chunk_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (!T.cta_tile.empty())
+    CK(ctx, cudaMemcpyAsync(L.cta_tile, T.cta_tile.data(), T.cta_tile.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemsetAsync(L.counters, 0, ((size_t)L.n_tiles + 1) * sizeof(unsigned int), ctx->stream));
   CK(ctx, cudaMemcpyAsync(L.row_item_ptr, T.row_item_ptr.data(), T.row_item_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   return M3B_OK;

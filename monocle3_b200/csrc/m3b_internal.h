@@ -83,6 +83,7 @@ struct m3b_ctx {
 // ---------------------------------------------------------------------------
 #define M3B_TILE_W_MAX 28672  // 224 KB of doubles in shared memory
 #define M3B_ITEM_MAX 2048     // entries per item (multiple of 128)
+#define M3B_ITEM_TAIL 512     // entries per item in the last part of a tile (short tail of the launch)
 
 struct ItemDesc {  // 16 bytes, loaded with one 128-bit load
   long long start;  // entry offset into idx/val (multiple of 4)
@@ -99,8 +100,14 @@ struct TiledLayout {
   double* val = nullptr;
   long long n_items = 0;
   ItemDesc* items = nullptr;
-  int n_units = 0;
-  int4* units = nullptr;       // {tile, item_begin, item_end, 0}
+  // scheduling: a CHUNK is a short contiguous item range (~2048 entries, ~512 near the end of
+  // a tile) that one warp claims with an atomic on its tile's counter
+  int n_chunks = 0;
+  int2* chunks = nullptr;          // {item_begin, item_end}, grouped by tile
+  int* tile_chunk_ptr = nullptr;   // [n_tiles+1] chunk ranges per tile
+  int* cta_tile = nullptr;         // [n_cta] tile a CTA starts on (CTAs split over tiles by entries)
+  int n_cta = 0;
+  unsigned int* counters = nullptr;  // [n_tiles+1]: per-tile chunk cursor, last = CTAs finished
   int* row_item_ptr = nullptr; // [n_tiles][rows+1] item ranges per (tile,row)
   double* partial = nullptr;   // [n_items]
   void free_all();
@@ -180,6 +187,9 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
 int jacobi_svd(int n, const double* B, double* U, double* s, double* Vt);
 
 static inline void count_launch(m3b_ctx* ctx, int n = 1) { ctx->stats.kernel_launches += n; }
+int spmv_init(m3b_ctx* ctx);
+int svd_init(m3b_ctx* ctx);
+int irlba_init(m3b_ctx* ctx);
 // event-pool helpers (api.cu)
 void spmv_timer_begin(m3b_ctx* ctx, int kind);
 void spmv_timer_end(m3b_ctx* ctx);

@@ -3,12 +3,11 @@
 // Replaces CHOLMOD's cholmod_sdmult inside irlba (the two products per Lanczos
 // step behind R/utils.R:417) and the DelayedMatrixStats passes of R/utils.R:383,389.
 //
-// Shape of the kernel: persistent CTAs (one per SM, 1024 threads) pull WORK
-// UNITS (a contiguous item range of one tile) from a global counter.  The
-// dense operand of the unit's tile (<= 28672 doubles = 224 KB) is staged in
-// shared memory once per tile change; each warp then streams one ITEM (a padded
-// row run, <= 2048 entries) with 64-/128-bit L1-bypassing loads, gathers from
-// shared memory, reduces in a fixed shuffle tree and writes ONE partial per
+// Shape of the kernel: persistent CTAs (one per SM, 512 threads).  The dense
+// operand of a CTA's tile (<= 28672 doubles = 224 KB) is staged in shared memory
+// once; each warp then claims CHUNKS of ITEMS (an item = a padded row run of
+// <= 2048 entries) and streams them with 64-/128-bit L1-bypassing loads, gathers
+// from shared memory, reduces in a fixed shuffle tree and writes ONE partial per
 // item.  A second tiny kernel adds the partials of a row in a fixed order, so
 // results are bit-reproducible run to run and independent of the CTA schedule.
 //
@@ -44,27 +43,87 @@ __device__ __forceinline__ double op_apply(double v, int id, const double* sx, d
   return d * d;
 }
 
+// Scheduling.  Every CTA starts on a tile (L.cta_tile, CTAs are split over the tiles by entry
+// count), stages that tile's slice of the dense operand once, and then its 32 warps claim
+// CHUNKS (short item ranges) of the tile independently with one atomic per chunk on the
+// tile's cursor -- no block barrier between chunks, so a slow warp never stalls the other 31
+// (the first cut synchronised the block after every ~35 items and lost ~45% of its issue
+// slots to barrier stalls; profiles/).  The next claim is issued before the current chunk is
+// streamed, so the atomic's latency is hidden.  When a tile runs dry the CTA moves to the
+// next tile that still has a worthwhile amount of work (one barrier + one re-stage).
+#define TS_THREADS 512  // 16 warps x <=128 registers: room for two register-resident load batches
+#define TS_BP 4         // pairs (of entries) per lane per batch
+
+struct Batch {
+  int2 i[TS_BP];
+  double2 v[TS_BP];
+};
+
+// one batch = 32 lanes x TS_BP pairs = 256 entries (3 KB) of the item's stream, predicated at the tail
+__device__ __forceinline__ void batch_load(Batch& b, const int2* __restrict__ ip, const double2* __restrict__ vp, int q0,
+                                           int n2) {
+#pragma unroll
+  for (int u = 0; u < TS_BP; ++u) {
+    const int q = q0 + 32 * u;
+    if (q < n2) {
+      b.i[u] = ld_stream_int2(ip + q);
+      b.v[u] = ld_stream_double2(vp + q);
+    } else {
+      b.i[u] = make_int2(0, 0);
+      b.v[u] = make_double2(0.0, 0.0);
+    }
+  }
+}
+
 template <int OP>
-__global__ void __launch_bounds__(1024, 1)
+__device__ __forceinline__ void batch_apply(const Batch& b, const double* sx, double mu, double (&a)[TS_BP], int q0,
+                                            int n2) {
+#pragma unroll
+  for (int u = 0; u < TS_BP; ++u) {
+    if (OP == OP_SQDEV) {
+      // predicated-off lanes hold zeros, which OP_SQDEV would count as (0-mu)^2
+      if (q0 + 32 * u < n2) {
+        a[u] += op_apply<OP>(b.v[u].x, b.i[u].x, sx, mu);
+        a[u] += op_apply<OP>(b.v[u].y, b.i[u].y, sx, mu);
+      }
+    } else {
+      a[u] += op_apply<OP>(b.v[u].x, b.i[u].x, sx, mu);
+      a[u] += op_apply<OP>(b.v[u].y, b.i[u].y, sx, mu);
+    }
+  }
+}
+
+// Scheduling.  Every CTA starts on a tile (L.cta_tile, CTAs are split over the tiles by entry
+// count), stages that tile's slice of the dense operand once, and then its warps claim
+// CHUNKS (short item ranges) of the tile independently with one atomic per chunk on the
+// tile's cursor -- no block barrier between chunks, so a slow warp never stalls the others
+// (the first cut synchronised the block after every ~35 items and lost ~45% of its issue
+// slots to barrier stalls; profiles/).  The next claim is issued before the current chunk is
+// streamed, so the atomic's latency is hidden.  Inside an item the stream is software-
+// pipelined over two register-resident batches: the loads of batch k+1 are in flight while
+// batch k is gathered and accumulated (the kernel is latency-bound, not issue-bound).
+// When a tile runs dry the CTA moves to the next tile that still has a worthwhile amount of
+// work (one barrier + one re-stage).
+template <int OP>
+__global__ void __launch_bounds__(TS_THREADS, 1)
 k_tile_stream(const int* __restrict__ idx, const double* __restrict__ val, const ItemDesc* __restrict__ items,
-              const int4* __restrict__ units, int n_units, int tile_w, long long cols,
-              const double* __restrict__ x, double* __restrict__ partial, unsigned int* __restrict__ sched) {
+              const int2* __restrict__ chunks, const int* __restrict__ tile_chunk_ptr,
+              const int* __restrict__ cta_tile, int n_tiles, int tile_w, long long cols,
+              const double* __restrict__ x, double* __restrict__ partial, unsigned int* __restrict__ counters) {
   extern __shared__ double sx[];
-  __shared__ int s_unit;
+  __shared__ int s_tile;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
-  int cur_tile = -1;
-  for (;;) {
-    if (threadIdx.x == 0) s_unit = (int)atomicAdd(&sched[0], 1u);
-    __syncthreads();
-    const int u = s_unit;
-    __syncthreads();
-    if (u >= n_units) break;
-    const int4 un = units[u];
-    if (OP == OP_DOT && un.x != cur_tile) {
+  int tile = cta_tile[blockIdx.x];
+  for (int visited = 0; visited < n_tiles && tile >= 0; ++visited) {
+    const int cbeg = tile_chunk_ptr[tile];
+    const int nch = tile_chunk_ptr[tile + 1] - cbeg;
+    unsigned int* cursor = counters + tile;
+    // claim the first chunk before staging: the atomic overlaps the fill
+    unsigned int c_next = 0;
+    if (lane == 0) c_next = atomicAdd(cursor, 1u);
+    if (OP == OP_DOT) {
       // stage the tile of the dense operand (coalesced 16-byte loads; x is L2-resident)
-      const long long off = (long long)un.x * tile_w;
+      const long long off = (long long)tile * tile_w;
       const int len = (int)min((long long)tile_w, cols - off);
       const double* xs0 = x + off;
       if ((reinterpret_cast<unsigned long long>(xs0) & 15ull) == 0ull) {
@@ -76,50 +135,77 @@ k_tile_stream(const int* __restrict__ idx, const double* __restrict__ val, const
       } else {  // odd leading dimension (e.g. an odd number of local cells): 8-byte loads
         for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] = xs0[k];
       }
-      cur_tile = un.x;
       __syncthreads();
     }
-    for (int it = un.y + warp; it < un.z; it += nwarps) {
-      const int4 raw = ld_stream_int4(reinterpret_cast<const int4*>(items + it));
-      const long long start = ((long long)(unsigned)raw.x) | ((long long)raw.y << 32);
-      const int len = raw.z;
-      const double mu = (OP == OP_SQDEV) ? x[raw.w] : 0.0;
-      const int2* ip = reinterpret_cast<const int2*>(idx + start);
-      const double2* vp = reinterpret_cast<const double2*>(val + start);
-      const int n2 = len >> 1;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int q = lane;
-      for (; q + 96 < n2; q += 128) {  // 4 independent pairs in flight per lane
-        const int2 i0 = ld_stream_int2(ip + q), i1 = ld_stream_int2(ip + q + 32);
-        const int2 i2 = ld_stream_int2(ip + q + 64), i3 = ld_stream_int2(ip + q + 96);
-        const double2 v0 = ld_stream_double2(vp + q), v1 = ld_stream_double2(vp + q + 32);
-        const double2 v2 = ld_stream_double2(vp + q + 64), v3 = ld_stream_double2(vp + q + 96);
-        a0 += op_apply<OP>(v0.x, i0.x, sx, mu);
-        a0 += op_apply<OP>(v0.y, i0.y, sx, mu);
-        a1 += op_apply<OP>(v1.x, i1.x, sx, mu);
-        a1 += op_apply<OP>(v1.y, i1.y, sx, mu);
-        a2 += op_apply<OP>(v2.x, i2.x, sx, mu);
-        a2 += op_apply<OP>(v2.y, i2.y, sx, mu);
-        a3 += op_apply<OP>(v3.x, i3.x, sx, mu);
-        a3 += op_apply<OP>(v3.y, i3.y, sx, mu);
-      }
-      for (; q < n2; q += 32) {
-        const int2 i0 = ld_stream_int2(ip + q);
-        const double2 v0 = ld_stream_double2(vp + q);
-        a0 += op_apply<OP>(v0.x, i0.x, sx, mu);
-        a0 += op_apply<OP>(v0.y, i0.y, sx, mu);
-      }
-      double acc = (a0 + a1) + (a2 + a3);
+    for (;;) {
+      const int c = (int)__shfl_sync(0xffffffffu, c_next, 0);
+      if (c >= nch) break;
+      if (lane == 0) c_next = atomicAdd(cursor, 1u);  // prefetch the next claim
+      const int2 ch = chunks[cbeg + c];
+      for (int ib = ch.x; ib < ch.y; ib += 32) {
+        // the descriptors of up to 32 items in one coalesced load
+        const int nit = min(32, ch.y - ib);
+        int4 mydesc = make_int4(0, 0, 0, 0);
+        if (lane < nit) mydesc = ld_stream_int4(reinterpret_cast<const int4*>(items + ib + lane));
+        for (int k = 0; k < nit; ++k) {
+          const int rx = __shfl_sync(0xffffffffu, mydesc.x, k), ry = __shfl_sync(0xffffffffu, mydesc.y, k);
+          const int len = __shfl_sync(0xffffffffu, mydesc.z, k);
+          const int row = __shfl_sync(0xffffffffu, mydesc.w, k);
+          const long long start = ((long long)(unsigned)rx) | ((long long)ry << 32);
+          const double mu = (OP == OP_SQDEV) ? x[row] : 0.0;
+          const int2* ip = reinterpret_cast<const int2*>(idx + start);
+          const double2* vp = reinterpret_cast<const double2*>(val + start);
+          const int n2 = len >> 1;
+          double a[TS_BP];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) partial[it] = acc;
+          for (int u = 0; u < TS_BP; ++u) a[u] = 0.0;
+          Batch b0, b1;
+          const int step = 32 * TS_BP;
+          int q = lane;
+          batch_load(b0, ip, vp, q, n2);
+          for (; q < n2 + lane; q += 2 * step) {  // q - lane is warp-uniform
+            const bool more1 = (q - lane + step) < n2;
+            if (more1) batch_load(b1, ip, vp, q + step, n2);
+            batch_apply<OP>(b0, sx, mu, a, q, n2);
+            if (!more1) break;
+            const bool more2 = (q - lane + 2 * step) < n2;
+            if (more2) batch_load(b0, ip, vp, q + 2 * step, n2);
+            batch_apply<OP>(b1, sx, mu, a, q + step, n2);
+            if (!more2) break;
+          }
+          double acc = (a[0] + a[1]) + (a[2] + a[3]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (lane == 0) partial[ib + k] = acc;
+        }
+      }
     }
+    if (n_tiles == 1) break;
+    // this tile is dry: look for another one that still has a worthwhile amount of work
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int found = -1, t2 = tile;
+      for (int k = 1; k < n_tiles; ++k) {
+        t2 = (t2 + 1 == n_tiles) ? 0 : t2 + 1;
+        const int n2c = tile_chunk_ptr[t2 + 1] - tile_chunk_ptr[t2];
+        const unsigned int used = *((volatile unsigned int*)(counters + t2));
+        if ((long long)n2c - (long long)used >= 32) {
+          found = t2;
+          break;
+        }
+      }
+      s_tile = found;
+    }
+    __syncthreads();
+    tile = s_tile;
   }
-  // the last CTA to leave re-arms the scheduler for the next launch
+  // the last CTA to leave re-arms the cursors for the next launch
+  __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    unsigned int done = atomicInc(&sched[1], gridDim.x - 1);
-    if (done == gridDim.x - 1) sched[0] = 0u;
+    unsigned int done = atomicInc(&counters[n_tiles], gridDim.x - 1);
+    if (done == gridDim.x - 1)
+      for (int t = 0; t < n_tiles; ++t) counters[t] = 0u;
   }
 }
 
@@ -128,30 +214,33 @@ static size_t tile_smem_bytes(const TiledLayout& L, int op) {
   return (size_t)L.tile_w * sizeof(double);
 }
 
+int spmv_init(m3b_ctx* ctx) {
+  const int bytes = (int)(M3B_TILE_W_MAX * sizeof(double));
+  CK(ctx, cudaFuncSetAttribute(k_tile_stream<OP_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(ctx, cudaFuncSetAttribute(k_tile_stream<OP_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(ctx, cudaFuncSetAttribute(k_tile_stream<OP_SQDEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return M3B_OK;
+}
+
 int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double* x) {
-  if (L.n_units == 0) return M3B_OK;
+  if (L.n_chunks == 0) return M3B_OK;
   const size_t smem = tile_smem_bytes(L, op);
-  const int grid = std::min(ctx->sm_count, L.n_units);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[op]) {
-    const void* fn = (op == OP_DOT)   ? (const void*)k_tile_stream<OP_DOT>
-                     : (op == OP_SUM) ? (const void*)k_tile_stream<OP_SUM>
-                                      : (const void*)k_tile_stream<OP_SQDEV>;
-    CK(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M3B_TILE_W_MAX * sizeof(double))));
-    attr_set[op] = true;
-  }
+  const int grid = L.n_cta;
   switch (op) {
     case OP_DOT:
-      k_tile_stream<OP_DOT><<<grid, 1024, smem, ctx->stream>>>(L.idx, L.val, L.items, L.units, L.n_units, L.tile_w,
-                                                               L.cols, x, L.partial, ctx->sched);
+      k_tile_stream<OP_DOT><<<grid, TS_THREADS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+                                                               L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
+                                                               L.counters);
       break;
     case OP_SUM:
-      k_tile_stream<OP_SUM><<<grid, 1024, smem, ctx->stream>>>(L.idx, L.val, L.items, L.units, L.n_units, L.tile_w,
-                                                               L.cols, x, L.partial, ctx->sched);
+      k_tile_stream<OP_SUM><<<grid, TS_THREADS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+                                                               L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
+                                                               L.counters);
       break;
     default:
-      k_tile_stream<OP_SQDEV><<<grid, 1024, smem, ctx->stream>>>(L.idx, L.val, L.items, L.units, L.n_units, L.tile_w,
-                                                                 L.cols, x, L.partial, ctx->sched);
+      k_tile_stream<OP_SQDEV><<<grid, TS_THREADS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+                                                                 L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
+                                                                 L.counters);
       break;
   }
   count_launch(ctx);

@@ -77,7 +77,10 @@ class Context:
     def stats(self):
         s = L.Stats()
         self.check(self.lib.m3b_get_stats(self.h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in L.Stats._fields_}
+        out = {k: getattr(s, k) for k, _ in L.Stats._fields_}
+        out["phase_ms"] = list(out["phase_ms"])
+        out["host_ms"] = list(out["host_ms"])
+        return out
 
     def set_flags(self, flags):
         self.check(self.lib.m3b_set_flags(self.h, int(flags)))
