@@ -301,7 +301,7 @@ def main():
                 "spmv_share_of_irlba": spmv_ms / max(sti["irlba_ms"], 1e-9),
                 "irlba_phase_ms": dict(zip(["spmv_cells_out", "spmv_genes_out", "orthog", "small_svd", "restart_gemm",
                                             "vector_epilogues", "allreduce"], [round(v, 3) for v in sti["phase_ms"][:7]])),
-                "irlba_ms": sti["irlba_ms"], "svd_sweeps": sti["svd_sweeps"],
+                "irlba_ms": sti["irlba_ms"], "svd_sweeps": sti["svd_sweeps"], "svd_fallbacks": sti["svd_fallbacks"],
                 "host_wall_ms": {k: round(v, 2) for k, v in wall.items()},
                 "irlba_host_ms": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in sti["host_ms"]])),
                 "irlba_host_ms_untimed_step": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in st["host_ms"]]))}

@@ -198,11 +198,14 @@ typedef struct m3b_stats {
   /* host wall clock of the last m3b_pca_irlba: [0] setup+allocation [1] Lanczos loop
    * [2] final GEMMs + result copies [3] release */
   double  host_ms[4];
+  int64_t svd_fallbacks;       /* restarts where the structured SVD gave up and Jacobi ran */
+  int64_t svd_fallback_reasons;/* OR of the reasons: 1 size, 2 irregular poles/weights, 4 root not converged, 8 Loewner */
 } m3b_stats;
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);
 int m3b_reset_stats(m3b_ctx* ctx);
 /* flags for m3b_create / m3b_set_flags */
 #define M3B_FLAG_TIME_SPMV 1  /* bracket every SpMV launch with CUDA events (read back after the run) */
+#define M3B_FLAG_JACOBI_ONLY 2 /* small SVD: always use the dense Jacobi kernel (no structured fast path) */
 int m3b_set_flags(m3b_ctx* ctx, int flags);
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this
  * library is launched on): start records an event, stop records a second one,

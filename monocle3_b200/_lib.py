@@ -25,6 +25,7 @@ M3B_E_ABORTED = -14
 NORM_LOG2, NORM_SIZE_ONLY, NORM_NONE, NORM_LOG10, NORM_BINARY = 0, 1, 2, 3, 4
 SF_TOTAL, SF_LOG_TOTAL = 0, 1
 FLAG_TIME_SPMV = 1
+FLAG_JACOBI_ONLY = 2
 COMM_ID_BYTES = 128
 
 SMALL_SVD_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -37,7 +38,8 @@ class Stats(C.Structure):
                 ("spmv_cells_out_ms", C.c_double), ("spmv_genes_out_ms", C.c_double), ("irlba_ms", C.c_double),
                 ("prepare_ms", C.c_double), ("spmv_bytes_cells_out", C.c_int64), ("spmv_bytes_genes_out", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("phase_ms", C.c_double * 8),
-                ("svd_sweeps", C.c_int64), ("host_ms", C.c_double * 4)]
+                ("svd_sweeps", C.c_int64), ("host_ms", C.c_double * 4),
+                ("svd_fallbacks", C.c_int64), ("svd_fallback_reasons", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/m3b.h declares

@@ -26,7 +26,10 @@
 
 #include "m3b_internal.h"
 
-int launch_jacobi_svd(m3b_ctx* ctx, int n, const double* B, double* U, double* s, double* V, double* scratch, int* info);
+int launch_jacobi_svd(m3b_ctx* ctx, int n, const double* B, double* U, double* s, double* V, double* scratch, int* info,
+                      const int* only_if);
+int launch_arrow_svd(m3b_ctx* ctx, int n, int k_host, const int* ctl_k, const double* B, double* U, double* S, double* V,
+                     double* scratch, int* flag);
 
 #define NT 256
 #define MAX_PART 592  // upper bound on per-kernel partial counts (4 * 148)
@@ -34,7 +37,7 @@ int launch_jacobi_svd(m3b_ctx* ctx, int n, const double* B, double* U, double* s
 // scalar slots in the device scalar buffer
 enum { SC_S = 0, SC_RF = 1, SC_SUMW = 2, SC_NRM2 = 3, SC_SUM = 4, SC_COUNT = 8 };
 // control block (ints)
-enum { CT_K = 0, CT_CONV = 1, CT_FLAG = 2, CT_SWEEPS = 3, CT_COUNT = 8 };
+enum { CT_K = 0, CT_CONV = 1, CT_FLAG = 2, CT_SWEEPS = 3, CT_SVDFLAG = 4, CT_COUNT = 8 };
 
 // --------------------------------------------------------------------------
 // deterministic block reduction (fixed tree): result valid in thread 0
@@ -798,7 +801,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     IR(I.alloc(&I.svr, (size_t)work));
     IR(I.alloc(&I.res, (size_t)work));
     IR(I.alloc(&I.Q, (size_t)work * work));
-    IR(I.alloc(&I.svd_scratch, (size_t)2 * work * work));
+    IR(I.alloc(&I.svd_scratch, (size_t)4 * work * work + 2 * work));
     IR(I.alloc(&I.ctl, (size_t)CT_COUNT));
     ICK(cudaMemsetAsync(I.Bm, 0, (size_t)work * work * sizeof(double), ctx->stream));
     ICK(cudaMemsetAsync(I.svr, 0, work * sizeof(double), ctx->stream));
@@ -885,8 +888,12 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         ICK(cudaMemcpyAsync(I.Q, hVt.data(), hVt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         k_transpose_small<<<(work * work + 255) / 256, 256, 0, ctx->stream>>>(I.Q, work, I.BV);
         count_launch(ctx);
+      } else if (it > 0 && k >= 1 && !(ctx->flags & M3B_FLAG_JACOBI_ONLY)) {
+        // structured fast path; the Jacobi kernel runs only if it raised its flag
+        IR(launch_arrow_svd(ctx, work, k, I.ctl + CT_K, I.Bm, I.BU, I.BS, I.BV, I.svd_scratch, I.ctl + CT_SVDFLAG));
+        IR(launch_jacobi_svd(ctx, work, I.Bm, I.BU, I.BS, I.BV, I.svd_scratch, I.ctl + CT_SWEEPS, I.ctl + CT_SVDFLAG));
       } else {
-        IR(launch_jacobi_svd(ctx, work, I.Bm, I.BU, I.BS, I.BV, I.svd_scratch, I.ctl + CT_SWEEPS));
+        IR(launch_jacobi_svd(ctx, work, I.Bm, I.BU, I.BS, I.BV, I.svd_scratch, I.ctl + CT_SWEEPS, nullptr));
       }
       k_restart_logic<<<1, 128, 0, ctx->stream>>>(work, nv, tol, svtol, I.BU, I.BS, I.svr, I.res, I.Bm, I.scal, I.ctl);
       count_launch(ctx);
@@ -905,7 +912,11 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         goto done;
       }
       k = hctl[CT_K];
-      ctx->stats.svd_sweeps += hctl[CT_SWEEPS];
+      if (it == 0 || hctl[CT_SVDFLAG] || (ctx->flags & M3B_FLAG_JACOBI_ONLY)) ctx->stats.svd_sweeps += hctl[CT_SWEEPS];
+      if (it > 0 && hctl[CT_SVDFLAG]) {
+        ctx->stats.svd_fallbacks++;
+        ctx->stats.svd_fallback_reasons |= hctl[CT_SVDFLAG];
+      }
       if (hctl[CT_CONV]) {
         converged = true;
         it++;

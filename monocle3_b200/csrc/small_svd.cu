@@ -45,7 +45,9 @@ template <int NIT>
 __global__ void __launch_bounds__(SVD_THREADS, 1)
 k_jacobi_svd(int n, const double* __restrict__ Bin, double* __restrict__ Uout, double* __restrict__ sout,
              double* __restrict__ Vout, double* __restrict__ gX, double* __restrict__ gJ, int use_smem,
-             int* __restrict__ info) {
+             int* __restrict__ info, const int* __restrict__ only_if) {
+  // only_if != nullptr: run only when the structured fast path (arrow_svd.cu) raised its flag
+  if (only_if && *only_if == 0) return;
   extern __shared__ double sm[];
   __shared__ int s_rot;
   __shared__ double s_nrm[SVD_NMAX];  // squared column norms of X (carried along)
@@ -252,7 +254,7 @@ int svd_init(m3b_ctx* ctx) {
 }
 
 int launch_jacobi_svd(m3b_ctx* ctx, int n, const double* B, double* U, double* s, double* V, double* scratch,
-                      int* info) {
+                      int* info, const int* only_if) {
   if (n > SVD_NMAX) {
     m3b_set_error(ctx, "small SVD: work=%d > %d is not supported", n, SVD_NMAX);
     return M3B_E_DIMS;
@@ -260,7 +262,7 @@ int launch_jacobi_svd(m3b_ctx* ctx, int n, const double* B, double* U, double* s
   size_t need = 2 * (size_t)n * n * sizeof(double);
   int use_smem = need <= 216 * 1024;
   const int nit = (n <= 128) ? (n + 15) / 16 : 0;
-  void (*fn)(int, const double*, double*, double*, double*, double*, double*, int, int*);
+  void (*fn)(int, const double*, double*, double*, double*, double*, double*, int, int*, const int*);
   switch (nit) {
     case 1: fn = k_jacobi_svd<1>; break;
     case 2: fn = k_jacobi_svd<2>; break;
@@ -272,7 +274,7 @@ int launch_jacobi_svd(m3b_ctx* ctx, int n, const double* B, double* U, double* s
     case 8: fn = k_jacobi_svd<8>; break;
     default: fn = k_jacobi_svd<0>; break;
   }
-  fn<<<1, SVD_THREADS, use_smem ? need : 0, ctx->stream>>>(n, B, U, s, V, scratch, scratch + (size_t)n * n, use_smem, info);
+  fn<<<1, SVD_THREADS, use_smem ? need : 0, ctx->stream>>>(n, B, U, s, V, scratch, scratch + (size_t)n * n, use_smem, info, only_if);
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
   return M3B_OK;

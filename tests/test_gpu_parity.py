@@ -89,8 +89,13 @@ def test_filter_nnz_moments(m3, request, name):
 
 
 def _check_pca(m3, counts, extra, num_dim, svd_mode="device", **kw):
-    from monocle3_b200 import engine
-    m3.set_context(engine.Context(device=0, small_svd=svd_mode))
+    """svd_mode: 'device' (structured secular-equation SVD of B, Jacobi fallback), 'jacobi'
+    (dense one-sided Jacobi kernel only), 'lapack' (host callback, the R shim's mode)."""
+    from monocle3_b200 import engine, _lib as L
+    if svd_mode == "jacobi":
+        m3.set_context(engine.Context(device=0, flags=L.FLAG_JACOBI_ONLY, small_svd="device"))
+    else:
+        m3.set_context(engine.Context(device=0, small_svd=svd_mode))
     cds = _cds(m3, counts, extra)
     cds = m3.preprocess_cds(cds, num_dim=num_dim, **kw)
     okw = dict(kw)
@@ -114,7 +119,7 @@ def _check_pca(m3, counts, extra, num_dim, svd_mode="device", **kw):
     return cds, o
 
 
-@pytest.mark.parametrize("svd_mode", ["device", "lapack"])
+@pytest.mark.parametrize("svd_mode", ["device", "jacobi", "lapack"])
 @pytest.mark.parametrize("num_dim", [20, 50])
 def test_pca_a549(m3, a549, num_dim, svd_mode):
     counts, extra = a549
@@ -170,10 +175,14 @@ def test_pca_log_pseudocount_dense_paths(m3, a549):
     _check_pca(m3, counts, extra, 10, "device", norm_method="log", scaling=False)
 
 
-@pytest.mark.parametrize("name,num_dim", [("worm_l2", 50), ("worm_embryo", 50)])
-def test_pca_worm(m3, request, name, num_dim):
+@pytest.mark.parametrize("svd_mode", ["device", "jacobi"])
+@pytest.mark.parametrize("name,num_dim", [("worm_l2", 50), ("worm_embryo", 50), ("worm_l2", 100)])
+def test_pca_worm(m3, request, name, num_dim, svd_mode):
     counts, extra = request.getfixturevalue(name)
-    _check_pca(m3, counts, extra, num_dim, "device")
+    cds, _ = _check_pca(m3, counts, extra, num_dim, svd_mode)
+    st = m3.get_context().stats()
+    if svd_mode == "device":  # the structured path must actually carry the restarts
+        assert st["svd_fallbacks"] <= max(2, cds.reduce_dim_aux["PCA"]["irlba"]["iter"] // 20)
 
 
 def test_transform_equals_embedding(m3, a549):
