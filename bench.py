@@ -257,11 +257,18 @@ def main():
     sampler.start()
     ctx.reset_stats()
     ctx.timer_start()
+    step_walls = []
     for _ in range(args.steps):
         res = device_step()
+        step_walls.append(dict(wall))
     ms_total = ctx.timer_stop()
     barrier()
     clocks = sampler.stop()
+    if os.environ.get("M3B_BENCH_DEBUG"):
+        print("DEBUG rank %d cpus=%s affinity=%d steps=%s host_ms=%s" % (
+            rank, os.cpu_count(), len(os.sched_getaffinity(0)),
+            [{k: round(v, 1) for k, v in w.items()} for w in step_walls],
+            [round(v, 1) for v in ctx.stats()["host_ms"]]), file=sys.stderr, flush=True)
     st = ctx.stats()
     ms_step = max_over_ranks(ms_total) / args.steps
     launches = int(sum_over_ranks(st["kernel_launches"]))

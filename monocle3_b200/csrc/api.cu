@@ -125,6 +125,7 @@ void m3b_destroy(m3b_ctx* ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  dev_pool_release(ctx->device);
   delete ctx;
 }
 

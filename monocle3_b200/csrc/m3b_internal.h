@@ -154,6 +154,7 @@ struct m3b_mat {
 template <typename T>
 int dev_alloc(m3b_ctx* ctx, T** p, size_t n);
 void dev_free(void* p);
+void dev_pool_release(int device);  // return the cached blocks of a device to the driver
 
 // layout.cu
 int k1_cell_totals(m3b_mat* m, int round_exprs, double* d_tot);

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Cell-sharded parity check (run under torchrun, one rank per GPU):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29511 tools/multi_gpu_check.py [fixture] [num_dim]
+
+Every rank loads the committed fixture, keeps its contiguous cell range (cut at nnz
+quantiles), runs estimate_size_factors + preprocess_cds through the public API with the
+NCCL allreduces inside libm3b.so, and rank 0 compares the gathered embedding / loadings
+with the oracle on the WHOLE matrix (same bars as the single-GPU tests)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as td
+    import monocle3_b200 as m3
+    from monocle3_b200 import engine, dist
+    from tests.conftest import load_fixture
+    from tests.parity import subspace_angle, sv_rel_err
+    name = sys.argv[1] if len(sys.argv) > 1 else "worm_l2"
+    nd = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    td.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    rank, world = td.get_rank(), td.get_world_size()
+    counts, _ = load_fixture(name)
+    ranges = dist.shard_ranges_by_nnz(counts.indptr, world)
+    lo, hi = ranges[rank]
+    ctx = engine.Context(device=lr, small_svd="device")
+    m3.set_context(ctx)
+    dist.init_comm(ctx)
+    cds = m3.new_cell_data_set(counts[:, lo:hi], shard=dist.make_shard(counts.shape[1]))
+    cds = m3.preprocess_cds(cds, num_dim=nd)
+    model = cds.reduce_dim_aux["PCA"]["model"]
+    x_local = np.ascontiguousarray(cds.reduced_dims["PCA"])
+    ag = dist.make_allgather()
+    # gather the embedding row blocks (column by column keeps the helper 1-D)
+    X = np.stack([ag(x_local[:, j].copy()) for j in range(x_local.shape[1])], axis=1)
+    sf_all = ag(m3.size_factors(cds))
+    ok = True
+    if rank == 0:
+        from oracle import monocle3_ref as ref
+        sf_o = ref.estimate_size_factors(counts)
+        o = ref.preprocess_cds(counts, sf_o, num_dim=nd)
+        ir = cds.reduce_dim_aux["PCA"]["irlba"]
+        res = dict(world=world, fixture=name, num_dim=nd, sf_exact=bool(np.array_equal(sf_all, sf_o)),
+                   iter=(ir["iter"], o["iter"]), mprod=(ir["mprod"], o["mprod"]),
+                   sv_rel=sv_rel_err(ir["d"], o["d"]), angle_v=subspace_angle(model["svd_v"], o["svd_v"]),
+                   angle_x=subspace_angle(X, o["PCA"]))
+        ok = res["sf_exact"] and res["sv_rel"] < 1e-6 and res["angle_v"] < 1e-4 and res["angle_x"] < 1e-4
+        res["ok"] = bool(ok)
+        print("MULTI_GPU_CHECK", res)
+    # replicated gene-space state must be bit-identical on every rank
+    v = np.ascontiguousarray(model["svd_v"]).ravel()
+    vs = ag(np.array([float(np.sum(v)), float(np.sum(np.abs(v))), float(v[0])]))
+    same = all(np.array_equal(vs[:3], vs[3 * r:3 * r + 3]) for r in range(world))
+    if rank == 0:
+        print("REPLICAS_IDENTICAL", same)
+    td.destroy_process_group()
+    sys.exit(0 if (ok and same) else 1)
+
+
+if __name__ == "__main__":
+    main()
