@@ -24,9 +24,7 @@
 
 #include "m3b_internal.h"
 
-#define AS_THREADS 1024
 #define AS_NMAX 256
-#define AS_MAXIT 60
 
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
@@ -39,32 +37,40 @@ __device__ __forceinline__ double wprod(double v) {
   return v;
 }
 
-// One arrow solve.  Poles pf[0..m-2] (descending, > 0) and pf[m-1] = 0; weights uf[0..m-1].
+// ---------------------------------------------------------------------------------------------
+// One arrow solve = two multi-CTA kernels (the first version ran everything in ONE block and was
+// instruction-bound on a single SM: ~190 us per solve, profiles/):
+//   k_arrow_roots   : 4 warps per CTA, one secular root per warp  -> org / mu / sg (global)
+//   k_arrow_vectors : 4 warps per CTA, one output column per warp (Loewner weights and the output
+//                     order are recomputed by every CTA: O(m^2) and cheaper than another launch)
+// Both start by rebuilding the problem (poles, weights, deflation) from B in shared memory with
+// the same deterministic code, so nothing but the roots has to travel between them.
+//
+// Poles pf[0..m-2] (descending, > 0) and pf[m-1] = 0; weights uf[0..m-1].
 //   mode 0: pf = diag(B)[0..m-2], uf = (B[0..m-2, m-1], B[m-1, m-1])          (first block)
 //   mode 1: pf = sig_in[0..m-2],  uf = (beta * Ycur[m-2, 0..m-2], alpha)      (tail merge)
 // Weights below 8 eps max(|pf|,|uf|) are DEFLATED (LAPACK dlasd2's rule): their pole is a
 // singular value with unit singular vectors e_i (converged Ritz values do this all the time);
 // the secular equation is solved on the remaining ACTIVE poles only.
-// Outputs: sig_out[m] (descending), Yp / Xp (m x m, ld n): left / right singular vectors of the
-// arrow.  *flag |= reason on any irregularity (1 size, 2 poles/weights, 4 root, 8 Loewner).
-__global__ void __launch_bounds__(AS_THREADS, 1)
-k_arrow_solve(int mode, int n, const int* __restrict__ ctl_k, int tail_j, const double* __restrict__ B,
-              const double* __restrict__ sig_in, const double* __restrict__ Ycur, double* __restrict__ sig_out,
-              double* __restrict__ Yp, double* __restrict__ Xp, int* __restrict__ flag) {
-  __shared__ double pf[AS_NMAX], uf[AS_NMAX];                 // full problem
-  __shared__ double p[AS_NMAX], u[AS_NMAX], mu[AS_NMAX], sg[AS_NMAX], uh[AS_NMAX];  // active problem
-  __shared__ int org[AS_NMAX], act[AS_NMAX], defl[AS_NMAX], rnk[AS_NMAX];
-  __shared__ int s_bad, s_ma;
-  __shared__ double s_tol;
-  if (mode == 1 && *flag) return;  // an earlier solve of this restart already gave up
-  const int k = ctl_k[0];
-  const int m = (mode == 0) ? k + 1 : tail_j + 1;  // size of this arrow
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  if (tid == 0) s_bad = 0;
-  if (m > n || m < 2 || m > AS_NMAX) {
-    if (tid == 0) atomicOr(flag, 1);  // reason 1: size
-    return;
-  }
+// *flag |= reason on any irregularity (1 size, 2 poles/weights, 4 root, 8 Loewner).
+// ---------------------------------------------------------------------------------------------
+#define AR_THREADS 128
+#define AR_WARPS 4
+
+struct ArrowProblem {  // shared-memory image of one arrow problem
+  double pf[AS_NMAX], uf[AS_NMAX];  // full
+  double p[AS_NMAX], u2[AS_NMAX];   // active poles, squared active weights
+  int act[AS_NMAX], defl[AS_NMAX];
+  int m, ma, bad;
+};
+
+// returns false (block-uniform) if the problem is irregular
+__device__ __forceinline__ bool arrow_setup(ArrowProblem& P, int mode, int n, int k, int tail_j,
+                                            const double* __restrict__ B, const double* __restrict__ sig_in,
+                                            const double* __restrict__ Ycur) {
+  const int tid = threadIdx.x;
+  const int m = (mode == 0) ? k + 1 : tail_j + 1;
+  if (m > n || m < 2 || m > AS_NMAX) return false;
   for (int i = tid; i < m; i += blockDim.x) {
     double pi, ui;
     if (mode == 0) {
@@ -75,104 +81,188 @@ k_arrow_solve(int mode, int n, const int* __restrict__ ctl_k, int tail_j, const 
       pi = (i < m - 1) ? sig_in[i] : 0.0;
       ui = (i < m - 1) ? B[(size_t)j * n + (j - 1)] * Ycur[(size_t)i * n + (m - 2)] : B[(size_t)j * n + j];
     }
-    pf[i] = pi;
-    uf[i] = ui;
+    P.pf[i] = pi;
+    P.uf[i] = ui;
   }
   __syncthreads();
-  // deflation + regularity checks (m <= 256: one thread walks the list)
-  if (tid == 0) {
+  // deflation + regularity checks, by warp 0 (ballot / popc compaction keeps the index order)
+  if (tid == 0) P.bad = 0;
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
     double umax = 0.0;
     bool bad = false;
-    for (int i = 0; i < m; ++i) {
-      umax = fmax(umax, fabs(uf[i]));
-      bad = bad || !isfinite(pf[i]) || !isfinite(uf[i]);
-      if (i < m - 1) bad = bad || !(pf[i] > 0.0) || !(pf[i] > pf[i + 1]);
+    for (int i = lane; i < m; i += 32) {
+      umax = fmax(umax, fabs(P.uf[i]));
+      bad = bad || !isfinite(P.pf[i]) || !isfinite(P.uf[i]);
+      if (i < m - 1) bad = bad || !(P.pf[i] > 0.0) || !(P.pf[i] > P.pf[i + 1]);
     }
-    const double tol = 8.0 * 2.220446049250313e-16 * fmax(pf[0], umax);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+    const double tol = 8.0 * 2.220446049250313e-16 * fmax(P.pf[0], umax);
     int ma = 0, nd = 0;
-    for (int i = 0; i < m; ++i) {
-      if (fabs(uf[i]) > tol) act[ma++] = i;
-      else defl[nd++] = i;
+    for (int i0 = 0; i0 < m; i0 += 32) {
+      const int i = i0 + lane;
+      const bool in = i < m;
+      const bool a = in && fabs(P.uf[i]) > tol;
+      const unsigned ba = __ballot_sync(0xffffffffu, a), bd = __ballot_sync(0xffffffffu, in && !a);
+      const unsigned lt = (1u << lane) - 1u;
+      if (a) P.act[ma + __popc(ba & lt)] = i;
+      if (in && !a) P.defl[nd + __popc(bd & lt)] = i;
+      ma += __popc(ba);
+      nd += __popc(bd);
     }
-    if (ma < 1 || act[ma - 1] != m - 1) bad = true;  // alpha itself negligible: singular B
-    for (int r = 0; r + 1 < ma && !bad; ++r)
-      if (!(pf[act[r]] - pf[act[r + 1]] > tol)) bad = true;  // coincident poles
-    s_ma = ma;
-    s_tol = tol;
-    if (bad) s_bad = 1;
+    __syncwarp();
+    if (ma < 1 || P.act[ma - 1] != m - 1) bad = true;  // alpha itself negligible: singular B
+    for (int r = lane; r + 1 < ma; r += 32)
+      if (!(P.pf[P.act[r]] - P.pf[P.act[r + 1]] > tol)) bad = true;  // coincident poles
+    if (__any_sync(0xffffffffu, bad) && lane == 0) P.bad = 1;
+    if (lane == 0) {
+      P.m = m;
+      P.ma = ma;
+    }
   }
   __syncthreads();
-  if (s_bad) {
-    if (tid == 0) atomicOr(flag, 2);  // reason 2: irregular poles / weights
+  if (P.bad) return false;
+  for (int r = tid; r < P.ma; r += blockDim.x) {
+    P.p[r] = P.pf[P.act[r]];
+    const double w = P.uf[P.act[r]];
+    P.u2[r] = w * w;
+  }
+  __syncthreads();
+  return true;
+}
+
+__global__ void __launch_bounds__(AR_THREADS)
+k_arrow_roots(int mode, int n, const int* __restrict__ ctl_k, int tail_j, const double* __restrict__ B,
+              const double* __restrict__ sig_in, const double* __restrict__ Ycur, int* __restrict__ org_g,
+              double* __restrict__ mu_g, double* __restrict__ sg_g, double* __restrict__ uh_g,
+              unsigned int* __restrict__ done_ctr, int* __restrict__ flag) {
+  __shared__ ArrowProblem P;
+  __shared__ int s_last;
+  if (mode == 1 && *flag) return;  // an earlier solve of this restart already gave up
+  if (!arrow_setup(P, mode, n, ctl_k[0], tail_j, B, sig_in, Ycur)) {
+    if (threadIdx.x == 0) atomicOr(flag, 2);
     return;
   }
-  const int ma = s_ma;
-  for (int r = tid; r < ma; r += blockDim.x) {
-    p[r] = pf[act[r]];
-    u[r] = uf[act[r]];
-  }
-  __syncthreads();
-  double un2 = 0.0;
-  for (int i = lane; i < ma; i += 32) un2 += u[i] * u[i];
-  un2 = wsum(un2);
-  const double unorm = sqrt(un2);
-  // ---- phase 1: one warp per root of the active problem ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ma = P.ma;
+  const int r = blockIdx.x * AR_WARPS + warp;
+  const double* p = P.p;
+  const double* u2 = P.u2;
+  if (r < ma) {
   // The root r lies in (p_r, p_{r-1}).  h(x) = f * (s - p_r) * (p_{r-1} - s) has no pole in
   // that interval, is negative at the lower pole and positive at the upper one; it is solved
   // with the Illinois variant of regula falsi in the offset x = s - p_o from the nearer pole o
   // (all pole differences are formed as (p_i - p_o) - x, never as p_i - s).
-  for (int r = warp; r < ma; r += nwarps) {
-    int o, up;
-    double lo, hi;
-    if (r == 0) {
-      o = 0;
-      up = -1;
-      lo = 0.0;
-      hi = unorm * (1.0 + 1e-12) + 1e-300;
-    } else {
-      up = r - 1;
-      const double mid = 0.5 * (p[r - 1] - p[r]);
-      double f = 0.0;
-      for (int i = lane; i < ma; i += 32) f += u[i] * u[i] / (((p[i] - p[r]) - mid) * ((p[i] + p[r]) + mid));
-      f = 1.0 + wsum(f);
-      if (f > 0.0) {
-        o = r;
-        lo = 0.0;
-        hi = mid;
-      } else {
-        o = r - 1;
-        lo = -mid;
-        hi = 0.0;
+  int o, up;
+  double lo, hi;
+  if (r == 0) {
+    double un2 = 0.0;
+    for (int i = lane; i < ma; i += 32) un2 += u2[i];
+    un2 = wsum(un2);
+    o = 0;
+    up = -1;
+    lo = 0.0;
+    hi = sqrt(un2) * (1.0 + 1e-12) + 1e-300;
+  } else {
+    up = r - 1;
+    const double mid = 0.5 * (p[r - 1] - p[r]);
+    double f = 0.0;
+    for (int i0 = 0; i0 < ma; i0 += 128) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + lane + 32 * q;
+        if (i < ma) f += u2[i] / (((p[i] - p[r]) - mid) * ((p[i] + p[r]) + mid));
       }
     }
-    const double po = p[o], pr = p[r], ur2 = u[r] * u[r];
-    const double pu = (up >= 0) ? p[up] : 0.0, uu2 = (up >= 0) ? u[up] * u[up] : 0.0;
-    auto hfun = [&](double x) -> double {
-      double psi = 0.0;
-      for (int i = lane; i < ma; i += 32)
-        if (i != r && i != up) psi += u[i] * u[i] / (((p[i] - po) - x) * ((p[i] + po) + x));
-      psi = 1.0 + wsum(psi);
-      const double sv = po + x;
-      const double dl = (po - pr) + x;
-      double L, tl;
-      if (pr > 0.0) {
-        L = dl;
-        tl = -ur2 / (pr + sv);
-      } else {
-        L = sv * sv;
-        tl = -ur2;
+    f = 1.0 + wsum(f);
+    if (f > 0.0) {
+      o = r;
+      lo = 0.0;
+      hi = mid;
+    } else {
+      o = r - 1;
+      lo = -mid;
+      hi = 0.0;
+    }
+  }
+  const double po = p[o], pr = p[r], ur2 = u2[r];
+  const double pu = (up >= 0) ? p[up] : 0.0, uu2 = (up >= 0) ? u2[up] : 0.0;
+  auto hfun = [&](double x) -> double {
+    double psi = 0.0;
+    for (int i0 = 0; i0 < ma; i0 += 128) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + lane + 32 * q;
+        if (i < ma && i != r && i != up) psi += u2[i] / (((p[i] - po) - x) * ((p[i] + po) + x));
       }
-      if (up >= 0) {
-        const double du = (pu - po) - x;
-        return du * L * psi + du * tl + uu2 * L / (pu + sv);
+    }
+    psi = 1.0 + wsum(psi);
+    const double sv = po + x;
+    const double dl = (po - pr) + x;
+    double L, tl;
+    if (pr > 0.0) {
+      L = dl;
+      tl = -ur2 / (pr + sv);
+    } else {
+      L = sv * sv;
+      tl = -ur2;
+    }
+    if (up >= 0) {
+      const double du = (pu - po) - x;
+      return du * L * psi + du * tl + uu2 * L / (pu + sv);
+    }
+    return L * psi + tl;
+  };
+  double xa = lo, xb = hi, ha = hfun(xa), hb = hfun(xb), x = xa;
+  bool ok = true;
+  if (ha == 0.0) x = xa;
+  else if (hb == 0.0) x = xb;
+  else if (!(ha < 0.0 && hb > 0.0)) ok = false;
+  else {
+    // tighten the bracket around the dominant-pole estimate  x ~ u_o^2 / (2 p_o c0)  (c0 = the
+    // rest of the secular function at the pole): converged Ritz values sit 1e-12 gaps from
+    // their pole, where plain regula falsi from the full interval degenerates into bisection
+    if (po > 0.0) {
+      double c0 = 0.0;
+      for (int i0 = 0; i0 < ma; i0 += 128) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + lane + 32 * q;
+          if (i < ma && i != o) c0 += u2[i] / ((p[i] - po) * (p[i] + po));
+        }
       }
-      return L * psi + tl;
-    };
-    double xa = lo, xb = hi, ha = hfun(xa), hb = hfun(xb), x = xa;
-    bool ok = true;
-    if (ha == 0.0) x = xa;
-    else if (hb == 0.0) x = xb;
-    else if (!(ha < 0.0 && hb > 0.0)) ok = false;
+      c0 = 1.0 + wsum(c0);
+      const double xg = u2[o] / (2.0 * po * c0);
+      if (isfinite(xg) && xg > xa && xg < xb) {
+        const double hg = hfun(xg);
+        if (hg < 0.0) {
+          xa = xg;
+          ha = hg;
+        } else if (hg > 0.0) {
+          xb = xg;
+          hb = hg;
+        } else {
+          xa = xb = xg;
+        }
+        // second probe on the far side of the estimate (factor 2 towards the root)
+        const double x2 = (hg < 0.0) ? ((xg > 0.0) ? 2.0 * xg : 0.5 * xg) : ((xg > 0.0) ? 0.5 * xg : 2.0 * xg);
+        if (xa < xb && x2 > xa && x2 < xb) {
+          const double h2 = hfun(x2);
+          if (h2 < 0.0) {
+            xa = x2;
+            ha = h2;
+          } else if (h2 > 0.0) {
+            xb = x2;
+            hb = h2;
+          } else {
+            xa = xb = x2;
+          }
+        }
+      }
+    }
+    if (xa == xb) x = xa;
     else {
       int side = 0;
       bool conv = false;
@@ -203,92 +293,130 @@ k_arrow_solve(int mode, int n, const int* __restrict__ ctl_k, int tail_j, const 
       }
       if (!conv && !(fabs(xb - xa) <= 1e-10 * fmax(fabs(xa), fabs(xb)))) ok = false;
     }
-    if (lane == 0) {
-      org[r] = o;
-      mu[r] = x;
-      sg[r] = po + x;
-      if (!ok || !isfinite(x) || x == 0.0) s_bad = 1;
-    }
+  }
+  if (lane == 0) {
+    org_g[r] = o;
+    mu_g[r] = x;
+    sg_g[r] = po + x;
+    if (!ok || !isfinite(x) || x == 0.0) atomicOr(flag, 4);  // reason 4: a secular root did not converge
+  }
+  }  // r < ma
+  // ---- the last CTA to finish computes the Loewner weights for everyone (one thread per i):
+  //   uh_i^2 = prod_j (s_j^2 - p_i^2) / prod_{j != i} (p_j^2 - p_i^2),  one division per 4 factors
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int d = atomicInc(done_ctr, gridDim.x - 1);
+    s_last = (d == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-  if (s_bad) {
-    if (tid == 0) atomicOr(flag, 4);  // reason 4: a secular root did not converge
-    return;
-  }
-  // ---- phase 2: Loewner weights  uh_i^2 = prod_j (s_j^2 - p_i^2) / prod_{j != i} (p_j^2 - p_i^2) ----
-  for (int i = warp; i < ma; i += nwarps) {
+  if (!s_last) return;
+  __threadfence();
+  if (*((volatile int*)flag)) return;
+  for (int i = threadIdx.x; i < ma; i += blockDim.x) {
+    const double pi = p[i];
     double pr = 1.0;
-    for (int j = lane; j < ma; j += 32) {
-      const double num = ((p[org[j]] - p[i]) + mu[j]) * (sg[j] + p[i]);
-      pr *= (j == i) ? num : num / ((p[j] - p[i]) * (p[j] + p[i]));
+    for (int j0 = 0; j0 < ma; j0 += 4) {
+      double num = 1.0, den = 1.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        if (j < ma) {
+          const int oj = __ldcg(org_g + j);
+          num *= ((p[oj] - pi) + __ldcg(mu_g + j)) * (__ldcg(sg_g + j) + pi);
+          if (j != i) den *= (p[j] - pi) * (p[j] + pi);
+        }
+      }
+      pr *= num / den;
     }
-    pr = wprod(pr);
-    if (lane == 0) {
-      uh[i] = copysign(sqrt(fabs(pr)), u[i]);
-      if (!isfinite(pr) || pr == 0.0) s_bad = 1;
-    }
+    uh_g[i] = copysign(sqrt(fabs(pr)), P.uf[P.act[i]]);
+    if (!isfinite(pr) || pr == 0.0) atomicOr(flag, 8);  // reason 8: Loewner product degenerate
+  }
+}
+
+// Outputs: sig_out[m] (descending), Yp / Xp (m x m, ld n): left / right singular vectors of the arrow.
+__global__ void __launch_bounds__(AR_THREADS)
+k_arrow_vectors(int mode, int n, const int* __restrict__ ctl_k, int tail_j, const double* __restrict__ B,
+                const double* __restrict__ sig_in, const double* __restrict__ Ycur, const int* __restrict__ org_g,
+                const double* __restrict__ mu_g, const double* __restrict__ sg_g, const double* __restrict__ uh_g,
+                double* __restrict__ sig_out, double* __restrict__ Yp, double* __restrict__ Xp,
+                int* __restrict__ flag) {
+  __shared__ ArrowProblem P;
+  __shared__ double mu[AS_NMAX], sg[AS_NMAX], uh[AS_NMAX];
+  __shared__ int org[AS_NMAX];
+  if (*flag) return;
+  if (!arrow_setup(P, mode, n, ctl_k[0], tail_j, B, sig_in, Ycur)) return;  // (roots already flagged it)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = P.m, ma = P.ma;
+  const double* p = P.p;
+  for (int r = tid; r < ma; r += blockDim.x) {
+    org[r] = org_g[r];
+    mu[r] = mu_g[r];
+    sg[r] = sg_g[r];
+    uh[r] = uh_g[r];
   }
   __syncthreads();
-  if (s_bad) {
-    if (tid == 0) atomicOr(flag, 8);  // reason 8: Loewner product degenerate
+  // this warp's output entry.  entry e < ma: active root e; e >= ma: deflated pole defl[e - ma]
+  const int e = blockIdx.x * AR_WARPS + warp;
+  if (e >= m) return;
+  const double me = (e < ma) ? sg[e] : P.pf[P.defl[e - ma]];
+  int rk = 0;
+  for (int q = lane; q < m; q += 32) {
+    const double ot = (q < ma) ? sg[q] : P.pf[P.defl[q - ma]];
+    rk += (ot > me || (ot == me && q < e)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+  const int dst = rk;
+  double* yc = Yp + (size_t)dst * n;
+  double* xc = Xp + (size_t)dst * n;
+  for (int i = lane; i < m; i += 32) {
+    yc[i] = 0.0;
+    xc[i] = 0.0;
+  }
+  __syncwarp();
+  if (e >= ma) {  // deflated: unit vectors
+    const int i0 = P.defl[e - ma];
+    if (lane == 0) {
+      yc[i0] = 1.0;
+      xc[i0] = 1.0;
+      sig_out[dst] = P.pf[i0];
+    }
     return;
   }
-  // ---- phase 3: output order.  entry e < ma: active root e; e >= ma: deflated pole defl[e - ma] ----
-  for (int e = tid; e < m; e += blockDim.x) {
-    const double me = (e < ma) ? sg[e] : pf[defl[e - ma]];
-    int rk = 0;
-    for (int q = 0; q < m; ++q) {
-      const double ot = (q < ma) ? sg[q] : pf[defl[q - ma]];
-      rk += (ot > me || (ot == me && q < e)) ? 1 : 0;
-    }
-    rnk[e] = rk;
+  // y_j(i) = uh_i / ((p_i - s_j)(p_i + s_j)); x_j = M^T y_j / s_j
+  const double po = p[org[e]], mj = mu[e], sj = sg[e];
+  double yv[AS_NMAX / 32];
+  double ny = 0.0, dot = 0.0;
+#pragma unroll
+  for (int q = 0; q < AS_NMAX / 32; ++q) {
+    const int i = lane + 32 * q;
+    yv[q] = (i < ma) ? uh[i] / (((p[i] - po) - mj) * (p[i] + sj)) : 0.0;
+    ny += yv[q] * yv[q];
+    dot += (i < ma) ? uh[i] * yv[q] : 0.0;
   }
-  __syncthreads();
-  // ---- phase 4: vectors.  y_j(i) = uh_i / ((p_i - s_j)(p_i + s_j)); x_j = M^T y_j / s_j ----
-  for (int e = warp; e < m; e += nwarps) {
-    const int dst = rnk[e];
-    double* yc = Yp + (size_t)dst * n;
-    double* xc = Xp + (size_t)dst * n;
-    for (int i = lane; i < m; i += 32) {
-      yc[i] = 0.0;
-      xc[i] = 0.0;
-    }
-    __syncwarp();
-    if (e >= ma) {  // deflated: unit vectors
-      const int i0 = defl[e - ma];
-      if (lane == 0) {
-        yc[i0] = 1.0;
-        xc[i0] = 1.0;
-        sig_out[dst] = pf[i0];
-      }
-      continue;
-    }
-    const double po = p[org[e]], mj = mu[e], sj = sg[e];
-    double ny = 0.0, dot = 0.0;
-    for (int i = lane; i < ma; i += 32) {
-      const double y = uh[i] / (((p[i] - po) - mj) * (p[i] + sj));
-      ny += y * y;
-      dot += uh[i] * y;
-    }
-    ny = wsum(ny);
-    dot = wsum(dot);
-    const double iy = 1.0 / sqrt(ny);
-    double nx = 0.0;
-    for (int i = lane; i < ma; i += 32) {
-      const double y = uh[i] / (((p[i] - po) - mj) * (p[i] + sj));
-      const double xv = (i < ma - 1) ? p[i] * y : dot;  // last active index is the pole 0 (alpha row)
-      nx += xv * xv;
-    }
-    nx = wsum(nx);
-    const double ix = 1.0 / sqrt(nx);
-    for (int i = lane; i < ma; i += 32) {
-      const double y = uh[i] / (((p[i] - po) - mj) * (p[i] + sj));
-      const double xv = (i < ma - 1) ? p[i] * y : dot;
-      yc[act[i]] = y * iy;
-      xc[act[i]] = xv * ix;
-    }
-    if (lane == 0) sig_out[dst] = sj;
+  ny = wsum(ny);
+  dot = wsum(dot);
+  const double iy = 1.0 / sqrt(ny);
+  double nx = 0.0;
+#pragma unroll
+  for (int q = 0; q < AS_NMAX / 32; ++q) {
+    const int i = lane + 32 * q;
+    const double xv = (i < ma - 1) ? p[i] * yv[q] : ((i == ma - 1) ? dot : 0.0);  // last active = pole 0 (alpha row)
+    nx += xv * xv;
   }
+  nx = wsum(nx);
+  const double ix = 1.0 / sqrt(nx);
+#pragma unroll
+  for (int q = 0; q < AS_NMAX / 32; ++q) {
+    const int i = lane + 32 * q;
+    if (i < ma) {
+      const double xv = (i < ma - 1) ? p[i] * yv[q] : dot;
+      yc[P.act[i]] = yv[q] * iy;
+      xc[P.act[i]] = xv * ix;
+    }
+  }
+  if (lane == 0) sig_out[dst] = sj;
 }
 
 // Fold an arrow's vectors into the accumulated ones:  Ynew[0:m-1, :] = Ycur[0:m-1, 0:m-1] * Yp[0:m-1, :],
@@ -354,7 +482,7 @@ __global__ void k_svd_signfix(int n, double* __restrict__ U, double* __restrict_
 }
 
 // Structured SVD of the restarted B (k = ctl[CT_K] kept Ritz values, known to the host as k_host).
-// Buffers: U/V (n x n outputs), S (n), scratch >= 4 n^2 doubles + 2 n, flag = device int (zeroed here).
+// Buffers: U/V (n x n outputs), S (n), scratch >= 4 n^2 + 6 n doubles, flag = device int (zeroed here).
 // On return *flag != 0 means "not done: run the Jacobi kernel".
 int launch_arrow_svd(m3b_ctx* ctx, int n, int k_host, const int* ctl_k, const double* B, double* U, double* S,
                      double* V, double* scratch, int* flag) {
@@ -366,6 +494,7 @@ int launch_arrow_svd(m3b_ctx* ctx, int n, int k_host, const int* ctl_k, const do
   double* sa = scratch + 4 * (size_t)n * n;   // sigma ping
   double* sb = sa + n;                        // sigma pong
   CK(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+  CK(ctx, cudaMemsetAsync(scratch + 4 * (size_t)n * n + 5 * (size_t)n, 0, 2 * n * sizeof(double), ctx->stream));
   const int ntail = n - (k_host + 1);
   // the accumulated vectors ping-pong between (U,V) and (Ya,Xa) so that the last fold lands in U,V
   double *Yc, *Xc, *Yn, *Xn;
@@ -381,15 +510,29 @@ int launch_arrow_svd(m3b_ctx* ctx, int n, int k_host, const int* ctl_k, const do
     Xn = V;
   }
   double* s_cur = (ntail == 0) ? S : sa;
-  k_arrow_solve<<<1, AS_THREADS, 0, ctx->stream>>>(0, n, ctl_k, 0, B, nullptr, nullptr, s_cur, Yc, Xc, flag);
-  count_launch(ctx);
+  // root buffers (org as ints, mu, sg) live behind the sigma ping-pong in the scratch area
+  double* mu_g = sb + n;
+  double* sg_g = mu_g + n;
+  double* uh_g = sg_g + n;
+  int* org_g = reinterpret_cast<int*>(uh_g + n);
+  unsigned int* done_ctr = reinterpret_cast<unsigned int*>(org_g + n);  // zeroed with the flag; self re-arming
+  auto solve = [&](int mode, int tail_j, int m, const double* sig_in, const double* Ycur_, double* sig_out_, double* Yo,
+                   double* Xo) {
+    const int grid = (m + AR_WARPS - 1) / AR_WARPS;
+    k_arrow_roots<<<grid, AR_THREADS, 0, ctx->stream>>>(mode, n, ctl_k, tail_j, B, sig_in, Ycur_, org_g, mu_g, sg_g, uh_g,
+                                                        done_ctr, flag);
+    k_arrow_vectors<<<grid, AR_THREADS, 0, ctx->stream>>>(mode, n, ctl_k, tail_j, B, sig_in, Ycur_, org_g, mu_g, sg_g,
+                                                          uh_g, sig_out_, Yo, Xo, flag);
+    count_launch(ctx, 2);
+  };
+  solve(0, 0, k_host + 1, nullptr, nullptr, s_cur, Yc, Xc);
   for (int t = 0; t < ntail; ++t) {
     const int j = k_host + 1 + t;  // new row / column
     double* s_next = (t == ntail - 1) ? S : (s_cur == sa ? sb : sa);
-    k_arrow_solve<<<1, AS_THREADS, 0, ctx->stream>>>(1, n, ctl_k, j, B, s_cur, Yc, s_next, Yp, Xp, flag);
+    solve(1, j, j + 1, s_cur, Yc, s_next, Yp, Xp);
     dim3 grid((j + 1 + 15) / 16, (j + 1 + 15) / 16, 2);
     k_arrow_fold<<<grid, 256, 0, ctx->stream>>>(n, j, Yc, Xc, Yp, Xp, Yn, Xn, flag);
-    count_launch(ctx, 2);
+    count_launch(ctx);
     std::swap(Yc, Yn);
     std::swap(Xc, Xn);
     s_cur = s_next;

@@ -801,7 +801,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     IR(I.alloc(&I.svr, (size_t)work));
     IR(I.alloc(&I.res, (size_t)work));
     IR(I.alloc(&I.Q, (size_t)work * work));
-    IR(I.alloc(&I.svd_scratch, (size_t)4 * work * work + 2 * work));
+    IR(I.alloc(&I.svd_scratch, (size_t)4 * work * work + 10 * work));
     IR(I.alloc(&I.ctl, (size_t)CT_COUNT));
     ICK(cudaMemsetAsync(I.Bm, 0, (size_t)work * work * sizeof(double), ctx->stream));
     ICK(cudaMemsetAsync(I.svr, 0, work * sizeof(double), ctx->stream));
