@@ -93,6 +93,7 @@ template int dev_alloc<int4>(m3b_ctx*, int4**, size_t);
 template int dev_alloc<int2>(m3b_ctx*, int2**, size_t);
 template int dev_alloc<unsigned int>(m3b_ctx*, unsigned int**, size_t);
 template int dev_alloc<unsigned char>(m3b_ctx*, unsigned char**, size_t);
+template int dev_alloc<unsigned short>(m3b_ctx*, unsigned short**, size_t);
 
 void dev_free(void* p) {
   if (!p) return;
@@ -475,7 +476,7 @@ __global__ void k_scan_chunks(int* __restrict__ H, int n_sel, int chunks_per_til
 }
 
 __global__ void k_fill_pads(const int* __restrict__ cnt, const long long* __restrict__ base, long long n_runs,
-                            int* __restrict__ idx, double* __restrict__ val) {
+                            unsigned short* __restrict__ idx, double* __restrict__ val) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= n_runs) return;
   int c = cnt[k];
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(256) k_scatter_B(const long long* __restrict__
                                                    const double* __restrict__ y, const int* __restrict__ sel_of_gene,
                                                    int n_sel, int tile_w, int chunks_per_tile, int cells_per_chunk,
                                                    long long n_cells, long long n_chunks, int* __restrict__ H,
-                                                   const long long* __restrict__ base, int* __restrict__ idx,
+                                                   const long long* __restrict__ base, unsigned short* __restrict__ idx,
                                                    double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   long long chunk = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(256) k_scatter_B(const long long* __restrict__
       if (r >= 0) {
         int pos = atomicAdd(Hc + r, 1);
         long long dst = bt[r] + pos;
-        idx[dst] = local;
+        idx[dst] = (unsigned short)local;
         val[dst] = ld_stream_f64(y + k);
       }
     }
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(256) k_count_A(const long long* __restrict__ p
 __global__ void __launch_bounds__(256) k_scatter_A(const long long* __restrict__ p, const int* __restrict__ gi,
                                                    const double* __restrict__ y, const int* __restrict__ kept_of_gene,
                                                    long long n_cells, int tile_w, int n_tiles,
-                                                   const long long* __restrict__ base, int* __restrict__ idx,
+                                                   const long long* __restrict__ base, unsigned short* __restrict__ idx,
                                                    double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -700,7 +701,7 @@ __global__ void __launch_bounds__(256) k_scatter_A(const long long* __restrict__
         unsigned m = __ballot_sync(0xffffffffu, g >= 0);
         if (g >= 0) {
           long long dst = dst0 + run + __popc(m & lt);
-          idx[dst] = g - t * tile_w;
+          idx[dst] = (unsigned short)(g - t * tile_w);
           val[dst] = v;
         }
         run += __popc(m);

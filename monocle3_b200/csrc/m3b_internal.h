@@ -78,7 +78,9 @@ struct m3b_ctx {
 //   rows x cols matrix; the gathered (cols) dimension is cut into tiles of
 //   tile_w columns so that the dense operand of one tile fits in shared memory;
 //   inside a tile the non-zeros are stored row by row, every run padded to a
-//   multiple of 4 entries (pad entries: idx 0, val 0.0).  An ITEM is one run (or
+//   multiple of 4 entries (pad entries: idx 0, val 0.0).  Because the index is
+//   tile-local it fits 16 bits, so the stream is 10 B/entry instead of the
+//   12 B/entry of an int32-indexed CSR.  An ITEM is one run (or
 //   a <= M3B_ITEM_MAX slice of a long run): the unit of work of one warp.
 // ---------------------------------------------------------------------------
 #define M3B_TILE_W_MAX 28672  // 224 KB of doubles in shared memory
@@ -96,7 +98,7 @@ struct TiledLayout {
   int tile_w = 0, n_tiles = 0;
   long long n_entries = 0;  // padded entries allocated
   long long nnz = 0;        // true stored entries referenced by items
-  int* idx = nullptr;       // tile-local column index
+  unsigned short* idx = nullptr;  // tile-local column index (tile_w <= 28672 < 2^16: 2 bytes/entry)
   double* val = nullptr;
   long long n_items = 0;
   ItemDesc* items = nullptr;

@@ -17,7 +17,7 @@
 
 #define PJ_CPL 4  // columns per lane => nv <= 128 per pass
 
-__global__ void __launch_bounds__(256) k_project(const int* __restrict__ idx, const double* __restrict__ val,
+__global__ void __launch_bounds__(256) k_project(const unsigned short* __restrict__ idx, const double* __restrict__ val,
                                                  const ItemDesc* __restrict__ items, const int* __restrict__ rip,
                                                  long long rows, int n_tiles, int tile_w,
                                                  const double* __restrict__ Vs /* [G'q][nv] row-major */,
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_project(const int* __restrict__ idx, co
           int myi = 0;
           double myv = 0.0;
           if (e0 + lane < d.len) {
-            myi = idx[d.start + e0 + lane];
+            myi = (int)idx[d.start + e0 + lane];
             myv = val[d.start + e0 + lane];
           }
           const int cnt = min(32, d.len - e0);

@@ -11,15 +11,17 @@
 // item.  A second tiny kernel adds the partials of a row in a fixed order, so
 // results are bit-reproducible run to run and independent of the CTA schedule.
 //
-// HBM traffic per launch is the 12 B/entry stream (8 B value + 4 B index) plus
-// 16 B/item descriptors and 8 B/item partials; the gathers never leave the SM.
+// HBM traffic per launch is the 10 B/entry stream (8 B value + 2 B tile-local
+// index; the ALGORITHMIC figure of SURVEY.md section 8d stays 12 B/nnz for an
+// int32-indexed CSR) plus 16 B/item descriptors and 8 B/item partials; the
+// gathers never leave the SM.
 #include <algorithm>
 
 #include "m3b_internal.h"
 
-__device__ __forceinline__ int2 ld_stream_int2(const int2* p) {
-  int2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+__device__ __forceinline__ unsigned int ld_stream_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ double2 ld_stream_double2(const double2* p) {
@@ -52,24 +54,24 @@ __device__ __forceinline__ double op_apply(double v, int id, const double* sx, d
 // streamed, so the atomic's latency is hidden.  When a tile runs dry the CTA moves to the
 // next tile that still has a worthwhile amount of work (one barrier + one re-stage).
 #define TS_THREADS 512  // 16 warps x <=128 registers: room for two register-resident load batches
-#define TS_BP 4         // pairs (of entries) per lane per batch
+#define TS_BP 6         // pairs (of entries) per lane per batch
 
 struct Batch {
-  int2 i[TS_BP];
+  unsigned int i[TS_BP];  // two 16-bit tile-local indices
   double2 v[TS_BP];
 };
 
 // one batch = 32 lanes x TS_BP pairs = 256 entries (3 KB) of the item's stream, predicated at the tail
-__device__ __forceinline__ void batch_load(Batch& b, const int2* __restrict__ ip, const double2* __restrict__ vp, int q0,
-                                           int n2) {
+__device__ __forceinline__ void batch_load(Batch& b, const unsigned int* __restrict__ ip,
+                                           const double2* __restrict__ vp, int q0, int n2) {
 #pragma unroll
   for (int u = 0; u < TS_BP; ++u) {
     const int q = q0 + 32 * u;
     if (q < n2) {
-      b.i[u] = ld_stream_int2(ip + q);
+      b.i[u] = ld_stream_u32(ip + q);
       b.v[u] = ld_stream_double2(vp + q);
     } else {
-      b.i[u] = make_int2(0, 0);
+      b.i[u] = 0u;
       b.v[u] = make_double2(0.0, 0.0);
     }
   }
@@ -83,12 +85,12 @@ __device__ __forceinline__ void batch_apply(const Batch& b, const double* sx, do
     if (OP == OP_SQDEV) {
       // predicated-off lanes hold zeros, which OP_SQDEV would count as (0-mu)^2
       if (q0 + 32 * u < n2) {
-        a[u] += op_apply<OP>(b.v[u].x, b.i[u].x, sx, mu);
-        a[u] += op_apply<OP>(b.v[u].y, b.i[u].y, sx, mu);
+        a[u] += op_apply<OP>(b.v[u].x, (int)(b.i[u] & 0xffffu), sx, mu);
+        a[u] += op_apply<OP>(b.v[u].y, (int)(b.i[u] >> 16), sx, mu);
       }
     } else {
-      a[u] += op_apply<OP>(b.v[u].x, b.i[u].x, sx, mu);
-      a[u] += op_apply<OP>(b.v[u].y, b.i[u].y, sx, mu);
+      a[u] += op_apply<OP>(b.v[u].x, (int)(b.i[u] & 0xffffu), sx, mu);
+      a[u] += op_apply<OP>(b.v[u].y, (int)(b.i[u] >> 16), sx, mu);
     }
   }
 }
@@ -106,7 +108,7 @@ __device__ __forceinline__ void batch_apply(const Batch& b, const double* sx, do
 // work (one barrier + one re-stage).
 template <int OP>
 __global__ void __launch_bounds__(TS_THREADS, 1)
-k_tile_stream(const int* __restrict__ idx, const double* __restrict__ val, const ItemDesc* __restrict__ items,
+k_tile_stream(const unsigned short* __restrict__ idx, const double* __restrict__ val, const ItemDesc* __restrict__ items,
               const int2* __restrict__ chunks, const int* __restrict__ tile_chunk_ptr,
               const int* __restrict__ cta_tile, int n_tiles, int tile_w, long long cols,
               const double* __restrict__ x, double* __restrict__ partial, unsigned int* __restrict__ counters) {
@@ -153,7 +155,7 @@ k_tile_stream(const int* __restrict__ idx, const double* __restrict__ val, const
           const int row = __shfl_sync(0xffffffffu, mydesc.w, k);
           const long long start = ((long long)(unsigned)rx) | ((long long)ry << 32);
           const double mu = (OP == OP_SQDEV) ? x[row] : 0.0;
-          const int2* ip = reinterpret_cast<const int2*>(idx + start);
+          const unsigned int* ip = reinterpret_cast<const unsigned int*>(idx + start);
           const double2* vp = reinterpret_cast<const double2*>(val + start);
           const int n2 = len >> 1;
           double a[TS_BP];
@@ -173,7 +175,9 @@ k_tile_stream(const int* __restrict__ idx, const double* __restrict__ val, const
             batch_apply<OP>(b1, sx, mu, a, q + step, n2);
             if (!more2) break;
           }
-          double acc = (a[0] + a[1]) + (a[2] + a[3]);
+          double acc = 0.0;
+#pragma unroll
+          for (int u = 0; u < TS_BP; ++u) acc += a[u];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
           if (lane == 0) partial[ib + k] = acc;
