@@ -19,7 +19,7 @@ void m3b_set_error(m3b_ctx* ctx, const char* fmt, ...) {
   ctx->err = buf;
 }
 
-void spmv_timer_begin(m3b_ctx* ctx, int kind) {
+void spmv_timer_begin(m3b_ctx* ctx, int kind, cudaStream_t stream) {
   if (!(ctx->flags & M3B_FLAG_TIME_SPMV)) return;
   if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
     for (int k = 0; k < 512; ++k) {
@@ -29,14 +29,15 @@ void spmv_timer_begin(m3b_ctx* ctx, int kind) {
     }
   }
   ctx->ev_kind.push_back(kind);
-  cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream);
+  cudaEventRecord(ctx->ev_pool[ctx->ev_used++], stream ? stream : ctx->stream);
 }
-void spmv_timer_end(m3b_ctx* ctx) {
+void spmv_timer_end(m3b_ctx* ctx, cudaStream_t stream) {
   if (!(ctx->flags & M3B_FLAG_TIME_SPMV)) return;
-  if (ctx->ev_used & 1) cudaEventRecord(ctx->ev_pool[ctx->ev_used++], ctx->stream);
+  if (ctx->ev_used & 1) cudaEventRecord(ctx->ev_pool[ctx->ev_used++], stream ? stream : ctx->stream);
 }
 void spmv_timer_collect(m3b_ctx* ctx) {
   if (!(ctx->flags & M3B_FLAG_TIME_SPMV)) return;
+  cudaStreamSynchronize(ctx->stream2);
   cudaStreamSynchronize(ctx->stream);
   for (size_t k = 0; k + 1 < ctx->ev_used; k += 2) {
     float ms = 0.f;
@@ -101,6 +102,7 @@ int m3b_create(int device, int flags, m3b_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaMalloc((void**)&ctx->sched, 4 * sizeof(unsigned int)) != cudaSuccess ||
       cudaMemset(ctx->sched, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
@@ -124,6 +126,7 @@ void m3b_destroy(m3b_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   dev_pool_release(ctx->device);
   delete ctx;

@@ -127,6 +127,30 @@ __global__ void __launch_bounds__(NT) k_fix_F(const double* __restrict__ Fraw, c
   }
 }
 
+// single-rank fusion of the K5 combine with the fix-ups (no allreduce in between):
+// F[g] = (sum of row g's partials)/s - (sumw*ce)/s - S*vj[g]
+__global__ void __launch_bounds__(NT) k_combine_fix_F(const double* __restrict__ partial, const int* __restrict__ rip,
+                                                      int rows, int n_tiles, const double* __restrict__ s,
+                                                      const double* __restrict__ ce, const double* __restrict__ vj,
+                                                      const double* __restrict__ scal, double* __restrict__ F) {
+  const double sumw = scal[SC_SUMW], S = scal[SC_S];
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < rows; g += gridDim.x * blockDim.x) {
+    double f = 0.0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int* p = rip + (long long)t * (rows + 1) + g;
+      const int b = p[0], e = p[1];
+      for (int k = b; k < e; ++k) f += partial[k];
+    }
+    if (s) f = f / s[g];
+    if (ce) {
+      double c = sumw * ce[g];
+      if (s) c = c / s[g];
+      f = f - c;
+    }
+    F[g] = f - S * vj[g];
+  }
+}
+
 // --------------------------------------------------------------------------
 // K6: tall-skinny orthogonalisation  y -= X (X^T y), one classical GS pass
 // --------------------------------------------------------------------------
@@ -278,6 +302,24 @@ __global__ void __launch_bounds__(NT) k_scale_w(double* __restrict__ w, long lon
     scal[SC_S] = S;
     scal[SC_SUMW] = buf2[1] * SS;
     if (!(S >= eps)) ctl[CT_FLAG] |= first ? 1 : 2;  // 1: start vector in null space, 2: breakdown
+  }
+}
+
+// single-rank fusion of k_reduce2 + k_scale_w: every block reduces the partials itself
+__global__ void __launch_bounds__(NT) k_scale_w_fused(double* __restrict__ w, long long rows, const double* __restrict__ pn,
+                                                      const double* __restrict__ ps, int np, double* __restrict__ scal,
+                                                      int* __restrict__ ctl, double eps, int first) {
+  __shared__ double sh[32];
+  const double n2 = block_sum_partials(pn, np, sh);
+  const double sm = block_sum_partials(ps, np, sh);
+  const double S = sqrt(n2);
+  const double SS = 1.0 / S;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+    w[r] *= SS;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[SC_S] = S;
+    scal[SC_SUMW] = sm * SS;
+    if (!(S >= eps)) ctl[CT_FLAG] |= first ? 1 : 2;
   }
 }
 
@@ -571,10 +613,12 @@ struct Irlba {
   }
 
   // W[:, jw] = Ax(V[:, jv]) given xs/pb already prepared; optional "- R_F * W[:, jw-1]"
-  int product_A(int jw, bool sub_prev) {
-    spmv_timer_begin(ctx, 0);
-    RET(launch_tile_stream(ctx, m->A, OP_DOT, xs));
-    spmv_timer_end(ctx);
+  int product_A(int jw, bool sub_prev, bool prelaunched = false) {
+    if (!prelaunched) {
+      spmv_timer_begin(ctx, 0);
+      RET(launch_tile_stream(ctx, m->A, OP_DOT, xs));
+      spmv_timer_end(ctx);
+    }
     ctx->stats.spmv_cells_out++;
     double* w = W + (long long)jw * mrows;
     spmv_timer_begin(ctx, 5);
@@ -594,6 +638,15 @@ struct Irlba {
     RET(launch_tile_stream(ctx, m->B, OP_DOT, W + (long long)j * mrows));
     spmv_timer_end(ctx);
     ctx->stats.spmv_genes_out++;
+    if (ctx->comm.world == 1) {
+      spmv_timer_begin(ctx, 5);
+      k_combine_fix_F<<<nb_n, NT, 0, ctx->stream>>>(m->B.partial, m->B.row_item_ptr, n, m->B.n_tiles, s, ce,
+                                                    V + (long long)j * n, scal, F);
+      count_launch(ctx);
+      spmv_timer_end(ctx);
+      CK(ctx, cudaGetLastError());
+      return M3B_OK;
+    }
     spmv_timer_begin(ctx, 5);
     RET(launch_combine_rows(ctx, m->B, Fraw));
     spmv_timer_end(ctx);
@@ -612,6 +665,15 @@ struct Irlba {
 
   // normalise W[:, jw] using pn/ps partials (cell side): S, sum(w)
   int finish_w(int jw, bool first, int np) {
+    if (ctx->comm.world == 1) {
+      spmv_timer_begin(ctx, 5);
+      k_scale_w_fused<<<nb_m, NT, 0, ctx->stream>>>(W + (long long)jw * mrows, mrows, pn, ps, np, scal, ctl, eps,
+                                                    first ? 1 : 0);
+      count_launch(ctx);
+      spmv_timer_end(ctx);
+      CK(ctx, cudaGetLastError());
+      return M3B_OK;
+    }
     spmv_timer_begin(ctx, 5);
     k_reduce2<<<1, NT, 0, ctx->stream>>>(pn, ps, np, buf2);
     count_launch(ctx);
@@ -757,7 +819,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
   I.nblk_n = std::max(1, (n + I.chunk_n - 1) / I.chunk_n);
   I.nblk_m = (int)std::max<long long>(1, (mloc + I.chunk_m - 1) / I.chunk_m);
   int status = M3B_OK;
-  cudaEvent_t evA = nullptr, evB = nullptr;
+  cudaEvent_t evA = nullptr, evB = nullptr, evF = nullptr, evK4 = nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_enter = now();
   double t_loop0 = 0, t_loop1 = 0, t_fin = 0;
@@ -836,15 +898,23 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     }
     ICK(cudaEventCreate(&evA));
     ICK(cudaEventCreate(&evB));
+    ICK(cudaEventCreateWithFlags(&evF, cudaEventDisableTiming));
+    ICK(cudaEventCreateWithFlags(&evK4, cudaEventDisableTiming));
     ICK(cudaEventRecord(evA, ctx->stream));
     t_loop0 = now();
 
+    bool pre_k4 = false;  // next cycle's first product already running on the side stream
     while (it < maxit) {
       int j = (it == 0) ? 0 : k;
       // W[:,j] = Ax(V[:,j])
-      k_make_xs<<<I.nb_n, NT, 0, ctx->stream>>>(I.V + (long long)j * n, I.s, I.ce, n, I.xs, I.pb);
-      count_launch(ctx);
-      IR(I.product_A(j, false));
+      if (pre_k4) {
+        ICK(cudaStreamWaitEvent(ctx->stream, evK4, 0));
+      } else {
+        k_make_xs<<<I.nb_n, NT, 0, ctx->stream>>>(I.V + (long long)j * n, I.s, I.ce, n, I.xs, I.pb);
+        count_launch(ctx);
+      }
+      IR(I.product_A(j, false, pre_k4));
+      pre_k4 = false;
       mprod++;
       if (it > 0) {
         IR(I.orthog(I.W, mloc, mloc, j, I.W + (long long)j * mloc, I.chunk_m, I.nblk_m, I.nbo_m, true));
@@ -873,6 +943,21 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         j++;
       }
       ICK(cudaGetLastError());
+      // The first product of the NEXT cycle is A * (F / s) with F the restart vector, which is
+      // final before the SVD: run it on the side stream underneath the (latency-bound, few-SM)
+      // restart SVD.  It takes all but 28 SMs so that the SVD kernels find free ones.  If this
+      // restart turns out to be the last one the product is simply not used.
+      if (!ctx->small_svd && m->A.n_tiles == 1 && ctx->sm_count > 56 && it + 1 < maxit) {
+        ICK(cudaEventRecord(evF, ctx->stream));
+        ICK(cudaStreamWaitEvent(ctx->stream2, evF, 0));
+        k_make_xs<<<I.nb_n, NT, 0, ctx->stream2>>>(I.F, I.s, I.ce, n, I.xs, I.pb);
+        count_launch(ctx);
+        spmv_timer_begin(ctx, 0, ctx->stream2);
+        IR(launch_tile_stream(ctx, m->A, OP_DOT, I.xs, ctx->stream2, ctx->sm_count - 28));
+        spmv_timer_end(ctx, ctx->stream2);
+        ICK(cudaEventRecord(evK4, ctx->stream2));
+        pre_k4 = true;
+      }
       // small SVD of B
       spmv_timer_begin(ctx, 3);
       if (ctx->small_svd) {
@@ -978,9 +1063,12 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     if (!converged) m3b_set_error(ctx, "did not converge--results might be invalid!; try increasing work or maxit");
   }
 done:
+  cudaStreamSynchronize(ctx->stream2);
+  cudaStreamSynchronize(ctx->stream);
   if (evA) cudaEventDestroy(evA);
   if (evB) cudaEventDestroy(evB);
-  cudaStreamSynchronize(ctx->stream);
+  if (evF) cudaEventDestroy(evF);
+  if (evK4) cudaEventDestroy(evK4);
   I.release();
   ctx->stats.host_ms[0] = t_loop0 - t_enter;  // moments + allocation + setup
   ctx->stats.host_ms[1] = t_loop1 - t_loop0;  // Lanczos loop (host wall clock)

@@ -57,6 +57,7 @@ struct m3b_ctx {
   int sm_count = 148;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: next cycle's first product runs under the restart SVD
   std::string err;
   Comm comm;
   m3b_small_svd_fn small_svd = nullptr;
@@ -171,7 +172,8 @@ int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* 
 enum StreamOp { OP_DOT = 0, OP_SUM = 1, OP_SQDEV = 2 };
 // partial[item] = sum over the item's entries of op(val, x[idx]); x is the dense operand
 // (length L.cols) for OP_DOT, ignored for OP_SUM, the per-row mean for OP_SQDEV.
-int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double* x);
+int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double* x, cudaStream_t stream = nullptr,
+                       int max_cta = 0);
 // out[row] = sum of the row's partials (fixed order: tile, then segment)
 int launch_combine_rows(m3b_ctx* ctx, const TiledLayout& L, double* out);
 long long spmv_algorithmic_bytes(const TiledLayout& L);
@@ -194,6 +196,6 @@ int spmv_init(m3b_ctx* ctx);
 int svd_init(m3b_ctx* ctx);
 int irlba_init(m3b_ctx* ctx);
 // event-pool helpers (api.cu)
-void spmv_timer_begin(m3b_ctx* ctx, int kind);
-void spmv_timer_end(m3b_ctx* ctx);
+void spmv_timer_begin(m3b_ctx* ctx, int kind, cudaStream_t stream = nullptr);
+void spmv_timer_end(m3b_ctx* ctx, cudaStream_t stream = nullptr);
 void spmv_timer_collect(m3b_ctx* ctx);

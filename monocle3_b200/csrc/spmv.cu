@@ -226,23 +226,25 @@ int spmv_init(m3b_ctx* ctx) {
   return M3B_OK;
 }
 
-int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double* x) {
+int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double* x, cudaStream_t stream, int max_cta) {
   if (L.n_chunks == 0) return M3B_OK;
   const size_t smem = tile_smem_bytes(L, op);
-  const int grid = L.n_cta;
+  if (!stream) stream = ctx->stream;
+  // fewer CTAs than SMs is allowed for a single-tile layout (chunks are claimed dynamically)
+  const int grid = (max_cta > 0 && L.n_tiles == 1) ? std::min(L.n_cta, max_cta) : L.n_cta;
   switch (op) {
     case OP_DOT:
-      k_tile_stream<OP_DOT><<<grid, TS_THREADS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+      k_tile_stream<OP_DOT><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
                                                                L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
                                                                L.counters);
       break;
     case OP_SUM:
-      k_tile_stream<OP_SUM><<<grid, TS_THREADS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+      k_tile_stream<OP_SUM><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
                                                                L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
                                                                L.counters);
       break;
     default:
-      k_tile_stream<OP_SQDEV><<<grid, TS_THREADS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+      k_tile_stream<OP_SQDEV><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
                                                                  L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
                                                                  L.counters);
       break;
