@@ -199,6 +199,8 @@ typedef struct m3b_stats {
    * [2] final GEMMs + result copies [3] release */
   double  host_ms[4];
   int64_t svd_fallbacks;       /* restarts where the structured SVD gave up and Jacobi ran */
+  double  k1_ms;               /* CUDA-event time of the last K1 (cell totals) kernel   */
+  double  k2_ms;               /* CUDA-event time of the last K2 (normalize) kernel     */
   int64_t svd_fallback_reasons;/* OR of the reasons: 1 size, 2 irregular poles/weights, 4 root not converged, 8 Loewner */
 } m3b_stats;
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);

@@ -39,7 +39,8 @@ class Stats(C.Structure):
                 ("prepare_ms", C.c_double), ("spmv_bytes_cells_out", C.c_int64), ("spmv_bytes_genes_out", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("phase_ms", C.c_double * 8),
                 ("svd_sweeps", C.c_int64), ("host_ms", C.c_double * 4),
-                ("svd_fallbacks", C.c_int64), ("svd_fallback_reasons", C.c_int64)]
+                ("svd_fallbacks", C.c_int64), ("k1_ms", C.c_double), ("k2_ms", C.c_double),
+                ("svd_fallback_reasons", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/m3b.h declares

@@ -259,6 +259,11 @@ int m3b_cell_totals(m3b_mat* m, int round_exprs, double* cell_total) {
       st = M3B_E_CUDA;
     }
     ctx->stats.d2h_bytes += m->n_cells * 8;
+    if (st == M3B_OK && ctx->k1_timed) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.k1_ms = ms;
+      ctx->k1_timed = false;
+    }
   }
   dev_free(d);
   return st;
@@ -352,6 +357,11 @@ int m3b_normalize(m3b_mat* m, const double* sf, int norm_method, double pseudo_c
   if (e != cudaSuccess) {
     m3b_set_error(ctx, "m3b_normalize: %s", cudaGetErrorString(e));
     return M3B_E_CUDA;
+  }
+  if (ctx->k2_timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.k2_ms = ms;
+    ctx->k2_timed = false;
   }
   m->normalized = true;
   m->selected = false;

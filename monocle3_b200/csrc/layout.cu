@@ -211,9 +211,16 @@ __global__ void __launch_bounds__(256) k_cell_totals(const long long* __restrict
   for (long long c = warp; c < n_cells; c += nwarps) {
     const long long lo = p[c], hi = p[c + 1];
     double acc = 0.0;
-    for (long long k = lo + lane; k < hi; k += 32) {
-      double v = ld_stream_f64(x + k);
-      acc += round_exprs ? rint(v) : v;  // R's round(): IEC 60559 half-to-even
+    long long k = lo + lane;
+    for (; k + 96 < hi; k += 128) {  // four independent 8-byte loads in flight per lane
+      const double v0 = ld_stream_f64(x + k), v1 = ld_stream_f64(x + k + 32);
+      const double v2 = ld_stream_f64(x + k + 64), v3 = ld_stream_f64(x + k + 96);
+      if (round_exprs) acc += (rint(v0) + rint(v1)) + (rint(v2) + rint(v3));  // R's round(): half-to-even
+      else acc += (v0 + v1) + (v2 + v3);
+    }
+    for (; k < hi; k += 32) {
+      const double v = ld_stream_f64(x + k);
+      acc += round_exprs ? rint(v) : v;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -225,9 +232,12 @@ int k1_cell_totals(m3b_mat* m, int round_exprs, double* d_tot) {
   m3b_ctx* ctx = m->ctx;
   if (m->n_cells == 0) return M3B_OK;
   int blocks = (int)std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8);
+  cudaEventRecord(ctx->ev0, ctx->stream);
   k_cell_totals<<<blocks, 256, 0, ctx->stream>>>(m->p, m->x, m->n_cells, round_exprs, d_tot);
+  cudaEventRecord(ctx->ev1, ctx->stream);
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
+  ctx->k1_timed = true;
   return M3B_OK;
 }
 
@@ -245,17 +255,47 @@ __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__
   for (long long c = warp; c < n_cells; c += nwarps) {
     const long long lo = p[c], hi = p[c + 1];
     const double s = (method == M3B_NORM_NONE || method == M3B_NORM_BINARY) ? 1.0 : sf[c];
-    for (long long k = lo + lane; k < hi; k += 32) {
-      double v = ld_stream_f64(x + k);
-      double r;
+    auto f = [&](double v) -> double {
       switch (method) {
-        case M3B_NORM_LOG2: r = log2(v / s + pc) - f0; break;
-        case M3B_NORM_LOG10: r = log10(v / s + pc); break;
-        case M3B_NORM_SIZE_ONLY: r = v / s; break;  // + pc is the implicit constant f0
-        case M3B_NORM_BINARY: r = (v > 0.0) ? 1.0 : 0.0; break;
-        default: r = v; break;
+        case M3B_NORM_LOG2: return log2(v / s + pc) - f0;
+        case M3B_NORM_LOG10: return log10(v / s + pc);
+        case M3B_NORM_SIZE_ONLY: return v / s;  // + pc is the implicit constant f0
+        case M3B_NORM_BINARY: return (v > 0.0) ? 1.0 : 0.0;
+        default: return v;
       }
-      y[k] = r;
+    };
+    // Counts are small integers (51-79% ones in the reference's fixtures): lane l keeps f(l+1)
+    // for this cell and entries with an integer value 1..32 are served by a shuffle instead of
+    // an fp64 log (which made the pass instruction-bound).  Same function, same argument =>
+    // bit-identical to evaluating f per entry.
+    const bool use_tbl = (method == M3B_NORM_LOG2 || method == M3B_NORM_LOG10);
+    const double tbl = use_tbl ? f((double)(lane + 1)) : 0.0;
+    auto g = [&](double v) -> double {
+      if (!use_tbl) return f(v);
+      const int iv = (int)v;
+      const bool hit = (v >= 1.0) && (v <= 32.0) && ((double)iv == v);
+      const double t = __shfl_sync(0xffffffffu, tbl, hit ? iv - 1 : 0);
+      return hit ? t : f(v);
+    };
+    long long k = lo + lane;
+    // the trip count is made warp-uniform (shuffles inside): lanes past the end compute on 0
+    const long long span = hi - lo;
+    const long long iters = (span + 31) / 32;
+    long long it = 0;
+    for (; it + 3 < iters; it += 4, k += 128) {  // four independent loads in flight per lane
+      const bool b0 = k < hi, b1 = k + 32 < hi, b2 = k + 64 < hi, b3 = k + 96 < hi;
+      const double v0 = b0 ? ld_stream_f64(x + k) : 0.0, v1 = b1 ? ld_stream_f64(x + k + 32) : 0.0;
+      const double v2 = b2 ? ld_stream_f64(x + k + 64) : 0.0, v3 = b3 ? ld_stream_f64(x + k + 96) : 0.0;
+      const double r0 = g(v0), r1 = g(v1), r2 = g(v2), r3 = g(v3);
+      if (b0) y[k] = r0;
+      if (b1) y[k + 32] = r1;
+      if (b2) y[k + 64] = r2;
+      if (b3) y[k + 96] = r3;
+    }
+    for (; it < iters; ++it, k += 32) {
+      const bool b0 = k < hi;
+      const double r0 = g(b0 ? ld_stream_f64(x + k) : 0.0);
+      if (b0) y[k] = r0;
     }
   }
 }
@@ -270,7 +310,10 @@ int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc) {
   m->f0 = f0;
   if (m->n_cells) {
     int blocks = (int)std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8);
+    cudaEventRecord(ctx->ev0, ctx->stream);
     k_normalize<<<blocks, 256, 0, ctx->stream>>>(m->p, m->x, d_sf, m->n_cells, method, pc, f0, m->y);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    ctx->k2_timed = true;
     count_launch(ctx);
     CK(ctx, cudaGetLastError());
   }

@@ -70,6 +70,7 @@ struct m3b_ctx {
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_kind;  // 0 = cells-out (K4), 1 = genes-out (K5)
   size_t ev_used = 0;
+  bool k1_timed = false, k2_timed = false;   // ev0/ev1 bracket the last K1 / K2 launch
   unsigned int* sched = nullptr;             // [2] dynamic unit counter + done counter (zeroed)
 };
 
