@@ -104,6 +104,7 @@ int m3b_create(int device, int flags, m3b_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess ||
       cudaMalloc((void**)&ctx->sched, 4 * sizeof(unsigned int)) != cudaSuccess ||
       cudaMemset(ctx->sched, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
     m3b_destroy(ctx);
@@ -125,6 +126,8 @@ void m3b_destroy(m3b_ctx* ctx) {
   if (ctx->sched) cudaFree(ctx->sched);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->evk0) cudaEventDestroy(ctx->evk0);
+  if (ctx->evk1) cudaEventDestroy(ctx->evk1);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -261,7 +264,7 @@ int m3b_cell_totals(m3b_mat* m, int round_exprs, double* cell_total) {
     ctx->stats.d2h_bytes += m->n_cells * 8;
     if (st == M3B_OK && ctx->k1_timed) {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.k1_ms = ms;
+      if (cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1) == cudaSuccess) ctx->stats.k1_ms = ms;
       ctx->k1_timed = false;
     }
   }
@@ -360,7 +363,7 @@ int m3b_normalize(m3b_mat* m, const double* sf, int norm_method, double pseudo_c
   }
   if (ctx->k2_timed) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.k2_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1) == cudaSuccess) ctx->stats.k2_ms = ms;
     ctx->k2_timed = false;
   }
   m->normalized = true;

@@ -232,9 +232,9 @@ int k1_cell_totals(m3b_mat* m, int round_exprs, double* d_tot) {
   m3b_ctx* ctx = m->ctx;
   if (m->n_cells == 0) return M3B_OK;
   int blocks = (int)std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8);
-  cudaEventRecord(ctx->ev0, ctx->stream);
+  cudaEventRecord(ctx->evk0, ctx->stream);
   k_cell_totals<<<blocks, 256, 0, ctx->stream>>>(m->p, m->x, m->n_cells, round_exprs, d_tot);
-  cudaEventRecord(ctx->ev1, ctx->stream);
+  cudaEventRecord(ctx->evk1, ctx->stream);
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
   ctx->k1_timed = true;
@@ -310,9 +310,9 @@ int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc) {
   m->f0 = f0;
   if (m->n_cells) {
     int blocks = (int)std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8);
-    cudaEventRecord(ctx->ev0, ctx->stream);
+    cudaEventRecord(ctx->evk0, ctx->stream);
     k_normalize<<<blocks, 256, 0, ctx->stream>>>(m->p, m->x, d_sf, m->n_cells, method, pc, f0, m->y);
-    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventRecord(ctx->evk1, ctx->stream);
     ctx->k2_timed = true;
     count_launch(ctx);
     CK(ctx, cudaGetLastError());

@@ -65,7 +65,8 @@ struct m3b_ctx {
   m3b_should_abort_fn should_abort = nullptr;
   void* should_abort_user = nullptr;
   m3b_stats stats{};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // scratch events
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // m3b_timer_start / m3b_timer_stop
+  cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // bracket the last K1 / K2 kernel
   // M3B_FLAG_TIME_SPMV: event pairs recorded around every SpMV launch, read back after the run
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_kind;  // 0 = cells-out (K4), 1 = genes-out (K5)
