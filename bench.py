@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--num-dim", type=int, default=CFG2["num_dim"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-cells", type=int, default=CPU_SAMPLE_CELLS)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (used for short ncu launch lists)")
+    ap.add_argument("--no-roofline-pass", action="store_true", help="skip the instrumented step (short ncu launch lists)")
     return ap.parse_args()
 
 
@@ -274,92 +276,96 @@ def main():
     launches = int(sum_over_ranks(st["kernel_launches"]))
     value = C_total / (ms_step / 1e3)
 
-    # ---- roofline of the dominant kernel (k_tile_stream<DOT>): one instrumented step ----
-    ctx.set_flags(L.FLAG_TIME_SPMV)
-    ctx.reset_stats()
-    res_i = device_step()
-    sti = ctx.stats()
-    ctx.set_flags(0)
-    nA, nB = sti["spmv_cells_out"], sti["spmv_genes_out"]
-    bytes_total = nA * sti["spmv_bytes_cells_out"] + nB * sti["spmv_bytes_genes_out"]
-    spmv_ms = sti["spmv_cells_out_ms"] + sti["spmv_genes_out_ms"]
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = bytes_total / (spmv_ms / 1e3) / 1e9 if spmv_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_tile_stream<OP_DOT> (K4 cells-out + K5 genes-out SpMV)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                "launches_timed": int(nA + nB), "avg_launch_us": 1e3 * spmv_ms / max(1, nA + nB),
-                "algorithmic_bytes_per_launch": bytes_total / max(1, nA + nB),
-                "cells_out": {"gbs": nA * sti["spmv_bytes_cells_out"] / max(sti["spmv_cells_out_ms"], 1e-9) / 1e6,
-                              "avg_us": 1e3 * sti["spmv_cells_out_ms"] / max(1, nA)},
-                "genes_out": {"gbs": nB * sti["spmv_bytes_genes_out"] / max(sti["spmv_genes_out_ms"], 1e-9) / 1e6,
-                              "avg_us": 1e3 * sti["spmv_genes_out_ms"] / max(1, nB)},
-                "spmv_share_of_irlba": spmv_ms / max(sti["irlba_ms"], 1e-9),
-                "stream_note": "the tiled layout stores 16-bit tile-local indices: 10 B/entry are streamed for the "
-                               "12 B/nnz algorithmic figure of an int32-indexed CSR (SURVEY 8d)",
-                "achieved_dram_model_gbs": achieved * (10.0 / 12.0),
-                "irlba_phase_ms": dict(zip(["spmv_cells_out", "spmv_genes_out", "orthog", "small_svd", "restart_gemm",
-                                            "vector_epilogues", "allreduce"], [round(v, 3) for v in sti["phase_ms"][:7]])),
-                "irlba_ms": sti["irlba_ms"], "svd_sweeps": sti["svd_sweeps"], "svd_fallbacks": sti["svd_fallbacks"],
-                "host_wall_ms": {k: round(v, 2) for k, v in wall.items()},
-                "irlba_host_ms": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in sti["host_ms"]])),
-                "irlba_host_ms_untimed_step": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in st["host_ms"]]))}
+    roofline = None
+    if not args.no_roofline_pass:
+        # ---- roofline of the dominant kernel (k_tile_stream<DOT>): one instrumented step ----
+        ctx.set_flags(L.FLAG_TIME_SPMV)
+        ctx.reset_stats()
+        res_i = device_step()
+        sti = ctx.stats()
+        ctx.set_flags(0)
+        nA, nB = sti["spmv_cells_out"], sti["spmv_genes_out"]
+        bytes_total = nA * sti["spmv_bytes_cells_out"] + nB * sti["spmv_bytes_genes_out"]
+        spmv_ms = sti["spmv_cells_out_ms"] + sti["spmv_genes_out_ms"]
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = bytes_total / (spmv_ms / 1e3) / 1e9 if spmv_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "k_tile_stream<OP_DOT> (K4 cells-out + K5 genes-out SpMV)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                    "launches_timed": int(nA + nB), "avg_launch_us": 1e3 * spmv_ms / max(1, nA + nB),
+                    "algorithmic_bytes_per_launch": bytes_total / max(1, nA + nB),
+                    "cells_out": {"gbs": nA * sti["spmv_bytes_cells_out"] / max(sti["spmv_cells_out_ms"], 1e-9) / 1e6,
+                                  "avg_us": 1e3 * sti["spmv_cells_out_ms"] / max(1, nA)},
+                    "genes_out": {"gbs": nB * sti["spmv_bytes_genes_out"] / max(sti["spmv_genes_out_ms"], 1e-9) / 1e6,
+                                  "avg_us": 1e3 * sti["spmv_genes_out_ms"] / max(1, nB)},
+                    "spmv_share_of_irlba": spmv_ms / max(sti["irlba_ms"], 1e-9),
+                    "stream_note": "the tiled layout stores 16-bit tile-local indices: 10 B/entry are streamed for the "
+                                   "12 B/nnz algorithmic figure of an int32-indexed CSR (SURVEY 8d)",
+                    "achieved_dram_model_gbs": achieved * (10.0 / 12.0),
+                    "irlba_phase_ms": dict(zip(["spmv_cells_out", "spmv_genes_out", "orthog", "small_svd", "restart_gemm",
+                                                "vector_epilogues", "allreduce"], [round(v, 3) for v in sti["phase_ms"][:7]])),
+                    "irlba_ms": sti["irlba_ms"], "svd_sweeps": sti["svd_sweeps"], "svd_fallbacks": sti["svd_fallbacks"],
+                    "host_wall_ms": {k: round(v, 2) for k, v in wall.items()},
+                    "irlba_host_ms": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in sti["host_ms"]])),
+                    "irlba_host_ms_untimed_step": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in st["host_ms"]]))}
 
-    # ---- the other HBM-bound passes of the path (K1 totals, K2 normalize), event-timed, 5 reps ----
-    def timed(fn, reps=5):
-        fn()
-        ctx.timer_start()
-        for _ in range(reps):
+        # ---- the other HBM-bound passes of the path (K1 totals, K2 normalize), event-timed, 5 reps ----
+        def timed(fn, reps=5):
             fn()
-        return ctx.timer_stop() / reps
-    timed(lambda: dev.cell_totals(True))
-    k1_ms = ctx.stats()["k1_ms"]
-    timed(lambda: dev.normalize(sf, L.NORM_LOG2, 1.0))
-    k2_ms = ctx.stats()["k2_ms"]
-    n_loc = hi - lo
-    aux = {"K1_cell_totals": {"kernel_ms": k1_ms, "gbs": (8 * nnz_local + 16 * n_loc) / max(k1_ms, 1e-9) / 1e6,
-                              "algorithmic_bytes": 8 * nnz_local + 16 * n_loc,
-                              "frac_of_measured_peak": (8 * nnz_local + 16 * n_loc) / max(k1_ms, 1e-9) / 1e6 / peak},
-           "K2_normalize_log2": {"kernel_ms": k2_ms, "gbs": (16 * nnz_local + 8 * n_loc) / max(k2_ms, 1e-9) / 1e6,
-                                 "algorithmic_bytes": 16 * nnz_local + 8 * n_loc,
-                                 "frac_of_measured_peak": (16 * nnz_local + 8 * n_loc) / max(k2_ms, 1e-9) / 1e6 / peak}}
-    roofline["other_hbm_passes"] = aux
+            ctx.timer_start()
+            for _ in range(reps):
+                fn()
+            return ctx.timer_stop() / reps
+        timed(lambda: dev.cell_totals(True))
+        k1_ms = ctx.stats()["k1_ms"]
+        timed(lambda: dev.normalize(sf, L.NORM_LOG2, 1.0))
+        k2_ms = ctx.stats()["k2_ms"]
+        n_loc = hi - lo
+        aux = {"K1_cell_totals": {"kernel_ms": k1_ms, "gbs": (8 * nnz_local + 16 * n_loc) / max(k1_ms, 1e-9) / 1e6,
+                                  "algorithmic_bytes": 8 * nnz_local + 16 * n_loc,
+                                  "frac_of_measured_peak": (8 * nnz_local + 16 * n_loc) / max(k1_ms, 1e-9) / 1e6 / peak},
+               "K2_normalize_log2": {"kernel_ms": k2_ms, "gbs": (16 * nnz_local + 8 * n_loc) / max(k2_ms, 1e-9) / 1e6,
+                                     "algorithmic_bytes": 16 * nnz_local + 8 * n_loc,
+                                     "frac_of_measured_peak": (16 * nnz_local + 8 * n_loc) / max(k2_ms, 1e-9) / 1e6 / peak}}
+        roofline["other_hbm_passes"] = aux
 
-    # ---- end-to-end arm: public API from pinned host buffers ----
-    def e2e_step():
-        c = m3.new_cell_data_set(counts, shard=shard)           # H2D of the CSC + size factors
-        c = m3.preprocess_cds(c, num_dim=args.num_dim)          # ... embedding + loadings back on the host
-        x = c.reduced_dims["PCA"]
-        c._dev.free()
-        return c, x
+    e2e = None
+    if not args.no_e2e:
+        # ---- end-to-end arm: public API from pinned host buffers ----
+        def e2e_step():
+            c = m3.new_cell_data_set(counts, shard=shard)           # H2D of the CSC + size factors
+            c = m3.preprocess_cds(c, num_dim=args.num_dim)          # ... embedding + loadings back on the host
+            x = c.reduced_dims["PCA"]
+            c._dev.free()
+            return c, x
 
-    dev.free()
-    cds._dev = None
-    for _ in range(max(1, min(args.warmup, 3))):
-        c_e, x_e = e2e_step()
-    barrier()
-    ctx.reset_stats()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        c_e, x_e = e2e_step()
-    ms_e2e_total = ctx.timer_stop()
-    barrier()
-    ste = ctx.stats()
-    ms_e2e = max_over_ranks(ms_e2e_total) / args.steps
-    e2e = {"value": C_total / (ms_e2e / 1e3), "unit": "cells/s",
-           "h2d_bytes_per_step": int(sum_over_ranks(ste["h2d_bytes"]) / args.steps),
-           "d2h_bytes_per_step": int(sum_over_ranks(ste["d2h_bytes"]) / args.steps), "ms_per_step": ms_e2e}
+        dev.free()
+        cds._dev = None
+        for _ in range(max(1, min(args.warmup, 3))):
+            c_e, x_e = e2e_step()
+        barrier()
+        ctx.reset_stats()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            c_e, x_e = e2e_step()
+        ms_e2e_total = ctx.timer_stop()
+        barrier()
+        ste = ctx.stats()
+        ms_e2e = max_over_ranks(ms_e2e_total) / args.steps
+        e2e = {"value": C_total / (ms_e2e / 1e3), "unit": "cells/s",
+               "h2d_bytes_per_step": int(sum_over_ranks(ste["h2d_bytes"]) / args.steps),
+               "d2h_bytes_per_step": int(sum_over_ranks(ste["d2h_bytes"]) / args.steps), "ms_per_step": ms_e2e}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle on a bounded sample ----
     cpu_baseline = None

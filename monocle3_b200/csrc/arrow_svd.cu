@@ -221,9 +221,8 @@ k_arrow_roots(int mode, int n, const int* __restrict__ ctl_k, int tail_j, const 
   else if (hb == 0.0) x = xb;
   else if (!(ha < 0.0 && hb > 0.0)) ok = false;
   else {
-    // tighten the bracket around the dominant-pole estimate  x ~ u_o^2 / (2 p_o c0)  (c0 = the
-    // rest of the secular function at the pole): converged Ritz values sit 1e-12 gaps from
-    // their pole, where plain regula falsi from the full interval degenerates into bisection
+    // probe the dominant-pole estimate  x ~ u_o^2 / (2 p_o c0)  (c0 = the rest of the secular
+    // function at the pole): converged Ritz values sit 1e-20 gaps from their pole
     if (po > 0.0) {
       double c0 = 0.0;
       for (int i0 = 0; i0 < ma; i0 += 128) {
@@ -246,52 +245,54 @@ k_arrow_roots(int mode, int n, const int* __restrict__ ctl_k, int tail_j, const 
         } else {
           xa = xb = xg;
         }
-        // second probe on the far side of the estimate (factor 2 towards the root)
-        const double x2 = (hg < 0.0) ? ((xg > 0.0) ? 2.0 * xg : 0.5 * xg) : ((xg > 0.0) ? 0.5 * xg : 2.0 * xg);
-        if (xa < xb && x2 > xa && x2 < xb) {
-          const double h2 = hfun(x2);
-          if (h2 < 0.0) {
-            xa = x2;
-            ha = h2;
-          } else if (h2 > 0.0) {
-            xb = x2;
-            hb = h2;
-          } else {
-            xa = xb = x2;
-          }
-        }
       }
     }
     if (xa == xb) x = xa;
     else {
-      int side = 0;
+      // Dekker's method with Brent's minimal step: bq = best iterate, aq = end of the bracket with
+      // the opposite sign, cq = previous iterate.  The secant runs through the two LATEST
+      // iterates, so a stale far end of the bracket does not slow it down (regula falsi /
+      // Illinois crept for ~50 iterations on roots that sit 1e-20 gaps from a pole).
+      double aq, hq_a, bq, hq_b;
+      if (fabs(ha) < fabs(hb)) {
+        aq = xb; hq_a = hb; bq = xa; hq_b = ha;
+      } else {
+        aq = xa; hq_a = ha; bq = xb; hq_b = hb;
+      }
+      double cq = aq, hq_c = hq_a;
       bool conv = false;
       for (int it = 0; it < 100; ++it) {
-        double xn = (xa * hb - xb * ha) / (hb - ha);
-        if (!(xn > xa && xn < xb)) xn = 0.5 * (xa + xb);
-        const double hn = hfun(xn);
-        x = xn;
-        if (hn == 0.0) {
+        if (hq_b == 0.0) {
           conv = true;
           break;
         }
-        if (hn < 0.0) {
-          xa = xn;
-          ha = hn;
-          if (side == -1) hb *= 0.5;
-          side = -1;
-        } else {
-          xb = xn;
-          hb = hn;
-          if (side == 1) ha *= 0.5;
-          side = 1;
-        }
-        if (fabs(xb - xa) <= 4.0 * 2.220446049250313e-16 * fmax(fabs(xa), fabs(xb))) {
+        const double tol1 = 2.0 * 2.220446049250313e-16 * fabs(bq);
+        const double mid = 0.5 * (aq - bq);
+        if (fabs(mid) <= tol1) {
           conv = true;
           break;
+        }
+        double st = (hq_b != hq_c) ? -hq_b * (bq - cq) / (hq_b - hq_c) : mid;
+        const double ratio = st / mid;
+        if (!(ratio > 0.0 && ratio < 1.0)) st = mid;  // keep the step inside (b, b + mid)
+        if (fabs(st) < tol1) st = (mid > 0.0) ? tol1 : -tol1;
+        cq = bq;
+        hq_c = hq_b;
+        bq = bq + st;
+        hq_b = hfun(bq);
+        if ((hq_b < 0.0) == (hq_a < 0.0)) {
+          aq = cq;
+          hq_a = hq_c;
+        }
+        if (fabs(hq_a) < fabs(hq_b)) {
+          const double ta = aq, tha = hq_a;
+          aq = bq; hq_a = hq_b;
+          bq = ta; hq_b = tha;
+          cq = aq; hq_c = hq_a;
         }
       }
-      if (!conv && !(fabs(xb - xa) <= 1e-10 * fmax(fabs(xa), fabs(xb)))) ok = false;
+      x = bq;
+      if (!conv) ok = false;
     }
   }
   if (lane == 0) {

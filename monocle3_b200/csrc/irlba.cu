@@ -133,21 +133,31 @@ __global__ void __launch_bounds__(NT) k_combine_fix_F(const double* __restrict__
                                                       int rows, int n_tiles, const double* __restrict__ s,
                                                       const double* __restrict__ ce, const double* __restrict__ vj,
                                                       const double* __restrict__ scal, double* __restrict__ F) {
+  // one warp per gene row: a heavy gene has tens of partials (one per <=2048-entry slice and
+  // tile); the lanes stride over them and the lane sums are added in a fixed shuffle tree
   const double sumw = scal[SC_SUMW], S = scal[SC_S];
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < rows; g += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < rows; g += gridDim.x * wpb) {
     double f = 0.0;
     for (int t = 0; t < n_tiles; ++t) {
       const int* p = rip + (long long)t * (rows + 1) + g;
       const int b = p[0], e = p[1];
-      for (int k = b; k < e; ++k) f += partial[k];
+      double a = 0.0;
+      for (int k = b + lane; k < e; k += 32) a += partial[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      f += a;
     }
-    if (s) f = f / s[g];
-    if (ce) {
-      double c = sumw * ce[g];
-      if (s) c = c / s[g];
-      f = f - c;
+    if (lane == 0) {
+      if (s) f = f / s[g];
+      if (ce) {
+        double c = sumw * ce[g];
+        if (s) c = c / s[g];
+        f = f - c;
+      }
+      F[g] = f - S * vj[g];
     }
-    F[g] = f - S * vj[g];
   }
 }
 
@@ -640,7 +650,7 @@ struct Irlba {
     ctx->stats.spmv_genes_out++;
     if (ctx->comm.world == 1) {
       spmv_timer_begin(ctx, 5);
-      k_combine_fix_F<<<nb_n, NT, 0, ctx->stream>>>(m->B.partial, m->B.row_item_ptr, n, m->B.n_tiles, s, ce,
+      k_combine_fix_F<<<std::max(1, std::min((n + 7) / 8, 4 * ctx->sm_count)), NT, 0, ctx->stream>>>(m->B.partial, m->B.row_item_ptr, n, m->B.n_tiles, s, ce,
                                                     V + (long long)j * n, scal, F);
       count_launch(ctx);
       spmv_timer_end(ctx);

@@ -254,23 +254,31 @@ int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double*
   return M3B_OK;
 }
 
-// out[row] = sum over tiles (ascending) and the row's items (ascending) of partial[]
-__global__ void k_combine_rows(const double* __restrict__ partial, const int* __restrict__ rip, long long rows,
-                               int n_tiles, double* __restrict__ out) {
-  long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  double acc = 0.0;
-  for (int t = 0; t < n_tiles; ++t) {
-    const int* p = rip + (long long)t * (rows + 1) + r;
-    const int b = p[0], e = p[1];
-    for (int k = b; k < e; ++k) acc += partial[k];
+// out[row] = sum of the row's partials: one warp per row, lanes stride over the row's items of a
+// tile, fixed shuffle tree, tiles added in ascending order (deterministic)
+__global__ void __launch_bounds__(256) k_combine_rows(const double* __restrict__ partial, const int* __restrict__ rip,
+                                                      long long rows, int n_tiles, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long wpb = blockDim.x >> 5;
+  for (long long r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    double acc = 0.0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int* p = rip + (long long)t * (rows + 1) + r;
+      const int b = p[0], e = p[1];
+      double a = 0.0;
+      for (int k = b + lane; k < e; k += 32) a += partial[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      acc += a;
+    }
+    if (lane == 0) out[r] = acc;
   }
-  out[r] = acc;
 }
 
 int launch_combine_rows(m3b_ctx* ctx, const TiledLayout& L, double* out) {
   if (L.rows == 0) return M3B_OK;
-  k_combine_rows<<<(unsigned)((L.rows + 255) / 256), 256, 0, ctx->stream>>>(L.partial, L.row_item_ptr, L.rows, L.n_tiles, out);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((L.rows + 7) / 8, 4LL * ctx->sm_count));
+  k_combine_rows<<<grid, 256, 0, ctx->stream>>>(L.partial, L.row_item_ptr, L.rows, L.n_tiles, out);
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
   return M3B_OK;
