@@ -268,3 +268,73 @@ def test_ragged_and_empty_inputs(m3):
     assert np.array_equal(r1["d"], r2["d"]) and np.array_equal(r1["x"], r2["x"])  # bit-reproducible
     o = ref.preprocess_cds(counts, sf, num_dim=10, v0=v0)
     assert sv_rel_err(r1["d"], o["d"]) < SV_TOL and subspace_angle(r1["x"], o["PCA"]) < ANGLE_TOL
+
+
+@pytest.mark.parametrize("scaling", [True, False])
+def test_pca_synthetic_vs_oracle(m3, scaling):
+    """Synthetic matrix from the bench generator (planted cell types, Poisson counts), small enough
+    for the oracle: full parity incl. iter/mprod."""
+    from monocle3_b200.synth import synth_csc
+    counts = synth_csc(2500, 3000, 0.08, 60, seed=5)
+    _check_pca(m3, counts, None, 50, "device", scaling=scaling)
+
+
+def test_pca_multi_tile_layouts(m3):
+    """More genes than one shared-memory tile holds (G' > 28672) and more cells than one tile
+    (C > 28672): both layouts are tiled, partials of a row are combined across tiles."""
+    from monocle3_b200 import engine, _lib as L
+    from monocle3_b200.synth import synth_csc
+    counts = synth_csc(30000, 29500, 0.004, 30, seed=7)  # ~3.5M nnz
+    sf = ref.estimate_sf_sparse(counts)[0]
+    ctx = m3.get_context()
+    dev = engine.DeviceMatrix.from_csc(ctx, counts)
+    dev.normalize(sf, L.NORM_LOG2, 1.0)
+    keep = dev.select_genes(None)
+    v0 = np.cos(np.arange(int(keep.sum())) * 0.37) + 0.1
+    r = dev.pca_irlba(12, v0, maxit=1000)
+    FM = ref.normalize_expr_data(counts, sf, "log")
+    FMf, kept = ref.select_and_filter_genes(FM)
+    assert np.array_equal(np.nonzero(keep)[0], kept) and len(kept) > 28672
+    o = ref.sparse_prcomp_irlba(FMf.T.tocsc(), 12, center=True, scale=True, v0=v0)
+    assert (r["iter"], r["mprod"]) == (o["iter"], o["mprod"])
+    assert sv_rel_err(r["d"], o["d"]) < SV_TOL
+    assert subspace_angle(r["v"], o["rotation"]) < ANGLE_TOL
+    assert subspace_angle(r["x"], o["x"]) < ANGLE_TOL
+
+
+def test_full_size_properties(m3):
+    """Size-independent properties at a size the oracle cannot iterate on in seconds
+    (20k cells x 8k genes, ~10M nnz): orthonormal loadings, singular-triplet residuals
+    ||A^ v_i - x_i|| <= 1e-8 sigma_1 checked with one host product per vector, embeddings
+    orthogonal with norms sigma_i, run-to-run bit reproducibility."""
+    from monocle3_b200 import engine, _lib as L
+    from monocle3_b200.synth import synth_csc
+    from monocle3_b200.r_rng import rnorm_after_seed
+    counts = synth_csc(8000, 20000, 0.06, 100, seed=11)
+    sf = ref.estimate_sf_sparse(counts)[0]
+    ctx = m3.get_context()
+    dev = engine.DeviceMatrix.from_csc(ctx, counts)
+    assert np.array_equal(dev.cell_totals(True), np.asarray(counts.sum(axis=0)).ravel())
+    dev.normalize(sf, L.NORM_LOG2, 1.0)
+    keep = dev.select_genes(None)
+    v0 = rnorm_after_seed(2016, int(keep.sum()))
+    r = dev.pca_irlba(30, v0)
+    r2 = dev.pca_irlba(30, v0)
+    assert r["status"] == 0 and np.array_equal(r["x"], r2["x"]) and np.array_equal(r["v"], r2["v"])
+    V, X, d = r["v"], r["x"], r["d"]
+    assert np.abs(V.T @ V - np.eye(30)).max() < 1e-10
+    G = X.T @ X
+    assert np.abs(G - np.diag(d ** 2)).max() < 1e-8 * d[0] ** 2
+    assert np.all(np.diff(d) <= 0)
+    FM = ref.normalize_expr_data(counts, sf, "log")
+    A = FM.tocsr()[keep, :].T.tocsr()                   # cells x kept genes
+    c, s = r["center"], r["scale"]
+    for i in (0, 7, 29):
+        xs = V[:, i] / s
+        w = A @ xs - np.dot(xs, c)
+        assert np.linalg.norm(w - X[:, i]) < 1e-8 * d[0]
+    # irlba's own stopping rule: residual of the accepted triplets below tol * sigma_1 (tol = 1e-5)
+    for i in (0, 29):
+        u = X[:, i] / d[i]
+        f = (A.T @ u) / s - np.sum(u) * c / s
+        assert np.linalg.norm(f - d[i] * V[:, i]) < 1e-4 * d[0]
