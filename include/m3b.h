@@ -66,6 +66,7 @@ extern "C" {
 #define M3B_E_NODEVICE       -13 /* no usable sm_100 device: there is no fallback   */
 #define M3B_E_ABORTED        -14 /* should_abort callback asked to stop             */
 
+/* (m3b_tfidf is documented next to m3b_gene_moments below) */
 /* norm_method codes for m3b_normalize */
 #define M3B_NORM_LOG2       0 /* log2(x/sf + pc)   preprocess_cds norm_method="log"        */
 #define M3B_NORM_SIZE_ONLY  1 /* x/sf + pc         norm_method="size_only"                 */
@@ -151,6 +152,16 @@ int m3b_gene_nnz(m3b_mat* mat, int64_t* nnz_per_sel_gene /* n_sel */);
 
 /* ---- gene moments (K3) -------------------------------------------------- */
 int m3b_gene_moments(m3b_mat* mat, double* center /* G' */, double* scale /* G' */);
+
+/* ---- TF-IDF (LSI branch: tfidf(), R/preprocess_cds.R:289-338; R/projection.R:190-216) ----- */
+/* Call after m3b_normalize + m3b_select_genes: rewrites the prepared matrix in place as
+ * log1p(FM / col_sums * scale_factor) * log(1 + num_cols / row_sums).  row_sums_in / num_cols:
+ * NULL / 0 when building a model (computed here: rowSums(FM > 0) over all ranks, total cells);
+ * the MODEL's values (per kept query gene) when projecting query cells.  col_sums_out
+ * (n_cells_local) and row_sums_out (G') are optional.  Follow with m3b_pca_irlba(center=0,
+ * scale=0) or m3b_project(center=NULL, scale=NULL). */
+int m3b_tfidf(m3b_mat* mat, int frequencies, int log_scale_tf, double scale_factor,
+              const double* row_sums_in, double num_cols, double* col_sums_out, double* row_sums_out);
 
 /* ---- IRLBA PCA (K4-K9) -------------------------------------------------- */
 /* nv: number of PCs; work: Lanczos subspace (0 => nv+7); v0: start vector (G').

@@ -8,8 +8,8 @@ names, argument meaning and error behaviour as the reference:
   estimate_size_factors   R/utils.R:26-50
   size_factors            R/methods-cell_data_set.R:36-41
   normalized_counts       R/utils.R:477-509
-  preprocess_cds          R/preprocess_cds.R:62-248   (PCA branch)
-  preprocess_transform    R/projection.R:72-155       (PCA branch)
+  preprocess_cds          R/preprocess_cds.R:62-248   (PCA and LSI branches)
+  preprocess_transform    R/projection.R:72-261       (PCA and LSI branches)
   new_cell_data_set       R/cell_data_set.R:67-137
   load_a549               R/io.R:10-26 (reads the committed fixture)
 
@@ -170,15 +170,13 @@ def _normalize_on_device(cds, norm_method, pseudo_count):
 
 def preprocess_cds(cds, method="PCA", num_dim=50, norm_method="log", use_genes=None, pseudo_count=None,
                    scaling=True, verbose=False, build_nn_index=False, nn_control=None, _irlba_args=None):
-    """R/preprocess_cds.R:62-248, PCA branch."""
+    """R/preprocess_cds.R:62-248 (PCA and LSI branches)."""
     if method not in ("PCA", "LSI"):
         raise ValueError("method must be one of 'PCA' or 'LSI'")
     if norm_method not in _NORM:
         raise ValueError("norm_method must be one of 'log', 'size_only' or 'none'")
     if not (isinstance(num_dim, (int, np.integer)) and num_dim > 0):
         raise ValueError("num_dim is not a count (a single positive integer)")
-    if method == "LSI":
-        raise NotImplementedError("the LSI branch is outside this build's scope (SURVEY.md section 8f)")
     if build_nn_index:
         raise NotImplementedError("nearest-neighbour indices are outside this build's scope (SURVEY.md section 8f)")
     gene_order = None
@@ -199,6 +197,8 @@ def preprocess_cds(cds, method="PCA", num_dim=50, norm_method="log", use_genes=N
     keep = dev.select_genes(gene_order)  # :117-122 + Matrix::t
     sel = np.arange(cds.counts.shape[0]) if gene_order is None else gene_order
     kept_idx = sel[keep]
+    if method == "LSI":
+        return _preprocess_lsi(cds, dev, kept_idx, num_dim, norm_method, use_genes, pseudo_count, _irlba_args)
     if verbose:
         print("Remove noise by PCA ...")
     n = min(num_dim, min(len(kept_idx), cds.n_cells_total) - 1)  # :140
@@ -220,6 +220,26 @@ def preprocess_cds(cds, method="PCA", num_dim=50, norm_method="log", use_genes=N
     return cds
 
 
+def _preprocess_lsi(cds, dev, kept_idx, num_dim, norm_method, use_genes, pseudo_count, irlba_args):
+    """LSI branch, R/preprocess_cds.R:185-241: tfidf(FM) then irlba without centre / scale."""
+    col_sums, row_sums = dev.tfidf(True, True, 100000.0)        # tfidf() defaults, :289-290
+    n = min(num_dim, min(len(kept_idx), cds.n_cells_total) - 1)  # :194
+    v0 = rnorm_after_seed(2016, len(kept_idx))
+    res = dev.pca_irlba(n, v0, center=False, scale=False, **(irlba_args or {}))
+    if res["status"] == L.M3B_W_NOT_CONVERGED:
+        warnings.warn("did not converge--results might be invalid!; try increasing work or maxit")
+    num_col = cds.n_cells_total
+    cds.reduced_dims["LSI"] = res["x"]                          # irlba_res$u %*% diag(irlba_res$d)  :196
+    cds.reduce_dim_aux["LSI"] = {"model": {
+        "num_dim": num_dim, "norm_method": norm_method, "use_genes": use_genes, "pseudo_count": pseudo_count,
+        "log_scale_tf": True, "frequencies": True, "scale_factor": 100000.0,
+        "col_sums": col_sums, "row_sums": row_sums, "num_cols": num_col,
+        "svd_v": res["v"], "svd_v_rownames": cds.gene_names[kept_idx],
+        "svd_sdev": res["d"] / np.sqrt(max(1, num_col - 1)),    # :213
+    }, "irlba": {"iter": res["iter"], "mprod": res["mprod"], "d": res["d"]}}
+    return cds
+
+
 def preprocess_transform(cds, reduction_method="PCA", block_size=None, cores=1):
     """R/projection.R:72-155, PCA branch.  block_size / cores are accepted for signature
     compatibility; the projection is a single sparse product on the device (K10)."""
@@ -231,9 +251,7 @@ def preprocess_transform(cds, reduction_method="PCA", block_size=None, cores=1):
         raise ValueError("One or more cells has a size factor of NA.")
     if cds.reduce_dim_aux.get(reduction_method) is None:
         raise ValueError("Reduction method '%s' is not in the model object." % reduction_method)
-    if reduction_method == "LSI":
-        raise NotImplementedError("the LSI branch is outside this build's scope (SURVEY.md section 8f)")
-    model = cds.reduce_dim_aux["PCA"]["model"]
+    model = cds.reduce_dim_aux[reduction_method]["model"]
     dev = _normalize_on_device(cds, model["norm_method"], model["pseudo_count"])  # :109
     if cds.counts.shape[0] == 0:
         raise ValueError("all rows have standard deviation zero")
@@ -255,6 +273,12 @@ def preprocess_transform(cds, reduction_method="PCA", block_size=None, cores=1):
         if not np.all(keep2):
             raise RuntimeError("internal: filter changed between passes")
         model_row = model_row[model_row >= 0]
-    Y = dev.project(model_row, model["svd_v"], model["svd_center"], model["svd_scale"])
-    cds.reduced_dims["PCA"] = Y
+    if reduction_method == "LSI":
+        # R/projection.R:190-216: the query's own column sums, the MODEL's row_sums / num_cols
+        dev.tfidf(model["frequencies"], model["log_scale_tf"], model["scale_factor"],
+                  row_sums=np.asarray(model["row_sums"])[model_row], num_cols=model["num_cols"])
+        Y = dev.project(model_row, model["svd_v"], None, None)
+    else:
+        Y = dev.project(model_row, model["svd_v"], model["svd_center"], model["svd_scale"])
+    cds.reduced_dims[reduction_method] = Y
     return cds

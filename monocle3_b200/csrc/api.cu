@@ -442,6 +442,7 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
   if (n_kept) *n_kept = m->n_kept;
   m->selected = true;
   m->moments_done = false;
+  m->tfidf_applied = false;
   ctx->stats.spmv_bytes_cells_out = spmv_algorithmic_bytes(m->A);
   ctx->stats.spmv_bytes_genes_out = spmv_algorithmic_bytes(m->B);
   return M3B_OK;
@@ -477,6 +478,13 @@ int m3b_gene_moments(m3b_mat* m, double* center, double* scale) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return M3B_OK;
+}
+
+int m3b_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor, const double* row_sums_in,
+              double num_cols, double* col_sums_out, double* row_sums_out) {
+  if (!m) return M3B_E_DIMS;
+  cudaSetDevice(m->ctx->device);
+  return run_tfidf(m, frequencies, log_scale_tf, scale_factor, row_sums_in, num_cols, col_sums_out, row_sums_out);
 }
 
 int m3b_pca_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol, const double* v0, int center,

@@ -131,6 +131,7 @@ struct m3b_mat {
   double* x = nullptr;     // [nnz] raw counts
   double* y = nullptr;     // [nnz] normalised values (after m3b_normalize)
   bool ended = false, normalized = false, selected = false, moments_done = false;
+  bool tfidf_applied = false;  // the layouts hold TF-IDF values (LSI branch), not the normalised ones
   int norm_method = -1;
   double pseudo_count = 0, f0 = 0;  // f0 = implicit value of the non-stored entries
   // gene selection
@@ -171,7 +172,7 @@ void m3b_mat_set_bbuild(m3b_mat* m, void* p);
 int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* i, const double* x);
 
 // spmv.cu
-enum StreamOp { OP_DOT = 0, OP_SUM = 1, OP_SQDEV = 2 };
+enum StreamOp { OP_DOT = 0, OP_SUM = 1, OP_SQDEV = 2, OP_COUNTPOS = 3 };
 // partial[item] = sum over the item's entries of op(val, x[idx]); x is the dense operand
 // (length L.cols) for OP_DOT, ignored for OP_SUM, the per-row mean for OP_SQDEV.
 int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double* x, cudaStream_t stream = nullptr,
@@ -179,6 +180,10 @@ int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double*
 // out[row] = sum of the row's partials (fixed order: tile, then segment)
 int launch_combine_rows(m3b_ctx* ctx, const TiledLayout& L, double* out);
 long long spmv_algorithmic_bytes(const TiledLayout& L);
+
+// tfidf.cu (LSI branch)
+int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor, const double* row_sums_in,
+              double num_cols, double* col_sums_out, double* row_sums_out);
 
 // irlba.cu
 int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol, const double* v0,

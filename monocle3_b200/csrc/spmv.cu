@@ -41,6 +41,7 @@ template <int OP>
 __device__ __forceinline__ double op_apply(double v, int id, const double* sx, double mu) {
   if (OP == OP_DOT) return v * sx[id];
   if (OP == OP_SUM) return v;
+  if (OP == OP_COUNTPOS) return (v > 0.0) ? 1.0 : 0.0;  // Matrix::rowSums(count_matrix > 0)
   double d = v - mu;  // OP_SQDEV (pad entries are corrected by the caller)
   return d * d;
 }
@@ -223,6 +224,7 @@ int spmv_init(m3b_ctx* ctx) {
   CK(ctx, cudaFuncSetAttribute(k_tile_stream<OP_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(ctx, cudaFuncSetAttribute(k_tile_stream<OP_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(ctx, cudaFuncSetAttribute(k_tile_stream<OP_SQDEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(ctx, cudaFuncSetAttribute(k_tile_stream<OP_COUNTPOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return M3B_OK;
 }
 
@@ -242,6 +244,11 @@ int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double*
       k_tile_stream<OP_SUM><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
                                                                L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
                                                                L.counters);
+      break;
+    case OP_COUNTPOS:
+      k_tile_stream<OP_COUNTPOS><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+                                                                    L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
+                                                                    L.counters);
       break;
     default:
       k_tile_stream<OP_SQDEV><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,

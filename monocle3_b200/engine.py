@@ -192,6 +192,15 @@ class DeviceMatrix:
         self.ctx.check(self.lib.m3b_gene_moments(self.h, _dp(c), _dp(s)))
         return c[:self.n_kept], s[:self.n_kept]
 
+    def tfidf(self, frequencies=True, log_scale_tf=True, scale_factor=100000.0, row_sums=None, num_cols=0):
+        """In-place TF-IDF of the prepared matrix (LSI branch). Returns (col_sums local, row_sums)."""
+        cs = np.empty(max(self.n_cells, 1))
+        rs = np.empty(max(self.n_kept, 1))
+        rin = None if row_sums is None else np.ascontiguousarray(row_sums, dtype=np.float64)
+        self.ctx.check(self.lib.m3b_tfidf(self.h, int(frequencies), int(log_scale_tf), float(scale_factor), _dp(rin),
+                                          float(num_cols), _dp(cs), _dp(rs)))
+        return cs[:self.n_cells], rs[:self.n_kept]
+
     def pca_irlba(self, nv, v0, center=True, scale=True, work=0, maxit=1000, tol=1e-5, svtol=None, want_x=True):
         """Returns dict(d, v, x, center, scale, iter, mprod, status)."""
         n = self.n_kept

@@ -170,6 +170,69 @@ def preprocess_cds(counts, sf, num_dim=50, norm_method="log", use_genes_idx=None
                 iter=res["iter"], mprod=res["mprod"], err=res["err"])
 
 
+def tfidf(FM, frequencies=True, log_scale_tf=True, scale_factor=100000.0):
+    """R/preprocess_cds.R:289-338 ("Andrew's tfidf") on a genes x cells csc matrix."""
+    FM = FM.tocsc().astype(np.float64)
+    num_cols = FM.shape[1]
+    if frequencies:
+        col_sums = np.asarray(FM.sum(axis=0)).ravel()
+        tf = FM.copy()
+        tf.data = tf.data / np.repeat(col_sums, np.diff(tf.indptr))  # t(t(count_matrix) / col_sums)
+    else:
+        col_sums = None
+        tf = FM.copy()
+    if log_scale_tf:
+        tf.data = np.log1p(tf.data * (scale_factor if frequencies else 1.0))
+    row_sums = np.asarray((FM > 0).sum(axis=1)).ravel().astype(np.float64)  # Matrix::rowSums(count_matrix > 0)
+    with np.errstate(divide="ignore"):
+        idf = np.log(1.0 + num_cols / row_sums)
+    out = sp.diags(idf) @ tf  # tf * idf recycles idf down the rows
+    return dict(tf_idf_counts=out.tocsc(), frequencies=frequencies, log_scale_tf=log_scale_tf,
+                scale_factor=scale_factor, col_sums=col_sums, row_sums=row_sums, num_cols=num_cols)
+
+
+def preprocess_cds_lsi(counts, sf, num_dim=50, norm_method="log", use_genes_idx=None, pseudo_count=None,
+                       v0=None, **irlba_args):
+    """LSI branch of R/preprocess_cds.R:185-241: TF-IDF then irlba without centre/scale."""
+    FM = normalize_expr_data(counts, sf, norm_method, pseudo_count)
+    if not sp.issparse(FM):
+        raise NotImplementedError("dense pseudo-count path with LSI")
+    FM, kept = select_and_filter_genes(FM, use_genes_idx)
+    t = tfidf(FM)
+    At = t["tf_idf_counts"].T.tocsc()
+    num_col = At.shape[1]  # R: num_col <- ncol(preproc_res) = number of CELLS of the genes x cells matrix
+    num_col = t["tf_idf_counts"].shape[1]
+    n = min(num_dim, min(FM.shape) - 1)
+    if v0 is None:
+        v0 = RRandom(2016).rnorm(At.shape[1])
+    s = irlba_ref.irlba(At, n, v0, **irlba_args)
+    if s.err not in (0, -2):
+        raise RuntimeError("irlba error %d" % s.err)
+    return dict(LSI=s.u * s.d[None, :], svd_v=s.v, svd_sdev=s.d / np.sqrt(max(1, num_col - 1)),
+                col_sums=t["col_sums"], row_sums=t["row_sums"], num_cols=t["num_cols"], kept_genes=kept,
+                frequencies=True, log_scale_tf=True, scale_factor=100000.0, norm_method=norm_method,
+                pseudo_count=pseudo_count, d=s.d, iter=s.iter, mprod=s.mprod)
+
+
+def preprocess_transform_lsi(counts, sf, model, gene_index_in_model):
+    """LSI branch of R/projection.R:156-241: the query's own column sums, the MODEL's idf."""
+    FM = normalize_expr_data(counts, sf, model["norm_method"], model.get("pseudo_count"))
+    rs = np.asarray(FM.sum(axis=1)).ravel()
+    keep = np.isfinite(rs) & (rs != 0)
+    gidx = np.asarray(gene_index_in_model)
+    q_rows = np.nonzero(keep & (gidx >= 0))[0]
+    order = np.argsort(gidx[q_rows], kind="stable")
+    q_rows = q_rows[order]
+    m_rows = gidx[q_rows]
+    F = FM.tocsr()[q_rows, :].tocsc()
+    cs = np.asarray(F.sum(axis=0)).ravel()
+    tf = F.copy()
+    tf.data = np.log1p(tf.data / np.repeat(cs, np.diff(tf.indptr)) * model["scale_factor"])
+    idf = np.log(1.0 + model["num_cols"] / model["row_sums"])[m_rows]
+    X = (sp.diags(idf) @ tf).T
+    return np.asarray(X @ model["svd_v"][m_rows, :])
+
+
 def preprocess_transform(counts, sf, model, gene_index_in_model):
     """PCA branch of R/projection.R:102-149.
 

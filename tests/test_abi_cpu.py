@@ -98,7 +98,9 @@ def test_host_argument_checks_need_no_device():
     with pytest.raises(ValueError, match="estimate_size_factors"):
         m3.preprocess_cds(cds)          # no Size_Factor column yet
     with pytest.raises(NotImplementedError):
-        m3.preprocess_cds(cds, method="LSI")
+        m3.set_size_factors(cds, np.ones(5))
+        m3.preprocess_cds(cds, build_nn_index=True)
+    m3.set_size_factors(cds, None)
     with pytest.raises(ValueError, match="reduction_method"):
         m3.preprocess_transform(cds, reduction_method="UMAP")
     m3.set_size_factors(cds, np.ones(5))

@@ -338,3 +338,36 @@ def test_full_size_properties(m3):
         u = X[:, i] / d[i]
         f = (A.T @ u) / s - np.sum(u) * c / s
         assert np.linalg.norm(f - d[i] * V[:, i]) < 1e-4 * d[0]
+
+
+def test_lsi_branch(m3, a549):
+    """LSI branch (tfidf + irlba without centre/scale) against the oracle and the reference's
+    goldens, tests/testthat/test-preprocessing.R:13-16,54-61, and the LSI transform equality of
+    tests/testthat/test-projection.R:32-34."""
+    from monocle3_b200 import engine
+    counts, extra = a549
+    m3.set_context(engine.Context(device=0, small_svd="lapack"))
+    cds = _cds(m3, counts, extra)
+    cds = m3.preprocess_cds(cds, method="LSI", num_dim=20)
+    o = ref.preprocess_cds_lsi(counts, m3.size_factors(cds), num_dim=20)
+    model, ir = cds.reduce_dim_aux["LSI"]["model"], cds.reduce_dim_aux["LSI"]["irlba"]
+    assert (ir["iter"], ir["mprod"]) == (o["iter"], o["mprod"])
+    assert sv_rel_err(ir["d"], o["d"]) < SV_TOL
+    assert subspace_angle(model["svd_v"], o["svd_v"]) < ANGLE_TOL
+    assert subspace_angle(cds.reduced_dims["LSI"], o["LSI"]) < ANGLE_TOL
+    np.testing.assert_allclose(model["col_sums"], o["col_sums"], rtol=1e-13)
+    assert np.array_equal(model["row_sums"], o["row_sums"])               # exact counts
+    assert cds.reduced_dims["LSI"][0, 0] == pytest.approx(13.73796, abs=1e-5)   # test-preprocessing.R:16
+    assert model["col_sums"][0] == pytest.approx(18.7, abs=1e-1)                 # :58
+    assert model["row_sums"][0] == pytest.approx(467, abs=1)                     # :59
+    assert model["svd_v"][0, 0] == pytest.approx(0.16318, abs=1e-3)              # :60
+    assert model["svd_sdev"][0] == pytest.approx(32.21, abs=1e-2)                # :61
+    for nm, gold in (("size_only", 13.49733), ("none", 13.49733)):                # :28, :40
+        c2 = m3.preprocess_cds(_cds(m3, counts, extra), method="LSI", num_dim=20, norm_method=nm)
+        assert c2.reduced_dims["LSI"][0, 0] == pytest.approx(gold, abs=1e-5)
+    # transform of the same cells == embedding
+    cds50 = m3.preprocess_cds(_cds(m3, counts, extra), method="LSI", num_dim=50)
+    q = _cds(m3, counts, extra)
+    q.reduce_dim_aux = {"LSI": cds50.reduce_dim_aux["LSI"]}
+    q = m3.preprocess_transform(q, reduction_method="LSI")
+    assert np.abs(q.reduced_dims["LSI"] - cds50.reduced_dims["LSI"]).max() < 1e-8

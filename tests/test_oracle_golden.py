@@ -105,3 +105,26 @@ def test_zero_read_cell_guard(a549):
     c = counts.tolil()
     c[:, 3] = 0
     assert ref.estimate_size_factors(c.tocsc()) is None  # R/utils.R:32-39
+
+
+def test_lsi_goldens(cds):
+    """LSI branch: tests/testthat/test-preprocessing.R:13-16,24-28,36-40,54-61."""
+    counts, sf, _ = cds
+    r = ref.preprocess_cds_lsi(counts, sf, num_dim=20)
+    assert r["LSI"].shape == (500, 20)
+    assert r["LSI"][0, 0] == pytest.approx(13.73796, abs=1e-5)          # test-preprocessing.R:16
+    assert r["col_sums"][0] == pytest.approx(18.7, abs=1e-1)            # :58
+    assert r["row_sums"][0] == pytest.approx(467, abs=1)                # :59
+    assert r["svd_v"][0, 0] == pytest.approx(0.16318, abs=1e-3)         # :60
+    assert r["svd_sdev"][0] == pytest.approx(32.21, abs=1e-2)           # :61
+    r2 = ref.preprocess_cds_lsi(counts, sf, num_dim=20, norm_method="size_only")
+    assert r2["LSI"][0, 0] == pytest.approx(13.49733, abs=1e-5)         # :28
+    r3 = ref.preprocess_cds_lsi(counts, sf, num_dim=20, norm_method="none")
+    assert r3["LSI"][0, 0] == pytest.approx(13.49733, abs=1e-5)         # :40
+    # test-projection.R:32-34: transform of the same cells reproduces the LSI embedding
+    r50 = ref.preprocess_cds_lsi(counts, sf, num_dim=50)
+    gidx = np.full(counts.shape[0], -1)
+    gidx[r50["kept_genes"]] = np.arange(len(r50["kept_genes"]))
+    y = ref.preprocess_transform_lsi(counts, sf, r50, gidx)
+    for (a, b) in ((0, 0), (1, 0), (0, 1)):
+        assert y[a, b] == pytest.approx(r50["LSI"][a, b], abs=1e-6)
