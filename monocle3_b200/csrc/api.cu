@@ -1,6 +1,7 @@
 // extern "C" entry points of libm3b.so (declared in include/m3b.h).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -101,6 +102,10 @@ int m3b_create(int device, int flags, m3b_ctx** out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (const char* e = getenv("M3B_TILE_W")) {  // tuning knob (multiple of 32, <= 28672)
+    int v = atoi(e);
+    if (v >= 32 && v <= M3B_TILE_W_MAX) ctx->tile_w_max = v & ~31;
+  }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||

@@ -462,16 +462,16 @@ static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T) {
   return M3B_OK;
 }
 
-static void choose_tiling(long long cols, int* tile_w, int* n_tiles) {
+static void choose_tiling(long long cols, int tile_w_max, int* tile_w, int* n_tiles) {
   if (cols <= 0) {
     *tile_w = 32;
     *n_tiles = 1;
     return;
   }
-  int nt = (int)((cols + M3B_TILE_W_MAX - 1) / M3B_TILE_W_MAX);
+  int nt = (int)((cols + tile_w_max - 1) / tile_w_max);
   long long tw = (cols + nt - 1) / nt;
   tw = (tw + 31) & ~31LL;
-  if (tw > M3B_TILE_W_MAX) tw = M3B_TILE_W_MAX;
+  if (tw > tile_w_max) tw = tile_w_max;
   *tile_w = (int)tw;
   *n_tiles = (int)((cols + tw - 1) / tw);
 }
@@ -577,7 +577,7 @@ int build_layout_B(m3b_mat* m) {
   const int n_sel = m->n_sel;
   L.rows = n_sel;
   L.cols = m->n_cells;
-  choose_tiling(L.cols, &L.tile_w, &L.n_tiles);
+  choose_tiling(L.cols, ctx->tile_w_max, &L.tile_w, &L.n_tiles);
   const int n_tiles = L.n_tiles;
   int cpt = (int)std::max<long long>(1, std::min<long long>((4096 + n_tiles - 1) / n_tiles, (L.tile_w + 7) / 8));
   // bound the cursor table to ~1.5 GB
@@ -765,7 +765,7 @@ int build_layout_A(m3b_mat* m) {
   L.free_all();
   L.rows = m->n_cells;
   L.cols = m->n_kept;
-  choose_tiling(L.cols, &L.tile_w, &L.n_tiles);
+  choose_tiling(L.cols, ctx->tile_w_max, &L.tile_w, &L.n_tiles);
   dev_free(m->kept_of_gene);
   RET(dev_alloc(ctx, &m->kept_of_gene, (size_t)std::max(m->n_genes, 1)));
   if (m->n_genes) {

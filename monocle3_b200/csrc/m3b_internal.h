@@ -48,6 +48,12 @@ void comm_destroy(m3b_ctx* ctx);
 int comm_allreduce_f64(m3b_ctx* ctx, double* dev, size_t n);
 int comm_allreduce_i64(m3b_ctx* ctx, long long* dev, size_t n);
 
+#define M3B_TILE_W_MAX 28672  // 224 KB of doubles: the most a CTA can stage
+// Default tile width.  The full 224 KB leaves the SM no L1: the streaming loads of the
+// product kernel are then throttled for lack of line buffers (ncu: lg_throttle, DRAM 56% vs 75%
+// for the same kernel with a 120 KB tile; profiles/).  160 KB tiles leave ~60 KB of L1 (sweep in DESIGN.md).
+#define M3B_TILE_W_DEFAULT 20480
+
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
@@ -56,6 +62,7 @@ struct m3b_ctx {
   int flags = 0;
   int sm_count = 148;
   size_t smem_optin = 0;
+  int tile_w_max = M3B_TILE_W_DEFAULT;  // columns per shared-memory tile of the dense operand
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream: next cycle's first product runs under the restart SVD
   std::string err;
@@ -86,7 +93,6 @@ struct m3b_ctx {
 //   12 B/entry of an int32-indexed CSR.  An ITEM is one run (or
 //   a <= M3B_ITEM_MAX slice of a long run): the unit of work of one warp.
 // ---------------------------------------------------------------------------
-#define M3B_TILE_W_MAX 28672  // 224 KB of doubles in shared memory
 #define M3B_ITEM_MAX 2048     // entries per item (multiple of 128)
 #define M3B_ITEM_TAIL 512     // entries per item in the last part of a tile (short tail of the launch)
 
