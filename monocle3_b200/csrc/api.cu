@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -419,11 +420,15 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
     }
     sel_of_gene[g] = s;
   }
+  const bool dbg = getenv("M3B_DEBUG_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   m->n_sel = n_sel;
   dev_free(m->sel_of_gene);
   RET(dev_alloc(ctx, &m->sel_of_gene, sel_of_gene.size()));
   CK(ctx, cudaMemcpyAsync(m->sel_of_gene, sel_of_gene.data(), sel_of_gene.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   RET(build_layout_B(m));
+  const double t1 = now();
   // global row sums of the (implicit dense) normalised matrix -> zero / non-finite filter
   dev_free(m->rowsum);
   RET(dev_alloc(ctx, &m->rowsum, (size_t)std::max(n_sel, 1)));
@@ -441,8 +446,13 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
     double v = rs[s] + (double)m->n_cells_total * m->f0;
     kp[s] = (std::isfinite(v) && v != 0.0) ? 1 : 0;  // R/preprocess_cds.R:121-122
   }
+  const double t2 = now();
   RET(finish_selection(m, kp.data()));
+  const double t3 = now();
   RET(build_layout_A(m));
+  if (dbg)
+    fprintf(stderr, "m3b_select_genes: layout B %.2f ms, row sums %.2f ms, remap %.2f ms, layout A %.2f ms\n", t1 - t0,
+            t2 - t1, t3 - t2, now() - t3);
   if (keep) memcpy(keep, kp.data(), n_sel);
   if (n_kept) *n_kept = m->n_kept;
   m->selected = true;

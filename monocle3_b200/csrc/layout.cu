@@ -5,7 +5,9 @@
 // Matrix::rowSums filter (R/preprocess_cds.R:117-122) and the Matrix::t()
 // materialisation handed to irlba (R/preprocess_cds.R:139).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "m3b_internal.h"
@@ -570,8 +572,14 @@ void m3b_mat_set_bbuild(m3b_mat* m, void* p) {
   m->b_host_tables = p;
 }
 
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int build_layout_B(m3b_mat* m) {
   m3b_ctx* ctx = m->ctx;
+  const bool dbg = getenv("M3B_DEBUG_TIMING") != nullptr;
+  const double tb0 = now_ms();
   TiledLayout& L = m->B;
   L.free_all();
   const int n_sel = m->n_sel;
@@ -605,9 +613,11 @@ int build_layout_B(m3b_mat* m) {
   std::vector<int> cnt((size_t)n_runs);
   if (n_runs) CK(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
+  const double tb1 = now_ms();
   HostTables T;
   compute_bases(cnt, n_tiles, n_sel, T);
   build_items(cnt, n_tiles, n_sel, nullptr, n_sel, ctx->sm_count, T);
+  const double tb2 = now_ms();
   L.n_entries = T.n_entries;
   RET(dev_alloc(ctx, &L.idx, (size_t)T.n_entries));
   RET(dev_alloc(ctx, &L.val, (size_t)T.n_entries));
@@ -623,7 +633,12 @@ int build_layout_B(m3b_mat* m) {
     }
   }
   CK(ctx, cudaGetLastError());
+  if (dbg) CK(ctx, cudaStreamSynchronize(ctx->stream));
+  const double tb3 = now_ms();
   RET(upload_tables(ctx, L, T));
+  if (dbg)
+    fprintf(stderr, "  layout B: count+scan %.2f ms (chunks %lld x %d), host tables %.2f ms, scatter %.2f ms, upload %.2f ms\n",
+            tb1 - tb0, n_chunks, n_sel, tb2 - tb1, tb3 - tb2, now_ms() - tb3);
   // exact nnz per selected gene (local shard)
   std::vector<long long> nnz_sel(n_sel, 0);
   for (int t = 0; t < n_tiles; ++t)
