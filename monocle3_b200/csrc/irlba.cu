@@ -444,20 +444,31 @@ __global__ void k_transpose_small(const double* __restrict__ in, int n, double* 
 
 // --------------------------------------------------------------------------
 // K9: in-place tall-skinny GEMM  X[:, :kout] = X[:, :kin] * Q   (Q: kin x kout, ld kin)
+// on the fp64 tensor-core path (DMMA, mma.sync.m8n8k4.f64) -- the one GEMM-shaped
+// operation of this path, and the only tensor-core use: tcgen05 has no fp64 kind.
 //
-// Persistent CTAs (one per SM, 256 threads).  Q is staged once per CTA in shared memory as
-// Qs[col][kinp]; the CTA then walks 64-row blocks of X, each staged TRANSPOSED as Xs[row][kinp]
-// with 8-byte cp.async (double-buffered: block i+1 lands while block i is multiplied), so the
-// update can be done in place (a block's rows are fully in shared memory before its outputs
-// are written).  kinp is padded so that kinp % 4 == 2: the 16-byte shared loads of two
-// consecutive k for 8 different rows then hit 8 different bank groups.  Thread = 2 rows x 13
-// columns of accumulators; per two k-steps it issues 2 + 13 LDS.128 and 52 DFMA.
-// (First cut, profiles/: 4.3 instructions per DFMA, fp64 pipe 25% busy, 2.2 waves of 1-CTA/SM
-// blocks.)
+// Why tensor cores here: the FMA version of this kernel (round 1, profiles/
+// r01_full_k_restart_gemm.txt) kept the fp64 pipe 36% busy and was bound by instruction
+// issue and shared-memory operand traffic (67 instructions and 7.7 KB of LDS per 1664 FMA
+// per warp); one DMMA does 256 FMA from two 8-byte operands per lane, i.e. ~6.5x fewer
+// instructions and 8x less shared-memory traffic for the same flops.
+//
+// Persistent CTAs (one per SM, 128 threads = 4 warps).  Q is staged once per CTA as
+// Qs[col][kinp]; the CTA walks 64-row blocks of X, each staged TRANSPOSED as Xs[row][kinp]
+// with 8-byte cp.async, double-buffered (block i+1 lands while block i is multiplied), so the
+// update can be done in place: a block's rows are complete in shared memory before its
+// outputs are written.  16 warps = 4 row groups (16 rows) x 4 column groups (fragments cg,
+// cg+4, ...): per k-step of 4 a warp loads 2 A and <= 4 B fragments (one LDS.64 per lane each)
+// and issues <= 8 DMMAs; 4 warps per scheduler hide the DMMA latency (with 4 warps per SM the
+// tensor pipe was 29% busy, profiles/).  kinp is padded to
+// kinp % 16 == 4 doubles so that the 8 rows (or columns) of a fragment land on disjoint banks.
 // --------------------------------------------------------------------------
-#define GEMM_CT 13
 #define GEMM_RB 64
-#define GEMM_CPP (8 * GEMM_CT)  // columns per pass = 104
+#define GEMM_NF 13                 // B fragments (8 columns each) per pass
+#define GEMM_CPP (8 * GEMM_NF)     // columns per pass = 104
+#define GEMM_NCG 4                 // column groups: warps = 4 row groups x GEMM_NCG
+#define GEMM_THREADS (128 * GEMM_NCG)
+#define GEMM_FPW ((GEMM_NF + GEMM_NCG - 1) / GEMM_NCG)  // fragments per warp (max)
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -467,6 +478,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ void gemm_stage_rows(double* Xs, const double* X, long long ld, long long rows, long long r0,
@@ -479,21 +495,20 @@ __device__ __forceinline__ void gemm_stage_rows(double* Xs, const double* X, lon
   }
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_restart_gemm(double* __restrict__ X, long long ld, long long rows, int kin, int kinp, int kout,
                const double* __restrict__ Q, int nbuf) {
   extern __shared__ double smg[];
   double* Qs = smg;                               // [GEMM_CPP][kinp]
   double* Xs0 = smg + (size_t)GEMM_CPP * kinp;    // [GEMM_RB][kinp] x nbuf
-  const int rl = threadIdx.x & 31;                // rows rl, rl + 32
-  const int cg = threadIdx.x >> 5;                // column group 0..7
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;      // fragment coordinates
   const long long nblk = (rows + GEMM_RB - 1) / GEMM_RB;
   const int npass = (kout + GEMM_CPP - 1) / GEMM_CPP;
-  // zero the k padding once (never written by the staging)
-  for (int e = threadIdx.x; e < (GEMM_CPP + nbuf * GEMM_RB) * (kinp - kin); e += blockDim.x) {
-    const int row = e / (kinp - kin), k = kin + e % (kinp - kin);
-    smg[(size_t)row * kinp + k] = 0.0;
-  }
+  const int ksteps = (kin + 3) >> 2;              // 4 * ksteps <= kinp
+  // zero the k padding once (never written by the staging) -- also rows of Xs that stay unloaded
+  for (int e = threadIdx.x; e < (GEMM_CPP + nbuf * GEMM_RB) * kinp; e += blockDim.x) smg[e] = 0.0;
+  __syncthreads();
   auto stage_q = [&](int pass) {
     const int c0 = pass * GEMM_CPP;
     for (int e = threadIdx.x; e < GEMM_CPP * kin; e += blockDim.x) {
@@ -517,39 +532,45 @@ k_restart_gemm(double* __restrict__ X, long long ld, long long rows, int kin, in
       cp_async_wait<0>();
     }
     __syncthreads();
-    const long long r0 = blk * GEMM_RB;
+    const int rg = warp & 3, cg = warp >> 2;            // row group, column group
+    const long long r0 = blk * GEMM_RB + rg * 16;       // this warp's 16 rows
+    const double* xa0 = Xs + (size_t)(rg * 16 + gid) * kinp + tig;  // A fragment, rows 0-7
+    const double* xa1 = xa0 + (size_t)8 * kinp;                     // rows 8-15
     for (int pass = 0; pass < npass; ++pass) {
       if (npass > 1) {
         __syncthreads();
         stage_q(pass);
         __syncthreads();
       }
-      double acc0[GEMM_CT], acc1[GEMM_CT];
+      double c[2][GEMM_FPW][2];
 #pragma unroll
-      for (int b = 0; b < GEMM_CT; ++b) acc0[b] = acc1[b] = 0.0;
-      const double2* x0 = reinterpret_cast<const double2*>(Xs + (size_t)rl * kinp);
-      const double2* x1 = reinterpret_cast<const double2*>(Xs + (size_t)(rl + 32) * kinp);
-      const double2* qb = reinterpret_cast<const double2*>(Qs + (size_t)cg * kinp);
-      const int kq = kinp >> 1;  // double2 per row
+      for (int f = 0; f < GEMM_FPW; ++f) c[0][f][0] = c[0][f][1] = c[1][f][0] = c[1][f][1] = 0.0;
+      // B fragment slot f of this warp: fragment cg + GEMM_NCG f, i.e. column 8 (cg + NCG f) + gid
+      const double* qb = Qs + (size_t)(8 * cg + gid) * kinp + tig;
 #pragma unroll 2
-      for (int k2 = 0; k2 < kq; ++k2) {
-        const double2 a = x0[k2], c = x1[k2];
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const double a0 = xa0[4 * ks], a1 = xa1[4 * ks];
 #pragma unroll
-        for (int b = 0; b < GEMM_CT; ++b) {
-          const double2 q = qb[(size_t)b * 8 * kq + k2];  // column cg + 8 b
-          acc0[b] += a.x * q.x;
-          acc0[b] += a.y * q.y;
-          acc1[b] += c.x * q.x;
-          acc1[b] += c.y * q.y;
+        for (int f = 0; f < GEMM_FPW; ++f) {
+          if (cg + GEMM_NCG * f < GEMM_NF) {  // warp-uniform
+            const double b = qb[(size_t)f * 8 * GEMM_NCG * kinp + 4 * ks];
+            dmma_m8n8k4(c[0][f][0], c[0][f][1], a0, b);
+            dmma_m8n8k4(c[1][f][0], c[1][f][1], a1, b);
+          }
         }
       }
-      const int cbase = pass * GEMM_CPP + cg;
+      // C fragment: row gid (+8), columns 8 (cg + NCG f) + 2 tig + {0,1}
 #pragma unroll
-      for (int b = 0; b < GEMM_CT; ++b) {
-        const int c = cbase + 8 * b;
-        if (c < kout) {
-          if (r0 + rl < rows) X[(long long)c * ld + r0 + rl] = acc0[b];
-          if (r0 + rl + 32 < rows) X[(long long)c * ld + r0 + rl + 32] = acc1[b];
+      for (int f = 0; f < GEMM_FPW; ++f) {
+        if (cg + GEMM_NCG * f < GEMM_NF) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = pass * GEMM_CPP + 8 * (cg + GEMM_NCG * f) + 2 * tig + h;
+            if (col < kout) {
+              if (r0 + gid < rows) X[(long long)col * ld + r0 + gid] = c[0][f][h];
+              if (r0 + gid + 8 < rows) X[(long long)col * ld + r0 + gid + 8] = c[1][f][h];
+            }
+          }
         }
       }
     }
@@ -698,8 +719,8 @@ struct Irlba {
   int gemm_inplace(double* X, long long ld, long long rows, int kin, int kout, const double* Qd) {
     if (rows == 0 || kout == 0) return M3B_OK;
     const size_t budget = 224 * 1024;
-    int kinp = kin + 1;
-    while ((kinp & 3) != 2) ++kinp;  // kinp % 4 == 2: conflict-free 16-byte row loads
+    int kinp = ((kin + 3) & ~3);
+    while ((kinp & 15) != 4) kinp += 4;  // kinp % 16 == 4: the 8 rows of a fragment hit disjoint banks
     int nbuf = 2;
     size_t smem = (size_t)(GEMM_CPP + nbuf * GEMM_RB) * kinp * sizeof(double);
     if (smem > budget) {
@@ -707,12 +728,12 @@ struct Irlba {
       smem = (size_t)(GEMM_CPP + GEMM_RB) * kinp * sizeof(double);
     }
     if (smem > budget) {
-      m3b_set_error(ctx, "restart GEMM: work=%d too large for the shared-memory tiling (max ~165)", kin);
+      m3b_set_error(ctx, "restart GEMM: work=%d too large for the shared-memory tiling (max ~160)", kin);
       return M3B_E_DIMS;
     }
     const long long nblk = (rows + GEMM_RB - 1) / GEMM_RB;
     const unsigned grid = (unsigned)std::min<long long>(nblk, ctx->sm_count);
-    k_restart_gemm<<<grid, 256, smem, ctx->stream>>>(X, ld, rows, kin, kinp, kout, Qd, nbuf);
+    k_restart_gemm<<<grid, GEMM_THREADS, smem, ctx->stream>>>(X, ld, rows, kin, kinp, kout, Qd, nbuf);
     count_launch(ctx);
     CK(ctx, cudaGetLastError());
     return M3B_OK;
