@@ -659,6 +659,8 @@ int build_layout_B(m3b_mat* m) {
   return M3B_OK;
 }
 
+static int bank_reorder(m3b_ctx* ctx, TiledLayout& L);
+
 // After the keep mask is known: re-map B's items to kept rows (no data movement).
 int finish_selection(m3b_mat* m, unsigned char* keep_host) {
   m3b_ctx* ctx = m->ctx;
@@ -696,6 +698,121 @@ int finish_selection(m3b_mat* m, unsigned char* keep_host) {
   CK(ctx, cudaMemcpyAsync(m->kept_padlen, padk.data(), std::max(nk, 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   m3b_mat_set_bbuild(m, nullptr);
+  RET(bank_reorder(ctx, m->B));
+  return M3B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Bank-aware ordering of the entries inside an item.
+//
+// The product kernel gathers x[idx] from shared memory with one 8-byte load per entry; lane l
+// of a warp reads the entries 2(q0+l) and 2(q0+l)+1 of the item.  With the entries in index
+// order the 16 lanes of a half-warp hit random bank pairs: ncu counted ~7 shared-memory
+// wavefronts per 32-lane gather where 2 are the minimum (profiles/).  The order of the entries
+// inside a row is free (it only fixes the summation order), so each item is permuted once at
+// build time such that the entry at position p has  idx mod 16 == (p >> 1) mod 16  wherever the
+// item has enough entries of that class: consecutive lanes then read 16 different bank pairs.
+// Entries of over-full classes fill the holes of under-full ones, in a fixed order, so the
+// layout stays deterministic.  One warp per item, staged through shared memory.
+// ---------------------------------------------------------------------------
+#define BR_WARPS 5
+#define BR_MAX M3B_ITEM_MAX
+
+__global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* __restrict__ idx, double* __restrict__ val,
+                                                               const ItemDesc* __restrict__ items, long long n_items) {
+  extern __shared__ unsigned char br_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // per-warp staging: source idx/val, destination position of every entry, hole list
+  unsigned char* base = br_smem + (size_t)warp * (BR_MAX * (2 + 8 + 2 + 2) + 256);
+  double* sval = reinterpret_cast<double*>(base);
+  unsigned short* sidx = reinterpret_cast<unsigned short*>(base + BR_MAX * 8);
+  unsigned short* dpos = sidx + BR_MAX;   // destination position of source entry e
+  unsigned short* hole = dpos + BR_MAX;   // positions of the holes, in class order
+  int* cnt = reinterpret_cast<int*>(hole + BR_MAX);  // [16] entries per class, then scratch [16..63]
+  const unsigned lt = (1u << lane) - 1u;
+  for (long long it = (long long)blockIdx.x * BR_WARPS + warp; it < n_items; it += (long long)gridDim.x * BR_WARPS) {
+    const ItemDesc d = items[it];
+    const int len = d.len;
+    if (len < 64 || len > BR_MAX) continue;  // too short to matter (or unexpected)
+    for (int e = lane; e < len; e += 32) {
+      sidx[e] = idx[d.start + e];
+      sval[e] = val[d.start + e];
+    }
+    if (lane < 32) cnt[lane] = 0, cnt[32 + lane] = 0;
+    __syncwarp();
+    // stable rank of every entry inside its class
+    for (int e0 = 0; e0 < len; e0 += 32) {
+      const int e = e0 + lane;
+      const bool in = e < len;
+      const int b = in ? (sidx[e] & 15) : 16 + (lane & 15);  // out-of-range lanes use dummy classes
+      const unsigned peers = __match_any_sync(0xffffffffu, b);
+      const int before = __popc(peers & lt);
+      int basec = 0;
+      if (in) basec = cnt[b];
+      __syncwarp();
+      if (in) {
+        dpos[e] = (unsigned short)(basec + before);  // rank for now
+        if (before == __popc(peers) - 1) cnt[b] = basec + __popc(peers);  // the last peer publishes
+      }
+      __syncwarp();
+    }
+    // native slots of class b inside len: positions p < len with ((p >> 1) & 15) == b
+    // nat[b] = 2 * floor(len / 32) + min(2, max(0, (len % 32) - 2 b))
+    int natb = 0, cntb = 0;
+    if (lane < 16) {
+      const int r = len & 31;
+      natb = 2 * (len >> 5) + min(2, max(0, r - 2 * lane));
+      cntb = cnt[lane];
+    }
+    const int over = max(0, cntb - natb), holes = max(0, natb - cntb);
+    // exclusive prefix sums over the 16 classes (lanes 0..15)
+    int po = over, ph = holes;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, po, o), h = __shfl_up_sync(0xffffffffu, ph, o);
+      if (lane >= o) {
+        po += a;
+        ph += h;
+      }
+    }
+    po -= over;
+    ph -= holes;
+    if (lane < 16) {
+      cnt[16 + lane] = natb;      // nat
+      cnt[32 + lane] = po;        // overflow prefix
+      // enumerate this class's holes: slots cntb .. natb-1
+      for (int s2 = cntb; s2 < natb; ++s2) hole[ph + (s2 - cntb)] = (unsigned short)(32 * (s2 >> 1) + 2 * lane + (s2 & 1));
+    }
+    __syncwarp();
+    for (int e = lane; e < len; e += 32) {
+      const int b = sidx[e] & 15, r = dpos[e], nb = cnt[16 + b];
+      int p;
+      if (r < nb) p = 32 * (r >> 1) + 2 * b + (r & 1);
+      else p = hole[cnt[32 + b] + (r - nb)];
+      dpos[e] = (unsigned short)p;
+    }
+    __syncwarp();
+    for (int e = lane; e < len; e += 32) {
+      const int p = dpos[e];
+      idx[d.start + p] = sidx[e];
+      val[d.start + p] = sval[e];
+    }
+    __syncwarp();
+  }
+}
+
+static int bank_reorder(m3b_ctx* ctx, TiledLayout& L) {
+  if (L.n_items == 0 || getenv("M3B_NO_BANK_REORDER")) return M3B_OK;
+  const size_t smem = (size_t)BR_WARPS * (BR_MAX * (2 + 8 + 2 + 2) + 256);
+  static bool attr = false;
+  if (!attr) {
+    CK(ctx, cudaFuncSetAttribute(k_bank_reorder, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const unsigned grid = (unsigned)std::min<long long>((L.n_items + BR_WARPS - 1) / BR_WARPS, (long long)ctx->sm_count * 4);
+  k_bank_reorder<<<grid, 32 * BR_WARPS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.n_items);
+  count_launch(ctx);
+  CK(ctx, cudaGetLastError());
   return M3B_OK;
 }
 
@@ -815,6 +932,7 @@ int build_layout_A(m3b_mat* m) {
   }
   CK(ctx, cudaGetLastError());
   RET(upload_tables(ctx, L, T));
+  RET(bank_reorder(ctx, L));
   dev_free(d_cnt);
   dev_free(d_base);
   return M3B_OK;
