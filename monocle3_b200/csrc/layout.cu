@@ -485,24 +485,39 @@ static void choose_tiling(long long cols, int tile_w_max, int* tile_w, int* n_ti
 // per-(chunk,row) cursor hands out slots in cell order => the transpose is
 // deterministic and every gene row is sorted by cell.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count_B(const long long* __restrict__ p, const int* __restrict__ gi,
-                                                 const int* __restrict__ sel_of_gene, int n_sel, int tile_w,
-                                                 int chunks_per_tile, int cells_per_chunk, long long n_cells,
-                                                 long long n_chunks, int* __restrict__ H) {
-  const int lane = threadIdx.x & 31;
-  long long chunk = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (chunk >= n_chunks) return;
-  long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
-  long long c0 = t * tile_w + s * cells_per_chunk;
-  long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
-  int* Hc = H + chunk * n_sel;
-  for (long long c = c0; c < c1; ++c) {
-    const long long lo = p[c], hi = p[c + 1];
-    for (long long k = lo + lane; k < hi; k += 32) {
-      int r = sel_of_gene[ld_stream_s32(gi + k)];
-      if (r >= 0) atomicAdd(Hc + r, 1);
+#define TB_THREADS 512
+#define TB_WARPS (TB_THREADS / 32)
+#define TB_GSEG_MAX 24576  // most selected rows per pass: 96 KB of cursors + 96 KB of cell masks in shared memory
+// Rows per pass (M3B_GSEG overrides).  Smaller passes were tried to keep the partially written
+// output sectors L2-resident; the extra passes over the index array cost more than they saved
+// (cfg3 shape: 1024/2048/4096/8192/24576 rows => 405/212/122/75/56 ms), so one pass takes as many
+// rows as shared memory holds.
+#define TB_GSEG_DEFAULT 24576
+
+// A CHUNK is a run of consecutive cells of one tile, owned by ONE CTA.  Pass 1 counts the
+// chunk's entries per selected row in a shared-memory histogram (rows [g0, g1) of this pass).
+__global__ void __launch_bounds__(TB_THREADS) k_count_B(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                        const int* __restrict__ sel_of_gene, int n_sel, int g0, int g1,
+                                                        int tile_w, int chunks_per_tile, int cells_per_chunk,
+                                                        long long n_cells, int* __restrict__ H) {
+  extern __shared__ int hist[];
+  const long long chunk = blockIdx.x;
+  const long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
+  const long long c0 = min(t * tile_w + s * (long long)cells_per_chunk, n_cells);
+  const long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
+  const int ng = g1 - g0;
+  for (int r = threadIdx.x; r < ng; r += blockDim.x) hist[r] = 0;
+  __syncthreads();
+  if (c0 < c1) {
+    const long long lo = p[c0], hi = p[c1];  // the chunk's entries are one contiguous range
+    for (long long k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+      const int r = sel_of_gene[ld_stream_s32(gi + k)];
+      if (r >= g0 && r < g1) atomicAdd(&hist[r - g0], 1);
     }
   }
+  __syncthreads();
+  int* Hc = H + chunk * n_sel + g0;
+  for (int r = threadIdx.x; r < ng; r += blockDim.x) Hc[r] = hist[r];
 }
 
 // exclusive scan over the chunks of a tile, per selected row; cnt = tile total
@@ -532,33 +547,77 @@ __global__ void k_fill_pads(const int* __restrict__ cnt, const long long* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) k_scatter_B(const long long* __restrict__ p, const int* __restrict__ gi,
-                                                   const double* __restrict__ y, const int* __restrict__ sel_of_gene,
-                                                   int n_sel, int tile_w, int chunks_per_tile, int cells_per_chunk,
-                                                   long long n_cells, long long n_chunks, int* __restrict__ H,
-                                                   const long long* __restrict__ base, unsigned short* __restrict__ idx,
-                                                   double* __restrict__ val) {
-  const int lane = threadIdx.x & 31;
-  long long chunk = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (chunk >= n_chunks) return;
-  long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
-  long long c0 = t * tile_w + s * cells_per_chunk;
-  long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
-  int* Hc = H + chunk * n_sel;
-  const long long* bt = base + t * n_sel;
-  for (long long c = c0; c < c1; ++c) {
-    const long long lo = p[c], hi = p[c + 1];
-    const int local = (int)(c - t * tile_w);
-    for (long long k = lo + lane; k < hi; k += 32) {
-      int r = sel_of_gene[ld_stream_s32(gi + k)];
-      if (r >= 0) {
-        int pos = atomicAdd(Hc + r, 1);
-        long long dst = bt[r] + pos;
-        idx[dst] = (unsigned short)local;
-        val[dst] = ld_stream_f64(y + k);
-      }
+// Pass 2: stable scatter.  The chunk's write cursors (one per selected row of this pass) live
+// in shared memory.  The CTA walks its cells 16 at a time, one warp per cell:
+//   A  every warp sets its bit in mask[row] for the rows its cell contains,
+//   B  an entry's slot is cursor[row] + (number of EARLIER cells of the group that contain the
+//      row) -- so every gene row ends up sorted by cell, deterministically, without a global
+//      atomic and without serialising the cells,
+//   C  the first cell of the group that contains a row advances its cursor and clears the mask.
+// (The first version used one warp per chunk with the cursors in a 0.5 GB global table: the
+// random read-modify-writes on it made the transpose DRAM-latency bound, 62 ms at 474 M nnz.)
+__global__ void __launch_bounds__(TB_THREADS) k_scatter_B(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                          const double* __restrict__ y, const int* __restrict__ sel_of_gene,
+                                                          int n_sel, int g0, int g1, int tile_w, int chunks_per_tile,
+                                                          int cells_per_chunk, long long n_cells, const int* __restrict__ H,
+                                                          const long long* __restrict__ base,
+                                                          unsigned short* __restrict__ idx, double* __restrict__ val) {
+  extern __shared__ int sm_tb[];
+  const int ng = g1 - g0;
+  int* cursor = sm_tb;                                         // [ng] slot inside the (tile,row) run
+  unsigned int* mask = reinterpret_cast<unsigned int*>(sm_tb + ng);  // [ng] cells of the current group
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long chunk = blockIdx.x;
+  const long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
+  const long long c0 = min(t * tile_w + s * (long long)cells_per_chunk, n_cells);
+  const long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
+  const int* Hc = H + chunk * n_sel + g0;
+  const long long* bt = base + t * n_sel + g0;
+  for (int r = threadIdx.x; r < ng; r += blockDim.x) {
+    cursor[r] = Hc[r];
+    mask[r] = 0u;
+  }
+  __syncthreads();
+  const unsigned int below = (1u << w) - 1u;
+  for (long long cg = c0; cg < c1; cg += TB_WARPS) {
+    const long long c = cg + w;
+    const bool have = c < c1;
+    const long long lo = have ? p[c] : 0, hi = have ? p[c + 1] : 0;
+    // every phase walks the cell's entries 4 x 32 at a time so that four index loads and four
+    // map look-ups are in flight per lane (one at a time made the kernel latency-bound)
+#define TB_FOR_ROWS(BODY)                                                       \
+    for (long long k0 = lo; k0 < hi; k0 += 128) {                                \
+      int rr[4];                                                                 \
+      long long kk[4];                                                           \
+      _Pragma("unroll") for (int u = 0; u < 4; ++u) {                            \
+        kk[u] = k0 + lane + 32 * u;                                              \
+        rr[u] = (kk[u] < hi) ? gi[kk[u]] : -1;                                   \
+      }                                                                          \
+      _Pragma("unroll") for (int u = 0; u < 4; ++u) rr[u] = (rr[u] >= 0) ? sel_of_gene[rr[u]] : -1; \
+      _Pragma("unroll") for (int u = 0; u < 4; ++u) {                            \
+        const int r = rr[u];                                                     \
+        const long long k = kk[u];                                               \
+        if (r >= g0 && r < g1) { BODY }                                          \
+      }                                                                          \
     }
-    __syncwarp();
+    TB_FOR_ROWS(atomicOr(&mask[r - g0], 1u << w); (void)k;)  // A
+    __syncthreads();
+    const int local = (int)(c - t * tile_w);
+    TB_FOR_ROWS(  // B
+        const int q = r - g0;
+        const long long dst = bt[q] + cursor[q] + __popc(mask[q] & below);
+        idx[dst] = (unsigned short)local;
+        val[dst] = ld_stream_f64(y + k);)
+    __syncthreads();
+    TB_FOR_ROWS(  // C
+        const int q = r - g0; (void)k;
+        const unsigned int mq = mask[q];
+        if ((mq & below) == 0u) {  // this warp's cell is the first of the group with this row
+          cursor[q] += __popc(mq);
+          mask[q] = 0u;
+        })
+#undef TB_FOR_ROWS
+    __syncthreads();
   }
 }
 
@@ -587,9 +646,9 @@ int build_layout_B(m3b_mat* m) {
   L.cols = m->n_cells;
   choose_tiling(L.cols, ctx->tile_w_max, &L.tile_w, &L.n_tiles);
   const int n_tiles = L.n_tiles;
-  int cpt = (int)std::max<long long>(1, std::min<long long>((4096 + n_tiles - 1) / n_tiles, (L.tile_w + 7) / 8));
-  // bound the cursor table to ~1.5 GB
-  while (cpt > 1 && (double)n_tiles * cpt * std::max(n_sel, 1) * 4.0 > 1.5e9) cpt = (cpt + 1) / 2;
+  // ~2 chunks per SM in total (one CTA each), never fewer than 16 cells per chunk
+  int cpt = (int)std::max<long long>(1, std::min<long long>((2LL * ctx->sm_count + n_tiles - 1) / n_tiles,
+                                                             (L.tile_w + TB_WARPS - 1) / TB_WARPS));
   const int cells_per_chunk = (L.tile_w + cpt - 1) / cpt;
   const long long n_chunks = (long long)n_tiles * cpt;
   int* H = nullptr;
@@ -597,12 +656,25 @@ int build_layout_B(m3b_mat* m) {
   long long* d_base = nullptr;
   RET(dev_alloc(ctx, &H, (size_t)n_chunks * std::max(n_sel, 1)));
   RET(dev_alloc(ctx, &d_cnt, (size_t)n_tiles * std::max(n_sel, 1)));
-  CK(ctx, cudaMemsetAsync(H, 0, (size_t)n_chunks * std::max(n_sel, 1) * sizeof(int), ctx->stream));
-  const unsigned blocks = (unsigned)((n_chunks * 32 + 255) / 256);
+  static bool tb_attr = false;
+  if (!tb_attr) {
+    CK(ctx, cudaFuncSetAttribute(k_count_B, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_GSEG_MAX * 4));
+    CK(ctx, cudaFuncSetAttribute(k_scatter_B, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_GSEG_MAX * 8));
+    tb_attr = true;
+  }
+  int TB_GSEG = TB_GSEG_DEFAULT;
+  if (const char* e = getenv("M3B_GSEG")) TB_GSEG = std::max(256, std::min(TB_GSEG_MAX, atoi(e)));
+  // the scatter asks for >= 120 KB of shared memory so that only ONE CTA is resident per SM
+  const size_t scatter_smem_min = 120 * 1024;
   if (m->n_cells && n_sel) {
-    k_count_B<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->sel_of_gene, n_sel, L.tile_w, cpt, cells_per_chunk,
-                                               m->n_cells, n_chunks, H);
-    count_launch(ctx);
+    for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG_MAX) {  // counting has no write working set: big passes
+      const int g1 = std::min(n_sel, g0 + TB_GSEG_MAX);
+      k_count_B<<<(unsigned)n_chunks, TB_THREADS, (size_t)(g1 - g0) * 4, ctx->stream>>>(
+          m->p, m->i, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H);
+      count_launch(ctx);
+    }
+  } else {
+    CK(ctx, cudaMemsetAsync(H, 0, (size_t)n_chunks * std::max(n_sel, 1) * sizeof(int), ctx->stream));
   }
   long long n_runs = (long long)n_tiles * n_sel;
   if (n_runs) {
@@ -627,9 +699,13 @@ int build_layout_B(m3b_mat* m) {
     k_fill_pads<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(d_cnt, d_base, n_runs, L.idx, L.val);
     count_launch(ctx);
     if (m->n_cells) {
-      k_scatter_B<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->sel_of_gene, n_sel, L.tile_w, cpt,
-                                                   cells_per_chunk, m->n_cells, n_chunks, H, d_base, L.idx, L.val);
-      count_launch(ctx);
+      for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG) {
+        const int g1 = std::min(n_sel, g0 + TB_GSEG);
+        k_scatter_B<<<(unsigned)n_chunks, TB_THREADS, std::max((size_t)(g1 - g0) * 8, scatter_smem_min), ctx->stream>>>(
+            m->p, m->i, m->y, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H, d_base, L.idx,
+            L.val);
+        count_launch(ctx);
+      }
     }
   }
   CK(ctx, cudaGetLastError());
