@@ -106,6 +106,14 @@ int         m3b_set_should_abort(m3b_ctx* ctx, m3b_should_abort_fn fn, void* use
 int m3b_comm_unique_id(m3b_ctx* ctx, char id[M3B_COMM_ID_BYTES]);              /* rank 0 */
 int m3b_comm_init(m3b_ctx* ctx, int rank, int world, const char id[M3B_COMM_ID_BYTES]);
 int m3b_comm_world(const m3b_ctx* ctx);                                        /* 1 if unsharded */
+/* Optional, one box only: peer-memory exchange over NVLink for the per-step gene-vector
+ * reduction (the K5 combine, the cross-rank sum and the centre/scale fix-ups then run as ONE
+ * kernel that reads the peers' partials directly; NCCL stays the fallback).  After
+ * m3b_comm_init every rank exports a 64-byte CUDA-IPC handle; the host gathers the world's
+ * handles (rank order) and hands them back to every rank. */
+#define M3B_P2P_HANDLE_BYTES 64
+int m3b_comm_p2p_handle(m3b_ctx* ctx, char handle[M3B_P2P_HANDLE_BYTES]);
+int m3b_comm_p2p_open(m3b_ctx* ctx, const char* handles /* world x 64 bytes */);
 
 /* ---- sparse ingest (K0) ------------------------------------------------ */
 /* n_cells_local cells will be appended to this context; n_cells_total is the

@@ -60,6 +60,8 @@ SIGNATURES = {
     "m3b_comm_unique_id": (C.c_int, [_P, C.c_char_p]),
     "m3b_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),
     "m3b_comm_world": (C.c_int, [_P]),
+    "m3b_comm_p2p_handle": (C.c_int, [_P, C.c_char_p]),
+    "m3b_comm_p2p_open": (C.c_int, [_P, C.c_char_p]),
     "m3b_matrix_begin": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_P)]),
     "m3b_matrix_append_csc": (C.c_int, [_P, C.c_int64, _ip, _ip, _dp]),
     "m3b_matrix_end": (C.c_int, [_P]),

@@ -167,6 +167,14 @@ int m3b_comm_init(m3b_ctx* ctx, int rank, int world, const char id[M3B_COMM_ID_B
   return comm_init(ctx, rank, world, id);
 }
 int m3b_comm_world(const m3b_ctx* ctx) { return ctx ? ctx->comm.world : 1; }
+int m3b_comm_p2p_handle(m3b_ctx* ctx, char handle[M3B_P2P_HANDLE_BYTES]) {
+  if (!ctx || !handle) return M3B_E_DIMS;
+  return comm_p2p_handle(ctx, handle);
+}
+int m3b_comm_p2p_open(m3b_ctx* ctx, const char* handles) {
+  if (!ctx || !handles) return M3B_E_DIMS;
+  return comm_p2p_open(ctx, handles);
+}
 
 // ---------------------------------------------------------------------------
 int m3b_matrix_begin(m3b_ctx* ctx, int32_t n_genes, int64_t n_cells_local, int64_t n_cells_total, int64_t nnz_hint,

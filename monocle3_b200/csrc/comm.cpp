@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "m3b_internal.h"
 
 struct NcclApi {
@@ -91,7 +93,66 @@ int comm_init(m3b_ctx* ctx, int rank, int world, const char* id) {
   return M3B_OK;
 }
 
+static size_t xchg_bytes(int world) {
+  return ((size_t)world * 2 * M3B_XCHG_FLAG_STRIDE + 2 * (size_t)M3B_XCHG_CAP) * sizeof(double);
+}
+
+// Peer-memory exchange buffer: allocate + export (step 1), import everybody's (step 2).
+int comm_p2p_handle(m3b_ctx* ctx, char* out64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  if (ctx->comm.world < 2 || ctx->comm.world > 16) {
+    m3b_set_error(ctx, "peer exchange needs 2..16 ranks");
+    return M3B_E_STATE;
+  }
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->comm.xchg) {
+    CK(ctx, cudaMalloc((void**)&ctx->comm.xchg, xchg_bytes(ctx->comm.world)));
+    CK(ctx, cudaMemset(ctx->comm.xchg, 0, xchg_bytes(ctx->comm.world)));
+  }
+  cudaIpcMemHandle_t h;
+  CK(ctx, cudaIpcGetMemHandle(&h, ctx->comm.xchg));
+  memcpy(out64, &h, 64);
+  return M3B_OK;
+}
+
+int comm_p2p_open(m3b_ctx* ctx, const char* handles) {
+  Comm& c = ctx->comm;
+  if (!c.xchg) {
+    m3b_set_error(ctx, "m3b_comm_p2p_open before m3b_comm_p2p_handle");
+    return M3B_E_STATE;
+  }
+  CK(ctx, cudaSetDevice(ctx->device));
+  std::vector<double*> ptrs(c.world, nullptr);
+  for (int q = 0; q < c.world; ++q) {
+    if (q == c.rank) {
+      ptrs[q] = c.xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)q * 64, 64);
+    void* p = nullptr;
+    CK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c.peer_base[q] = p;
+    ptrs[q] = (double*)p;
+  }
+  if (!c.peers_dev) CK(ctx, cudaMalloc((void**)&c.peers_dev, 16 * sizeof(double*)));
+  CK(ctx, cudaMemcpy(c.peers_dev, ptrs.data(), c.world * sizeof(double*), cudaMemcpyHostToDevice));
+  c.xchg_seq = 0;
+  c.p2p = true;
+  return M3B_OK;
+}
+
 void comm_destroy(m3b_ctx* ctx) {
+  for (int q = 0; q < 16; ++q)
+    if (ctx->comm.peer_base[q]) {
+      cudaIpcCloseMemHandle(ctx->comm.peer_base[q]);
+      ctx->comm.peer_base[q] = nullptr;
+    }
+  if (ctx->comm.peers_dev) cudaFree(ctx->comm.peers_dev);
+  if (ctx->comm.xchg) cudaFree(ctx->comm.xchg);
+  ctx->comm.peers_dev = nullptr;
+  ctx->comm.xchg = nullptr;
+  ctx->comm.p2p = false;
   if (ctx->comm.comm) {
     NcclApi* api = nccl_api(ctx);
     if (api) api->CommDestroy((ncclComm_t)ctx->comm.comm);

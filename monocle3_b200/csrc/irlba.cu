@@ -68,6 +68,17 @@ __device__ __forceinline__ double block_sum_partials(const double* __restrict__ 
   return bc;
 }
 
+// sum of a row's partials: its slots are contiguous; 8 lanes per row, fixed shuffle tree.
+// Must be called by all 32 lanes of a warp (rows beyond the end pass b == e).
+__device__ __forceinline__ double row_sum8(const double* __restrict__ partial, int b, int e, int sub) {
+  double a = 0.0;
+  for (int k = b + sub; k < e; k += 8) a += partial[k];
+  a += __shfl_xor_sync(0xffffffffu, a, 4);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  return a;
+}
+
 // --------------------------------------------------------------------------
 // gene-side vector kernels
 // --------------------------------------------------------------------------
@@ -88,23 +99,24 @@ __global__ void __launch_bounds__(NT) k_make_xs(const double* __restrict__ v, co
 }
 
 // w[r] = sum(partials of row r) - beta - R_F * wprev[r]      (K4 epilogue)
-__global__ void __launch_bounds__(NT) k_combine_A(const double* __restrict__ partial, const int* __restrict__ rip,
-                                                  long long rows, int n_tiles, const double* __restrict__ pb, int npb,
+__global__ void __launch_bounds__(NT) k_combine_A(const double* __restrict__ partial, const int* __restrict__ rsp,
+                                                  long long rows, const double* __restrict__ pb, int npb,
                                                   const double* __restrict__ wprev, const double* __restrict__ scal,
                                                   double* __restrict__ w) {
   __shared__ double sh[32];
   const double beta = pb ? block_sum_partials(pb, npb, sh) : 0.0;
   const double rf = wprev ? scal[SC_RF] : 0.0;
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int* p = rip + (long long)t * (rows + 1) + r;
-      const int b = p[0], e = p[1];
-      for (int k = b; k < e; ++k) acc += partial[k];
+  const int sub = threadIdx.x & 7;
+  const long long rpb = blockDim.x >> 3;
+  for (long long r0 = blockIdx.x * rpb; r0 < rows; r0 += (long long)gridDim.x * rpb) {
+    const long long r = r0 + (threadIdx.x >> 3);
+    const int b = (r < rows) ? rsp[r] : 0, e = (r < rows) ? rsp[r + 1] : 0;
+    double acc = row_sum8(partial, b, e, sub);
+    if (r < rows && sub == 0) {
+      acc -= beta;
+      if (wprev) acc -= rf * wprev[r];
+      w[r] = acc;
     }
-    acc -= beta;
-    if (wprev) acc -= rf * wprev[r];
-    w[r] = acc;
   }
 }
 
@@ -129,27 +141,18 @@ __global__ void __launch_bounds__(NT) k_fix_F(const double* __restrict__ Fraw, c
 
 // single-rank fusion of the K5 combine with the fix-ups (no allreduce in between):
 // F[g] = (sum of row g's partials)/s - (sumw*ce)/s - S*vj[g]
-__global__ void __launch_bounds__(NT) k_combine_fix_F(const double* __restrict__ partial, const int* __restrict__ rip,
-                                                      int rows, int n_tiles, const double* __restrict__ s,
+__global__ void __launch_bounds__(NT) k_combine_fix_F(const double* __restrict__ partial, const int* __restrict__ rsp,
+                                                      int rows, const double* __restrict__ s,
                                                       const double* __restrict__ ce, const double* __restrict__ vj,
                                                       const double* __restrict__ scal, double* __restrict__ F) {
-  // one warp per gene row: a heavy gene has tens of partials (one per <=2048-entry slice and
-  // tile); the lanes stride over them and the lane sums are added in a fixed shuffle tree
   const double sumw = scal[SC_SUMW], S = scal[SC_S];
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < rows; g += gridDim.x * wpb) {
-    double f = 0.0;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int* p = rip + (long long)t * (rows + 1) + g;
-      const int b = p[0], e = p[1];
-      double a = 0.0;
-      for (int k = b + lane; k < e; k += 32) a += partial[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      f += a;
-    }
-    if (lane == 0) {
+  const int sub = threadIdx.x & 7;
+  const int rpb = blockDim.x >> 3;
+  for (int g0 = blockIdx.x * rpb; g0 < rows; g0 += gridDim.x * rpb) {
+    const int g = g0 + (threadIdx.x >> 3);
+    const int b = (g < rows) ? rsp[g] : 0, e = (g < rows) ? rsp[g + 1] : 0;
+    double f = row_sum8(partial, b, e, sub);
+    if (g < rows && sub == 0) {
       if (s) f = f / s[g];
       if (ce) {
         double c = sumw * ce[g];
@@ -158,6 +161,112 @@ __global__ void __launch_bounds__(NT) k_combine_fix_F(const double* __restrict__
       }
       F[g] = f - S * vj[g];
     }
+  }
+}
+
+// --------------------------------------------------------------------------
+// K5 combine + cross-rank sum + fix-ups in ONE kernel over peer memory (NVLink / NVSwitch).
+//
+// Cells are sharded, so every rank holds a partial A^T w (a gene-length vector, 160-240 KB).
+// Instead of  combine -> ncclAllReduce -> fix-ups  (three launches, one NCCL round trip of
+// ~15-20 us per Lanczos step) each rank
+//   1. adds the partials of its gene rows and writes them into ITS slot of the exchange buffer,
+//   2. the last CTA to finish publishes a sequence number into every peer's flag array
+//      (system-scope release stores through the peers' mapped pointers),
+//   3. every CTA waits until all peers have published the same number, then reads the peers'
+//      slots DIRECTLY (ld over NVLink), adds the world's partials in rank order -- the same
+//      order on every rank, so the replicated gene-space state stays bit-identical -- and
+//      applies  /s - sum(w) ce / s - S v_j.
+// Two slots alternate (a peer can lag at most one step behind: it cannot publish step k+1
+// before it has finished reading step k).  The grid (<= 296 CTAs) is always co-resident, so the
+// in-kernel wait cannot starve the publishing CTA.  A bounded spin (about a second) turns a
+// missing peer into an error flag instead of a hang.
+// --------------------------------------------------------------------------
+#define XF_CTAS 296  // two CTAs per SM: always co-resident (256 threads, no shared memory to speak of)
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(NT)
+k_combine_xchg_fix_F(const double* __restrict__ partial, const int* __restrict__ rsp, int rows,
+                     const double* __restrict__ s, const double* __restrict__ ce, const double* __restrict__ vj,
+                     const double* __restrict__ scal, double* __restrict__ F, double* const* __restrict__ peers,
+                     int rank, int world, unsigned long long seq, unsigned int* __restrict__ done_ctr,
+                     int* __restrict__ ctl) {
+  __shared__ int s_ok;
+  if (*((volatile int*)(ctl + CT_FLAG)) & 4) return;  // an earlier exchange already timed out: do not wait again
+  const int slot = (int)(seq & 1ull);
+  const size_t flags_doubles = (size_t)world * 2 * M3B_XCHG_FLAG_STRIDE;
+  double* mine = peers[rank] + flags_doubles + (size_t)slot * M3B_XCHG_CAP;
+  // contiguous row range of this CTA
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int g_lo = blockIdx.x * per, g_hi = min(rows, g_lo + per);
+  // 1. local combine (8 lanes per gene row, fixed shuffle tree)
+  {
+    const int sub = threadIdx.x & 7, rpb = blockDim.x >> 3;
+    for (int g0 = g_lo; g0 < g_hi; g0 += rpb) {
+      const int g = g0 + (threadIdx.x >> 3);
+      const int b = (g < g_hi) ? rsp[g] : 0, e = (g < g_hi) ? rsp[g + 1] : 0;
+      const double f = row_sum8(partial, b, e, sub);
+      if (g < g_hi && sub == 0) mine[g] = f;
+    }
+  }
+  // 2. publish: the last CTA of this rank writes seq into every peer's flag for (rank, slot)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int d = atomicInc(done_ctr, gridDim.x - 1);
+    if (d == gridDim.x - 1) {
+      __threadfence_system();
+      for (int q = 0; q < world; ++q) {
+        unsigned long long* fl =
+            reinterpret_cast<unsigned long long*>(peers[q] + ((size_t)rank * 2 + slot) * M3B_XCHG_FLAG_STRIDE);
+        st_release_sys_u64(fl, seq);
+      }
+    }
+    // 3a. wait for every rank's flag in MY buffer (bounded spin)
+    int ok = 1;
+    const long long t0 = clock64();
+    for (int q = 0; q < world && ok; ++q) {
+      const unsigned long long* fl =
+          reinterpret_cast<const unsigned long long*>(peers[rank] + ((size_t)q * 2 + slot) * M3B_XCHG_FLAG_STRIDE);
+      while (ld_acquire_sys_u64(fl) != seq) {
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived
+          ok = 0;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    s_ok = ok;
+    if (!ok) atomicOr(ctl + CT_FLAG, 4);
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  // 3b. sum the world's partials in rank order straight out of the peers' memory, then fix up
+  const double sumw = scal[SC_SUMW], S = scal[SC_S];
+  for (int g = g_lo + threadIdx.x; g < g_hi; g += blockDim.x) {
+    double f = 0.0;
+    for (int q = 0; q < world; ++q)
+      f += ld_relaxed_sys_f64(peers[q] + flags_doubles + (size_t)slot * M3B_XCHG_CAP + g);
+    if (s) f = f / s[g];
+    if (ce) {
+      double c = sumw * ce[g];
+      if (s) c = c / s[g];
+      f = f - c;
+    }
+    F[g] = f - S * vj[g];
   }
 }
 
@@ -603,7 +712,9 @@ struct Irlba {
   double *scal = nullptr, *Bm = nullptr, *BU = nullptr, *BV = nullptr, *BS = nullptr, *svr = nullptr, *res = nullptr;
   double *Q = nullptr, *svd_scratch = nullptr;
   int* ctl = nullptr;
+  unsigned int* xf_done = nullptr;  // CTA counter of the fused exchange kernel (self re-arming)
   int nb_n, nb_m;        // blocks of the vector kernels (gene side / cell side)
+  int nb_ca;             // blocks of k_combine_A (32 rows per block)
   int nbo_n, nbo_m;      // blocks of k_apply_orth (= number of pn/ps partials it writes)
   int chunk_n, chunk_m;  // rows per block of k_dots
   int nblk_n, nblk_m;
@@ -654,7 +765,7 @@ struct Irlba {
     double* w = W + (long long)jw * mrows;
     spmv_timer_begin(ctx, 5);
     if (mrows) {
-      k_combine_A<<<nb_m, NT, 0, ctx->stream>>>(m->A.partial, m->A.row_item_ptr, mrows, m->A.n_tiles, ce ? pb : nullptr,
+      k_combine_A<<<nb_ca, NT, 0, ctx->stream>>>(m->A.partial, m->A.row_slot_ptr, mrows, ce ? pb : nullptr,
                                                 nb_n, sub_prev ? (w - mrows) : nullptr, scal, w);
       count_launch(ctx);
     }
@@ -671,8 +782,19 @@ struct Irlba {
     ctx->stats.spmv_genes_out++;
     if (ctx->comm.world == 1) {
       spmv_timer_begin(ctx, 5);
-      k_combine_fix_F<<<std::max(1, std::min((n + 7) / 8, 4 * ctx->sm_count)), NT, 0, ctx->stream>>>(m->B.partial, m->B.row_item_ptr, n, m->B.n_tiles, s, ce,
+      k_combine_fix_F<<<std::max(1, std::min((n + 31) / 32, 8 * ctx->sm_count)), NT, 0, ctx->stream>>>(m->B.partial, m->B.row_slot_ptr, n, s, ce,
                                                     V + (long long)j * n, scal, F);
+      count_launch(ctx);
+      spmv_timer_end(ctx);
+      CK(ctx, cudaGetLastError());
+      return M3B_OK;
+    }
+    if (ctx->comm.p2p && n <= M3B_XCHG_CAP) {
+      spmv_timer_begin(ctx, 6);
+      ctx->comm.xchg_seq++;
+      k_combine_xchg_fix_F<<<std::max(1, std::min(XF_CTAS, (n + 31) / 32)), NT, 0, ctx->stream>>>(
+          m->B.partial, m->B.row_slot_ptr, n, s, ce, V + (long long)j * n, scal, F, ctx->comm.peers_dev,
+          ctx->comm.rank, ctx->comm.world, ctx->comm.xchg_seq, xf_done, ctl);
       count_launch(ctx);
       spmv_timer_end(ctx);
       CK(ctx, cudaGetLastError());
@@ -843,6 +965,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
   I.eps = 2.220446049250313e-16;
   I.nb_n = std::max(1, std::min((n + NT - 1) / NT, 64));
   I.nb_m = (int)std::max<long long>(1, std::min<long long>((mloc + NT - 1) / NT, MAX_PART));
+  I.nb_ca = (int)std::max<long long>(1, std::min<long long>((mloc + 31) / 32, 8LL * ctx->sm_count));
   I.nbo_n = std::max(1, std::min((n + 63) / 64, MAX_PART));
   I.nbo_m = (int)std::max<long long>(1, std::min<long long>((mloc + 63) / 64, MAX_PART));
   I.chunk_n = Irlba::pick_chunk(n, ctx->sm_count);
@@ -896,6 +1019,8 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     IR(I.alloc(&I.Q, (size_t)work * work));
     IR(I.alloc(&I.svd_scratch, (size_t)4 * work * work + 10 * work));
     IR(I.alloc(&I.ctl, (size_t)CT_COUNT));
+    IR(I.alloc(&I.xf_done, (size_t)4));
+    ICK(cudaMemsetAsync(I.xf_done, 0, 4 * sizeof(unsigned int), ctx->stream));
     ICK(cudaMemsetAsync(I.Bm, 0, (size_t)work * work * sizeof(double), ctx->stream));
     ICK(cudaMemsetAsync(I.svr, 0, work * sizeof(double), ctx->stream));
     ICK(cudaMemsetAsync(I.scal, 0, SC_COUNT * sizeof(double), ctx->stream));
@@ -1020,6 +1145,11 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       if (hctl[CT_FLAG] & 1) {
         m3b_set_error(ctx, "starting vector near the null space");
         status = M3B_E_NULLSPACE;
+        goto done;
+      }
+      if (hctl[CT_FLAG] & 4) {
+        m3b_set_error(ctx, "peer exchange timed out: a rank did not reach Lanczos restart %d", it);
+        status = M3B_E_NCCL;
         goto done;
       }
       if (hctl[CT_FLAG] & 2) {

@@ -122,6 +122,8 @@ void TiledLayout::free_all() {
   dev_free(cta_tile);
   dev_free(counters);
   dev_free(row_item_ptr);
+  dev_free(item_slot);
+  dev_free(row_slot_ptr);
   dev_free(partial);
   *this = TiledLayout();
 }
@@ -333,7 +335,7 @@ int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc) {
 struct HostTables {
   std::vector<long long> base;
   std::vector<ItemDesc> items;
-  std::vector<int> row_item_ptr;
+  std::vector<int> row_item_ptr, item_slot, row_slot_ptr;
   std::vector<int2> chunks;
   std::vector<int> tile_chunk_ptr, cta_tile;
   long long n_entries = 0, nnz = 0;
@@ -407,6 +409,15 @@ static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows
     rip[rows_out] = (int)T.items.size();
   }
   T.tile_chunk_ptr[n_tiles] = (int)T.chunks.size();
+  // partial slots: contiguous per output row, in (tile, segment) order
+  T.row_slot_ptr.assign((size_t)rows_out + 1, 0);
+  for (const ItemDesc& d : T.items) T.row_slot_ptr[(size_t)d.row + 1]++;
+  for (long long r = 0; r < rows_out; ++r) T.row_slot_ptr[r + 1] += T.row_slot_ptr[r];
+  {
+    std::vector<int> fill(T.row_slot_ptr.begin(), T.row_slot_ptr.end() - 1);
+    T.item_slot.resize(T.items.size());
+    for (size_t i = 0; i < T.items.size(); ++i) T.item_slot[i] = fill[T.items[i].row]++;
+  }
   // CTA -> starting tile, proportional to the tiles' entry counts (every non-empty tile gets >= 1)
   T.cta_tile.assign(sm_count, 0);
   long long total = 0;
@@ -432,7 +443,11 @@ static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T) {
   dev_free(L.cta_tile);
   dev_free(L.counters);
   dev_free(L.row_item_ptr);
+  dev_free(L.item_slot);
+  dev_free(L.row_slot_ptr);
   dev_free(L.partial);
+  L.item_slot = nullptr;
+  L.row_slot_ptr = nullptr;
   L.items = nullptr;
   L.chunks = nullptr;
   L.tile_chunk_ptr = nullptr;
@@ -451,6 +466,11 @@ static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T) {
   RET(dev_alloc(ctx, &L.counters, (size_t)L.n_tiles + 1));
   RET(dev_alloc(ctx, &L.row_item_ptr, T.row_item_ptr.size()));
   RET(dev_alloc(ctx, &L.partial, T.items.size()));
+  RET(dev_alloc(ctx, &L.item_slot, T.item_slot.size()));
+  RET(dev_alloc(ctx, &L.row_slot_ptr, T.row_slot_ptr.size()));
+  if (!T.item_slot.empty())
+    CK(ctx, cudaMemcpyAsync(L.item_slot, T.item_slot.data(), T.item_slot.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(L.row_slot_ptr, T.row_slot_ptr.data(), T.row_slot_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   if (!T.items.empty())
     CK(ctx, cudaMemcpyAsync(L.items, T.items.data(), T.items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, ctx->stream));
   if (!T.chunks.empty())

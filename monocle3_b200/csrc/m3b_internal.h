@@ -37,9 +37,19 @@ void m3b_set_error(m3b_ctx* ctx, const char* fmt, ...);
 // NCCL, e.g. torch, shares that copy instead of clashing with a second one)
 // ---------------------------------------------------------------------------
 struct NcclApi;
+#define M3B_XCHG_CAP 131072      // doubles per exchange slot (kept genes <= 131072 for the fused path)
+#define M3B_XCHG_FLAG_STRIDE 16  // doubles (128 B) between two flags
 struct Comm {
   int rank = 0, world = 1;
   void* comm = nullptr;  // ncclComm_t
+  // peer-memory exchange (one box, NVLink/NVSwitch): every rank owns one buffer
+  //   [flags: world x 2 slots, 128 B apart][slot 0: CAP doubles][slot 1: CAP doubles]
+  // mapped into every other rank with CUDA IPC.  See k_combine_xchg_fix_F (irlba.cu).
+  double* xchg = nullptr;          // own buffer
+  double** peers_dev = nullptr;    // [world] device array of the ranks' buffers (own included)
+  void* peer_base[16] = {nullptr}; // opened IPC mappings (to close)
+  unsigned long long xchg_seq = 0; // use counter (same on every rank)
+  bool p2p = false;
 };
 int comm_get_unique_id(m3b_ctx* ctx, char* id);
 int comm_init(m3b_ctx* ctx, int rank, int world, const char* id);
@@ -47,6 +57,8 @@ void comm_destroy(m3b_ctx* ctx);
 // in-place sum-allreduce of n doubles / int64 on the context stream (no-op if world==1)
 int comm_allreduce_f64(m3b_ctx* ctx, double* dev, size_t n);
 int comm_allreduce_i64(m3b_ctx* ctx, long long* dev, size_t n);
+int comm_p2p_handle(m3b_ctx* ctx, char* out64);
+int comm_p2p_open(m3b_ctx* ctx, const char* handles /* world x 64 bytes */);
 
 #define M3B_TILE_W_MAX 28672  // 224 KB of doubles: the most a CTA can stage
 // Default tile width.  The full 224 KB leaves the SM no L1: the streaming loads of the
@@ -120,7 +132,11 @@ struct TiledLayout {
   int n_cta = 0;
   unsigned int* counters = nullptr;  // [n_tiles+1]: per-tile chunk cursor, last = CTAs finished
   int* row_item_ptr = nullptr; // [n_tiles][rows+1] item ranges per (tile,row)
-  double* partial = nullptr;   // [n_items]
+  // The partial of item i is written to slot item_slot[i]; the slots of a row are contiguous
+  // (tile, then segment order): out[row] = sum of partial[row_slot_ptr[row] .. row_slot_ptr[row+1]).
+  int* item_slot = nullptr;    // [n_items]
+  int* row_slot_ptr = nullptr; // [rows+1]
+  double* partial = nullptr;   // [n_items], indexed by slot
   void free_all();
 };
 

@@ -110,9 +110,10 @@ __device__ __forceinline__ void batch_apply(const Batch& b, const double* sx, do
 template <int OP>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 k_tile_stream(const unsigned short* __restrict__ idx, const double* __restrict__ val, const ItemDesc* __restrict__ items,
-              const int2* __restrict__ chunks, const int* __restrict__ tile_chunk_ptr,
-              const int* __restrict__ cta_tile, int n_tiles, int tile_w, long long cols,
-              const double* __restrict__ x, double* __restrict__ partial, unsigned int* __restrict__ counters) {
+              const int* __restrict__ item_slot, const int2* __restrict__ chunks,
+              const int* __restrict__ tile_chunk_ptr, const int* __restrict__ cta_tile, int n_tiles, int tile_w,
+              long long cols, const double* __restrict__ x, double* __restrict__ partial,
+              unsigned int* __restrict__ counters) {
   extern __shared__ double sx[];
   __shared__ int s_tile;
   const int lane = threadIdx.x & 31;
@@ -149,7 +150,11 @@ k_tile_stream(const unsigned short* __restrict__ idx, const double* __restrict__
         // the descriptors of up to 32 items in one coalesced load
         const int nit = min(32, ch.y - ib);
         int4 mydesc = make_int4(0, 0, 0, 0);
-        if (lane < nit) mydesc = ld_stream_int4(reinterpret_cast<const int4*>(items + ib + lane));
+        int myslot = 0;
+        if (lane < nit) {
+          mydesc = ld_stream_int4(reinterpret_cast<const int4*>(items + ib + lane));
+          myslot = item_slot[ib + lane];
+        }
         for (int k = 0; k < nit; ++k) {
           const int rx = __shfl_sync(0xffffffffu, mydesc.x, k), ry = __shfl_sync(0xffffffffu, mydesc.y, k);
           const int len = __shfl_sync(0xffffffffu, mydesc.z, k);
@@ -181,7 +186,8 @@ k_tile_stream(const unsigned short* __restrict__ idx, const double* __restrict__
           for (int u = 0; u < TS_BP; ++u) acc += a[u];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-          if (lane == 0) partial[ib + k] = acc;
+          const int slot = __shfl_sync(0xffffffffu, myslot, k);
+          if (lane == 0) partial[slot] = acc;
         }
       }
     }
@@ -236,22 +242,22 @@ int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double*
   const int grid = (max_cta > 0 && L.n_tiles == 1) ? std::min(L.n_cta, max_cta) : L.n_cta;
   switch (op) {
     case OP_DOT:
-      k_tile_stream<OP_DOT><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+      k_tile_stream<OP_DOT><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.item_slot, L.chunks, L.tile_chunk_ptr,
                                                                L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
                                                                L.counters);
       break;
     case OP_SUM:
-      k_tile_stream<OP_SUM><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+      k_tile_stream<OP_SUM><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.item_slot, L.chunks, L.tile_chunk_ptr,
                                                                L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
                                                                L.counters);
       break;
     case OP_COUNTPOS:
-      k_tile_stream<OP_COUNTPOS><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+      k_tile_stream<OP_COUNTPOS><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.item_slot, L.chunks, L.tile_chunk_ptr,
                                                                     L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
                                                                     L.counters);
       break;
     default:
-      k_tile_stream<OP_SQDEV><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.chunks, L.tile_chunk_ptr,
+      k_tile_stream<OP_SQDEV><<<grid, TS_THREADS, smem, stream>>>(L.idx, L.val, L.items, L.item_slot, L.chunks, L.tile_chunk_ptr,
                                                                  L.cta_tile, L.n_tiles, L.tile_w, L.cols, x, L.partial,
                                                                  L.counters);
       break;
@@ -261,31 +267,30 @@ int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double*
   return M3B_OK;
 }
 
-// out[row] = sum of the row's partials: one warp per row, lanes stride over the row's items of a
-// tile, fixed shuffle tree, tiles added in ascending order (deterministic)
-__global__ void __launch_bounds__(256) k_combine_rows(const double* __restrict__ partial, const int* __restrict__ rip,
-                                                      long long rows, int n_tiles, double* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long long wpb = blockDim.x >> 5;
-  for (long long r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-    double acc = 0.0;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int* p = rip + (long long)t * (rows + 1) + r;
-      const int b = p[0], e = p[1];
-      double a = 0.0;
-      for (int k = b + lane; k < e; k += 32) a += partial[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      acc += a;
+// out[row] = sum of the row's partials (contiguous slots, tile-then-segment order): 8 lanes per
+// row stride over the slots, fixed 3-step shuffle tree => deterministic
+__global__ void __launch_bounds__(256) k_combine_rows(const double* __restrict__ partial, const int* __restrict__ rsp,
+                                                      long long rows, double* __restrict__ out) {
+  const int sub = threadIdx.x & 7;
+  const long long rpb = blockDim.x >> 3;
+  for (long long r0 = blockIdx.x * rpb; r0 < rows; r0 += gridDim.x * rpb) {
+    const long long r = r0 + (threadIdx.x >> 3);
+    double a = 0.0;
+    if (r < rows) {
+      const int b = rsp[r], e = rsp[r + 1];
+      for (int k = b + sub; k < e; k += 8) a += partial[k];
     }
-    if (lane == 0) out[r] = acc;
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    if (r < rows && sub == 0) out[r] = a;
   }
 }
 
 int launch_combine_rows(m3b_ctx* ctx, const TiledLayout& L, double* out) {
   if (L.rows == 0) return M3B_OK;
-  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((L.rows + 7) / 8, 4LL * ctx->sm_count));
-  k_combine_rows<<<grid, 256, 0, ctx->stream>>>(L.partial, L.row_item_ptr, L.rows, L.n_tiles, out);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((L.rows + 31) / 32, 8LL * ctx->sm_count));
+  k_combine_rows<<<grid, 256, 0, ctx->stream>>>(L.partial, L.row_slot_ptr, L.rows, out);
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
   return M3B_OK;

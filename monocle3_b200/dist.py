@@ -74,6 +74,12 @@ def init_comm(ctx, group=None):
     obj = [ctx.comm_unique_id() if rank == 0 else None]
     td.broadcast_object_list(obj, src=0, group=group)
     ctx.comm_init(rank, world, obj[0])
+    # peer-memory exchange for the fused per-step reduction (one box; M3B_NO_P2P=1 keeps NCCL only)
+    import os
+    if world > 1 and not os.environ.get("M3B_NO_P2P"):
+        handles = [None] * world
+        td.all_gather_object(handles, ctx.comm_p2p_handle(), group=group)
+        ctx.comm_p2p_open(handles)
     return rank, world
 
 

@@ -74,6 +74,14 @@ class Context:
         self.check(self.lib.m3b_comm_init(self.h, int(rank), int(world), uid))
         self.rank, self.world = rank, world
 
+    def comm_p2p_handle(self):
+        buf = C.create_string_buffer(64)
+        self.check(self.lib.m3b_comm_p2p_handle(self.h, buf))
+        return buf.raw
+
+    def comm_p2p_open(self, handles):
+        self.check(self.lib.m3b_comm_p2p_open(self.h, b"".join(handles)))
+
     def stats(self):
         s = L.Stats()
         self.check(self.lib.m3b_get_stats(self.h, C.byref(s)))
