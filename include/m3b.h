@@ -227,6 +227,8 @@ int m3b_reset_stats(m3b_ctx* ctx);
 /* flags for m3b_create / m3b_set_flags */
 #define M3B_FLAG_TIME_SPMV 1  /* bracket every SpMV launch with CUDA events (read back after the run) */
 #define M3B_FLAG_JACOBI_ONLY 2 /* small SVD: always use the dense Jacobi kernel (no structured fast path) */
+#define M3B_FLAG_NO_UNIT_SPLIT 4 /* m3b_select_genes: keep count-1 entries in the 10 B/entry stream instead of the
+                                    2 B/entry index-only "unit" stream (A/B switch for measurements) */
 int m3b_set_flags(m3b_ctx* ctx, int flags);
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this
  * library is launched on): start records an event, stop records a second one,

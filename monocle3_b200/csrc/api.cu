@@ -229,6 +229,7 @@ void m3b_matrix_free(m3b_mat* m) {
   dev_free(m->i);
   dev_free(m->x);
   dev_free(m->y);
+  dev_free(m->unit_val);
   dev_free(m->sel_of_gene);
   dev_free(m->kept_of_sel);
   dev_free(m->kept_of_gene);
@@ -435,7 +436,14 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
   dev_free(m->sel_of_gene);
   RET(dev_alloc(ctx, &m->sel_of_gene, sel_of_gene.size()));
   CK(ctx, cudaMemcpyAsync(m->sel_of_gene, sel_of_gene.data(), sel_of_gene.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  RET(build_layout_B(m));
+  // count-1 entries go to the index-only unit layouts whenever their value is a function of the
+  // cell alone (every size-factor based method); TF-IDF rewrites the values per (gene, cell), so
+  // the LSI branch re-builds unsplit (tfidf.cu)
+  const bool split = !(ctx->flags & M3B_FLAG_NO_UNIT_SPLIT) && !getenv("M3B_NO_UNIT_SPLIT") &&
+                     (m->norm_method == M3B_NORM_LOG2 || m->norm_method == M3B_NORM_LOG10 ||
+                      m->norm_method == M3B_NORM_SIZE_ONLY);
+  RET(build_layout_B(m, split));
+  m->split = split;
   const double t1 = now();
   // global row sums of the (implicit dense) normalised matrix -> zero / non-finite filter
   dev_free(m->rowsum);
@@ -455,9 +463,10 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
     kp[s] = (std::isfinite(v) && v != 0.0) ? 1 : 0;  // R/preprocess_cds.R:121-122
   }
   const double t2 = now();
+  m->keep_mask = kp;
   RET(finish_selection(m, kp.data()));
   const double t3 = now();
-  RET(build_layout_A(m));
+  RET(build_layout_A(m, split));
   if (dbg)
     fprintf(stderr, "m3b_select_genes: layout B %.2f ms, row sums %.2f ms, remap %.2f ms, layout A %.2f ms\n", t1 - t0,
             t2 - t1, t3 - t2, now() - t3);

@@ -1,0 +1,557 @@
+// K4 / K5, the product kernel proper (OP_DOT): flat streaming with a static plan.
+//
+// Replaces CHOLMOD's cholmod_sdmult inside irlba (the two products per Lanczos step behind
+// R/utils.R:417).  The per-item kernels of spmv.cu pay one exposed DRAM latency per item, which
+// was invisible while items were ~1000 entries of a 10 B/entry stream but dominates once the
+// count-1 entries live in the 2 B/entry unit stream (items of a few hundred bytes; ncu: 1.7 TB/s,
+// long-scoreboard stalls).  Here the stream of a tile is cut ONCE, at build time, into one
+// contiguous, item-aligned piece per warp (equal bytes), and a warp streams its piece flat:
+//   * two register batches of FL_K rounds (32 lanes x one group each) keep 4-8 KB per warp in
+//     flight regardless of where items begin and end;
+//   * bit 15 of the first index of a group marks "this group starts a new item" (tile-local
+//     indices are < 28672, so the bit is free): one ballot per round tells the warp whether an
+//     item boundary is inside the round.  No boundary: lanes just accumulate.  Boundary: the open
+//     item is closed with a shuffle tree, items that lie completely inside the round with a
+//     segmented scan -- all in a fixed order, so results stay bit-reproducible;
+//   * the item's partial goes to its slot (spmv.cu's combine kernels are unchanged).
+// The general stream (idx + val, 10 B/entry) and the unit stream (idx only, 2 B/entry) of a tile
+// are processed by the same CTA from the same staged tile; on layout B the tile is rescaled by
+// the per-cell unit value between the two phases.
+#include <algorithm>
+#include <vector>
+
+#include "m3b_internal.h"
+
+#define FL_THREADS 512
+#define FL_WARPS (FL_THREADS / 32)
+#define FL_K 6  // rounds per register batch (two batches per warp)
+
+struct FlatPlan {
+  int n_cta = 0, n_visits = 0;
+  int* cta_visit_ptr = nullptr;  // [n_cta+1]
+  int* visit_tile = nullptr;     // [n_visits]
+  int* gp_ptr = nullptr;         // [n_visits*FL_WARPS+1] piece ranges of (visit, warp), general stream
+  int4* gp = nullptr;            // {first group (pairs), groups, first item, -}
+  int* up_ptr = nullptr;         // the same for the unit stream (groups of 8 entries)
+  int4* up = nullptr;
+};
+
+void flat_plan_free(FlatPlan* p) {
+  if (!p) return;
+  dev_free(p->cta_visit_ptr);
+  dev_free(p->visit_tile);
+  dev_free(p->gp_ptr);
+  dev_free(p->gp);
+  dev_free(p->up_ptr);
+  dev_free(p->up);
+  delete p;
+}
+
+// ---------------------------------------------------------------------------
+// host: the plan
+// ---------------------------------------------------------------------------
+// items [i0, i1) of one tile -> pieces for W warps.  The tile's stream is cut into item-aligned
+// pieces of ~target entries and dealt round-robin: at any time the W warps work inside one
+// window of W consecutive pieces that moves through the stream.  (Giving every warp ONE long
+// contiguous share instead spread the 2368 concurrent read streams over the whole 700 MB array;
+// ncu then showed 4 us of load latency -- TLB and DRAM-page misses -- and 2.7 TB/s.)
+// A piece is contiguous in memory (holes exist only where dropped rows had entries).
+static void split_tile(const std::vector<ItemDesc>& items, int i0, int i1, int W, int group, long long target,
+                       std::vector<std::vector<int4>>& out) {
+  out.assign(W, std::vector<int4>());
+  long long total = 0;
+  for (int i = i0; i < i1; ++i) total += items[i].len;
+  if (total == 0) return;
+  const long long segs = std::max<long long>(1, (total + (long long)W * target - 1) / ((long long)W * target));
+  const long long P = segs * W;
+  long long cum = 0, cur_p = -1;
+  long long prev_end = -1;
+  int w = 0;
+  for (int i = i0; i < i1; ++i) {
+    const ItemDesc& d = items[i];
+    long long pc = std::min<long long>(P - 1, (long long)(((double)cum + 0.5 * d.len) * (double)P / (double)total));
+    if (pc < cur_p) pc = cur_p;
+    if (pc != cur_p || d.start != prev_end) {
+      w = (int)(pc % W);
+      out[w].push_back(make_int4((int)(d.start / group), 0, i, 0));
+      cur_p = pc;
+    }
+    out[w].back().y += d.len / group;
+    prev_end = d.start + d.len;
+    cum += d.len;
+  }
+}
+
+template <typename T>
+static int upload_vec(m3b_ctx* ctx, T** dst, const std::vector<T>& v) {
+  RET(dev_alloc(ctx, dst, std::max<size_t>(v.size(), 1)));
+  if (!v.empty()) CK(ctx, cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return M3B_OK;
+}
+static long long env_ll(const char* name, long long dflt) {
+  const char* e = getenv(name);
+  return e ? std::max(64LL, atoll(e)) : dflt;
+}
+// entries per piece (M3B_FLAT_PIECE_G / M3B_FLAT_PIECE_U override, for sweeps)
+static long long fl_piece_general() { return env_ll("M3B_FLAT_PIECE_G", 2048); }
+static long long fl_piece_unit() { return env_ll("M3B_FLAT_PIECE_U", 8192); }
+
+static int build_one_plan(m3b_ctx* ctx, const TiledLayout& L, const HostTables& Tg, const HostTables* Tu, int n_cta,
+                          FlatPlan** out) {
+  const int n_tiles = L.n_tiles;
+  const long long rows = L.rows;
+  auto tile_items = [&](const HostTables& T, int t, int* i0, int* i1) {
+    *i0 = T.row_item_ptr[(size_t)t * (rows + 1)];
+    *i1 = T.row_item_ptr[(size_t)t * (rows + 1) + rows];
+  };
+  std::vector<double> bytes(n_tiles, 0.0);
+  for (int t = 0; t < n_tiles; ++t) {
+    int i0, i1;
+    tile_items(Tg, t, &i0, &i1);
+    for (int i = i0; i < i1; ++i) bytes[t] += 10.0 * Tg.items[i].len;
+    if (Tu) {
+      tile_items(*Tu, t, &i0, &i1);
+      for (int i = i0; i < i1; ++i) bytes[t] += 2.0 * Tu->items[i].len;
+    }
+  }
+  double total = 0;
+  for (double b : bytes) total += b;
+  // tiles -> CTAs
+  std::vector<std::vector<int>> cta_tiles(n_cta);  // visits of every CTA
+  std::vector<std::vector<int>> tile_ctas(n_tiles);
+  if (total > 0) {
+    if (n_tiles <= n_cta) {
+      // proportional to the tiles' bytes, every non-empty tile gets at least one CTA
+      std::vector<int> n_of(n_tiles, 0);
+      int used = 0, nonempty = 0;
+      for (int t = 0; t < n_tiles; ++t) nonempty += bytes[t] > 0;
+      for (int t = 0; t < n_tiles; ++t)
+        if (bytes[t] > 0) {
+          n_of[t] = std::max(1, (int)(bytes[t] / total * (n_cta - nonempty)) + 1);
+          used += n_of[t];
+        }
+      // hand the remaining CTAs to the tiles with the most bytes per CTA
+      while (used < n_cta) {
+        int best = -1;
+        for (int t = 0; t < n_tiles; ++t)
+          if (bytes[t] > 0 && (best < 0 || bytes[t] / n_of[t] > bytes[best] / n_of[best])) best = t;
+        n_of[best]++;
+        used++;
+      }
+      while (used > n_cta) {
+        int best = -1;
+        for (int t = 0; t < n_tiles; ++t)
+          if (n_of[t] > 1 && (best < 0 || bytes[t] / n_of[t] < bytes[best] / n_of[best])) best = t;
+        n_of[best]--;
+        used--;
+      }
+      int c = 0;
+      for (int t = 0; t < n_tiles; ++t)
+        for (int k = 0; k < n_of[t]; ++k, ++c) {
+          cta_tiles[c].push_back(t);
+          tile_ctas[t].push_back(c);
+        }
+    } else {
+      // more tiles than CTAs: greedy, heaviest tile to the least loaded CTA
+      std::vector<int> order(n_tiles);
+      for (int t = 0; t < n_tiles; ++t) order[t] = t;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bytes[a] > bytes[b]; });
+      std::vector<double> load(n_cta, 0.0);
+      for (int t : order) {
+        if (bytes[t] <= 0) continue;
+        int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[c] += bytes[t];
+        cta_tiles[c].push_back(t);
+        tile_ctas[t].push_back(c);
+      }
+    }
+  }
+  // visits, in CTA order
+  std::vector<int> cta_visit_ptr(n_cta + 1, 0), visit_tile;
+  std::vector<std::vector<int>> visit_of(n_cta);
+  for (int c = 0; c < n_cta; ++c) {
+    cta_visit_ptr[c] = (int)visit_tile.size();
+    for (int t : cta_tiles[c]) {
+      visit_of[c].push_back((int)visit_tile.size());
+      visit_tile.push_back(t);
+    }
+  }
+  cta_visit_ptr[n_cta] = (int)visit_tile.size();
+  const int n_visits = (int)visit_tile.size();
+  // shares of every (visit, warp)
+  std::vector<std::vector<int4>> gshare((size_t)n_visits * FL_WARPS), ushare((size_t)n_visits * FL_WARPS);
+  for (int t = 0; t < n_tiles; ++t) {
+    const int nc = (int)tile_ctas[t].size();
+    if (nc == 0) continue;
+    const int W = nc * FL_WARPS;
+    for (int pass = 0; pass < (Tu ? 2 : 1); ++pass) {
+      const HostTables& T = pass ? *Tu : Tg;
+      int i0, i1;
+      tile_items(T, t, &i0, &i1);
+      std::vector<std::vector<int4>> sh;
+      split_tile(T.items, i0, i1, W, pass ? 8 : 2, pass ? fl_piece_unit() : fl_piece_general(), sh);
+      for (int k = 0; k < nc; ++k) {
+        const int c = tile_ctas[t][k];
+        // the visit of CTA c that is tile t
+        int v = -1;
+        for (size_t q = 0; q < cta_tiles[c].size(); ++q)
+          if (cta_tiles[c][q] == t) v = visit_of[c][q];
+        for (int w = 0; w < FL_WARPS; ++w) {
+          if (sh.empty()) continue;
+          (pass ? ushare : gshare)[(size_t)v * FL_WARPS + w] = sh[(size_t)k * FL_WARPS + w];
+        }
+      }
+    }
+  }
+  std::vector<int> gp_ptr, up_ptr;
+  std::vector<int4> gp, up;
+  for (size_t k = 0; k < gshare.size(); ++k) {
+    gp_ptr.push_back((int)gp.size());
+    gp.insert(gp.end(), gshare[k].begin(), gshare[k].end());
+    up_ptr.push_back((int)up.size());
+    up.insert(up.end(), ushare[k].begin(), ushare[k].end());
+  }
+  gp_ptr.push_back((int)gp.size());
+  up_ptr.push_back((int)up.size());
+  FlatPlan* P = new FlatPlan();
+  *out = P;
+  P->n_cta = n_cta;
+  P->n_visits = n_visits;
+  RET(upload_vec(ctx, &P->cta_visit_ptr, cta_visit_ptr));
+  RET(upload_vec(ctx, &P->visit_tile, visit_tile));
+  RET(upload_vec(ctx, &P->gp_ptr, gp_ptr));
+  RET(upload_vec(ctx, &P->gp, gp));
+  RET(upload_vec(ctx, &P->up_ptr, up_ptr));
+  RET(upload_vec(ctx, &P->up, up));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+  return M3B_OK;
+}
+
+__global__ void k_mark_heads(unsigned short* __restrict__ idx, const ItemDesc* __restrict__ items, long long n_items) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n_items) idx[items[i].start] |= (unsigned short)0x8000;
+}
+
+__global__ void k_item_scale(const ItemDesc* __restrict__ items, long long n_items, const double* __restrict__ rowscale,
+                             double* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n_items) out[i] = rowscale[items[i].row];
+}
+
+// Called when the items of a layout (and of its unit sibling) are final and bank-ordered.
+int flat_build_plans(m3b_ctx* ctx, TiledLayout& L, const HostTables& Tg, const HostTables* Tu) {
+  for (int k = 0; k < 2; ++k) {
+    flat_plan_free(L.plan[k]);
+    L.plan[k] = nullptr;
+  }
+  if (getenv("M3B_NO_FLAT")) return M3B_OK;
+  if (L.n_entries / 2 >= (1LL << 31) || (L.unit && L.unit->n_entries / 8 >= (1LL << 31))) return M3B_OK;  // 32-bit group offsets
+  RET(build_one_plan(ctx, L, Tg, Tu, ctx->sm_count, &L.plan[0]));
+  if (L.n_tiles == 1 && ctx->sm_count > 2 * M3B_SIDE_CTA_RESERVE)
+    RET(build_one_plan(ctx, L, Tg, Tu, ctx->sm_count - M3B_SIDE_CTA_RESERVE, &L.plan[1]));
+  if (L.n_items) {
+    k_mark_heads<<<(unsigned)((L.n_items + 255) / 256), 256, 0, ctx->stream>>>(L.idx, L.items, L.n_items);
+    count_launch(ctx);
+  }
+  if (L.unit && L.unit->n_items) {
+    TiledLayout& U = *L.unit;
+    k_mark_heads<<<(unsigned)((U.n_items + 255) / 256), 256, 0, ctx->stream>>>(U.idx, U.items, U.n_items);
+    count_launch(ctx);
+    dev_free(U.item_scale);
+    U.item_scale = nullptr;
+    if (U.rowscale) {
+      RET(dev_alloc(ctx, &U.item_scale, (size_t)U.n_items));
+      k_item_scale<<<(unsigned)((U.n_items + 255) / 256), 256, 0, ctx->stream>>>(U.items, U.n_items, U.rowscale, U.item_scale);
+      count_launch(ctx);
+    }
+  }
+  CK(ctx, cudaGetLastError());
+  return M3B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 fl_ld_uint4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned int fl_ld_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 fl_ld_double2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+struct FlatState {
+  double acc;     // this lane's running sum of the open item
+  int item;       // the open item, or (if none is open) the next item to start
+  bool open;
+  int wbase;      // window: lane l holds slot / scale of item wbase + l
+  int wslot;
+  double wscale;
+};
+
+__device__ __forceinline__ void fl_window(FlatState& st, int base, const int* __restrict__ slot,
+                                          const double* __restrict__ scale, int n_items, int lane) {
+  st.wbase = base;
+  const int i = base + lane;
+  st.wslot = (i < n_items) ? slot[i] : 0;
+  st.wscale = (scale != nullptr && i < n_items) ? scale[i] : 1.0;
+}
+
+__device__ __forceinline__ double fl_warp_sum(double a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
+// one round: v = this lane's group sum, mask = lanes whose group starts a new item
+__device__ __forceinline__ void fl_round(FlatState& st, double v, unsigned mask, int lane, const int* __restrict__ slot,
+                                         const double* __restrict__ scale, int n_items, double* __restrict__ partial) {
+  if (mask == 0u) {
+    st.acc += v;
+    return;
+  }
+  const int h0 = __ffs(mask) - 1;
+  const int nh = __popc(mask);
+  const int first_new = st.open ? st.item + 1 : st.item;
+  const int lo = st.open ? st.item : first_new;
+  if (first_new + nh - 1 >= st.wbase + 32) fl_window(st, lo, slot, scale, n_items, lane);
+  if (st.open) {
+    const double tot = fl_warp_sum(st.acc + ((lane < h0) ? v : 0.0));
+    const int sl = __shfl_sync(0xffffffffu, st.wslot, st.item - st.wbase);
+    const double sc = __shfl_sync(0xffffffffu, st.wscale, st.item - st.wbase);
+    if (lane == 0) partial[sl] = sc * tot;
+  }
+  if (nh == 1) {
+    st.acc = (lane >= h0) ? v : 0.0;
+  } else {
+    // items that begin and end inside this round: segmented inclusive scan over the lanes >= h0
+    const unsigned le = mask & (0xffffffffu >> (31 - lane));  // heads at or below this lane
+    const bool in = lane >= h0;
+    const int seg_start = in ? 31 - __clz(le) : 0;
+    double s = in ? v : 0.0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, s, d);
+      if (in && lane - d >= seg_start) s += t;
+    }
+    const bool last = (lane < 31) && ((mask >> (lane + 1)) & 1u);
+    const int my_item = first_new + __popc(le) - 1;
+    const int src = in ? (my_item - st.wbase) & 31 : 0;
+    const int sl = __shfl_sync(0xffffffffu, st.wslot, src);
+    const double sc = __shfl_sync(0xffffffffu, st.wscale, src);
+    if (in && last) partial[sl] = sc * s;
+    const int hl = 31 - __clz(mask);
+    st.acc = (lane >= hl) ? v : 0.0;
+  }
+  st.item = first_new + nh - 1;
+  st.open = true;
+}
+
+__device__ __forceinline__ void fl_finish(FlatState& st, int lane, const int* __restrict__ slot,
+                                          const double* __restrict__ scale, int n_items, double* __restrict__ partial) {
+  if (!st.open) return;
+  const double tot = fl_warp_sum(st.acc);
+  // (a round of 32 heads can leave the open item one past the window)
+  if (st.item - st.wbase >= 32) fl_window(st, st.item, slot, scale, n_items, lane);
+  const int sl = __shfl_sync(0xffffffffu, st.wslot, st.item - st.wbase);
+  const double sc = __shfl_sync(0xffffffffu, st.wscale, st.item - st.wbase);
+  if (lane == 0) partial[sl] = sc * tot;
+}
+
+struct FlatArgs {
+  const unsigned short* gidx;
+  const double* gval;
+  const int* gslot;
+  const int4* gp;
+  const int* gp_ptr;
+  int g_items;
+  const unsigned short* uidx;
+  const int* uslot;
+  const double* uscale;
+  const int4* up;
+  const int* up_ptr;
+  int u_items;
+  const int* cta_visit_ptr;
+  const int* visit_tile;
+  int tile_w;
+  long long cols;
+  const double* x;
+  const double* colscale;  // unit phase: tile *= colscale (layout B); nullptr on layout A
+  double* partial;
+};
+
+__global__ void __launch_bounds__(FL_THREADS, 1) k_flat_dot(const FlatArgs a) {
+  extern __shared__ double sx[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile_w = a.tile_w;
+  const int v0 = a.cta_visit_ptr[blockIdx.x], v1 = a.cta_visit_ptr[blockIdx.x + 1];
+  for (int vis = v0; vis < v1; ++vis) {
+    const int tile = a.visit_tile[vis];
+    const long long off = (long long)tile * tile_w;
+    const int len = (int)min((long long)tile_w, a.cols - off);
+    if (vis > v0) __syncthreads();  // the previous tile is still being read
+    {
+      // stage the tile of the dense operand (coalesced 16-byte loads; x is L2-resident); the
+      // slots [len, tile_w] read as 0 (tile_w is where the unit stream's pads point)
+      const double* xs0 = a.x + off;
+      if ((reinterpret_cast<unsigned long long>(xs0) & 15ull) == 0ull) {
+        const double2* src = reinterpret_cast<const double2*>(xs0);
+        double2* dst = reinterpret_cast<double2*>(sx);
+        const int n2 = len >> 1;
+        for (int k = threadIdx.x; k < n2; k += blockDim.x) dst[k] = src[k];
+        if ((len & 1) && threadIdx.x == 0) sx[len - 1] = xs0[len - 1];
+      } else {
+        for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] = xs0[k];
+      }
+      for (int k = len + threadIdx.x; k <= tile_w; k += blockDim.x) sx[k] = 0.0;
+      __syncthreads();
+    }
+    // ---- general stream: groups of 2 entries (u32 index pair + double2 values)
+    {
+      const int p0 = a.gp_ptr[vis * FL_WARPS + warp], p1 = a.gp_ptr[vis * FL_WARPS + warp + 1];
+      for (int p = p0; p < p1; ++p) {
+        const int4 pc = a.gp[p];
+        const unsigned int* ip = reinterpret_cast<const unsigned int*>(a.gidx) + pc.x;
+        const double2* vp = reinterpret_cast<const double2*>(a.gval) + pc.x;
+        const int ng = pc.y, nr = (ng + 31) >> 5;
+        FlatState st;
+        st.acc = 0.0;
+        st.item = pc.z;
+        st.open = false;
+        fl_window(st, pc.z, a.gslot, nullptr, a.g_items, lane);
+        // Two register-resident batches of FL_K rounds, software-pipelined: batch k+1 is in flight
+        // while batch k is consumed.  What the SASS of earlier versions taught:
+        //  * loads are UNCONDITIONAL (addresses past the end are clamped to the last group, the data
+        //    is ignored when the round is consumed): "in range ? load : 0" became a load into a
+        //    temporary with a select right behind it, which waits for the load where it is issued;
+        //  * a finer ring (one load per step, 7 in flight) ran at 2.7 TB/s: a warp has six
+        //    scoreboards, ptxas has to share them between the slots, and waiting for the oldest
+        //    load then waits for the newest one on the same scoreboard.  Two big batches map onto
+        //    two scoreboards.
+        unsigned int i0[FL_K], i1[FL_K];
+        double2 w0[FL_K], w1[FL_K];
+#define FL_GLOAD(BI, BV, R0)                                        \
+  _Pragma("unroll") for (int u = 0; u < FL_K; ++u) {                \
+    const int g = min(32 * ((R0) + u) + lane, ng - 1);              \
+    BI[u] = fl_ld_u32(ip + g);                                      \
+    BV[u] = fl_ld_double2(vp + g);                                  \
+  }
+#define FL_GUSE(BI, BV, R0)                                                                     \
+  _Pragma("unroll") for (int u = 0; u < FL_K; ++u) {                                            \
+    if ((R0) + u < nr) {                                                                        \
+      const bool valid = 32 * ((R0) + u) + lane < ng;                                           \
+      const unsigned mask = __ballot_sync(0xffffffffu, valid && ((BI[u] >> 15) & 1u));          \
+      double v = fma(BV[u].y, sx[BI[u] >> 16], BV[u].x * sx[BI[u] & 0x7fffu]);                  \
+      v = valid ? v : 0.0;                                                                      \
+      fl_round(st, v, mask, lane, a.gslot, nullptr, a.g_items, a.partial);                      \
+    }                                                                                           \
+  }
+        FL_GLOAD(i0, w0, 0)
+        for (int r0 = 0; r0 < nr; r0 += 2 * FL_K) {
+          FL_GLOAD(i1, w1, r0 + FL_K)
+          FL_GUSE(i0, w0, r0)
+          if (r0 + FL_K >= nr) break;
+          FL_GLOAD(i0, w0, r0 + 2 * FL_K)
+          FL_GUSE(i1, w1, r0 + FL_K)
+        }
+#undef FL_GLOAD
+#undef FL_GUSE
+        fl_finish(st, lane, a.gslot, nullptr, a.g_items, a.partial);
+      }
+    }
+    // ---- unit stream: groups of 8 indices, value applied on the dense side
+    if (a.uidx) {
+      if (a.colscale) {
+        __syncthreads();
+        const double* cs = a.colscale + off;
+        for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] *= cs[k];
+        __syncthreads();
+      }
+      const int p0 = a.up_ptr[vis * FL_WARPS + warp], p1 = a.up_ptr[vis * FL_WARPS + warp + 1];
+      for (int p = p0; p < p1; ++p) {
+        const int4 pc = a.up[p];
+        const uint4* ip = reinterpret_cast<const uint4*>(a.uidx) + pc.x;
+        const int ng = pc.y, nr = (ng + 31) >> 5;
+        FlatState st;
+        st.acc = 0.0;
+        st.item = pc.z;
+        st.open = false;
+        fl_window(st, pc.z, a.uslot, a.uscale, a.u_items, lane);
+        uint4 q0[FL_K], q1[FL_K];
+#define FL_ULOAD(B, R0) \
+  _Pragma("unroll") for (int u = 0; u < FL_K; ++u) B[u] = fl_ld_uint4(ip + min(32 * ((R0) + u) + lane, ng - 1));
+#define FL_UUSE(B, R0)                                                                                      \
+  _Pragma("unroll") for (int u = 0; u < FL_K; ++u) {                                                        \
+    if ((R0) + u < nr) {                                                                                    \
+      const uint4 b = B[u];                                                                                 \
+      const bool valid = 32 * ((R0) + u) + lane < ng;                                                       \
+      const unsigned mask = __ballot_sync(0xffffffffu, valid && ((b.x >> 15) & 1u));                        \
+      double v = ((sx[b.x & 0x7fffu] + sx[b.x >> 16]) + (sx[b.y & 0xffffu] + sx[b.y >> 16])) +              \
+                 ((sx[b.z & 0xffffu] + sx[b.z >> 16]) + (sx[b.w & 0xffffu] + sx[b.w >> 16]));               \
+      v = valid ? v : 0.0;                                                                                  \
+      fl_round(st, v, mask, lane, a.uslot, a.uscale, a.u_items, a.partial);                                 \
+    }                                                                                                       \
+  }
+        FL_ULOAD(q0, 0)
+        for (int r0 = 0; r0 < nr; r0 += 2 * FL_K) {
+          FL_ULOAD(q1, r0 + FL_K)
+          FL_UUSE(q0, r0)
+          if (r0 + FL_K >= nr) break;
+          FL_ULOAD(q0, r0 + 2 * FL_K)
+          FL_UUSE(q1, r0 + FL_K)
+        }
+#undef FL_ULOAD
+#undef FL_UUSE
+        fl_finish(st, lane, a.uslot, a.uscale, a.u_items, a.partial);
+      }
+    }
+  }
+}
+
+int flat_init(m3b_ctx* ctx) {
+  CK(ctx, cudaFuncSetAttribute(k_flat_dot, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)((M3B_TILE_W_MAX + 2) * sizeof(double))));
+  return M3B_OK;
+}
+
+int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStream_t stream, int max_cta) {
+  const FlatPlan* P = L.plan[0];
+  if (max_cta > 0 && L.plan[1] && L.plan[1]->n_cta == max_cta) P = L.plan[1];
+  if (!P || P->n_visits == 0) return M3B_OK;
+  const TiledLayout* U = L.unit;
+  FlatArgs a;
+  a.gidx = L.idx;
+  a.gval = L.val;
+  a.gslot = L.item_slot;
+  a.gp = P->gp;
+  a.gp_ptr = P->gp_ptr;
+  a.g_items = (int)L.n_items;
+  a.uidx = (U && U->n_items) ? U->idx : nullptr;
+  a.uslot = U ? U->item_slot : nullptr;
+  a.uscale = U ? U->item_scale : nullptr;
+  a.up = P->up;
+  a.up_ptr = P->up_ptr;
+  a.u_items = U ? (int)U->n_items : 0;
+  a.cta_visit_ptr = P->cta_visit_ptr;
+  a.visit_tile = P->visit_tile;
+  a.tile_w = L.tile_w;
+  a.cols = L.cols;
+  a.x = x;
+  a.colscale = U ? U->colscale : nullptr;
+  a.partial = L.partial;
+  const size_t smem = ((size_t)L.tile_w + 2) * sizeof(double);
+  k_flat_dot<<<P->n_cta, FL_THREADS, smem, stream ? stream : ctx->stream>>>(a);
+  count_launch(ctx);
+  CK(ctx, cudaGetLastError());
+  return M3B_OK;
+}

@@ -1109,7 +1109,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         k_make_xs<<<I.nb_n, NT, 0, ctx->stream2>>>(I.F, I.s, I.ce, n, I.xs, I.pb);
         count_launch(ctx);
         spmv_timer_begin(ctx, 0, ctx->stream2);
-        IR(launch_tile_stream(ctx, m->A, OP_DOT, I.xs, ctx->stream2, ctx->sm_count - 28));
+        IR(launch_tile_stream(ctx, m->A, OP_DOT, I.xs, ctx->stream2, ctx->sm_count - M3B_SIDE_CTA_RESERVE));
         spmv_timer_end(ctx, ctx->stream2);
         ICK(cudaEventRecord(evK4, ctx->stream2));
         pre_k4 = true;

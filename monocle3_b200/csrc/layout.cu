@@ -114,6 +114,15 @@ void dev_free(void* p) {
 }
 
 void TiledLayout::free_all() {
+  if (unit) {
+    unit->partial = nullptr;  // shared with this layout
+    unit->row_slot_ptr = nullptr;
+    unit->free_all();
+    delete unit;
+  }
+  flat_plan_free(plan[0]);
+  flat_plan_free(plan[1]);
+  dev_free(item_scale);
   dev_free(idx);
   dev_free(val);
   dev_free(items);
@@ -252,7 +261,8 @@ int k1_cell_totals(m3b_mat* m, int round_exprs, double* d_tot) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__ p, const double* __restrict__ x,
                                                    const double* __restrict__ sf, long long n_cells, int method,
-                                                   double pc, double f0, double* __restrict__ y) {
+                                                   double pc, double f0, double* __restrict__ y,
+                                                   double* __restrict__ unit_val) {
   const int lane = threadIdx.x & 31;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -274,6 +284,7 @@ __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__
     // bit-identical to evaluating f per entry.
     const bool use_tbl = (method == M3B_NORM_LOG2 || method == M3B_NORM_LOG10);
     const double tbl = use_tbl ? f((double)(lane + 1)) : 0.0;
+    if (lane == 0) unit_val[c] = f(1.0);  // value of the cell's count-1 entries (the UNIT layouts)
     auto g = [&](double v) -> double {
       if (!use_tbl) return f(v);
       const int iv = (int)v;
@@ -307,6 +318,7 @@ __global__ void __launch_bounds__(256) k_normalize(const long long* __restrict__
 int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc) {
   m3b_ctx* ctx = m->ctx;
   if (!m->y) RET(dev_alloc(ctx, &m->y, (size_t)std::max<long long>(m->nnz, 1)));
+  if (!m->unit_val) RET(dev_alloc(ctx, &m->unit_val, (size_t)std::max<long long>(m->n_cells, 1)));
   double f0 = 0.0;
   if (method == M3B_NORM_LOG2) f0 = (pc == 1.0) ? 0.0 : std::log2(pc);
   if (method == M3B_NORM_SIZE_ONLY) f0 = pc;
@@ -315,7 +327,7 @@ int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc) {
   if (m->n_cells) {
     int blocks = (int)std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8);
     cudaEventRecord(ctx->evk0, ctx->stream);
-    k_normalize<<<blocks, 256, 0, ctx->stream>>>(m->p, m->x, d_sf, m->n_cells, method, pc, f0, m->y);
+    k_normalize<<<blocks, 256, 0, ctx->stream>>>(m->p, m->x, d_sf, m->n_cells, method, pc, f0, m->y, m->unit_val);
     cudaEventRecord(ctx->evk1, ctx->stream);
     ctx->k2_timed = true;
     count_launch(ctx);
@@ -332,29 +344,49 @@ int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc) {
 // that get storage; storage is laid out for ALL input rows so that a later
 // re-map needs no data movement).
 // ---------------------------------------------------------------------------
-struct HostTables {
-  std::vector<long long> base;
-  std::vector<ItemDesc> items;
-  std::vector<int> row_item_ptr, item_slot, row_slot_ptr;
-  std::vector<int2> chunks;
-  std::vector<int> tile_chunk_ptr, cta_tile;
-  long long n_entries = 0, nnz = 0;
-};
 
 static inline long long pad4(long long n) { return (n + 3) & ~3LL; }
+static inline long long padn(long long n, int pad) { return (n + pad - 1) / pad * pad; }
 
-static void compute_bases(const std::vector<int>& cnt, int n_tiles, long long rows_in, HostTables& T) {
+// shape of a layout's runs / items: general layouts pad runs to 4 entries, unit layouts to 8
+struct ItemShape {
+  int pad, item_max, item_tail;
+};
+static const ItemShape SHAPE_GENERAL = {4, M3B_ITEM_MAX, M3B_ITEM_TAIL};
+static const ItemShape SHAPE_UNIT = {8, M3B_UITEM_MAX, M3B_UITEM_TAIL};
+
+static void compute_bases(const std::vector<int>& cnt, int n_tiles, long long rows_in, HostTables& T,
+                          const ItemShape& sh) {
   T.base.resize((size_t)n_tiles * rows_in);
   long long off = 0;
   for (size_t k = 0; k < T.base.size(); ++k) {
     T.base[k] = off;
-    off += pad4(cnt[k]);
+    off += padn(cnt[k], sh.pad);
   }
   T.n_entries = off;
 }
 
+// partial slots: contiguous per output row -- the row's general items (tile, segment order)
+// followed by its unit items
+static void assign_slots(HostTables& G, HostTables* U, long long rows_out) {
+  std::vector<int>& rsp = G.row_slot_ptr;
+  rsp.assign((size_t)rows_out + 1, 0);
+  for (const ItemDesc& d : G.items) rsp[(size_t)d.row + 1]++;
+  if (U)
+    for (const ItemDesc& d : U->items) rsp[(size_t)d.row + 1]++;
+  for (long long r = 0; r < rows_out; ++r) rsp[r + 1] += rsp[r];
+  std::vector<int> fill(rsp.begin(), rsp.end() - 1);
+  G.item_slot.resize(G.items.size());
+  for (size_t i = 0; i < G.items.size(); ++i) G.item_slot[i] = fill[G.items[i].row]++;
+  if (U) {
+    U->item_slot.resize(U->items.size());
+    for (size_t i = 0; i < U->items.size(); ++i) U->item_slot[i] = fill[U->items[i].row]++;
+    U->row_slot_ptr.clear();
+  }
+}
+
 static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows_in, const int* row_map,
-                        long long rows_out, int sm_count, HostTables& T) {
+                        long long rows_out, int sm_count, HostTables& T, const ItemShape& sh) {
   T.items.clear();
   T.chunks.clear();
   T.tile_chunk_ptr.assign(n_tiles + 1, 0);
@@ -371,7 +403,7 @@ static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows
   for (int t = 0; t < n_tiles; ++t)
     for (long long ro = 0; ro < rows_out; ++ro) {
       long long ri = row_map ? in_of_out[ro] : ro;
-      if (ri >= 0) tile_len[t] += pad4(cnt[(size_t)t * rows_in + ri]);
+      if (ri >= 0) tile_len[t] += padn(cnt[(size_t)t * rows_in + ri], sh.pad);
     }
   for (int t = 0; t < n_tiles; ++t) {
     int* rip = &T.row_item_ptr[(size_t)t * (rows_out + 1)];
@@ -389,9 +421,9 @@ static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows
       long long c = cnt[(size_t)t * rows_in + ri];
       if (c == 0) continue;
       T.nnz += c;
-      long long len = pad4(c), start = T.base[(size_t)t * rows_in + ri];
+      long long len = padn(c, sh.pad), start = T.base[(size_t)t * rows_in + ri];
       while (len > 0) {
-        const int lim = (seen >= tail_from) ? M3B_ITEM_TAIL : M3B_ITEM_MAX;
+        const int lim = (seen >= tail_from) ? sh.item_tail : sh.item_max;
         int l = (int)std::min<long long>(len, lim);
         T.items.push_back(ItemDesc{start, l, (int)ro});
         start += l;
@@ -409,15 +441,6 @@ static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows
     rip[rows_out] = (int)T.items.size();
   }
   T.tile_chunk_ptr[n_tiles] = (int)T.chunks.size();
-  // partial slots: contiguous per output row, in (tile, segment) order
-  T.row_slot_ptr.assign((size_t)rows_out + 1, 0);
-  for (const ItemDesc& d : T.items) T.row_slot_ptr[(size_t)d.row + 1]++;
-  for (long long r = 0; r < rows_out; ++r) T.row_slot_ptr[r + 1] += T.row_slot_ptr[r];
-  {
-    std::vector<int> fill(T.row_slot_ptr.begin(), T.row_slot_ptr.end() - 1);
-    T.item_slot.resize(T.items.size());
-    for (size_t i = 0; i < T.items.size(); ++i) T.item_slot[i] = fill[T.items[i].row]++;
-  }
   // CTA -> starting tile, proportional to the tiles' entry counts (every non-empty tile gets >= 1)
   T.cta_tile.assign(sm_count, 0);
   long long total = 0;
@@ -436,7 +459,10 @@ static void build_items(const std::vector<int>& cnt, int n_tiles, long long rows
   }
 }
 
-static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T) {
+// n_partial: slots of the shared partial array (general + unit items); a unit layout borrows
+// its parent's partial and row_slot_ptr (upload the parent first)
+static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T, size_t n_partial,
+                         const TiledLayout* parent = nullptr) {
   dev_free(L.items);
   dev_free(L.chunks);
   dev_free(L.tile_chunk_ptr);
@@ -444,8 +470,10 @@ static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T) {
   dev_free(L.counters);
   dev_free(L.row_item_ptr);
   dev_free(L.item_slot);
-  dev_free(L.row_slot_ptr);
-  dev_free(L.partial);
+  if (!L.is_unit) {
+    dev_free(L.row_slot_ptr);
+    dev_free(L.partial);
+  }
   L.item_slot = nullptr;
   L.row_slot_ptr = nullptr;
   L.items = nullptr;
@@ -465,12 +493,17 @@ static int upload_tables(m3b_ctx* ctx, TiledLayout& L, const HostTables& T) {
   RET(dev_alloc(ctx, &L.cta_tile, T.cta_tile.size()));
   RET(dev_alloc(ctx, &L.counters, (size_t)L.n_tiles + 1));
   RET(dev_alloc(ctx, &L.row_item_ptr, T.row_item_ptr.size()));
-  RET(dev_alloc(ctx, &L.partial, T.items.size()));
   RET(dev_alloc(ctx, &L.item_slot, T.item_slot.size()));
-  RET(dev_alloc(ctx, &L.row_slot_ptr, T.row_slot_ptr.size()));
   if (!T.item_slot.empty())
     CK(ctx, cudaMemcpyAsync(L.item_slot, T.item_slot.data(), T.item_slot.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CK(ctx, cudaMemcpyAsync(L.row_slot_ptr, T.row_slot_ptr.data(), T.row_slot_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (L.is_unit) {
+    L.partial = parent->partial;
+    L.row_slot_ptr = parent->row_slot_ptr;
+  } else {
+    RET(dev_alloc(ctx, &L.partial, n_partial));
+    RET(dev_alloc(ctx, &L.row_slot_ptr, T.row_slot_ptr.size()));
+    CK(ctx, cudaMemcpyAsync(L.row_slot_ptr, T.row_slot_ptr.data(), T.row_slot_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
   if (!T.items.empty())
     CK(ctx, cudaMemcpyAsync(L.items, T.items.data(), T.items.size() * sizeof(ItemDesc), cudaMemcpyHostToDevice, ctx->stream));
   if (!T.chunks.empty())
@@ -505,6 +538,14 @@ static void choose_tiling(long long cols, int tile_w_max, int* tile_w, int* n_ti
 // per-(chunk,row) cursor hands out slots in cell order => the transpose is
 // deterministic and every gene row is sorted by cell.
 // ---------------------------------------------------------------------------
+// Entry classes of a build pass: 0 = every stored entry (unsplit layouts), 1 = raw count != 1
+// (general layout of a split matrix), 2 = raw count == 1 (unit layout).
+__device__ __forceinline__ bool in_class(int cls, const double* __restrict__ xraw, long long k) {
+  if (cls == 0) return true;
+  const bool one = ld_stream_f64(xraw + k) == 1.0;
+  return (cls == 2) == one;
+}
+
 #define TB_THREADS 512
 #define TB_WARPS (TB_THREADS / 32)
 #define TB_GSEG_MAX 24576  // most selected rows per pass: 96 KB of cursors + 96 KB of cell masks in shared memory
@@ -517,6 +558,7 @@ static void choose_tiling(long long cols, int tile_w_max, int* tile_w, int* n_ti
 // A CHUNK is a run of consecutive cells of one tile, owned by ONE CTA.  Pass 1 counts the
 // chunk's entries per selected row in a shared-memory histogram (rows [g0, g1) of this pass).
 __global__ void __launch_bounds__(TB_THREADS) k_count_B(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                        const double* __restrict__ xraw, int cls,
                                                         const int* __restrict__ sel_of_gene, int n_sel, int g0, int g1,
                                                         int tile_w, int chunks_per_tile, int cells_per_chunk,
                                                         long long n_cells, int* __restrict__ H) {
@@ -532,7 +574,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_count_B(const long long* __restr
     const long long lo = p[c0], hi = p[c1];  // the chunk's entries are one contiguous range
     for (long long k = lo + threadIdx.x; k < hi; k += blockDim.x) {
       const int r = sel_of_gene[ld_stream_s32(gi + k)];
-      if (r >= g0 && r < g1) atomicAdd(&hist[r - g0], 1);
+      if (r >= g0 && r < g1 && in_class(cls, xraw, k)) atomicAdd(&hist[r - g0], 1);
     }
   }
   __syncthreads();
@@ -555,15 +597,17 @@ __global__ void k_scan_chunks(int* __restrict__ H, int n_sel, int chunks_per_til
   cnt[k] = run;
 }
 
-__global__ void k_fill_pads(const int* __restrict__ cnt, const long long* __restrict__ base, long long n_runs,
-                            unsigned short* __restrict__ idx, double* __restrict__ val) {
+// pads of a run: general layouts idx 0 / val 0.0; unit layouts (val == nullptr) idx == tile_w,
+// the zero slot behind the staged tile
+__global__ void k_fill_pads(const int* __restrict__ cnt, const long long* __restrict__ base, long long n_runs, int pad,
+                            int pad_idx, unsigned short* __restrict__ idx, double* __restrict__ val) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= n_runs) return;
   int c = cnt[k];
   long long b = base[k];
-  for (int e = c; e < ((c + 3) & ~3); ++e) {
-    idx[b + e] = 0;
-    val[b + e] = 0.0;
+  for (int e = c; e < (c + pad - 1) / pad * pad; ++e) {
+    idx[b + e] = (unsigned short)pad_idx;
+    if (val) val[b + e] = 0.0;
   }
 }
 
@@ -577,7 +621,8 @@ __global__ void k_fill_pads(const int* __restrict__ cnt, const long long* __rest
 // (The first version used one warp per chunk with the cursors in a 0.5 GB global table: the
 // random read-modify-writes on it made the transpose DRAM-latency bound, 62 ms at 474 M nnz.)
 __global__ void __launch_bounds__(TB_THREADS) k_scatter_B(const long long* __restrict__ p, const int* __restrict__ gi,
-                                                          const double* __restrict__ y, const int* __restrict__ sel_of_gene,
+                                                          const double* __restrict__ y, const double* __restrict__ xraw,
+                                                          int cls, const int* __restrict__ sel_of_gene,
                                                           int n_sel, int g0, int g1, int tile_w, int chunks_per_tile,
                                                           int cells_per_chunk, long long n_cells, const int* __restrict__ H,
                                                           const long long* __restrict__ base,
@@ -611,7 +656,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_scatter_B(const long long* __res
       long long kk[4];                                                           \
       _Pragma("unroll") for (int u = 0; u < 4; ++u) {                            \
         kk[u] = k0 + lane + 32 * u;                                              \
-        rr[u] = (kk[u] < hi) ? gi[kk[u]] : -1;                                   \
+        rr[u] = (kk[u] < hi && in_class(cls, xraw, kk[u])) ? gi[kk[u]] : -1;     \
       }                                                                          \
       _Pragma("unroll") for (int u = 0; u < 4; ++u) rr[u] = (rr[u] >= 0) ? sel_of_gene[rr[u]] : -1; \
       _Pragma("unroll") for (int u = 0; u < 4; ++u) {                            \
@@ -627,7 +672,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_scatter_B(const long long* __res
         const int q = r - g0;
         const long long dst = bt[q] + cursor[q] + __popc(mask[q] & below);
         idx[dst] = (unsigned short)local;
-        val[dst] = ld_stream_f64(y + k);)
+        if (cls != 2) val[dst] = ld_stream_f64(y + k);)
     __syncthreads();
     TB_FOR_ROWS(  // C
         const int q = r - g0; (void)k;
@@ -643,8 +688,8 @@ __global__ void __launch_bounds__(TB_THREADS) k_scatter_B(const long long* __res
 
 // host copies kept for the re-map after the zero-gene filter
 struct BBuild {
-  std::vector<int> cnt;
-  HostTables T;
+  std::vector<int> cnt, cnt_u;  // per-(tile, selected row) entries of the general / unit layout
+  HostTables T, Tu;
 };
 void m3b_mat_set_bbuild(m3b_mat* m, void* p) {
   delete (BBuild*)m->b_host_tables;
@@ -655,7 +700,7 @@ static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-int build_layout_B(m3b_mat* m) {
+int build_layout_B(m3b_mat* m, bool split) {
   m3b_ctx* ctx = m->ctx;
   const bool dbg = getenv("M3B_DEBUG_TIMING") != nullptr;
   const double tb0 = now_ms();
@@ -665,17 +710,21 @@ int build_layout_B(m3b_mat* m) {
   L.rows = n_sel;
   L.cols = m->n_cells;
   choose_tiling(L.cols, ctx->tile_w_max, &L.tile_w, &L.n_tiles);
+  if (split) {
+    L.unit = new TiledLayout();
+    L.unit->is_unit = true;
+    L.unit->rows = L.rows;
+    L.unit->cols = L.cols;
+    L.unit->tile_w = L.tile_w;
+    L.unit->n_tiles = L.n_tiles;
+    L.unit->colscale = m->unit_val;  // columns are cells
+  }
   const int n_tiles = L.n_tiles;
   // ~2 chunks per SM in total (one CTA each), never fewer than 16 cells per chunk
   int cpt = (int)std::max<long long>(1, std::min<long long>((2LL * ctx->sm_count + n_tiles - 1) / n_tiles,
                                                              (L.tile_w + TB_WARPS - 1) / TB_WARPS));
   const int cells_per_chunk = (L.tile_w + cpt - 1) / cpt;
   const long long n_chunks = (long long)n_tiles * cpt;
-  int* H = nullptr;
-  int* d_cnt = nullptr;
-  long long* d_base = nullptr;
-  RET(dev_alloc(ctx, &H, (size_t)n_chunks * std::max(n_sel, 1)));
-  RET(dev_alloc(ctx, &d_cnt, (size_t)n_tiles * std::max(n_sel, 1)));
   static bool tb_attr = false;
   if (!tb_attr) {
     CK(ctx, cudaFuncSetAttribute(k_count_B, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_GSEG_MAX * 4));
@@ -686,72 +735,104 @@ int build_layout_B(m3b_mat* m) {
   if (const char* e = getenv("M3B_GSEG")) TB_GSEG = std::max(256, std::min(TB_GSEG_MAX, atoi(e)));
   // the scatter asks for >= 120 KB of shared memory so that only ONE CTA is resident per SM
   const size_t scatter_smem_min = 120 * 1024;
-  if (m->n_cells && n_sel) {
-    for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG_MAX) {  // counting has no write working set: big passes
-      const int g1 = std::min(n_sel, g0 + TB_GSEG_MAX);
-      k_count_B<<<(unsigned)n_chunks, TB_THREADS, (size_t)(g1 - g0) * 4, ctx->stream>>>(
-          m->p, m->i, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H);
-      count_launch(ctx);
-    }
-  } else {
-    CK(ctx, cudaMemsetAsync(H, 0, (size_t)n_chunks * std::max(n_sel, 1) * sizeof(int), ctx->stream));
-  }
-  long long n_runs = (long long)n_tiles * n_sel;
-  if (n_runs) {
-    k_scan_chunks<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(H, n_sel, cpt, n_tiles, d_cnt);
-    count_launch(ctx);
-  }
-  CK(ctx, cudaGetLastError());
-  std::vector<int> cnt((size_t)n_runs);
-  if (n_runs) CK(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(ctx, cudaStreamSynchronize(ctx->stream));
-  const double tb1 = now_ms();
-  HostTables T;
-  compute_bases(cnt, n_tiles, n_sel, T);
-  build_items(cnt, n_tiles, n_sel, nullptr, n_sel, ctx->sm_count, T);
-  const double tb2 = now_ms();
-  L.n_entries = T.n_entries;
-  RET(dev_alloc(ctx, &L.idx, (size_t)T.n_entries));
-  RET(dev_alloc(ctx, &L.val, (size_t)T.n_entries));
-  RET(dev_alloc(ctx, &d_base, (size_t)std::max<long long>(n_runs, 1)));
-  if (n_runs) {
-    CK(ctx, cudaMemcpyAsync(d_base, T.base.data(), n_runs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-    k_fill_pads<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(d_cnt, d_base, n_runs, L.idx, L.val);
-    count_launch(ctx);
-    if (m->n_cells) {
-      for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG) {
-        const int g1 = std::min(n_sel, g0 + TB_GSEG);
-        k_scatter_B<<<(unsigned)n_chunks, TB_THREADS, std::max((size_t)(g1 - g0) * 8, scatter_smem_min), ctx->stream>>>(
-            m->p, m->i, m->y, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H, d_base, L.idx,
-            L.val);
+  const long long n_runs = (long long)n_tiles * n_sel;
+  // one pass per entry class: {all} or {general, unit}
+  const int n_cls = split ? 2 : 1;
+  int* H[2] = {nullptr, nullptr};
+  int* d_cnt[2] = {nullptr, nullptr};
+  long long* d_base[2] = {nullptr, nullptr};
+  std::vector<int> cnt[2];
+  HostTables T[2];
+  TiledLayout* Ls[2] = {&L, L.unit};
+  for (int q = 0; q < n_cls; ++q) {
+    const int cls = split ? q + 1 : 0;
+    RET(dev_alloc(ctx, &H[q], (size_t)n_chunks * std::max(n_sel, 1)));
+    RET(dev_alloc(ctx, &d_cnt[q], (size_t)n_tiles * std::max(n_sel, 1)));
+    if (m->n_cells && n_sel) {
+      for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG_MAX) {  // counting has no write working set: big passes
+        const int g1 = std::min(n_sel, g0 + TB_GSEG_MAX);
+        k_count_B<<<(unsigned)n_chunks, TB_THREADS, (size_t)(g1 - g0) * 4, ctx->stream>>>(
+            m->p, m->i, m->x, cls, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[q]);
         count_launch(ctx);
       }
+    } else {
+      CK(ctx, cudaMemsetAsync(H[q], 0, (size_t)n_chunks * std::max(n_sel, 1) * sizeof(int), ctx->stream));
     }
+    if (n_runs) {
+      k_scan_chunks<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(H[q], n_sel, cpt, n_tiles, d_cnt[q]);
+      count_launch(ctx);
+    }
+    CK(ctx, cudaGetLastError());
+    cnt[q].resize((size_t)n_runs);
+    if (n_runs)
+      CK(ctx, cudaMemcpyAsync(cnt[q].data(), d_cnt[q], n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   }
-  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  const double tb1 = now_ms();
+  for (int q = 0; q < n_cls; ++q) {
+    const ItemShape& sh = (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL;
+    compute_bases(cnt[q], n_tiles, n_sel, T[q], sh);
+    build_items(cnt[q], n_tiles, n_sel, nullptr, n_sel, ctx->sm_count, T[q], sh);
+  }
+  assign_slots(T[0], split ? &T[1] : nullptr, n_sel);
+  const double tb2 = now_ms();
+  for (int q = 0; q < n_cls; ++q) {
+    TiledLayout& Lq = *Ls[q];
+    const int cls = split ? q + 1 : 0;
+    Lq.n_entries = T[q].n_entries;
+    RET(dev_alloc(ctx, &Lq.idx, (size_t)T[q].n_entries));
+    if (q == 0) RET(dev_alloc(ctx, &Lq.val, (size_t)T[q].n_entries));
+    RET(dev_alloc(ctx, &d_base[q], (size_t)std::max<long long>(n_runs, 1)));
+    if (n_runs) {
+      CK(ctx, cudaMemcpyAsync(d_base[q], T[q].base.data(), n_runs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+      k_fill_pads<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(d_cnt[q], d_base[q], n_runs, q == 1 ? 8 : 4,
+                                                                            q == 1 ? Lq.tile_w : 0, Lq.idx, Lq.val);
+      count_launch(ctx);
+      if (m->n_cells) {
+        for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG) {
+          const int g1 = std::min(n_sel, g0 + TB_GSEG);
+          k_scatter_B<<<(unsigned)n_chunks, TB_THREADS, std::max((size_t)(g1 - g0) * 8, scatter_smem_min), ctx->stream>>>(
+              m->p, m->i, m->y, m->x, cls, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[q],
+              d_base[q], Lq.idx, Lq.val);
+          count_launch(ctx);
+        }
+      }
+    }
+    CK(ctx, cudaGetLastError());
+  }
   if (dbg) CK(ctx, cudaStreamSynchronize(ctx->stream));
   const double tb3 = now_ms();
-  RET(upload_tables(ctx, L, T));
+  const size_t n_partial = T[0].items.size() + (split ? T[1].items.size() : 0);
+  RET(upload_tables(ctx, L, T[0], n_partial));
+  if (split) RET(upload_tables(ctx, *L.unit, T[1], n_partial, &L));
   if (dbg)
     fprintf(stderr, "  layout B: count+scan %.2f ms (chunks %lld x %d), host tables %.2f ms, scatter %.2f ms, upload %.2f ms\n",
             tb1 - tb0, n_chunks, n_sel, tb2 - tb1, tb3 - tb2, now_ms() - tb3);
   // exact nnz per selected gene (local shard)
   std::vector<long long> nnz_sel(n_sel, 0);
-  for (int t = 0; t < n_tiles; ++t)
-    for (int r = 0; r < n_sel; ++r) nnz_sel[r] += cnt[(size_t)t * n_sel + r];
+  for (int q = 0; q < n_cls; ++q)
+    for (int t = 0; t < n_tiles; ++t)
+      for (int r = 0; r < n_sel; ++r) nnz_sel[r] += cnt[q][(size_t)t * n_sel + r];
   dev_free(m->sel_nnz);
   RET(dev_alloc(ctx, &m->sel_nnz, (size_t)std::max(n_sel, 1)));
   if (n_sel) CK(ctx, cudaMemcpyAsync(m->sel_nnz, nnz_sel.data(), n_sel * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   // stash the host tables for the re-map (kept in the matrix via a heap object)
   BBuild* bb = new BBuild();
-  bb->cnt.swap(cnt);
-  bb->T.base.swap(T.base);
-  bb->T.n_entries = T.n_entries;
+  bb->cnt.swap(cnt[0]);
+  bb->T.base.swap(T[0].base);
+  bb->T.n_entries = T[0].n_entries;
+  if (split) {
+    bb->cnt_u.swap(cnt[1]);
+    bb->Tu.base.swap(T[1].base);
+    bb->Tu.n_entries = T[1].n_entries;
+  }
   m3b_mat_set_bbuild(m, bb);
-  dev_free(H);
-  dev_free(d_cnt);
-  dev_free(d_base);
+  for (int q = 0; q < 2; ++q) {
+    dev_free(H[q]);
+    dev_free(d_cnt[q]);
+    dev_free(d_base[q]);
+  }
   return M3B_OK;
 }
 
@@ -766,25 +847,38 @@ int finish_selection(m3b_mat* m, unsigned char* keep_host) {
     return M3B_E_STATE;
   }
   const int n_sel = m->n_sel;
+  const bool split = m->B.unit != nullptr;
   std::vector<int> kept_of_sel(n_sel);
   int nk = 0;
   for (int s = 0; s < n_sel; ++s) kept_of_sel[s] = keep_host[s] ? nk++ : -1;
   m->n_kept = nk;
-  HostTables T;
+  HostTables T, Tu;
   T.base = bb->T.base;
-  build_items(bb->cnt, m->B.n_tiles, n_sel, kept_of_sel.data(), nk, ctx->sm_count, T);
+  build_items(bb->cnt, m->B.n_tiles, n_sel, kept_of_sel.data(), nk, ctx->sm_count, T, SHAPE_GENERAL);
+  if (split) {
+    Tu.base = bb->Tu.base;
+    build_items(bb->cnt_u, m->B.n_tiles, n_sel, kept_of_sel.data(), nk, ctx->sm_count, Tu, SHAPE_UNIT);
+  }
+  assign_slots(T, split ? &Tu : nullptr, nk);
   m->B.rows = nk;
-  RET(upload_tables(ctx, m->B, T));
+  const size_t n_partial = T.items.size() + Tu.items.size();
+  RET(upload_tables(ctx, m->B, T, n_partial));
+  if (split) {
+    m->B.unit->rows = nk;
+    RET(upload_tables(ctx, *m->B.unit, Tu, n_partial, &m->B));
+  }
   dev_free(m->kept_of_sel);
   RET(dev_alloc(ctx, &m->kept_of_sel, (size_t)std::max(n_sel, 1)));
   if (n_sel) CK(ctx, cudaMemcpyAsync(m->kept_of_sel, kept_of_sel.data(), n_sel * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  // per-kept-gene nnz
+  // per-kept-gene nnz, and the pad entries of the GENERAL runs (OP_SQDEV counts those as (0-mu)^2;
+  // the unit kernel skips its pads itself)
   std::vector<long long> nnzk(std::max(nk, 1), 0), padk(std::max(nk, 1), 0);
   for (int t = 0; t < m->B.n_tiles; ++t)
     for (int s = 0; s < n_sel; ++s)
       if (kept_of_sel[s] >= 0) {
-        nnzk[kept_of_sel[s]] += bb->cnt[(size_t)t * n_sel + s];
-        padk[kept_of_sel[s]] += pad4(bb->cnt[(size_t)t * n_sel + s]);
+        const int c = bb->cnt[(size_t)t * n_sel + s], cu = split ? bb->cnt_u[(size_t)t * n_sel + s] : 0;
+        nnzk[kept_of_sel[s]] += c + cu;
+        padk[kept_of_sel[s]] += pad4(c) + cu;
       }
   dev_free(m->kept_nnz);
   dev_free(m->kept_padlen);
@@ -795,6 +889,8 @@ int finish_selection(m3b_mat* m, unsigned char* keep_host) {
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   m3b_mat_set_bbuild(m, nullptr);
   RET(bank_reorder(ctx, m->B));
+  if (split) RET(bank_reorder(ctx, *m->B.unit));
+  RET(flat_build_plans(ctx, m->B, T, split ? &Tu : nullptr));
   return M3B_OK;
 }
 
@@ -810,12 +906,16 @@ int finish_selection(m3b_mat* m, unsigned char* keep_host) {
 // item has enough entries of that class: consecutive lanes then read 16 different bank pairs.
 // Entries of over-full classes fill the holes of under-full ones, in a fixed order, so the
 // layout stays deterministic.  One warp per item, staged through shared memory.
+// In general: a lane's load covers S consecutive entries (S = 2 for the general stream, S = 8
+// for the index-only unit stream, whose lanes gather component j of their 16-byte load together),
+// so position p belongs to lane class (p / S) mod 16.
 // ---------------------------------------------------------------------------
-#define BR_WARPS 5
-#define BR_MAX M3B_ITEM_MAX
+#define BR_WARPS 3
+#define BR_MAX M3B_UITEM_MAX  // >= M3B_ITEM_MAX
 
 __global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* __restrict__ idx, double* __restrict__ val,
-                                                               const ItemDesc* __restrict__ items, long long n_items) {
+                                                               const ItemDesc* __restrict__ items, long long n_items,
+                                                               int S /* 2 or 8 */, int lgS) {
   extern __shared__ unsigned char br_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // per-warp staging: source idx/val, destination position of every entry, hole list
@@ -832,7 +932,7 @@ __global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* 
     if (len < 64 || len > BR_MAX) continue;  // too short to matter (or unexpected)
     for (int e = lane; e < len; e += 32) {
       sidx[e] = idx[d.start + e];
-      sval[e] = val[d.start + e];
+      if (val) sval[e] = val[d.start + e];
     }
     if (lane < 32) cnt[lane] = 0, cnt[32 + lane] = 0;
     __syncwarp();
@@ -852,12 +952,13 @@ __global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* 
       }
       __syncwarp();
     }
-    // native slots of class b inside len: positions p < len with ((p >> 1) & 15) == b
-    // nat[b] = 2 * floor(len / 32) + min(2, max(0, (len % 32) - 2 b))
+    // native slots of class b inside len: positions p < len with ((p / S) & 15) == b
+    // nat[b] = S * floor(len / 16S) + min(S, max(0, (len % 16S) - S b))
     int natb = 0, cntb = 0;
+    const int period = 16 * S;
     if (lane < 16) {
-      const int r = len & 31;
-      natb = 2 * (len >> 5) + min(2, max(0, r - 2 * lane));
+      const int r = len % period;
+      natb = S * (len / period) + min(S, max(0, r - S * lane));
       cntb = cnt[lane];
     }
     const int over = max(0, cntb - natb), holes = max(0, natb - cntb);
@@ -877,13 +978,14 @@ __global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* 
       cnt[16 + lane] = natb;      // nat
       cnt[32 + lane] = po;        // overflow prefix
       // enumerate this class's holes: slots cntb .. natb-1
-      for (int s2 = cntb; s2 < natb; ++s2) hole[ph + (s2 - cntb)] = (unsigned short)(32 * (s2 >> 1) + 2 * lane + (s2 & 1));
+      for (int s2 = cntb; s2 < natb; ++s2)
+        hole[ph + (s2 - cntb)] = (unsigned short)(period * (s2 >> lgS) + S * lane + (s2 & (S - 1)));
     }
     __syncwarp();
     for (int e = lane; e < len; e += 32) {
       const int b = sidx[e] & 15, r = dpos[e], nb = cnt[16 + b];
       int p;
-      if (r < nb) p = 32 * (r >> 1) + 2 * b + (r & 1);
+      if (r < nb) p = period * (r >> lgS) + S * b + (r & (S - 1));
       else p = hole[cnt[32 + b] + (r - nb)];
       dpos[e] = (unsigned short)p;
     }
@@ -891,7 +993,7 @@ __global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* 
     for (int e = lane; e < len; e += 32) {
       const int p = dpos[e];
       idx[d.start + p] = sidx[e];
-      val[d.start + p] = sval[e];
+      if (val) val[d.start + p] = sval[e];
     }
     __syncwarp();
   }
@@ -906,7 +1008,8 @@ static int bank_reorder(m3b_ctx* ctx, TiledLayout& L) {
     attr = true;
   }
   const unsigned grid = (unsigned)std::min<long long>((L.n_items + BR_WARPS - 1) / BR_WARPS, (long long)ctx->sm_count * 4);
-  k_bank_reorder<<<grid, 32 * BR_WARPS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.n_items);
+  k_bank_reorder<<<grid, 32 * BR_WARPS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.n_items, L.is_unit ? 8 : 2,
+                                                             L.is_unit ? 3 : 1);
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
   return M3B_OK;
@@ -926,6 +1029,7 @@ __global__ void k_compose_maps(const int* __restrict__ sel_of_gene, const int* _
 }
 
 __global__ void __launch_bounds__(256) k_count_A(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                 const double* __restrict__ xraw, int cls,
                                                  const int* __restrict__ kept_of_gene, long long n_cells, int tile_w,
                                                  int n_tiles, int* __restrict__ cnt) {
   const int lane = threadIdx.x & 31;
@@ -937,7 +1041,7 @@ __global__ void __launch_bounds__(256) k_count_A(const long long* __restrict__ p
       int n = 0;
       for (long long k = lo + lane; k < hi; k += 32) {
         int g = kept_of_gene[ld_stream_s32(gi + k)];
-        n += (g >= 0 && g / tile_w == t) ? 1 : 0;
+        n += (g >= 0 && g / tile_w == t && in_class(cls, xraw, k)) ? 1 : 0;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
@@ -947,7 +1051,8 @@ __global__ void __launch_bounds__(256) k_count_A(const long long* __restrict__ p
 }
 
 __global__ void __launch_bounds__(256) k_scatter_A(const long long* __restrict__ p, const int* __restrict__ gi,
-                                                   const double* __restrict__ y, const int* __restrict__ kept_of_gene,
+                                                   const double* __restrict__ y, const double* __restrict__ xraw, int cls,
+                                                   const int* __restrict__ kept_of_gene,
                                                    long long n_cells, int tile_w, int n_tiles,
                                                    const long long* __restrict__ base, unsigned short* __restrict__ idx,
                                                    double* __restrict__ val) {
@@ -966,34 +1071,47 @@ __global__ void __launch_bounds__(256) k_scatter_A(const long long* __restrict__
         double v = 0.0;
         if (k < hi) {
           g = kept_of_gene[ld_stream_s32(gi + k)];
-          if (g >= 0 && g / tile_w == t) v = ld_stream_f64(y + k);
-          else g = -1;
+          if (g >= 0 && g / tile_w == t && in_class(cls, xraw, k)) {
+            if (cls != 2) v = ld_stream_f64(y + k);
+          } else {
+            g = -1;
+          }
         }
         unsigned m = __ballot_sync(0xffffffffu, g >= 0);
         if (g >= 0) {
           long long dst = dst0 + run + __popc(m & lt);
           idx[dst] = (unsigned short)(g - t * tile_w);
-          val[dst] = v;
+          if (cls != 2) val[dst] = v;
         }
         run += __popc(m);
       }
-      // pads
-      int padded = (run + 3) & ~3;
+      // pads (unit runs: to 8 entries, pointing at the zero slot behind the tile)
+      const int pad = (cls == 2) ? 8 : 4;
+      int padded = (run + pad - 1) / pad * pad;
       if (lane < padded - run) {
-        idx[dst0 + run + lane] = 0;
-        val[dst0 + run + lane] = 0.0;
+        idx[dst0 + run + lane] = (cls == 2) ? (unsigned short)tile_w : (unsigned short)0;
+        if (cls != 2) val[dst0 + run + lane] = 0.0;
       }
     }
   }
 }
 
-int build_layout_A(m3b_mat* m) {
+int build_layout_A(m3b_mat* m, bool split) {
   m3b_ctx* ctx = m->ctx;
   TiledLayout& L = m->A;
   L.free_all();
   L.rows = m->n_cells;
   L.cols = m->n_kept;
   choose_tiling(L.cols, ctx->tile_w_max, &L.tile_w, &L.n_tiles);
+  if (split) {
+    L.unit = new TiledLayout();
+    L.unit->is_unit = true;
+    L.unit->rows = L.rows;
+    L.unit->cols = L.cols;
+    L.unit->tile_w = L.tile_w;
+    L.unit->n_tiles = L.n_tiles;
+    L.unit->rowscale = m->unit_val;  // rows are cells
+  }
   dev_free(m->kept_of_gene);
   RET(dev_alloc(ctx, &m->kept_of_gene, (size_t)std::max(m->n_genes, 1)));
   if (m->n_genes) {
@@ -1001,35 +1119,69 @@ int build_layout_A(m3b_mat* m) {
     count_launch(ctx);
   }
   const long long n_runs = (long long)L.n_tiles * L.rows;
-  int* d_cnt = nullptr;
-  long long* d_base = nullptr;
-  RET(dev_alloc(ctx, &d_cnt, (size_t)std::max<long long>(n_runs, 1)));
+  const int n_cls = split ? 2 : 1;
+  int* d_cnt[2] = {nullptr, nullptr};
+  long long* d_base[2] = {nullptr, nullptr};
+  std::vector<int> cnt[2];
+  HostTables T[2];
+  TiledLayout* Ls[2] = {&L, L.unit};
   int blocks = (int)std::max<long long>(1, std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8));
-  if (m->n_cells) {
-    k_count_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, d_cnt);
-    count_launch(ctx);
+  for (int q = 0; q < n_cls; ++q) {
+    RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
+    if (m->n_cells) {
+      k_count_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, split ? q + 1 : 0, m->kept_of_gene, m->n_cells, L.tile_w,
+                                                 L.n_tiles, d_cnt[q]);
+      count_launch(ctx);
+    }
+    CK(ctx, cudaGetLastError());
+    cnt[q].resize((size_t)n_runs);
+    if (n_runs) CK(ctx, cudaMemcpyAsync(cnt[q].data(), d_cnt[q], n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   }
-  CK(ctx, cudaGetLastError());
-  std::vector<int> cnt((size_t)n_runs);
-  if (n_runs) CK(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
-  HostTables T;
-  compute_bases(cnt, L.n_tiles, L.rows, T);
-  build_items(cnt, L.n_tiles, L.rows, nullptr, L.rows, ctx->sm_count, T);
-  L.n_entries = T.n_entries;
-  RET(dev_alloc(ctx, &L.idx, (size_t)T.n_entries));
-  RET(dev_alloc(ctx, &L.val, (size_t)T.n_entries));
-  RET(dev_alloc(ctx, &d_base, (size_t)std::max<long long>(n_runs, 1)));
-  if (n_runs) {
-    CK(ctx, cudaMemcpyAsync(d_base, T.base.data(), n_runs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-    k_scatter_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles,
-                                                 d_base, L.idx, L.val);
-    count_launch(ctx);
+  for (int q = 0; q < n_cls; ++q) {
+    const ItemShape& sh = (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL;
+    compute_bases(cnt[q], L.n_tiles, L.rows, T[q], sh);
+    build_items(cnt[q], L.n_tiles, L.rows, nullptr, L.rows, ctx->sm_count, T[q], sh);
   }
-  CK(ctx, cudaGetLastError());
-  RET(upload_tables(ctx, L, T));
+  assign_slots(T[0], split ? &T[1] : nullptr, L.rows);
+  for (int q = 0; q < n_cls; ++q) {
+    TiledLayout& Lq = *Ls[q];
+    Lq.n_entries = T[q].n_entries;
+    RET(dev_alloc(ctx, &Lq.idx, (size_t)T[q].n_entries));
+    if (q == 0) RET(dev_alloc(ctx, &Lq.val, (size_t)T[q].n_entries));
+    RET(dev_alloc(ctx, &d_base[q], (size_t)std::max<long long>(n_runs, 1)));
+    if (n_runs) {
+      CK(ctx, cudaMemcpyAsync(d_base[q], T[q].base.data(), n_runs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+      k_scatter_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, split ? q + 1 : 0, m->kept_of_gene, m->n_cells,
+                                                   L.tile_w, L.n_tiles, d_base[q], Lq.idx, Lq.val);
+      count_launch(ctx);
+    }
+    CK(ctx, cudaGetLastError());
+  }
+  const size_t n_partial = T[0].items.size() + (split ? T[1].items.size() : 0);
+  RET(upload_tables(ctx, L, T[0], n_partial));
   RET(bank_reorder(ctx, L));
-  dev_free(d_cnt);
-  dev_free(d_base);
+  if (split) {
+    RET(upload_tables(ctx, *L.unit, T[1], n_partial, &L));
+    RET(bank_reorder(ctx, *L.unit));
+  }
+  RET(flat_build_plans(ctx, L, T[0], split ? &T[1] : nullptr));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int q = 0; q < 2; ++q) {
+    dev_free(d_cnt[q]);
+    dev_free(d_base[q]);
+  }
+  return M3B_OK;
+}
+
+int rebuild_layouts(m3b_mat* m, bool split) {
+  if (!m->selected || (int)m->keep_mask.size() < m->n_sel) {
+    m3b_set_error(m->ctx, "internal: rebuild_layouts without a selection");
+    return M3B_E_STATE;
+  }
+  RET(build_layout_B(m, split));
+  m->split = split;
+  RET(finish_selection(m, m->keep_mask.data()));
+  RET(build_layout_A(m, split));
   return M3B_OK;
 }

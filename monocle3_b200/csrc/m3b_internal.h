@@ -65,6 +65,8 @@ int comm_p2p_open(m3b_ctx* ctx, const char* handles /* world x 64 bytes */);
 // product kernel are then throttled for lack of line buffers (ncu: lg_throttle, DRAM 56% vs 75%
 // for the same kernel with a 120 KB tile; profiles/).  160 KB tiles leave ~60 KB of L1 (sweep in DESIGN.md).
 #define M3B_TILE_W_DEFAULT 20480
+// SMs left to the restart SVD while the next cycle's first product runs on the side stream
+#define M3B_SIDE_CTA_RESERVE 28
 
 // ---------------------------------------------------------------------------
 // context
@@ -107,6 +109,9 @@ struct m3b_ctx {
 // ---------------------------------------------------------------------------
 #define M3B_ITEM_MAX 2048     // entries per item (multiple of 128)
 #define M3B_ITEM_TAIL 512     // entries per item in the last part of a tile (short tail of the launch)
+// UNIT layouts (see "unit entries" below): index-only streams, 2 B/entry, runs padded to 8
+#define M3B_UITEM_MAX 4096
+#define M3B_UITEM_TAIL 1024
 
 struct ItemDesc {  // 16 bytes, loaded with one 128-bit load
   long long start;  // entry offset into idx/val (multiple of 4)
@@ -137,7 +142,33 @@ struct TiledLayout {
   int* item_slot = nullptr;    // [n_items]
   int* row_slot_ptr = nullptr; // [rows+1]
   double* partial = nullptr;   // [n_items], indexed by slot
+  // UNIT ENTRIES.  Most stored counts are exactly 1 (51-84% in the reference's fixtures and the
+  // synthetic benchmark matrix), and the normalised value of a count-1 entry depends on its cell
+  // only: u_c = f(1 / size_factor_c).  Those entries are kept in a sibling layout that stores NO
+  // values -- a 2 B/entry index stream -- and are multiplied by u on the dense side:
+  //   layout A (row = cell):  partial = u[row] * sum x[idx]        (rowscale)
+  //   layout B (col = cell):  the staged tile holds x[c] * u[c]     (colscale)
+  // The sibling shares the parent's partial array and slot numbering (a row's slots are its
+  // general items followed by its unit items), so the combine kernels see one layout.
+  TiledLayout* unit = nullptr;       // owned; nullptr when the matrix is not split
+  bool is_unit = false;              // val == nullptr, runs padded to 8 with idx == tile_w (a zero slot)
+  const double* colscale = nullptr;  // unit layouts: per-column factor (length cols) or nullptr
+  const double* rowscale = nullptr;  // unit layouts: per-row factor (length rows) or nullptr
+  // static work plans of the flat product kernel (flat.cu); [0] = whole grid, [1] = the reduced
+  // grid of the side-stream launch (single-tile layouts only).  Owned by the general layout.
+  struct FlatPlan* plan[2] = {nullptr, nullptr};
+  double* item_scale = nullptr;  // unit layouts with a rowscale: rowscale[row of item], per item
   void free_all();
+};
+
+// host-side tables of a layout while it is being built (layout.cu), input of the flat plan (flat.cu)
+struct HostTables {
+  std::vector<long long> base;
+  std::vector<ItemDesc> items;
+  std::vector<int> row_item_ptr, item_slot, row_slot_ptr;
+  std::vector<int2> chunks;
+  std::vector<int> tile_chunk_ptr, cta_tile;
+  long long n_entries = 0, nnz = 0;
 };
 
 // the matrix handle
@@ -152,6 +183,9 @@ struct m3b_mat {
   int* i = nullptr;        // [nnz]
   double* x = nullptr;     // [nnz] raw counts
   double* y = nullptr;     // [nnz] normalised values (after m3b_normalize)
+  double* unit_val = nullptr;  // [n_cells] normalised value of a count-1 entry of the cell
+  bool split = false;          // the layouts keep count-1 entries in index-only siblings
+  std::vector<unsigned char> keep_mask;  // zero-gene filter of the last selection (per selected gene)
   bool ended = false, normalized = false, selected = false, moments_done = false;
   bool tfidf_applied = false;  // the layouts hold TF-IDF values (LSI branch), not the normalised ones
   int norm_method = -1;
@@ -187,9 +221,10 @@ void dev_pool_release(int device);  // return the cached blocks of a device to t
 // layout.cu
 int k1_cell_totals(m3b_mat* m, int round_exprs, double* d_tot);
 int k2_normalize(m3b_mat* m, const double* d_sf, int method, double pc);
-int build_layout_B(m3b_mat* m);
+int build_layout_B(m3b_mat* m, bool split);
 int finish_selection(m3b_mat* m, unsigned char* keep_host);
-int build_layout_A(m3b_mat* m);
+int build_layout_A(m3b_mat* m, bool split);
+int rebuild_layouts(m3b_mat* m, bool split);  // same selection and keep mask, other split mode
 void m3b_mat_set_bbuild(m3b_mat* m, void* p);
 int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* i, const double* x);
 
@@ -202,6 +237,13 @@ int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double*
 // out[row] = sum of the row's partials (fixed order: tile, then segment)
 int launch_combine_rows(m3b_ctx* ctx, const TiledLayout& L, double* out);
 long long spmv_algorithmic_bytes(const TiledLayout& L);
+
+// flat.cu: the product kernel proper (OP_DOT) -- static, item-aligned partition of each tile's
+// entry stream over the warps, streamed flat with a register ring and reduced per item
+void flat_plan_free(struct FlatPlan* p);
+int flat_build_plans(m3b_ctx* ctx, TiledLayout& L, const HostTables& Tg, const HostTables* Tu);
+int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStream_t stream, int max_cta);
+int flat_init(m3b_ctx* ctx);
 
 // tfidf.cu (LSI branch)
 int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor, const double* row_sums_in,

@@ -17,8 +17,13 @@
 
 #define PJ_CPL 4  // columns per lane => nv <= 128 per pass
 
+// The row's entries come from up to two layouts: the general one (idx + val) and the unit one
+// (count-1 entries: index only, value = uval[row]; pads carry idx == tile_w).
 __global__ void __launch_bounds__(256) k_project(const unsigned short* __restrict__ idx, const double* __restrict__ val,
                                                  const ItemDesc* __restrict__ items, const int* __restrict__ rip,
+                                                 const unsigned short* __restrict__ uidx,
+                                                 const ItemDesc* __restrict__ uitems, const int* __restrict__ urip,
+                                                 const double* __restrict__ uval,
                                                  long long rows, int n_tiles, int tile_w,
                                                  const double* __restrict__ Vs /* [G'q][nv] row-major */,
                                                  const double* __restrict__ b, int nv, int col0,
@@ -30,18 +35,26 @@ __global__ void __launch_bounds__(256) k_project(const unsigned short* __restric
     double acc[PJ_CPL];
 #pragma unroll
     for (int a = 0; a < PJ_CPL; ++a) acc[a] = 0.0;
+    for (int pass = 0; pass < (uidx ? 2 : 1); ++pass)
     for (int t = 0; t < n_tiles; ++t) {
-      const int* p = rip + (long long)t * (rows + 1) + r;
+      const int* p = (pass ? urip : rip) + (long long)t * (rows + 1) + r;
       const int ib = p[0], ie = p[1];
       const long long goff = (long long)t * tile_w;
+      const double ur = pass ? uval[r] : 0.0;
       for (int it = ib; it < ie; ++it) {
-        const ItemDesc d = items[it];
+        const ItemDesc d = pass ? uitems[it] : items[it];
         for (int e0 = 0; e0 < d.len; e0 += 32) {
           int myi = 0;
           double myv = 0.0;
           if (e0 + lane < d.len) {
-            myi = (int)idx[d.start + e0 + lane];
-            myv = val[d.start + e0 + lane];
+            if (pass) {
+              myi = (int)(uidx[d.start + e0 + lane] & 0x7fff);
+              myv = (myi < tile_w) ? ur : 0.0;
+              if (myi >= tile_w) myi = 0;
+            } else {
+              myi = (int)(idx[d.start + e0 + lane] & 0x7fff);
+              myv = val[d.start + e0 + lane];
+            }
           }
           const int cnt = min(32, d.len - e0);
           for (int q = 0; q < cnt; ++q) {
@@ -110,8 +123,11 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
     if (rows) {
       int blocks = (int)std::min<long long>((rows + 7) / 8, (long long)ctx->sm_count * 8);
       for (int col0 = 0; col0 < nv; col0 += 32 * PJ_CPL) {
-        k_project<<<blocks, 256, 0, ctx->stream>>>(q->A.idx, q->A.val, q->A.items, q->A.row_item_ptr, rows, q->A.n_tiles,
-                                                   q->A.tile_w, dVs, db, nv, col0, dY, rows);
+        const TiledLayout* U = q->A.unit;
+        k_project<<<blocks, 256, 0, ctx->stream>>>(q->A.idx, q->A.val, q->A.items, q->A.row_item_ptr,
+                                                   U ? U->idx : nullptr, U ? U->items : nullptr,
+                                                   U ? U->row_item_ptr : nullptr, U ? U->rowscale : nullptr, rows,
+                                                   q->A.n_tiles, q->A.tile_w, dVs, db, nv, col0, dY, rows);
         count_launch(ctx);
       }
       if ((e = cudaGetLastError()) != cudaSuccess) break;

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_tfidf_items(unsigned short* __restrict_
     for (int e = lane; e < d.len; e += 32) {
       const double v = val[d.start + e];
       if (v == 0.0) continue;  // pads and explicit zeros stay zero (log1p(0) * idf = 0)
-      const long long other = off + idx[d.start + e];
+      const long long other = off + (idx[d.start + e] & 0x7fff);  // bit 15: head flag (flat.cu)
       double t = v;
       if (frequencies) t = t / (ROWS_ARE_CELLS ? colsum[d.row] : colsum[other]);
       if (log_scale_tf) t = log1p(t * (frequencies ? scale_factor : 1.0));
@@ -71,6 +71,9 @@ int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor
     m3b_set_error(ctx, "TF-IDF on the dense pseudo-count path is not supported");
     return M3B_E_STATE;
   }
+  // TF-IDF rewrites every stored value per (gene, cell): the index-only unit layouts cannot hold
+  // that, so the layouts are re-built with all entries in the general stream first
+  if (m->split) RET(rebuild_layouts(m, false));
   const int n = m->n_kept;
   const long long C = m->n_cells;
   if (num_cols <= 0) num_cols = (double)m->n_cells_total;
