@@ -22,9 +22,23 @@
 
 #include "m3b_internal.h"
 
-#define FL_THREADS 512
-#define FL_WARPS (FL_THREADS / 32)
-#define FL_K 6  // rounds per register batch (two batches per warp)
+// Kernel variants <rounds per register batch, threads per CTA>; one CTA per SM either way (the tile
+// takes the shared memory), so the thread count trades registers per thread (batch depth) against
+// warps per scheduler (latency hiding).  M3B_FLAT_VARIANT selects one for sweeps.
+struct FlatVariant {
+  int k, threads;
+};
+static const FlatVariant FL_VARIANTS[] = {{6, 512}, {3, 1024}, {2, 1024}, {4, 768}, {4, 1024}};
+static int fl_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("M3B_FLAT_VARIANT");
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v >= (int)(sizeof(FL_VARIANTS) / sizeof(FL_VARIANTS[0]))) v = 0;
+  }
+  return v;
+}
+#define FL_WARPS (FL_VARIANTS[fl_variant()].threads / 32)
 
 struct FlatPlan {
   int n_cta = 0, n_visits = 0;
@@ -93,8 +107,8 @@ static long long env_ll(const char* name, long long dflt) {
   return e ? std::max(64LL, atoll(e)) : dflt;
 }
 // entries per piece (M3B_FLAT_PIECE_G / M3B_FLAT_PIECE_U override, for sweeps)
-static long long fl_piece_general() { return env_ll("M3B_FLAT_PIECE_G", 2048); }
-static long long fl_piece_unit() { return env_ll("M3B_FLAT_PIECE_U", 8192); }
+static long long fl_piece_general() { return env_ll("M3B_FLAT_PIECE_G", 8192); }
+static long long fl_piece_unit() { return env_ll("M3B_FLAT_PIECE_U", 32768); }
 
 static int build_one_plan(m3b_ctx* ctx, const TiledLayout& L, const HostTables& Tg, const HostTables* Tu, int n_cta,
                           FlatPlan** out) {
@@ -368,6 +382,15 @@ __device__ __forceinline__ void fl_finish(FlatState& st, int lane, const int* __
   if (lane == 0) partial[sl] = sc * tot;
 }
 
+template <int K>
+__device__ __forceinline__ double fl_tree(const double (&v)[K]) {
+  static_assert(K == 2 || K == 3 || K == 4 || K == 6, "fl_tree: unsupported batch depth");
+  if (K == 6) return ((v[0] + v[1]) + (v[2] + v[3])) + (v[4 % K] + v[5 % K]);
+  if (K == 4) return (v[0] + v[1]) + (v[2] + v[3 % K]);
+  if (K == 3) return (v[0] + v[1]) + v[2 % K];
+  return v[0] + v[1];
+}
+
 struct FlatArgs {
   const unsigned short* gidx;
   const double* gval;
@@ -388,9 +411,12 @@ struct FlatArgs {
   const double* x;
   const double* colscale;  // unit phase: tile *= colscale (layout B); nullptr on layout A
   double* partial;
+  int debug_skip;  // timing experiments only (M3B_FLAT_SKIP): 1 = no general phase, 2 = no unit phase
 };
 
-__global__ void __launch_bounds__(FL_THREADS, 1) k_flat_dot(const FlatArgs a) {
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
+  constexpr int NWARPS = THREADS / 32;
   extern __shared__ double sx[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile_w = a.tile_w;
@@ -417,8 +443,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flat_dot(const FlatArgs a) {
       __syncthreads();
     }
     // ---- general stream: groups of 2 entries (u32 index pair + double2 values)
-    {
-      const int p0 = a.gp_ptr[vis * FL_WARPS + warp], p1 = a.gp_ptr[vis * FL_WARPS + warp + 1];
+    if (a.debug_skip != 1) {
+      const int p0 = a.gp_ptr[vis * NWARPS + warp], p1 = a.gp_ptr[vis * NWARPS + warp + 1];
       for (int p = p0; p < p1; ++p) {
         const int4 pc = a.gp[p];
         const unsigned int* ip = reinterpret_cast<const unsigned int*>(a.gidx) + pc.x;
@@ -429,7 +455,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flat_dot(const FlatArgs a) {
         st.item = pc.z;
         st.open = false;
         fl_window(st, pc.z, a.gslot, nullptr, a.g_items, lane);
-        // Two register-resident batches of FL_K rounds, software-pipelined: batch k+1 is in flight
+        // Two register-resident batches of K rounds, software-pipelined: batch k+1 is in flight
         // while batch k is consumed.  What the SASS of earlier versions taught:
         //  * loads are UNCONDITIONAL (addresses past the end are clamped to the last group, the data
         //    is ignored when the round is consumed): "in range ? load : 0" became a load into a
@@ -438,31 +464,41 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flat_dot(const FlatArgs a) {
         //    scoreboards, ptxas has to share them between the slots, and waiting for the oldest
         //    load then waits for the newest one on the same scoreboard.  Two big batches map onto
         //    two scoreboards.
-        unsigned int i0[FL_K], i1[FL_K];
-        double2 w0[FL_K], w1[FL_K];
+        unsigned int i0[K], i1[K];
+        double2 w0[K], w1[K];
 #define FL_GLOAD(BI, BV, R0)                                        \
-  _Pragma("unroll") for (int u = 0; u < FL_K; ++u) {                \
+  _Pragma("unroll") for (int u = 0; u < K; ++u) {                \
     const int g = min(32 * ((R0) + u) + lane, ng - 1);              \
     BI[u] = fl_ld_u32(ip + g);                                      \
     BV[u] = fl_ld_double2(vp + g);                                  \
   }
+  // all gathers / products of a batch first (independent => the LDS and DFMA latencies overlap),
+  // then the item bookkeeping; a batch without an item start is just one tree of adds
 #define FL_GUSE(BI, BV, R0)                                                                     \
-  _Pragma("unroll") for (int u = 0; u < FL_K; ++u) {                                            \
-    if ((R0) + u < nr) {                                                                        \
+  {                                                                                             \
+    double v[K];                                                                             \
+    unsigned mk[K], any = 0u;                                                                \
+    _Pragma("unroll") for (int u = 0; u < K; ++u) {                                          \
       const bool valid = 32 * ((R0) + u) + lane < ng;                                           \
-      const unsigned mask = __ballot_sync(0xffffffffu, valid && ((BI[u] >> 15) & 1u));          \
-      double v = fma(BV[u].y, sx[BI[u] >> 16], BV[u].x * sx[BI[u] & 0x7fffu]);                  \
-      v = valid ? v : 0.0;                                                                      \
-      fl_round(st, v, mask, lane, a.gslot, nullptr, a.g_items, a.partial);                      \
+      mk[u] = __ballot_sync(0xffffffffu, valid && ((BI[u] >> 15) & 1u));                        \
+      any |= mk[u];                                                                             \
+      const double t = fma(BV[u].y, sx[BI[u] >> 16], BV[u].x * sx[BI[u] & 0x7fffu]);            \
+      v[u] = valid ? t : 0.0;                                                                   \
+    }                                                                                           \
+    if (any == 0u) {                                                                            \
+      st.acc += fl_tree<K>(v);                                                                     \
+    } else {                                                                                    \
+      _Pragma("unroll") for (int u = 0; u < K; ++u)                                          \
+        if ((R0) + u < nr) fl_round(st, v[u], mk[u], lane, a.gslot, nullptr, a.g_items, a.partial); \
     }                                                                                           \
   }
         FL_GLOAD(i0, w0, 0)
-        for (int r0 = 0; r0 < nr; r0 += 2 * FL_K) {
-          FL_GLOAD(i1, w1, r0 + FL_K)
+        for (int r0 = 0; r0 < nr; r0 += 2 * K) {
+          FL_GLOAD(i1, w1, r0 + K)
           FL_GUSE(i0, w0, r0)
-          if (r0 + FL_K >= nr) break;
-          FL_GLOAD(i0, w0, r0 + 2 * FL_K)
-          FL_GUSE(i1, w1, r0 + FL_K)
+          if (r0 + K >= nr) break;
+          FL_GLOAD(i0, w0, r0 + 2 * K)
+          FL_GUSE(i1, w1, r0 + K)
         }
 #undef FL_GLOAD
 #undef FL_GUSE
@@ -470,14 +506,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flat_dot(const FlatArgs a) {
       }
     }
     // ---- unit stream: groups of 8 indices, value applied on the dense side
-    if (a.uidx) {
+    if (a.uidx && a.debug_skip != 2) {
       if (a.colscale) {
         __syncthreads();
         const double* cs = a.colscale + off;
         for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] *= cs[k];
         __syncthreads();
       }
-      const int p0 = a.up_ptr[vis * FL_WARPS + warp], p1 = a.up_ptr[vis * FL_WARPS + warp + 1];
+      const int p0 = a.up_ptr[vis * NWARPS + warp], p1 = a.up_ptr[vis * NWARPS + warp + 1];
       for (int p = p0; p < p1; ++p) {
         const int4 pc = a.up[p];
         const uint4* ip = reinterpret_cast<const uint4*>(a.uidx) + pc.x;
@@ -487,28 +523,36 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flat_dot(const FlatArgs a) {
         st.item = pc.z;
         st.open = false;
         fl_window(st, pc.z, a.uslot, a.uscale, a.u_items, lane);
-        uint4 q0[FL_K], q1[FL_K];
+        uint4 q0[K], q1[K];
 #define FL_ULOAD(B, R0) \
-  _Pragma("unroll") for (int u = 0; u < FL_K; ++u) B[u] = fl_ld_uint4(ip + min(32 * ((R0) + u) + lane, ng - 1));
+  _Pragma("unroll") for (int u = 0; u < K; ++u) B[u] = fl_ld_uint4(ip + min(32 * ((R0) + u) + lane, ng - 1));
 #define FL_UUSE(B, R0)                                                                                      \
-  _Pragma("unroll") for (int u = 0; u < FL_K; ++u) {                                                        \
-    if ((R0) + u < nr) {                                                                                    \
+  {                                                                                                         \
+    double v[K];                                                                                         \
+    unsigned mk[K], any = 0u;                                                                            \
+    _Pragma("unroll") for (int u = 0; u < K; ++u) {                                                      \
       const uint4 b = B[u];                                                                                 \
       const bool valid = 32 * ((R0) + u) + lane < ng;                                                       \
-      const unsigned mask = __ballot_sync(0xffffffffu, valid && ((b.x >> 15) & 1u));                        \
-      double v = ((sx[b.x & 0x7fffu] + sx[b.x >> 16]) + (sx[b.y & 0xffffu] + sx[b.y >> 16])) +              \
-                 ((sx[b.z & 0xffffu] + sx[b.z >> 16]) + (sx[b.w & 0xffffu] + sx[b.w >> 16]));               \
-      v = valid ? v : 0.0;                                                                                  \
-      fl_round(st, v, mask, lane, a.uslot, a.uscale, a.u_items, a.partial);                                 \
+      mk[u] = __ballot_sync(0xffffffffu, valid && ((b.x >> 15) & 1u));                                      \
+      any |= mk[u];                                                                                         \
+      const double t = ((sx[b.x & 0x7fffu] + sx[b.x >> 16]) + (sx[b.y & 0xffffu] + sx[b.y >> 16])) +        \
+                       ((sx[b.z & 0xffffu] + sx[b.z >> 16]) + (sx[b.w & 0xffffu] + sx[b.w >> 16]));         \
+      v[u] = valid ? t : 0.0;                                                                               \
+    }                                                                                                       \
+    if (any == 0u) {                                                                                        \
+      st.acc += fl_tree<K>(v);                                                                                 \
+    } else {                                                                                                \
+      _Pragma("unroll") for (int u = 0; u < K; ++u)                                                      \
+        if ((R0) + u < nr) fl_round(st, v[u], mk[u], lane, a.uslot, a.uscale, a.u_items, a.partial);        \
     }                                                                                                       \
   }
         FL_ULOAD(q0, 0)
-        for (int r0 = 0; r0 < nr; r0 += 2 * FL_K) {
-          FL_ULOAD(q1, r0 + FL_K)
+        for (int r0 = 0; r0 < nr; r0 += 2 * K) {
+          FL_ULOAD(q1, r0 + K)
           FL_UUSE(q0, r0)
-          if (r0 + FL_K >= nr) break;
-          FL_ULOAD(q0, r0 + 2 * FL_K)
-          FL_UUSE(q1, r0 + FL_K)
+          if (r0 + K >= nr) break;
+          FL_ULOAD(q0, r0 + 2 * K)
+          FL_UUSE(q1, r0 + K)
         }
 #undef FL_ULOAD
 #undef FL_UUSE
@@ -518,9 +562,19 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flat_dot(const FlatArgs a) {
   }
 }
 
-int flat_init(m3b_ctx* ctx) {
-  CK(ctx, cudaFuncSetAttribute(k_flat_dot, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int K, int THREADS>
+static int fl_init_one(m3b_ctx* ctx) {
+  CK(ctx, cudaFuncSetAttribute(k_flat_dot<K, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)((M3B_TILE_W_MAX + 2) * sizeof(double))));
+  return M3B_OK;
+}
+
+int flat_init(m3b_ctx* ctx) {
+  RET((fl_init_one<6, 512>(ctx)));
+  RET((fl_init_one<3, 1024>(ctx)));
+  RET((fl_init_one<2, 1024>(ctx)));
+  RET((fl_init_one<4, 768>(ctx)));
+  RET((fl_init_one<4, 1024>(ctx)));
   return M3B_OK;
 }
 
@@ -549,8 +603,17 @@ int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStr
   a.x = x;
   a.colscale = U ? U->colscale : nullptr;
   a.partial = L.partial;
+  static const int dbg_skip = getenv("M3B_FLAT_SKIP") ? atoi(getenv("M3B_FLAT_SKIP")) : 0;
+  a.debug_skip = dbg_skip;
   const size_t smem = ((size_t)L.tile_w + 2) * sizeof(double);
-  k_flat_dot<<<P->n_cta, FL_THREADS, smem, stream ? stream : ctx->stream>>>(a);
+  cudaStream_t st = stream ? stream : ctx->stream;
+  switch (fl_variant()) {
+    case 1: k_flat_dot<3, 1024><<<P->n_cta, 1024, smem, st>>>(a); break;
+    case 2: k_flat_dot<2, 1024><<<P->n_cta, 1024, smem, st>>>(a); break;
+    case 3: k_flat_dot<4, 768><<<P->n_cta, 768, smem, st>>>(a); break;
+    case 4: k_flat_dot<4, 1024><<<P->n_cta, 1024, smem, st>>>(a); break;
+    default: k_flat_dot<6, 512><<<P->n_cta, 512, smem, st>>>(a); break;
+  }
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
   return M3B_OK;
