@@ -32,6 +32,7 @@ int launch_arrow_svd(m3b_ctx* ctx, int n, int k_host, const int* ctl_k, const do
                      double* scratch, int* flag);
 
 #define NT 256
+#define M3B_OF_SMEM_MAX (200 * 1024)  // dynamic shared memory the fused vector kernel may ask for
 #define MAX_PART 592  // upper bound on per-kernel partial counts (4 * 148)
 
 // scalar slots in the device scalar buffer
@@ -374,6 +375,275 @@ __global__ void __launch_bounds__(NT) k_apply_orth(const double* __restrict__ X,
   }
 }
 
+
+// --------------------------------------------------------------------------
+// Single-rank fusion of one half Lanczos step's vector work into ONE cooperative kernel:
+//   combine (row sums of the product's partials + operator fix-ups)  ->  y chunk in shared memory
+//   partial dots X^T y            | grid barrier
+//   t = sum of the partial dots, y -= X t, partial ||y||^2 and sum(y)   | grid barrier
+//   norm, scaling and the scalars of the step (k_scale_w_fused / k_finish_F / k_finish_last)
+// The separate kernels (k_combine_*, k_dots, k_reduce_dots, k_apply_orth, k_finish_*) each cost a
+// launch gap plus a ramp and a tail on vectors of 20-40 k elements: ~50 us per half step for
+// ~10 us of memory time.  Every CTA owns one contiguous chunk of rows for the whole kernel; all
+// reductions keep a fixed order (bit-reproducible).  The multi-rank path keeps the separate
+// kernels because its allreduces sit between the phases.
+// --------------------------------------------------------------------------
+#define OF_THREADS 1024
+enum { OF_W = 0, OF_F = 1, OF_FLAST = 2 };
+
+struct OrthArgs {
+  int mode;
+  long long rows;
+  int chunk;
+  // combine
+  const double* partial;
+  const int* rsp;
+  const double* pb_in;  // W side: partials of beta (nullptr: beta = 0)
+  int npb_in;
+  const double* wprev;  // W side: nullptr or the previous W column
+  const double* s;      // gene sd or nullptr
+  const double* ce;     // effective centre or nullptr
+  const double* vj;     // F side: V[:, j]
+  // orthogonalisation
+  const double* X;
+  long long ld;
+  int ncols;
+  double* y;
+  double* part;  // [grid][ncols]
+  double* pn;    // [grid]
+  double* ps;    // [grid]
+  // finish
+  double* vnext;
+  double* xs;
+  double* pb_out;  // [grid]
+  double* Bm;
+  int work, j;
+  double eps;
+  double* scal;
+  int* ctl;
+  unsigned long long* bar;
+  unsigned long long bar_base;
+};
+
+// All CTAs are co-resident (cooperative launch).  The spin is bounded (~2 s) so that a lost CTA
+// turns into an error (CT_FLAG bit 8) instead of a hung device.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target, int* ctl) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1ULL);
+    unsigned long long v;
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (clock64() - t0 > 4000000000LL) {
+        atomicOr(ctl + CT_FLAG, 8);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// deterministic sum of a short array written by other CTAs of this launch (L1-bypassing loads)
+__device__ __forceinline__ double block_sum_cg(const double* p, int np, double* sh, double* bc) {
+  double v = 0.0;
+  for (int k = threadIdx.x; k < np; k += blockDim.x) v += __ldcg(p + k);
+  double r = block_sum(v, sh);
+  if (threadIdx.x == 0) *bc = r;
+  __syncthreads();
+  const double out = *bc;
+  __syncthreads();
+  return out;
+}
+
+__global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) {
+  extern __shared__ double of_smem[];
+  double* ys = of_smem;                      // [chunk]   this CTA's rows of y
+  double* ts = ys + a.chunk;                 // [ncols]
+  double* red = ts + ((a.ncols + 1) & ~1);   // [1024]    scratch of the two reductions
+  __shared__ double sh[32];
+  __shared__ double bc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long r0 = (long long)blockIdx.x * a.chunk;
+  const int len = (int)max(0LL, min((long long)a.chunk, a.rows - r0));
+  const int ncols = a.ncols;
+  // ---- phase 0: combine (4 lanes per row)
+  {
+    double beta = 0.0, rf = 0.0, sumw = 0.0, S = 0.0;
+    if (a.mode == OF_W) {
+      if (a.pb_in) beta = block_sum_cg(a.pb_in, a.npb_in, sh, &bc);
+      if (a.wprev) rf = a.scal[SC_RF];
+    } else {
+      sumw = a.scal[SC_SUMW];
+      S = a.scal[SC_S];
+    }
+    const int sub = tid & 3;
+    for (int q0 = 0; q0 < len; q0 += OF_THREADS / 4) {
+      const int q = q0 + (tid >> 2);
+      const long long r = r0 + q;
+      int b = 0, e = 0;
+      if (q < len) {
+        b = a.rsp[r];
+        e = a.rsp[r + 1];
+      }
+      double f = 0.0;
+      for (int k = b + sub; k < e; k += 4) f += a.partial[k];
+      f += __shfl_xor_sync(0xffffffffu, f, 2);
+      f += __shfl_xor_sync(0xffffffffu, f, 1);
+      if (q < len && sub == 0) {
+        if (a.mode == OF_W) {
+          f -= beta;
+          if (a.wprev) f -= rf * a.wprev[r];
+        } else {
+          if (a.s) f = f / a.s[r];
+          if (a.ce) {
+            double c = sumw * a.ce[r];
+            if (a.s) c = c / a.s[r];
+            f = f - c;
+          }
+          f = f - S * a.vj[r];
+        }
+        ys[q] = f;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- phase 1: partial dots of this chunk, a warp takes 4 columns at a time
+  for (int c0 = warp * 4; c0 < ncols; c0 += (OF_THREADS / 32) * 4) {
+    const int nc = min(4, ncols - c0);
+    const double* x0 = a.X + (long long)c0 * a.ld + r0;
+    const double* x1 = x0 + (nc > 1 ? a.ld : 0);
+    const double* x2 = x0 + (nc > 2 ? 2 * a.ld : 0);
+    const double* x3 = x0 + (nc > 3 ? 3 * a.ld : 0);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+    for (int k = lane; k < len; k += 32) {
+      const double yv = ys[k];
+      a0 += x0[k] * yv;
+      a1 += x1[k] * yv;
+      a2 += x2[k] * yv;
+      a3 += x3[k] * yv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (lane == 0) {
+      double* pp = a.part + (long long)blockIdx.x * ncols + c0;
+      pp[0] = a0;
+      if (nc > 1) pp[1] = a1;
+      if (nc > 2) pp[2] = a2;
+      if (nc > 3) pp[3] = a3;
+    }
+  }
+  grid_barrier(a.bar, a.bar_base + gridDim.x, a.ctl);
+  // ---- phase 2a: t = sum over the CTAs' partial dots (group q of threads sums blocks q, q+G, ...)
+  {
+    const int G = OF_THREADS / max(ncols, 1);
+    const int c = tid % max(ncols, 1), q = tid / max(ncols, 1);
+    if (q < G && ncols > 0) {
+      double v = 0.0;
+      for (int b = q; b < (int)gridDim.x; b += G) v += __ldcg(a.part + (long long)b * ncols + c);
+      red[q * ncols + c] = v;
+    }
+    __syncthreads();
+    if (tid < ncols) {
+      double v = 0.0;
+      for (int q2 = 0; q2 < G; ++q2) v += red[q2 * ncols + tid];
+      ts[tid] = v;
+    }
+    __syncthreads();
+  }
+  // ---- phase 2b: y -= X t on this chunk (128 rows x 8 column groups per pass)
+  double n2 = 0.0, sm = 0.0;
+  {
+    const int rl = tid & 127, cg = tid >> 7;
+    for (int q0 = 0; q0 < len; q0 += 128) {
+      const int q = q0 + rl;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (q < len) {
+        const double* xr = a.X + r0 + q;
+        int c = cg;
+        for (; c + 24 < ncols; c += 32) {
+          a0 += xr[(long long)c * a.ld] * ts[c];
+          a1 += xr[(long long)(c + 8) * a.ld] * ts[c + 8];
+          a2 += xr[(long long)(c + 16) * a.ld] * ts[c + 16];
+          a3 += xr[(long long)(c + 24) * a.ld] * ts[c + 24];
+        }
+        for (; c < ncols; c += 8) a0 += xr[(long long)c * a.ld] * ts[c];
+      }
+      red[cg * 128 + rl] = (a0 + a1) + (a2 + a3);
+      __syncthreads();
+      if (cg == 0 && q < len) {
+        double d = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) d += red[g * 128 + rl];
+        const double v = ys[q] - d;
+        ys[q] = v;
+        n2 += v * v;
+        sm += v;
+      }
+      __syncthreads();
+    }
+  }
+  {
+    const double r1 = block_sum(n2, sh);
+    const double r2 = block_sum(sm, sh);
+    if (tid == 0) {
+      a.pn[blockIdx.x] = r1;
+      a.ps[blockIdx.x] = r2;
+    }
+  }
+  grid_barrier(a.bar, a.bar_base + 2ULL * gridDim.x, a.ctl);
+  // ---- phase 3: norm, scaling, scalars
+  const double nn = block_sum_cg(a.pn, gridDim.x, sh, &bc);
+  if (a.mode == OF_W) {
+    const double ssum = block_sum_cg(a.ps, gridDim.x, sh, &bc);
+    const double S = sqrt(nn), SS = 1.0 / S;
+    for (int q = tid; q < len; q += OF_THREADS) a.y[r0 + q] = ys[q] * SS;
+    if (blockIdx.x == 0 && tid == 0) {
+      a.scal[SC_S] = S;
+      a.scal[SC_SUMW] = ssum * SS;
+      if (!(S >= a.eps)) a.ctl[CT_FLAG] |= 2;
+    }
+  } else if (a.mode == OF_F) {
+    const double rf = sqrt(nn), R = 1.0 / rf;
+    double acc = 0.0;
+    for (int q = tid; q < len; q += OF_THREADS) {
+      const long long g = r0 + q;
+      const double v = ys[q] * R;
+      a.y[g] = ys[q];
+      a.vnext[g] = v;
+      const double x = a.s ? v / a.s[g] : v;
+      a.xs[g] = x;
+      if (a.ce) acc += x * a.ce[g];
+    }
+    const double r = block_sum(acc, sh);
+    if (tid == 0) {
+      a.pb_out[blockIdx.x] = r;
+      if (blockIdx.x == 0) {
+        a.scal[SC_RF] = rf;
+        a.Bm[(long long)a.j * a.work + a.j] = a.scal[SC_S];
+        a.Bm[(long long)(a.j + 1) * a.work + a.j] = rf;
+        if (!(rf >= a.eps)) a.ctl[CT_FLAG] |= 2;
+      }
+    }
+  } else {
+    const double rf = sqrt(nn), R = 1.0 / rf;
+    for (int q = tid; q < len; q += OF_THREADS) a.y[r0 + q] = ys[q] * R;
+    if (blockIdx.x == 0 && tid == 0) {
+      a.scal[SC_RF] = (rf < a.eps) ? 0.0 : rf;
+      a.Bm[(long long)a.j * a.work + a.j] = a.scal[SC_S];
+    }
+  }
+}
+
 // plain norm/sum partials of a vector (first Lanczos vector: no orthogonalisation)
 __global__ void __launch_bounds__(NT) k_norm_partials(const double* __restrict__ y, long long rows,
                                                       double* __restrict__ pn, double* __restrict__ ps) {
@@ -695,6 +965,7 @@ k_restart_gemm(double* __restrict__ X, long long ld, long long rows, int kin, in
 
 int irlba_init(m3b_ctx* ctx) {
   CK(ctx, cudaFuncSetAttribute(k_restart_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  CK(ctx, cudaFuncSetAttribute(k_orth_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, M3B_OF_SMEM_MAX));
   return M3B_OK;
 }
 
@@ -713,6 +984,12 @@ struct Irlba {
   double *Q = nullptr, *svd_scratch = nullptr;
   int* ctl = nullptr;
   unsigned int* xf_done = nullptr;  // CTA counter of the fused exchange kernel (self re-arming)
+  // single-rank fused vector kernel (k_orth_fused)
+  bool fused = false;
+  int of_grid = 0, of_chunk_n = 0, of_chunk_m = 0;
+  int pb_n = 0;  // valid entries of pb (k_make_xs: nb_n, k_orth_fused: of_grid)
+  unsigned long long* bar = nullptr;
+  unsigned long long bar_seq = 0;
   int nb_n, nb_m;        // blocks of the vector kernels (gene side / cell side)
   int nb_ca;             // blocks of k_combine_A (32 rows per block)
   int nbo_n, nbo_m;      // blocks of k_apply_orth (= number of pn/ps partials it writes)
@@ -754,19 +1031,72 @@ struct Irlba {
     return M3B_OK;
   }
 
+  // one half Lanczos step's vector work after a product, single rank (see k_orth_fused)
+  int orth_fused(int mode, int jcol, int ncols, bool sub_prev) {
+    OrthArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = mode;
+    const bool wside = mode == OF_W;
+    const TiledLayout& L = wside ? m->A : m->B;
+    a.rows = wside ? mrows : n;
+    a.chunk = wside ? of_chunk_m : of_chunk_n;
+    a.partial = L.partial;
+    a.rsp = L.row_slot_ptr;
+    a.s = s;
+    a.ce = ce;
+    if (wside) {
+      a.pb_in = ce ? pb : nullptr;
+      a.npb_in = pb_n;
+      a.y = W + (long long)jcol * mrows;
+      a.wprev = sub_prev ? a.y - mrows : nullptr;
+      a.X = W;
+      a.ld = mrows;
+    } else {
+      a.vj = V + (long long)jcol * n;
+      a.y = F;
+      a.X = V;
+      a.ld = n;
+      a.vnext = V + (long long)(jcol + 1) * n;  // unused by OF_FLAST
+      a.xs = xs;
+      a.pb_out = pb;
+    }
+    a.ncols = ncols;
+    a.part = part;
+    a.pn = pn;
+    a.ps = ps;
+    a.Bm = Bm;
+    a.work = work;
+    a.j = jcol;
+    a.eps = eps;
+    a.scal = scal;
+    a.ctl = ctl;
+    a.bar = bar;
+    a.bar_base = bar_seq;
+    bar_seq += 2ULL * of_grid;
+    void* args[] = {&a};
+    const size_t smem = ((size_t)a.chunk + ((ncols + 1) & ~1) + 1024) * sizeof(double);
+    spmv_timer_begin(ctx, 2);
+    CK(ctx, cudaLaunchCooperativeKernel((void*)k_orth_fused, dim3(of_grid), dim3(OF_THREADS), args, smem, ctx->stream));
+    count_launch(ctx);
+    spmv_timer_end(ctx);
+    if (mode == OF_F) pb_n = of_grid;
+    return M3B_OK;
+  }
+
   // W[:, jw] = Ax(V[:, jv]) given xs/pb already prepared; optional "- R_F * W[:, jw-1]"
-  int product_A(int jw, bool sub_prev, bool prelaunched = false) {
+  int product_A(int jw, bool sub_prev, bool prelaunched = false, bool combine = true) {
     if (!prelaunched) {
       spmv_timer_begin(ctx, 0);
       RET(launch_tile_stream(ctx, m->A, OP_DOT, xs));
       spmv_timer_end(ctx);
     }
     ctx->stats.spmv_cells_out++;
+    if (!combine) return M3B_OK;
     double* w = W + (long long)jw * mrows;
     spmv_timer_begin(ctx, 5);
     if (mrows) {
       k_combine_A<<<nb_ca, NT, 0, ctx->stream>>>(m->A.partial, m->A.row_slot_ptr, mrows, ce ? pb : nullptr,
-                                                nb_n, sub_prev ? (w - mrows) : nullptr, scal, w);
+                                                pb_n, sub_prev ? (w - mrows) : nullptr, scal, w);
       count_launch(ctx);
     }
     spmv_timer_end(ctx);
@@ -775,11 +1105,12 @@ struct Irlba {
   }
 
   // F = Atw(W[:, j]) - S * V[:, j]
-  int product_B(int j) {
+  int product_B(int j, bool combine = true) {
     spmv_timer_begin(ctx, 1);
     RET(launch_tile_stream(ctx, m->B, OP_DOT, W + (long long)j * mrows));
     spmv_timer_end(ctx);
     ctx->stats.spmv_genes_out++;
+    if (!combine) return M3B_OK;
     if (ctx->comm.world == 1) {
       spmv_timer_begin(ctx, 5);
       k_combine_fix_F<<<std::max(1, std::min((n + 31) / 32, 8 * ctx->sm_count)), NT, 0, ctx->stream>>>(m->B.partial, m->B.row_slot_ptr, n, s, ce,
@@ -997,7 +1328,16 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     int hctl[CT_COUNT];
     int it = 0, mprod = 0, k = 0;
     bool converged = false;
-    const size_t part_sz = (size_t)std::max(I.nblk_n, I.nblk_m) * work;
+    // fused vector kernel: single rank, one CTA per SM, every CTA owns ceil(rows / grid) rows
+    I.of_grid = ctx->sm_count;
+    I.of_chunk_n = (n + I.of_grid - 1) / I.of_grid;
+    I.of_chunk_m = (int)((mloc + I.of_grid - 1) / I.of_grid);
+    {
+      const size_t smem = ((size_t)std::max(I.of_chunk_n, I.of_chunk_m) + work + 2 + 1024) * sizeof(double);
+      I.fused = ctx->comm.world == 1 && work <= 1024 && I.of_grid <= 1024 && I.of_grid <= MAX_PART &&
+                smem <= (size_t)M3B_OF_SMEM_MAX && !getenv("M3B_NO_FUSED_ORTH");
+    }
+    const size_t part_sz = (size_t)std::max(std::max(I.nblk_n, I.nblk_m), I.of_grid) * work;
     IR(I.alloc(&I.V, (size_t)n * work));
     IR(I.alloc(&I.W, (size_t)std::max<long long>(mloc, 1) * work));
     IR(I.alloc(&I.F, (size_t)n));
@@ -1007,7 +1347,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     IR(I.alloc(&I.t, (size_t)work));
     IR(I.alloc(&I.pn, (size_t)MAX_PART));
     IR(I.alloc(&I.ps, (size_t)MAX_PART));
-    IR(I.alloc(&I.pb, (size_t)64));
+    IR(I.alloc(&I.pb, (size_t)1024));
     IR(I.alloc(&I.buf2, (size_t)4));
     IR(I.alloc(&I.scal, (size_t)SC_COUNT));
     IR(I.alloc(&I.Bm, (size_t)work * work));
@@ -1025,7 +1365,9 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     ICK(cudaMemsetAsync(I.svr, 0, work * sizeof(double), ctx->stream));
     ICK(cudaMemsetAsync(I.scal, 0, SC_COUNT * sizeof(double), ctx->stream));
     ICK(cudaMemsetAsync(I.ctl, 0, CT_COUNT * sizeof(int), ctx->stream));
-    ICK(cudaMemsetAsync(I.pb, 0, 64 * sizeof(double), ctx->stream));
+    ICK(cudaMemsetAsync(I.pb, 0, 1024 * sizeof(double), ctx->stream));
+    IR(I.alloc(&I.bar, (size_t)2));
+    ICK(cudaMemsetAsync(I.bar, 0, 2 * sizeof(unsigned long long), ctx->stream));
     // operator vectors
     I.s = use_scale ? m->scale : nullptr;
     if (use_center) {
@@ -1069,18 +1411,38 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         k_make_xs<<<I.nb_n, NT, 0, ctx->stream>>>(I.V + (long long)j * n, I.s, I.ce, n, I.xs, I.pb);
         count_launch(ctx);
       }
-      IR(I.product_A(j, false, pre_k4));
+      I.pb_n = I.nb_n;
+      const bool fz = I.fused;
+      IR(I.product_A(j, false, pre_k4, !(fz && it > 0)));
       pre_k4 = false;
       mprod++;
-      if (it > 0) {
-        IR(I.orthog(I.W, mloc, mloc, j, I.W + (long long)j * mloc, I.chunk_m, I.nblk_m, I.nbo_m, true));
+      if (fz && it > 0) {
+        IR(I.orth_fused(OF_W, j, j, false));
       } else {
-        k_norm_partials<<<I.nb_m, NT, 0, ctx->stream>>>(I.W + (long long)j * mloc, mloc, I.pn, I.ps);
-        count_launch(ctx);
+        if (it > 0) {
+          IR(I.orthog(I.W, mloc, mloc, j, I.W + (long long)j * mloc, I.chunk_m, I.nblk_m, I.nbo_m, true));
+        } else {
+          k_norm_partials<<<I.nb_m, NT, 0, ctx->stream>>>(I.W + (long long)j * mloc, mloc, I.pn, I.ps);
+          count_launch(ctx);
+        }
+        IR(I.finish_w(j, it == 0 && j == 0, it > 0 ? I.nbo_m : I.nb_m));
       }
-      IR(I.finish_w(j, it == 0 && j == 0, it > 0 ? I.nbo_m : I.nb_m));
       // Lanczos process
       while (j < work) {
+        if (fz) {
+          IR(I.product_B(j, false));
+          mprod++;
+          if (j + 1 < work) {
+            IR(I.orth_fused(OF_F, j, j + 1, false));
+            IR(I.product_A(j + 1, true, false, false));
+            mprod++;
+            IR(I.orth_fused(OF_W, j + 1, j + 1, true));
+          } else {
+            IR(I.orth_fused(OF_FLAST, j, j + 1, false));
+          }
+          j++;
+          continue;
+        }
         IR(I.product_B(j));
         mprod++;
         IR(I.orthog(I.V, n, n, j + 1, I.F, I.chunk_n, I.nblk_n, I.nbo_n, false));
@@ -1150,6 +1512,11 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       if (hctl[CT_FLAG] & 4) {
         m3b_set_error(ctx, "peer exchange timed out: a rank did not reach Lanczos restart %d", it);
         status = M3B_E_NCCL;
+        goto done;
+      }
+      if (hctl[CT_FLAG] & 8) {
+        m3b_set_error(ctx, "internal: grid barrier of the fused vector kernel timed out at restart %d", it);
+        status = M3B_E_CUDA;
         goto done;
       }
       if (hctl[CT_FLAG] & 2) {

@@ -96,6 +96,7 @@ template int dev_alloc<int2>(m3b_ctx*, int2**, size_t);
 template int dev_alloc<unsigned int>(m3b_ctx*, unsigned int**, size_t);
 template int dev_alloc<unsigned char>(m3b_ctx*, unsigned char**, size_t);
 template int dev_alloc<unsigned short>(m3b_ctx*, unsigned short**, size_t);
+template int dev_alloc<unsigned long long>(m3b_ctx*, unsigned long long**, size_t);
 
 void dev_free(void* p) {
   if (!p) return;
