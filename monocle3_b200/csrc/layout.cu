@@ -820,13 +820,12 @@ int build_layout_B(m3b_mat* m, bool split) {
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   // stash the host tables for the re-map (kept in the matrix via a heap object)
   BBuild* bb = new BBuild();
+  // (whole tables: when the zero-gene filter drops nothing they are final as they are)
   bb->cnt.swap(cnt[0]);
-  bb->T.base.swap(T[0].base);
-  bb->T.n_entries = T[0].n_entries;
+  std::swap(bb->T, T[0]);
   if (split) {
     bb->cnt_u.swap(cnt[1]);
-    bb->Tu.base.swap(T[1].base);
-    bb->Tu.n_entries = T[1].n_entries;
+    std::swap(bb->Tu, T[1]);
   }
   m3b_mat_set_bbuild(m, bb);
   for (int q = 0; q < 2; ++q) {
@@ -853,21 +852,26 @@ int finish_selection(m3b_mat* m, unsigned char* keep_host) {
   int nk = 0;
   for (int s = 0; s < n_sel; ++s) kept_of_sel[s] = keep_host[s] ? nk++ : -1;
   m->n_kept = nk;
-  HostTables T, Tu;
-  T.base = bb->T.base;
-  build_items(bb->cnt, m->B.n_tiles, n_sel, kept_of_sel.data(), nk, ctx->sm_count, T, SHAPE_GENERAL);
-  if (split) {
-    Tu.base = bb->Tu.base;
-    build_items(bb->cnt_u, m->B.n_tiles, n_sel, kept_of_sel.data(), nk, ctx->sm_count, Tu, SHAPE_UNIT);
+  HostTables Tn, Tun;
+  const bool all_kept = nk == n_sel;  // nothing dropped: the tables of build_layout_B are final
+  if (!all_kept) {
+    Tn.base = bb->T.base;
+    build_items(bb->cnt, m->B.n_tiles, n_sel, kept_of_sel.data(), nk, ctx->sm_count, Tn, SHAPE_GENERAL);
+    if (split) {
+      Tun.base = bb->Tu.base;
+      build_items(bb->cnt_u, m->B.n_tiles, n_sel, kept_of_sel.data(), nk, ctx->sm_count, Tun, SHAPE_UNIT);
+    }
+    assign_slots(Tn, split ? &Tun : nullptr, nk);
+    m->B.rows = nk;
+    const size_t n_partial = Tn.items.size() + Tun.items.size();
+    RET(upload_tables(ctx, m->B, Tn, n_partial));
+    if (split) {
+      m->B.unit->rows = nk;
+      RET(upload_tables(ctx, *m->B.unit, Tun, n_partial, &m->B));
+    }
   }
-  assign_slots(T, split ? &Tu : nullptr, nk);
-  m->B.rows = nk;
-  const size_t n_partial = T.items.size() + Tu.items.size();
-  RET(upload_tables(ctx, m->B, T, n_partial));
-  if (split) {
-    m->B.unit->rows = nk;
-    RET(upload_tables(ctx, *m->B.unit, Tu, n_partial, &m->B));
-  }
+  const HostTables& T = all_kept ? bb->T : Tn;
+  const HostTables& Tu = all_kept ? bb->Tu : Tun;
   dev_free(m->kept_of_sel);
   RET(dev_alloc(ctx, &m->kept_of_sel, (size_t)std::max(n_sel, 1)));
   if (n_sel) CK(ctx, cudaMemcpyAsync(m->kept_of_sel, kept_of_sel.data(), n_sel * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -888,10 +892,10 @@ int finish_selection(m3b_mat* m, unsigned char* keep_host) {
   CK(ctx, cudaMemcpyAsync(m->kept_nnz, nnzk.data(), std::max(nk, 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaMemcpyAsync(m->kept_padlen, padk.data(), std::max(nk, 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
-  m3b_mat_set_bbuild(m, nullptr);
   RET(bank_reorder(ctx, m->B));
   if (split) RET(bank_reorder(ctx, *m->B.unit));
   RET(flat_build_plans(ctx, m->B, T, split ? &Tu : nullptr));
+  m3b_mat_set_bbuild(m, nullptr);
   return M3B_OK;
 }
 
