@@ -24,11 +24,14 @@
 
 // Kernel variants <rounds per register batch, threads per CTA>; one CTA per SM either way (the tile
 // takes the shared memory), so the thread count trades registers per thread (batch depth) against
-// warps per scheduler (latency hiding).  M3B_FLAT_VARIANT selects one for sweeps.
+// warps per scheduler (latency hiding).  M3B_FLAT_VARIANT selects one for sweeps.  Measured on cfg2
+// (us per launch): <6,512> 78.7, <3,1024> 65.1 (default), <2,1024> 64.9; rotating three batches
+// instead of two (<2,1024,3>, <1,1024,3>) changed nothing or lost: the kernel is no longer waiting
+// for DRAM but spread thin over issue slots, shared-memory gathers and load latency (profiles/).
 struct FlatVariant {
   int k, threads;
 };
-static const FlatVariant FL_VARIANTS[] = {{6, 512}, {3, 1024}, {2, 1024}, {4, 768}, {4, 1024}};
+static const FlatVariant FL_VARIANTS[] = {{6, 512}, {3, 1024}, {2, 1024}};
 static int fl_variant() {
   static int v = -1;
   if (v < 0) {
@@ -304,6 +307,26 @@ __device__ __forceinline__ double2 fl_ld_double2(const double2* p) {
   return v;
 }
 
+// Gathers from the staged tile by shared-window byte address: index extraction + one IMAD
+// (idx * 8 + base) + LDS.  Plain sx[idx] cost a shift, a mask and an add per gather.
+__device__ __forceinline__ double fl_lds(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+// both addresses of an index pair: unpack the halves, one 16-bit multiply-add each
+__device__ __forceinline__ void fl_addr2(unsigned pair, unsigned sbase, unsigned& alo, unsigned& ahi) {
+  asm("{\n .reg .b16 l, h;\n mov.b32 {l, h}, %2;\n mad.wide.u16 %0, l, 8, %3;\n mad.wide.u16 %1, h, 8, %3;\n}"
+      : "=r"(alo), "=r"(ahi)
+      : "r"(pair), "r"(sbase));
+}
+// x[lo] + x[hi] of an index pair
+__device__ __forceinline__ double fl_gsum(unsigned sbase, unsigned pair) {
+  unsigned a0, a1;
+  fl_addr2(pair, sbase, a0, a1);
+  return fl_lds(a0) + fl_lds(a1);
+}
+
 struct FlatState {
   double acc;     // this lane's running sum of the open item
   int item;       // the open item, or (if none is open) the next item to start
@@ -384,11 +407,12 @@ __device__ __forceinline__ void fl_finish(FlatState& st, int lane, const int* __
 
 template <int K>
 __device__ __forceinline__ double fl_tree(const double (&v)[K]) {
-  static_assert(K == 2 || K == 3 || K == 4 || K == 6, "fl_tree: unsupported batch depth");
+  static_assert(K == 1 || K == 2 || K == 3 || K == 4 || K == 6, "fl_tree: unsupported batch depth");
+  if (K == 1) return v[0];
   if (K == 6) return ((v[0] + v[1]) + (v[2] + v[3])) + (v[4 % K] + v[5 % K]);
   if (K == 4) return (v[0] + v[1]) + (v[2] + v[3 % K]);
   if (K == 3) return (v[0] + v[1]) + v[2 % K];
-  return v[0] + v[1];
+  return v[0] + v[1 % K];
 }
 
 struct FlatArgs {
@@ -420,6 +444,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
   extern __shared__ double sx[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile_w = a.tile_w;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sx);
   const int v0 = a.cta_visit_ptr[blockIdx.x], v1 = a.cta_visit_ptr[blockIdx.x + 1];
   for (int vis = v0; vis < v1; ++vis) {
     const int tile = a.visit_tile[vis];
@@ -482,7 +507,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
       const bool valid = 32 * ((R0) + u) + lane < ng;                                           \
       mk[u] = __ballot_sync(0xffffffffu, valid && ((BI[u] >> 15) & 1u));                        \
       any |= mk[u];                                                                             \
-      const double t = fma(BV[u].y, sx[BI[u] >> 16], BV[u].x * sx[BI[u] & 0x7fffu]);            \
+      unsigned ga, gb;                                                                          \
+      fl_addr2(BI[u] & 0xffff7fffu, sbase, ga, gb);                                             \
+      const double t = fma(BV[u].y, fl_lds(gb), BV[u].x * fl_lds(ga));                          \
       v[u] = valid ? t : 0.0;                                                                   \
     }                                                                                           \
     if (any == 0u) {                                                                            \
@@ -535,8 +562,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
       const bool valid = 32 * ((R0) + u) + lane < ng;                                                       \
       mk[u] = __ballot_sync(0xffffffffu, valid && ((b.x >> 15) & 1u));                                      \
       any |= mk[u];                                                                                         \
-      const double t = ((sx[b.x & 0x7fffu] + sx[b.x >> 16]) + (sx[b.y & 0xffffu] + sx[b.y >> 16])) +        \
-                       ((sx[b.z & 0xffffu] + sx[b.z >> 16]) + (sx[b.w & 0xffffu] + sx[b.w >> 16]));         \
+      const double t = (fl_gsum(sbase, b.x & 0xffff7fffu) + fl_gsum(sbase, b.y)) +                          \
+                       (fl_gsum(sbase, b.z) + fl_gsum(sbase, b.w));                                         \
       v[u] = valid ? t : 0.0;                                                                               \
     }                                                                                                       \
     if (any == 0u) {                                                                                        \
@@ -573,8 +600,6 @@ int flat_init(m3b_ctx* ctx) {
   RET((fl_init_one<6, 512>(ctx)));
   RET((fl_init_one<3, 1024>(ctx)));
   RET((fl_init_one<2, 1024>(ctx)));
-  RET((fl_init_one<4, 768>(ctx)));
-  RET((fl_init_one<4, 1024>(ctx)));
   return M3B_OK;
 }
 
@@ -610,8 +635,6 @@ int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStr
   switch (fl_variant()) {
     case 1: k_flat_dot<3, 1024><<<P->n_cta, 1024, smem, st>>>(a); break;
     case 2: k_flat_dot<2, 1024><<<P->n_cta, 1024, smem, st>>>(a); break;
-    case 3: k_flat_dot<4, 768><<<P->n_cta, 768, smem, st>>>(a); break;
-    case 4: k_flat_dot<4, 1024><<<P->n_cta, 1024, smem, st>>>(a); break;
     default: k_flat_dot<6, 512><<<P->n_cta, 512, smem, st>>>(a); break;
   }
   count_launch(ctx);
