@@ -26,6 +26,7 @@ NORM_LOG2, NORM_SIZE_ONLY, NORM_NONE, NORM_LOG10, NORM_BINARY = 0, 1, 2, 3, 4
 SF_TOTAL, SF_LOG_TOTAL = 0, 1
 FLAG_TIME_SPMV = 1
 FLAG_JACOBI_ONLY = 2
+FLAG_NO_UNIT_SPLIT = 4  # keep count-1 entries in the 10 B/entry stream (A/B switch)
 COMM_ID_BYTES = 128
 
 SMALL_SVD_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),

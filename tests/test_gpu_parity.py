@@ -302,6 +302,64 @@ def test_pca_multi_tile_layouts(m3):
     assert subspace_angle(r["x"], o["x"]) < ANGLE_TOL
 
 
+def _pca_direct(ctx, counts, nd, v0=None, method=None, pc=1.0):
+    from monocle3_b200 import engine, _lib as L
+    sf = ref.estimate_sf_sparse(counts)[0]
+    dev = engine.DeviceMatrix.from_csc(ctx, counts)
+    dev.normalize(sf, L.NORM_LOG2 if method is None else method, pc)
+    keep = dev.select_genes(None)
+    if v0 is None:
+        v0 = np.cos(np.arange(int(keep.sum())) * 0.37) + 0.1
+    r = dev.pca_irlba(nd, v0, maxit=1000)
+    r["keep"] = keep
+    r["moments"] = dev.gene_moments()
+    return r, sf, v0
+
+
+def test_unit_split_matches_unsplit(m3, worm_l2):
+    """Count-1 entries in the index-only unit layouts vs everything in the general stream: same
+    moments, same iteration, same singular triplets (the two differ in summation order only)."""
+    from monocle3_b200 import engine, _lib as L
+    counts, _ = worm_l2
+    r1, _, v0 = _pca_direct(engine.Context(device=0, small_svd="device"), counts, 30)
+    r0, _, _ = _pca_direct(engine.Context(device=0, flags=L.FLAG_NO_UNIT_SPLIT, small_svd="device"), counts, 30, v0)
+    assert np.array_equal(r1["keep"], r0["keep"])
+    np.testing.assert_allclose(r1["moments"][0], r0["moments"][0], rtol=1e-13)
+    np.testing.assert_allclose(r1["moments"][1], r0["moments"][1], rtol=1e-12)
+    assert (r1["iter"], r1["mprod"]) == (r0["iter"], r0["mprod"])
+    assert sv_rel_err(r1["d"], r0["d"]) < 1e-11
+    assert subspace_angle(r1["v"], r0["v"]) < 1e-8 and subspace_angle(r1["x"], r0["x"]) < 1e-8
+
+
+@pytest.mark.parametrize("case", ["all_ones", "no_ones", "tiny_rows", "size_only"])
+def test_unit_split_edge_cases(m3, case):
+    """Edge cases of the unit / general split against the oracle: a binary matrix (general stream
+    empty), no count-1 entry at all (unit stream empty), thousands of 1-3 entry rows (dozens of
+    item starts per 32-lane round, slot windows re-based mid-round), and the size_only values."""
+    from monocle3_b200 import _lib as L
+    from monocle3_b200.synth import synth_csc
+    method, nm, pc = None, "log", 1.0
+    if case == "tiny_rows":
+        counts = synth_csc(9000, 2200, 0.0015, 20, seed=3)
+    else:
+        counts = synth_csc(1800, 2100, 0.05, 20, seed=4)
+    if case == "all_ones":
+        counts.data[:] = 1.0
+    elif case == "no_ones":
+        counts.data[:] = counts.data + 1.0
+    elif case == "size_only":
+        method, nm, pc = L.NORM_SIZE_ONLY, "size_only", 0.0
+    r, sf, v0 = _pca_direct(m3.get_context(), counts, 15, method=method, pc=pc)
+    FM = ref.normalize_expr_data(counts, sf, nm, pseudo_count=pc)
+    FMf, kept = ref.select_and_filter_genes(FM)
+    assert np.array_equal(np.nonzero(r["keep"])[0], kept)
+    o = ref.sparse_prcomp_irlba(FMf.T.tocsc(), 15, center=True, scale=True, v0=v0)
+    assert (r["iter"], r["mprod"]) == (o["iter"], o["mprod"])
+    assert sv_rel_err(r["d"], o["d"]) < SV_TOL
+    assert subspace_angle(r["v"], o["rotation"]) < ANGLE_TOL
+    assert subspace_angle(r["x"], o["x"]) < ANGLE_TOL
+
+
 def test_full_size_properties(m3):
     """Size-independent properties at a size the oracle cannot iterate on in seconds
     (20k cells x 8k genes, ~10M nnz): orthonormal loadings, singular-triplet residuals
