@@ -17,6 +17,17 @@
 //     solved the same way and folded in with two small GEMMs.
 // Work per restart: (n-k) secular solves (O(n^2) each, fully parallel) + 2(n-k-1) n^3 GEMMs
 // spread over the whole chip, instead of ~6 Jacobi sweeps of n^3 serialised on one SM.
+//
+// ONE secular solve per restart (mode 2, the default).  With T the (n-k)^2 bidiagonal tail
+// block (T[0,0] = a) and T' = T with that corner removed,
+//     B B^T = blockdiag(D^2, T' T'^T) + u u^T,   u = (z, a e_1):
+// the tail couples to the kept Ritz values through its first column only.  T' is at most 7x7:
+// its SVD T' = P S' R^T comes from the Jacobi kernel in a few microseconds (one singular value is
+// exactly 0, T' has a zero column), and in the basis blockdiag(I, P) the whole of B B^T is
+// diag(d^2, s'^2) + u~ u~^T with u~ = (z, a P^T e_1): a single rank-one update, one secular
+// solve of size n over the merged poles.  Left vectors U = blockdiag(I, P) Y (Loewner), right
+// vectors V = B^T U S^-1.  The sequential tail merges above (kept as M3B_SVD_TAILMERGE=1) cost
+// n-k dependent solves; this costs one.
 // Any irregularity (non-descending or coincident poles, a zero weight, a root that does not
 // converge, non-finite values) raises a flag and the Jacobi kernel redoes that restart.
 #include <algorithm>
@@ -25,6 +36,9 @@
 #include "m3b_internal.h"
 
 #define AS_NMAX 256
+
+int launch_jacobi_svd(m3b_ctx* ctx, int n, const double* B, double* U, double* s, double* V, double* scratch, int* info,
+                      const int* only_if);
 
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
@@ -61,6 +75,7 @@ struct ArrowProblem {  // shared-memory image of one arrow problem
   double pf[AS_NMAX], uf[AS_NMAX];  // full
   double p[AS_NMAX], u2[AS_NMAX];   // active poles, squared active weights
   int act[AS_NMAX], defl[AS_NMAX];
+  int src[AS_NMAX];  // mode 2: index in the concatenated (D, tail) basis of every merged pole
   int m, ma, bad;
 };
 
@@ -69,9 +84,42 @@ __device__ __forceinline__ bool arrow_setup(ArrowProblem& P, int mode, int n, in
                                             const double* __restrict__ B, const double* __restrict__ sig_in,
                                             const double* __restrict__ Ycur) {
   const int tid = threadIdx.x;
-  const int m = (mode == 0) ? k + 1 : tail_j + 1;
+  const int m = (mode == 2) ? n : ((mode == 0) ? k + 1 : tail_j + 1);
   if (m > n || m < 2 || m > AS_NMAX) return false;
-  for (int i = tid; i < m; i += blockDim.x) {
+  if (mode == 2) {
+    // merged poles: the k kept Ritz values (descending) and the t-1 non-zero singular values of T'
+    // (sig_in, descending), then the zero pole; Ycur = P (t x t, col-major, ld t)
+    const int t = n - k;
+    if (k < 1 || t < 2 || t > 32) return false;
+    const double alpha = B[(size_t)k * n + k];
+    for (int q = tid; q < n; q += blockDim.x) {
+      double pole, wt;
+      int pos;
+      if (q < k) {
+        pole = B[(size_t)q * n + q];
+        wt = B[(size_t)k * n + q];
+        int c = 0;
+        for (int j = 0; j < t - 1; ++j) c += (sig_in[j] > pole) ? 1 : 0;
+        pos = q + c;
+      } else {
+        const int j = q - k;
+        wt = alpha * Ycur[(size_t)j * t];
+        if (j < t - 1) {
+          pole = sig_in[j];
+          int c = 0;
+          for (int qq = 0; qq < k; ++qq) c += (B[(size_t)qq * n + qq] >= pole) ? 1 : 0;
+          pos = j + c;
+        } else {
+          pole = 0.0;
+          pos = n - 1;
+        }
+      }
+      P.pf[pos] = pole;
+      P.uf[pos] = wt;
+      P.src[pos] = q;
+    }
+  }
+  for (int i = tid; i < m && mode != 2; i += blockDim.x) {
     double pi, ui;
     if (mode == 0) {
       pi = (i < m - 1) ? B[(size_t)i * n + i] : 0.0;
@@ -350,6 +398,10 @@ k_arrow_vectors(int mode, int n, const int* __restrict__ ctl_k, int tail_j, cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = P.m, ma = P.ma;
   const double* p = P.p;
+  if (mode == 2 && blockIdx.x == 0) {  // the merge order, for k_tail_finish (stored behind the roots' org array)
+    int* src_g = const_cast<int*>(org_g) + n;
+    for (int r = tid; r < m; r += blockDim.x) src_g[r] = P.src[r];
+  }
   for (int r = tid; r < ma; r += blockDim.x) {
     org[r] = org_g[r];
     mu[r] = mu_g[r];
@@ -483,6 +535,66 @@ __global__ void k_svd_signfix(int n, double* __restrict__ U, double* __restrict_
 }
 
 // Structured SVD of the restarted B (k = ctl[CT_K] kept Ritz values, known to the host as k_host).
+// T' (t x t, col-major, ld t): the bidiagonal tail block of B without its corner
+__global__ void k_tail_prep(int n, const int* __restrict__ ctl_k, const double* __restrict__ B, double* __restrict__ Tm) {
+  const int k = ctl_k[0], t = n - k;
+  for (int e = threadIdx.x; e < t * t; e += blockDim.x) {
+    const int r = e % t, c = e / t;
+    Tm[e] = (r == 0 && c == 0) ? 0.0 : B[(size_t)(k + c) * n + (k + r)];
+  }
+}
+
+// Column c of the outputs: U[:, c] = blockdiag(I, P) y_c (y_c un-merged through src),
+// V[:, c] = B^T U[:, c] / s_c.  One block per column.
+__global__ void __launch_bounds__(128) k_tail_finish(int n, const int* __restrict__ ctl_k, const double* __restrict__ B,
+                                                     const double* __restrict__ Pu, const int* __restrict__ src_g,
+                                                     const double* __restrict__ Ym, const double* __restrict__ S,
+                                                     double* __restrict__ U, double* __restrict__ V,
+                                                     int* __restrict__ flag) {
+  __shared__ double ycat[AS_NMAX], ucol[AS_NMAX];
+  __shared__ double sh[4];
+  if (*flag) return;
+  const int k = ctl_k[0], t = n - k, c = blockIdx.x, tid = threadIdx.x;
+  for (int pos = tid; pos < n; pos += blockDim.x) ycat[src_g[pos]] = Ym[(size_t)c * n + pos];
+  __syncthreads();
+  for (int q = tid; q < n; q += blockDim.x) {
+    double v;
+    if (q < k) {
+      v = ycat[q];
+    } else {
+      v = 0.0;
+      const int a = q - k;
+      for (int j = 0; j < t; ++j) v += Pu[(size_t)j * t + a] * ycat[k + j];
+    }
+    ucol[q] = v;
+    U[(size_t)c * n + q] = v;
+  }
+  __syncthreads();
+  const double sc = S[c];
+  double nn = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double* bc = B + (size_t)i * n;  // column i of B = row i of B^T
+    double a0 = 0.0, a1 = 0.0;
+    int r = 0;
+    for (; r + 1 < n; r += 2) {
+      a0 += bc[r] * ucol[r];
+      a1 += bc[r + 1] * ucol[r + 1];
+    }
+    if (r < n) a0 += bc[r] * ucol[r];
+    const double v = (a0 + a1) / sc;
+    V[(size_t)c * n + i] = v;
+    nn += v * v;
+  }
+  // ||v|| must be 1: anything else means s_c was too small for B^T u / s (fall back to Jacobi)
+  nn = wsum(nn);
+  if ((tid & 31) == 0) sh[tid >> 5] = nn;
+  __syncthreads();
+  if (tid == 0) {
+    const double tot = ((sh[0] + sh[1]) + sh[2]) + sh[3];
+    if (!(fabs(tot - 1.0) < 1e-9)) atomicOr(flag, 16);
+  }
+}
+
 // Buffers: U/V (n x n outputs), S (n), scratch >= 4 n^2 + 6 n doubles, flag = device int (zeroed here).
 // On return *flag != 0 means "not done: run the Jacobi kernel".
 int launch_arrow_svd(m3b_ctx* ctx, int n, int k_host, const int* ctl_k, const double* B, double* U, double* S,
@@ -496,6 +608,36 @@ int launch_arrow_svd(m3b_ctx* ctx, int n, int k_host, const int* ctl_k, const do
   double* sb = sa + n;                        // sigma pong
   CK(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
   CK(ctx, cudaMemsetAsync(scratch + 4 * (size_t)n * n + 5 * (size_t)n, 0, 2 * n * sizeof(double), ctx->stream));
+  const int tt = n - k_host;
+  if (!getenv("M3B_SVD_TAILMERGE") && tt >= 2 && tt <= 32 && 5 * tt * tt + tt + 2 <= n * n && 2 * n + 4 <= 2 * n * n) {
+    // one secular solve over the merged poles (see the header); small buffers live in the Ya / Xa areas
+    const int t = tt;
+    double* Tm = Ya;           // t*t
+    double* Pu = Tm + t * t;   // t*t   left vectors of T'
+    double* Pv = Pu + t * t;   // t*t
+    double* sT = Pv + t * t;   // t
+    double* jscr = sT + t;     // 2*t*t
+    int* jinfo = reinterpret_cast<int*>(jscr + 2 * t * t);
+    double* mu_g = sb + n;
+    double* sg_g = mu_g + n;
+    double* uh_g = sg_g + n;
+    int* org_g = reinterpret_cast<int*>(Xa);  // org[n], src[n], done counter
+    unsigned int* done_ctr = reinterpret_cast<unsigned int*>(org_g + 2 * n);
+    CK(ctx, cudaMemsetAsync(done_ctr, 0, sizeof(unsigned int), ctx->stream));
+    k_tail_prep<<<1, 64, 0, ctx->stream>>>(n, ctl_k, B, Tm);
+    count_launch(ctx);
+    RET(launch_jacobi_svd(ctx, t, Tm, Pu, sT, Pv, jscr, jinfo, nullptr));
+    const int grid = (n + AR_WARPS - 1) / AR_WARPS;
+    k_arrow_roots<<<grid, AR_THREADS, 0, ctx->stream>>>(2, n, ctl_k, 0, B, sT, Pu, org_g, mu_g, sg_g, uh_g, done_ctr, flag);
+    k_arrow_vectors<<<grid, AR_THREADS, 0, ctx->stream>>>(2, n, ctl_k, 0, B, sT, Pu, org_g, mu_g, sg_g, uh_g, S, Yp, Xp,
+                                                          flag);
+    k_tail_finish<<<n, 128, 0, ctx->stream>>>(n, ctl_k, B, Pu, org_g + n, Yp, S, U, V, flag);
+    count_launch(ctx, 3);
+    k_svd_signfix<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(n, U, V, flag);
+    count_launch(ctx);
+    CK(ctx, cudaGetLastError());
+    return M3B_OK;
+  }
   const int ntail = n - (k_host + 1);
   // the accumulated vectors ping-pong between (U,V) and (Ya,Xa) so that the last fold lands in U,V
   double *Yc, *Xc, *Yn, *Xn;
