@@ -535,6 +535,92 @@ __global__ void k_svd_signfix(int n, double* __restrict__ U, double* __restrict_
 }
 
 // Structured SVD of the restarted B (k = ctl[CT_K] kept Ritz values, known to the host as k_host).
+// SVD of the tail block T' (t <= 8) in ONE warp: Hestenes Jacobi on the ROWS of T' (columns of
+// A = T'^T): A Q = W with orthogonal columns, so T' = Q diag(|w_j|) (..)^T and the accumulated
+// rotations Q are the left singular vectors -- including the null vector that belongs to the zero
+// column of T'.  8 lanes per column pair (one per row), 4 disjoint pairs per step, 7 steps per sweep
+// (round-robin).  Outputs: Pu (t x t, col-major, ld t; columns ordered by descending singular
+// value), sT (t).
+__global__ void __launch_bounds__(32) k_tail_svd8(int n, const int* __restrict__ ctl_k, const double* __restrict__ B,
+                                                  double* __restrict__ Pu, double* __restrict__ sT,
+                                                  int* __restrict__ flag) {
+  __shared__ double A[8][9], Q[8][9];  // [column][row]
+  __shared__ double nrm[8];
+  const int lane = threadIdx.x, k = ctl_k[0], t = n - k;
+  if (t < 2 || t > 8) {
+    if (lane == 0) atomicOr(flag, 1);
+    return;
+  }
+  for (int e = lane; e < 64; e += 32) {
+    const int c = e >> 3, r = e & 7;  // column c of A = row c of T':  A[c][r] = T'[c, r] = B[k+c, k+r]
+    double v = 0.0;
+    if (c < t && r < t && !(c == 0 && r == 0)) v = B[(size_t)(k + r) * n + (k + c)];
+    A[c][r] = v;
+    Q[c][r] = (c == r) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  // columns whose norm has dropped to rounding level (the null direction) are left alone:
+  // against them every inner product is noise and the sweeps would never settle
+  double fro = 0.0;
+  for (int e = lane; e < 64; e += 32) fro += A[e >> 3][e & 7] * A[e >> 3][e & 7];
+  fro = wsum(fro);
+  const double tiny2 = 1e-30 * fro;
+  const int pr = lane >> 3, row = lane & 7;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    int rotated = 0;
+    for (int st = 0; st < 7; ++st) {
+      int i, j;
+      if (pr == 0) {
+        i = 7;
+        j = st;
+      } else {
+        i = (st + pr) % 7;
+        j = (st + 7 - pr) % 7;
+      }
+      if (i > j) {
+        const int tmp = i;
+        i = j;
+        j = tmp;
+      }
+      const double ai = A[i][row], aj = A[j][row];
+      double al = ai * ai, be = aj * aj, ga = ai * aj;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        al += __shfl_xor_sync(0xffffffffu, al, o);
+        be += __shfl_xor_sync(0xffffffffu, be, o);
+        ga += __shfl_xor_sync(0xffffffffu, ga, o);
+      }
+      const bool rot = al > tiny2 && be > tiny2 && fabs(ga) > 1e-15 * sqrt(al * be);
+      if (rot) {
+        const double zeta = (be - al) / (2.0 * ga);
+        const double tn = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + tn * tn), sn = c * tn;
+        const double qi = Q[i][row], qj = Q[j][row];
+        A[i][row] = c * ai - sn * aj;
+        A[j][row] = sn * ai + c * aj;
+        Q[i][row] = c * qi - sn * qj;
+        Q[j][row] = sn * qi + c * qj;
+      }
+      rotated |= __any_sync(0xffffffffu, rot) ? 1 : 0;
+      __syncwarp();
+    }
+    if (!rotated) break;
+  }
+  // column norms, rank by descending norm (ties by index), write out the first t
+  if (lane < 8) {
+    double v = 0.0;
+    for (int r = 0; r < 8; ++r) v += A[lane][r] * A[lane][r];
+    nrm[lane] = sqrt(v);
+  }
+  __syncwarp();
+  if (lane < t) {
+    int rk = 0;
+    for (int q = 0; q < t; ++q) rk += (nrm[q] > nrm[lane] || (nrm[q] == nrm[lane] && q < lane)) ? 1 : 0;
+    sT[rk] = nrm[lane];
+    for (int r = 0; r < t; ++r) Pu[(size_t)rk * t + r] = Q[lane][r];
+  }
+}
+
 // T' (t x t, col-major, ld t): the bidiagonal tail block of B without its corner
 __global__ void k_tail_prep(int n, const int* __restrict__ ctl_k, const double* __restrict__ B, double* __restrict__ Tm) {
   const int k = ctl_k[0], t = n - k;
@@ -553,6 +639,7 @@ __global__ void __launch_bounds__(128) k_tail_finish(int n, const int* __restric
                                                      int* __restrict__ flag) {
   __shared__ double ycat[AS_NMAX], ucol[AS_NMAX];
   __shared__ double sh[4];
+  __shared__ int s_flip;
   if (*flag) return;
   const int k = ctl_k[0], t = n - k, c = blockIdx.x, tid = threadIdx.x;
   for (int pos = tid; pos < n; pos += blockDim.x) ycat[src_g[pos]] = Ym[(size_t)c * n + pos];
@@ -593,6 +680,33 @@ __global__ void __launch_bounds__(128) k_tail_finish(int n, const int* __restric
     const double tot = ((sh[0] + sh[1]) + sh[2]) + sh[3];
     if (!(fabs(tot - 1.0) < 1e-9)) atomicOr(flag, 16);
   }
+  // sign convention of the Jacobi kernel (k_svd_signfix): largest |u| component positive
+  if (tid < 32) {
+    double best = 0.0;
+    int bi = n;
+    for (int i = tid; i < n; i += 32) {
+      const double x = fabs(ucol[i]);
+      if (x > best) {
+        best = x;
+        bi = i;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (tid == 0) s_flip = (bi < n && ucol[bi] < 0.0) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_flip)
+    for (int i = tid; i < n; i += blockDim.x) {
+      U[(size_t)c * n + i] = -U[(size_t)c * n + i];
+      V[(size_t)c * n + i] = -V[(size_t)c * n + i];
+    }
 }
 
 // Buffers: U/V (n x n outputs), S (n), scratch >= 4 n^2 + 6 n doubles, flag = device int (zeroed here).
@@ -624,17 +738,20 @@ int launch_arrow_svd(m3b_ctx* ctx, int n, int k_host, const int* ctl_k, const do
     int* org_g = reinterpret_cast<int*>(Xa);  // org[n], src[n], done counter
     unsigned int* done_ctr = reinterpret_cast<unsigned int*>(org_g + 2 * n);
     CK(ctx, cudaMemsetAsync(done_ctr, 0, sizeof(unsigned int), ctx->stream));
-    k_tail_prep<<<1, 64, 0, ctx->stream>>>(n, ctl_k, B, Tm);
-    count_launch(ctx);
-    RET(launch_jacobi_svd(ctx, t, Tm, Pu, sT, Pv, jscr, jinfo, nullptr));
+    if (t <= 8) {
+      k_tail_svd8<<<1, 32, 0, ctx->stream>>>(n, ctl_k, B, Pu, sT, flag);
+      count_launch(ctx);
+    } else {
+      k_tail_prep<<<1, 64, 0, ctx->stream>>>(n, ctl_k, B, Tm);
+      count_launch(ctx);
+      RET(launch_jacobi_svd(ctx, t, Tm, Pu, sT, Pv, jscr, jinfo, nullptr));
+    }
     const int grid = (n + AR_WARPS - 1) / AR_WARPS;
     k_arrow_roots<<<grid, AR_THREADS, 0, ctx->stream>>>(2, n, ctl_k, 0, B, sT, Pu, org_g, mu_g, sg_g, uh_g, done_ctr, flag);
     k_arrow_vectors<<<grid, AR_THREADS, 0, ctx->stream>>>(2, n, ctl_k, 0, B, sT, Pu, org_g, mu_g, sg_g, uh_g, S, Yp, Xp,
                                                           flag);
     k_tail_finish<<<n, 128, 0, ctx->stream>>>(n, ctl_k, B, Pu, org_g + n, Yp, S, U, V, flag);
     count_launch(ctx, 3);
-    k_svd_signfix<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(n, U, V, flag);
-    count_launch(ctx);
     CK(ctx, cudaGetLastError());
     return M3B_OK;
   }
