@@ -220,7 +220,8 @@ typedef struct m3b_stats {
   int64_t svd_fallbacks;       /* restarts where the structured SVD gave up and Jacobi ran */
   double  k1_ms;               /* CUDA-event time of the last K1 (cell totals) kernel   */
   double  k2_ms;               /* CUDA-event time of the last K2 (normalize) kernel     */
-  int64_t svd_fallback_reasons;/* OR of the reasons: 1 size, 2 irregular poles/weights, 4 root not converged, 8 Loewner */
+  int64_t svd_fallback_reasons;/* OR of the reasons: 1 size, 2 irregular poles/weights, 4 root not converged, 8 Loewner,
+                                  16 right vectors B^T u / s not unit (tiny singular value) */
 } m3b_stats;
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);
 int m3b_reset_stats(m3b_ctx* ctx);
