@@ -459,7 +459,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
         const double2* src = reinterpret_cast<const double2*>(xs0);
         double2* dst = reinterpret_cast<double2*>(sx);
         const int n2 = len >> 1;
-        for (int k = threadIdx.x; k < n2; k += blockDim.x) dst[k] = src[k];
+        // five independent 16-byte loads in flight per thread (a plain copy loop kept one or two:
+        // the staging showed up as 8 % of the stall samples)
+        for (int k0 = threadIdx.x; k0 < n2; k0 += 5 * THREADS) {
+          double2 v[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int k = k0 + u * THREADS;
+            v[u] = (k < n2) ? src[k] : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int k = k0 + u * THREADS;
+            if (k < n2) dst[k] = v[u];
+          }
+        }
         if ((len & 1) && threadIdx.x == 0) sx[len - 1] = xs0[len - 1];
       } else {
         for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] = xs0[k];
@@ -537,7 +551,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
       if (a.colscale) {
         __syncthreads();
         const double* cs = a.colscale + off;
-        for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] *= cs[k];
+        if ((reinterpret_cast<unsigned long long>(cs) & 15ull) == 0ull) {
+          const double2* cs2 = reinterpret_cast<const double2*>(cs);
+          double2* d2 = reinterpret_cast<double2*>(sx);
+          const int n2 = len >> 1;
+          for (int k0 = threadIdx.x; k0 < n2; k0 += 5 * THREADS) {
+            double2 v[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+              const int k = k0 + u * THREADS;
+              v[u] = (k < n2) ? cs2[k] : make_double2(1.0, 1.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+              const int k = k0 + u * THREADS;
+              if (k < n2) {
+                double2 t = d2[k];
+                t.x *= v[u].x;
+                t.y *= v[u].y;
+                d2[k] = t;
+              }
+            }
+          }
+          if ((len & 1) && threadIdx.x == 0) sx[len - 1] *= cs[len - 1];
+        } else {
+          for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] *= cs[k];
+        }
         __syncthreads();
       }
       const int p0 = a.up_ptr[vis * NWARPS + warp], p1 = a.up_ptr[vis * NWARPS + warp + 1];
