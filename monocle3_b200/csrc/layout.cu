@@ -770,12 +770,7 @@ int build_layout_B(m3b_mat* m, bool split) {
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   const double tb1 = now_ms();
-  for (int q = 0; q < n_cls; ++q) {
-    const ItemShape& sh = (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL;
-    compute_bases(cnt[q], n_tiles, n_sel, T[q], sh);
-    build_items(cnt[q], n_tiles, n_sel, nullptr, n_sel, ctx->sm_count, T[q], sh);
-  }
-  assign_slots(T[0], split ? &T[1] : nullptr, n_sel);
+  for (int q = 0; q < n_cls; ++q) compute_bases(cnt[q], n_tiles, n_sel, T[q], (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL);
   const double tb2 = now_ms();
   for (int q = 0; q < n_cls; ++q) {
     TiledLayout& Lq = *Ls[q];
@@ -801,6 +796,10 @@ int build_layout_B(m3b_mat* m, bool split) {
     }
     CK(ctx, cudaGetLastError());
   }
+  // the item / slot tables are built on the host while the GPU scatters
+  for (int q = 0; q < n_cls; ++q)
+    build_items(cnt[q], n_tiles, n_sel, nullptr, n_sel, ctx->sm_count, T[q], (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL);
+  assign_slots(T[0], split ? &T[1] : nullptr, n_sel);
   if (dbg) CK(ctx, cudaStreamSynchronize(ctx->stream));
   const double tb3 = now_ms();
   const size_t n_partial = T[0].items.size() + (split ? T[1].items.size() : 0);
@@ -1143,12 +1142,7 @@ int build_layout_A(m3b_mat* m, bool split) {
     if (n_runs) CK(ctx, cudaMemcpyAsync(cnt[q].data(), d_cnt[q], n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
-  for (int q = 0; q < n_cls; ++q) {
-    const ItemShape& sh = (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL;
-    compute_bases(cnt[q], L.n_tiles, L.rows, T[q], sh);
-    build_items(cnt[q], L.n_tiles, L.rows, nullptr, L.rows, ctx->sm_count, T[q], sh);
-  }
-  assign_slots(T[0], split ? &T[1] : nullptr, L.rows);
+  for (int q = 0; q < n_cls; ++q) compute_bases(cnt[q], L.n_tiles, L.rows, T[q], (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL);
   for (int q = 0; q < n_cls; ++q) {
     TiledLayout& Lq = *Ls[q];
     Lq.n_entries = T[q].n_entries;
@@ -1163,6 +1157,10 @@ int build_layout_A(m3b_mat* m, bool split) {
     }
     CK(ctx, cudaGetLastError());
   }
+  // the item / slot tables are built on the host while the GPU scatters
+  for (int q = 0; q < n_cls; ++q)
+    build_items(cnt[q], L.n_tiles, L.rows, nullptr, L.rows, ctx->sm_count, T[q], (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL);
+  assign_slots(T[0], split ? &T[1] : nullptr, L.rows);
   const size_t n_partial = T[0].items.size() + (split ? T[1].items.size() : 0);
   RET(upload_tables(ctx, L, T[0], n_partial));
   RET(bank_reorder(ctx, L));
