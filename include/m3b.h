@@ -171,6 +171,22 @@ int m3b_gene_moments(m3b_mat* mat, double* center /* G' */, double* scale /* G' 
 int m3b_tfidf(m3b_mat* mat, int frequencies, int log_scale_tf, double scale_factor,
               const double* row_sums_in, double num_cols, double* col_sums_out, double* row_sums_out);
 
+/* ---- detect_genes / aggregate_gene_expression -------- */
+/* detect_genes (R/utils.R:449-457): num_cells_expressed[G] = rowSums(counts > min_expr) over ALL
+ * ranks' cells, num_genes_expressed[n_cells_local] = colSums(counts > min_expr).  Works on the raw
+ * counts (any time after m3b_matrix_end).  Collective across ranks. */
+int m3b_detect_genes(m3b_mat* mat, double min_expr, int64_t* num_cells_expressed, int64_t* num_genes_expressed);
+/* The group sums of aggregate_gene_expression (R/cluster_genes.R:447-536) on the values of the
+ * last m3b_normalize (normalized_counts): gene_group[G] = group id in [0, n_gene_groups) or -1
+ * (gene not in any group); gene_agg_mean: 0 = colSums, 1 = colMeans over the member genes.
+ * cell_group == NULL: out is n_gene_groups x n_cells_local (one column per local cell).
+ * Otherwise cell_group[n_cells_local] = id in [0, n_cell_groups) or -1 and out is
+ * n_gene_groups x n_cell_groups, summed (cell_agg_mean = 0) or averaged (1) over each group's
+ * cells of ALL ranks (collective).  out is column-major with leading dimension ld_out. */
+int m3b_aggregate_expression(m3b_mat* mat, const int32_t* gene_group, int32_t n_gene_groups, int gene_agg_mean,
+                             const int32_t* cell_group, int32_t n_cell_groups, int cell_agg_mean,
+                             double* out, int64_t ld_out);
+
 /* ---- IRLBA PCA (K4-K9) -------------------------------------------------- */
 /* nv: number of PCs; work: Lanczos subspace (0 => nv+7); v0: start vector (G').
  * center/scale: 0/1 flags (preprocess_cds passes scaling for both).

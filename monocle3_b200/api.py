@@ -61,7 +61,8 @@ class CellDataSet:
         self.cell_names = np.asarray(cell_names if cell_names is not None else [str(i) for i in range(C)])
         if len(self.gene_names) != G or len(self.cell_names) != C:
             raise ValueError("dimnames do not match the expression matrix")
-        self.col_data = {}           # colData(cds): 'Size_Factor'
+        self.col_data = {}           # colData(cds): 'Size_Factor', 'num_genes_expressed'
+        self.row_data = {}           # rowData(cds): 'num_cells_expressed'
         self.reduced_dims = {}       # reducedDims(cds)
         self.reduce_dim_aux = {}     # cds@reduce_dim_aux
         self.shard = shard
@@ -153,6 +154,123 @@ def normalized_counts(cds, norm_method="log", pseudocount=1):
     if norm_method == "binary":
         out.eliminate_zeros()
     return out
+
+
+def detect_genes(cds, min_expr=0):
+    """R/utils.R:449-457: rowData$num_cells_expressed = rowSums(counts > min_expr) (over all
+    ranks' cells), colData$num_genes_expressed = colSums(counts > min_expr)."""
+    if not isinstance(cds, CellDataSet):
+        raise TypeError("cds is not a cell_data_set")
+    if not isinstance(min_expr, (int, float, np.integer, np.floating)) or isinstance(min_expr, bool):
+        raise TypeError("min_expr is not a numeric or integer vector")
+    per_gene, per_cell = cds.device_matrix().detect_genes(float(min_expr))
+    cds.row_data["num_cells_expressed"] = per_gene
+    cds.col_data["num_genes_expressed"] = per_cell
+    return cds
+
+
+def _pairs(df):
+    """A two-column table (sequence of (id, group) pairs, dict of two columns, 2-column array or
+    pandas DataFrame) as a list of pairs."""
+    if hasattr(df, "iloc"):
+        return list(zip(df.iloc[:, 0].tolist(), df.iloc[:, 1].tolist()))
+    if isinstance(df, dict):
+        cols = list(df.values())
+        return list(zip(list(cols[0]), list(cols[1])))
+    return [(r[0], r[1]) for r in df]
+
+
+def aggregate_gene_expression(cds, gene_group_df=None, cell_group_df=None, norm_method="log", pseudocount=1,
+                              scale_agg_values=True, max_agg_value=3, min_agg_value=-3, exclude_na=True,
+                              gene_agg_fun="sum", cell_agg_fun="mean"):
+    """R/cluster_genes.R:447-536.  The group sums run on the device over the normalised values
+    (normalized_counts, never exported); the row scaling / clamping of the small dense result is
+    host work, as in the reference.  Gene ids are matched against the row names only (this
+    stand-in carries no gene_short_name column).  Returns (matrix, row_names, col_names); not
+    available on a cell-sharded cds without cell groups beyond the local columns."""
+    if gene_group_df is None and cell_group_df is None:
+        raise ValueError("one of either gene_group_df or cell_group_df must not be NULL.")
+    if norm_method not in ("log", "binary", "size_only"):
+        raise ValueError("'arg' should be one of 'log', 'binary', 'size_only'")
+    if gene_agg_fun not in ("sum", "mean") or cell_agg_fun not in ("sum", "mean"):
+        raise ValueError("aggregation functions must be 'sum' or 'mean'")
+    dev = cds.device_matrix()
+    if norm_method == "binary":
+        dev.normalize(None, L.NORM_BINARY, 0.0)
+    else:
+        if norm_method == "log" and pseudocount != 1:
+            raise ValueError("Pseudocount must equal 1 with sparse expression matrices")
+        dev.normalize(size_factors(cds), L.NORM_LOG10 if norm_method == "log" else L.NORM_SIZE_ONLY,
+                      1.0 if norm_method == "log" else 0.0)
+    G, C = cds.counts.shape
+    if gene_group_df is not None:
+        glut = {g: k for k, g in enumerate(cds.gene_names.tolist())}
+        pairs = [(g, grp) for g, grp in _pairs(gene_group_df) if g in glut]
+        groups, members = [], {}
+        for g, grp in pairs:                      # unique() keeps the order of first appearance
+            if grp not in members:
+                members[grp] = []
+                groups.append(grp)
+            if g not in members[grp]:
+                members[grp].append(g)
+        groups = [grp for grp in groups if len(members[grp]) >= 2]  # a single row has no dim(): NA, dropped (:490-491)
+        # The device pass takes ONE group id per gene.  A gene listed under several groups counts
+        # in each of them in the reference, so the groups are dealt into layers inside which no
+        # gene repeats (almost always a single layer) and every layer is one pass.
+        layers = []  # [(gene_group array, [group positions])]
+        for q, grp in enumerate(groups):
+            idx = [glut[g] for g in members[grp]]
+            for arr, pos in layers:
+                if np.all(arr[idx] < 0):
+                    arr[idx] = len(pos)
+                    pos.append(q)
+                    break
+            else:
+                arr = np.full(G, -1, dtype=np.int32)
+                arr[idx] = 0
+                layers.append((arr, [q]))
+        row_names = list(groups)
+    else:
+        layers = []  # every gene is its own row: passes of at most 1024 rows (the device limit)
+        for g0 in range(0, G, 1024):
+            g1 = min(G, g0 + 1024)
+            arr = np.full(G, -1, dtype=np.int32)
+            arr[g0:g1] = np.arange(g1 - g0, dtype=np.int32)
+            layers.append((arr, list(range(g0, g1))))
+        groups = list(range(G))
+        row_names = cds.gene_names.tolist()
+    if len(groups) == 0:
+        return np.zeros((0, 0)), [], []
+    cell_group, levels = None, []
+    if cell_group_df is not None:
+        clut = {c: k for k, c in enumerate(cds.cell_names.tolist())}
+        pairs = [(c, grp) for c, grp in _pairs(cell_group_df) if c in clut]
+        levels = sorted(set(grp for _, grp in pairs))  # as.factor()
+        lv = {l: q for q, l in enumerate(levels)}
+        cell_group = np.full(C, -1, dtype=np.int32)
+        for c, grp in pairs:
+            cell_group[clut[c]] = lv[grp]
+        col_names = list(levels)
+    else:
+        col_names = cds.cell_names.tolist()
+    agg = np.zeros((len(groups), len(col_names)))
+    for arr, pos in layers:
+        part = dev.aggregate(arr, len(pos), gene_agg_fun == "mean", cell_group, len(levels), cell_agg_fun == "mean")
+        agg[pos, :] = part
+    if scale_agg_values:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mu = agg.mean(axis=1, keepdims=True)
+            sd = agg.std(axis=1, ddof=1, keepdims=True) if agg.shape[1] > 1 else np.full((agg.shape[0], 1), np.nan)
+            agg = (agg - mu) / sd
+        agg[np.isnan(agg)] = 0
+        agg = np.clip(agg, min_agg_value, max_agg_value)
+    if exclude_na:
+        rk = [k for k, n in enumerate(row_names) if n != "NA"]
+        ck = [k for k, n in enumerate(col_names) if n != "NA"]
+        agg = agg[np.ix_(rk, ck)]
+        row_names = [row_names[k] for k in rk]
+        col_names = [col_names[k] for k in ck]
+    return agg, row_names, col_names
 
 
 _NORM = {"log": L.NORM_LOG2, "size_only": L.NORM_SIZE_ONLY, "none": L.NORM_NONE}

@@ -480,6 +480,26 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
   return M3B_OK;
 }
 
+int m3b_detect_genes(m3b_mat* m, double min_expr, int64_t* num_cells_expressed, int64_t* num_genes_expressed) {
+  if (!m || !num_cells_expressed || !num_genes_expressed) return M3B_E_DIMS;
+  if (!m->ended) {
+    m3b_set_error(m->ctx, "m3b_detect_genes before m3b_matrix_end");
+    return M3B_E_STATE;
+  }
+  cudaSetDevice(m->ctx->device);
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t");
+  return run_detect_genes(m, min_expr, reinterpret_cast<long long*>(num_cells_expressed),
+                          reinterpret_cast<long long*>(num_genes_expressed));
+}
+
+int m3b_aggregate_expression(m3b_mat* m, const int32_t* gene_group, int32_t n_gene_groups, int gene_agg_mean,
+                             const int32_t* cell_group, int32_t n_cell_groups, int cell_agg_mean, double* out,
+                             int64_t ld_out) {
+  if (!m || !gene_group || !out) return M3B_E_DIMS;
+  cudaSetDevice(m->ctx->device);
+  return run_aggregate(m, gene_group, n_gene_groups, gene_agg_mean, cell_group, n_cell_groups, cell_agg_mean, out, ld_out);
+}
+
 int m3b_gene_nnz(m3b_mat* m, int64_t* nnz_per_sel_gene) {
   if (!m || !nnz_per_sel_gene) return M3B_E_DIMS;
   m3b_ctx* ctx = m->ctx;

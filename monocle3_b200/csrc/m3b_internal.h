@@ -245,6 +245,11 @@ int flat_build_plans(m3b_ctx* ctx, TiledLayout& L, const HostTables& Tg, const H
 int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStream_t stream, int max_cta);
 int flat_init(m3b_ctx* ctx);
 
+// aggregate.cu
+int run_detect_genes(m3b_mat* m, double min_expr, long long* num_cells_expressed, long long* num_genes_expressed);
+int run_aggregate(m3b_mat* m, const int* gene_group, int n_groups, int gene_mean, const int* cell_group, int n_cell_groups,
+                  int cell_mean, double* out, long long ld_out);
+
 // tfidf.cu (LSI branch)
 int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor, const double* row_sums_in,
               double num_cols, double* col_sums_out, double* row_sums_out);

@@ -194,6 +194,27 @@ class DeviceMatrix:
         self.ctx.check(self.lib.m3b_gene_nnz(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return out[:self.n_sel]
 
+    def detect_genes(self, min_expr=0.0):
+        """(num_cells_expressed[G] over all ranks, num_genes_expressed[local cells])."""
+        pg = np.zeros(max(self.n_genes, 1), dtype=np.int64)
+        pc = np.zeros(max(self.n_cells, 1), dtype=np.int64)
+        self.ctx.check(self.lib.m3b_detect_genes(self.h, float(min_expr), pg.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 pc.ctypes.data_as(C.POINTER(C.c_int64))))
+        return pg[:self.n_genes], pc[:self.n_cells]
+
+    def aggregate(self, gene_group, n_gene_groups, gene_mean=False, cell_group=None, n_cell_groups=0, cell_mean=True):
+        """Group sums of the normalised values: (n_gene_groups x n_cell_groups) or (n_gene_groups x local cells)."""
+        gg = np.ascontiguousarray(gene_group, dtype=np.int32)
+        ncol = n_cell_groups if cell_group is not None else self.n_cells
+        out = np.zeros((max(ncol, 1), max(n_gene_groups, 1)))  # column-major n_gene_groups x ncol
+        cg = None if cell_group is None else np.ascontiguousarray(cell_group, dtype=np.int32)
+        ip = C.POINTER(C.c_int32)
+        self.ctx.check(self.lib.m3b_aggregate_expression(
+            self.h, gg.ctypes.data_as(ip), int(n_gene_groups), int(bool(gene_mean)),
+            None if cg is None else cg.ctypes.data_as(ip), int(n_cell_groups), int(bool(cell_mean)), _dp(out),
+            int(max(n_gene_groups, 1))))
+        return out[:ncol, :n_gene_groups].T.copy()
+
     def gene_moments(self):
         c = np.empty(max(self.n_kept, 1))
         s = np.empty(max(self.n_kept, 1))

@@ -8,6 +8,10 @@ Third-party arithmetic (irlba, Matrix, DelayedMatrixStats, base-R RNG) is
 restated in irlba_ref.py / r_rng.py.  Parity is pinned by the reference's own
 golden values -- tests/test_oracle_golden.py.
 
+detect_genes / aggregate_gene_expression are PARITY UNPINNED: the
+reference's tests hold no expected values for them (test-cluster_genes.R only runs the call),
+so they are restated from the R source alone.
+
 Conventions: `counts` is a scipy.sparse.csc_matrix, genes x cells (the
 `dgCMatrix` of counts(cds), R/cell_data_set.R:117,123).
 """
@@ -256,3 +260,86 @@ def preprocess_transform(counts, sf, model, gene_index_in_model):
         Xd = (np.asarray(X.todense()) if sp.issparse(X) else X)
         return ((Xd - c[None, :]) / s[None, :]) @ V  # :141-148, densified like DelayedArray does
     return np.asarray(X @ V)
+
+
+def detect_genes(counts, min_expr=0):
+    """R/utils.R:449-457: (rowSums(counts > min_expr), colSums(counts > min_expr)).  PARITY UNPINNED."""
+    C = counts.tocsc()
+    G, N = C.shape
+    on = C.data > min_expr
+    per_gene = np.bincount(C.indices[on], minlength=G).astype(np.int64)
+    per_cell = np.add.reduceat(np.concatenate([on.astype(np.int64), [0]]), C.indptr[:-1])
+    per_cell = np.where(np.diff(C.indptr) > 0, per_cell, 0).astype(np.int64)
+    if min_expr < 0:  # the implicit zeros qualify as well
+        per_gene += N - np.bincount(C.indices, minlength=G)
+        per_cell += G - np.diff(C.indptr)
+    return per_gene, per_cell
+
+
+def _factor_levels(labels):
+    """as.factor(): sorted unique values (numbers numerically, strings lexicographically)."""
+    return sorted(set(labels))
+
+
+def aggregate_gene_expression(counts, sf, gene_names, cell_names, gene_group_df=None, cell_group_df=None,
+                              norm_method="log", pseudocount=1, scale_agg_values=True, max_agg_value=3,
+                              min_agg_value=-3, exclude_na=True, gene_agg_fun="sum", cell_agg_fun="mean"):
+    """R/cluster_genes.R:447-536.  *_group_df: sequences of (id, group) pairs.  Returns
+    (matrix, row_names, col_names).  PARITY UNPINNED (no expected values in the reference's tests)."""
+    if gene_group_df is None and cell_group_df is None:
+        raise ValueError("one of either gene_group_df or cell_group_df must not be NULL.")
+    agg = normalized_counts(counts, sf, norm_method=norm_method, pseudocount=pseudocount).tocsr()
+    row_names, col_names = list(gene_names), list(cell_names)
+    if gene_group_df is not None:
+        glut = {g: k for k, g in enumerate(gene_names)}
+        pairs = [(g, grp) for g, grp in gene_group_df if g in glut]           # :466-469
+        groups = []
+        for _, grp in pairs:                                                  # unique(), first appearance
+            if grp not in groups:
+                groups.append(grp)
+        rows, names = [], []
+        for grp in groups:
+            members = []
+            for g, gg in pairs:
+                if gg == grp and g not in members:
+                    members.append(g)
+            if len(members) < 2:                                              # :490-491 a single row has no dim
+                continue
+            sub = agg[[glut[g] for g in members], :]
+            res = np.asarray(sub.sum(axis=0)).ravel()
+            if gene_agg_fun == "mean":
+                res = res / len(members)
+            rows.append(res)
+            names.append(grp)
+        agg = np.vstack(rows) if rows else np.zeros((0, agg.shape[1]))
+        row_names = names
+    else:
+        agg = agg.toarray()
+    if cell_group_df is not None:
+        clut = {c: k for k, c in enumerate(cell_names)}
+        pairs = [(c, grp) for c, grp in cell_group_df if c in clut]           # :517-518
+        sub = agg[:, [clut[c] for c, _ in pairs]]                             # :519
+        labels = [grp for _, grp in pairs]
+        levels = _factor_levels(labels)                                       # as.factor
+        out = np.zeros((agg.shape[0], len(levels)))
+        for q, lv in enumerate(levels):
+            idx = [k for k, l in enumerate(labels) if l == lv]
+            out[:, q] = sub[:, idx].sum(axis=1)
+            if cell_agg_fun == "mean":
+                out[:, q] /= len(idx)
+        agg = out
+        col_names = levels
+    if scale_agg_values:                                                      # :526-536
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mu = agg.mean(axis=1, keepdims=True)
+            sd = agg.std(axis=1, ddof=1, keepdims=True) if agg.shape[1] > 1 else np.full((agg.shape[0], 1), np.nan)
+            agg = (agg - mu) / sd
+        agg[np.isnan(agg)] = 0
+        agg = np.clip(agg, min_agg_value, max_agg_value)
+    if exclude_na:
+        rk = [k for k, n in enumerate(row_names) if n != "NA"]
+        ck = [k for k, n in enumerate(col_names) if n != "NA"]
+        agg = agg[np.ix_(rk, ck)]
+        row_names = [row_names[k] for k in rk]
+        col_names = [col_names[k] for k in ck]
+    return agg, row_names, col_names

@@ -118,4 +118,34 @@ NumericMatrix m3b_preprocess_transform(S4 counts, NumericVector sf, int norm_met
   return Y;
 }
 
+// detect_genes (R/utils.R:449-457): list(num_cells_expressed, num_genes_expressed)
+// [[Rcpp::export]]
+List m3b_detect_genes_(S4 counts, double min_expr) {
+  m3b_mat* m = upload(counts);
+  IntegerVector dim = counts.slot("Dim");
+  std::vector<int64_t> per_gene(dim[0]), per_cell(dim[1]);
+  int st = m3b_detect_genes(m, min_expr, per_gene.data(), per_cell.data());
+  m3b_matrix_free(m);
+  m3b_check(the_ctx(), st);
+  return List::create(_["num_cells_expressed"] = NumericVector(per_gene.begin(), per_gene.end()),
+                      _["num_genes_expressed"] = NumericVector(per_cell.begin(), per_cell.end()));
+}
+
+// group sums behind aggregate_gene_expression (R/cluster_genes.R:486-522).  gene_group / cell_group are
+// 0-based ids (-1 = not in a group; the R side builds them from the data frames: unique() order for gene
+// groups, factor levels for cell groups); the scale()/clamp step (:526-536) stays in R.
+// [[Rcpp::export]]
+NumericMatrix m3b_aggregate_(S4 counts, NumericVector sf, int norm_method, IntegerVector gene_group, int n_gene_groups,
+                             bool gene_mean, IntegerVector cell_group, int n_cell_groups, bool cell_mean) {
+  m3b_ctx* ctx = the_ctx();
+  m3b_mat* m = upload(counts);
+  m3b_check(ctx, m3b_normalize(m, sf.begin(), norm_method, norm_method == M3B_NORM_LOG10 ? 1.0 : 0.0));
+  NumericMatrix out(n_gene_groups, n_cell_groups);
+  int st = m3b_aggregate_expression(m, gene_group.begin(), n_gene_groups, gene_mean, cell_group.begin(), n_cell_groups,
+                                    cell_mean, out.begin(), n_gene_groups);
+  m3b_matrix_free(m);
+  m3b_check(ctx, st);
+  return out;
+}
+
 // registration, as in src/RcppExports.cpp:38-47 (generated by Rcpp::compileAttributes() in practice)

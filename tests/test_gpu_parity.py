@@ -429,3 +429,42 @@ def test_lsi_branch(m3, a549):
     q.reduce_dim_aux = {"LSI": cds50.reduce_dim_aux["LSI"]}
     q = m3.preprocess_transform(q, reduction_method="LSI")
     assert np.abs(q.reduced_dims["LSI"] - cds50.reduced_dims["LSI"]).max() < 1e-8
+
+
+@pytest.mark.parametrize("min_expr", [0, 0.1, 2, -1])
+def test_detect_genes(m3, a549, min_expr):
+    """SURVEY 8f row 2 / R/utils.R:449-457: thresholded expression counts, exact (integers)."""
+    counts, extra = a549
+    cds = m3.detect_genes(_cds(m3, counts, extra), min_expr=min_expr)
+    pg, pc = ref.detect_genes(counts, min_expr)
+    assert np.array_equal(cds.row_data["num_cells_expressed"], pg)
+    assert np.array_equal(cds.col_data["num_genes_expressed"], pc)
+    if min_expr == 0:  # dense cross-check of the restatement itself
+        D = counts.toarray()
+        assert np.array_equal(pg, (D > 0).sum(axis=1)) and np.array_equal(pc, (D > 0).sum(axis=0))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(norm_method="size_only", gene_agg_fun="mean", cell_agg_fun="sum"),
+                                dict(norm_method="binary", scale_agg_values=False), dict(cells=False),
+                                dict(genes=False, scale_agg_values=False)])
+def test_aggregate_gene_expression(m3, worm_l2, kw):
+    """SURVEY 8f row 2 / R/cluster_genes.R:447-536 against the restatement: gene groups (one with a
+    single gene -> dropped, one gene in two groups, an unknown id), cell groups incl. 'NA'."""
+    counts, extra = worm_l2
+    kw = dict(kw)
+    cds = _cds(m3, counts, extra)
+    genes, cells = cds.gene_names.tolist(), cds.cell_names.tolist()
+    rng = np.random.default_rng(3)
+    gsel = rng.choice(len(genes), 400, replace=False)
+    gdf = [(genes[g], "mod%d" % (k % 7)) for k, g in enumerate(gsel)]
+    gdf += [(genes[gsel[0]], "mod3"), ("not_a_gene", "mod1"), (genes[gsel[1]], "solo")]
+    labels = ["NA" if k % 11 == 0 else "part%d" % (k % 5) for k in range(len(cells))]
+    cdf = [(c, l) for c, l in zip(cells, labels)][::-1]  # the order of the table must not matter
+    use_g = gdf if kw.pop("genes", True) else None
+    use_c = cdf if kw.pop("cells", True) else None
+    A, rn, cn = m3.aggregate_gene_expression(cds, use_g, use_c, **kw)
+    Ao, rno, cno = ref.aggregate_gene_expression(counts, m3.size_factors(cds), genes, cells, use_g, use_c, **kw)
+    assert rn == rno and cn == cno and A.shape == Ao.shape
+    if use_g is not None:
+        assert "solo" not in rn
+    np.testing.assert_allclose(A, Ao, rtol=1e-10, atol=1e-12)
