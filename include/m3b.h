@@ -89,6 +89,11 @@ typedef struct m3b_mat m3b_mat;
 typedef int (*m3b_small_svd_fn)(int n, const double* B, double* U, double* s, double* Vt, void* user);
 /* Polled once per restart (irlba polls R_CheckUserInterrupt after each product). */
 typedef int (*m3b_should_abort_fn)(void* user);
+/* Standard normals from the CALLER's random stream (the R shim: rnorm(n)).  irlba replaces a
+ * Lanczos vector by a random one when the process hits an invariant subspace (irlb.c: R_F < eps or
+ * S < eps); with this callback set the library does the same (single rank), without it that case
+ * returns M3B_E_LINDEP.  Return 0 on success. */
+typedef int (*m3b_rnorm_fn)(int64_t n, double* out, void* user);
 
 /* ---- library / context ------------------------------------------------ */
 int         m3b_abi_version(void);
@@ -100,6 +105,7 @@ void        m3b_destroy(m3b_ctx* ctx);
 const char* m3b_last_error(const m3b_ctx* ctx);
 int         m3b_set_small_svd(m3b_ctx* ctx, m3b_small_svd_fn fn, void* user);
 int         m3b_set_should_abort(m3b_ctx* ctx, m3b_should_abort_fn fn, void* user);
+int         m3b_set_rnorm(m3b_ctx* ctx, m3b_rnorm_fn fn, void* user);
 
 /* ---- multi-GPU plumbing (one context per rank) ------------------------ */
 #define M3B_COMM_ID_BYTES 128

@@ -29,6 +29,7 @@ FLAG_JACOBI_ONLY = 2
 FLAG_NO_UNIT_SPLIT = 4  # keep count-1 entries in the 10 B/entry stream (A/B switch)
 COMM_ID_BYTES = 128
 
+RNORM_FN = C.CFUNCTYPE(C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_void_p)
 SMALL_SVD_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                            C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 SHOULD_ABORT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
@@ -57,6 +58,7 @@ SIGNATURES = {
     "m3b_destroy": (None, [_P]),
     "m3b_last_error": (C.c_char_p, [_P]),
     "m3b_set_small_svd": (C.c_int, [_P, SMALL_SVD_FN, _P]),
+    "m3b_set_rnorm": (C.c_int, [_P, RNORM_FN, _P]),
     "m3b_set_should_abort": (C.c_int, [_P, SHOULD_ABORT_FN, _P]),
     "m3b_comm_unique_id": (C.c_int, [_P, C.c_char_p]),
     "m3b_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),

@@ -24,7 +24,7 @@ import scipy.sparse as sp
 
 from . import _lib as L
 from . import engine
-from .r_rng import rnorm_after_seed
+from .r_rng import RStream, rnorm_after_seed  # noqa: F401
 
 _default_ctx = None
 
@@ -320,9 +320,15 @@ def preprocess_cds(cds, method="PCA", num_dim=50, norm_method="log", use_genes=N
     if verbose:
         print("Remove noise by PCA ...")
     n = min(num_dim, min(len(kept_idx), cds.n_cells_total) - 1)  # :140
-    # set.seed(2016) (:110); irlba draws rnorm(ncol(A)) for its start vector
-    v0 = rnorm_after_seed(2016, len(kept_idx))
-    res = dev.pca_irlba(n, v0, center=scaling, scale=scaling, **(_irlba_args or {}))
+    # set.seed(2016) (:110); irlba draws rnorm(ncol(A)) for its start vector, and further vectors
+    # from the same stream if the Lanczos process hits an invariant subspace
+    stream = RStream(2016)
+    v0 = stream.rnorm(len(kept_idx))
+    dev.ctx.set_rnorm(stream.rnorm if not cds.shard else None)
+    try:
+        res = dev.pca_irlba(n, v0, center=scaling, scale=scaling, **(_irlba_args or {}))
+    finally:
+        dev.ctx.set_rnorm(None)
     if res["status"] == L.M3B_W_NOT_CONVERGED:
         warnings.warn("did not converge--results might be invalid!; try increasing work or maxit")
     C_tot = cds.n_cells_total

@@ -23,11 +23,21 @@ __device__ __forceinline__ double ag_ld_f64(const double* p) {
 // per cell: stored entries above the threshold; per gene: the same (integer atomics: exact and
 // order-independent) plus the stored-entry count, needed when the threshold is negative and the
 // implicit zeros qualify too
-__global__ void __launch_bounds__(256) k_detect(const long long* __restrict__ p, const int* __restrict__ gi,
-                                                const double* __restrict__ x, long long n_cells, double min_expr,
+// use_smem: the per-gene counters of a CTA live in shared memory (2 x n_genes x 4 B) and are
+// flushed once; otherwise global atomics per entry (very many genes)
+__global__ void __launch_bounds__(512) k_detect(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                const double* __restrict__ x, long long n_cells, int n_genes,
+                                                double min_expr, int need_nnz, int use_smem,
                                                 unsigned long long* __restrict__ gene_gt,
                                                 unsigned long long* __restrict__ gene_nnz,
                                                 long long* __restrict__ cell_gt) {
+  extern __shared__ unsigned int dg_hist[];  // [2][n_genes] when use_smem
+  unsigned int* h_gt = dg_hist;
+  unsigned int* h_nz = dg_hist + n_genes;
+  if (use_smem) {
+    for (int g = threadIdx.x; g < 2 * n_genes; g += blockDim.x) dg_hist[g] = 0u;
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -37,15 +47,25 @@ __global__ void __launch_bounds__(256) k_detect(const long long* __restrict__ p,
     for (long long k = lo + lane; k < hi; k += 32) {
       const int g = gi[k];
       const bool on = ag_ld_f64(x + k) > min_expr;
-      atomicAdd(gene_nnz + g, 1ULL);
-      if (on) {
-        atomicAdd(gene_gt + g, 1ULL);
-        ++n;
+      if (use_smem) {
+        if (need_nnz) atomicAdd(h_nz + g, 1u);
+        if (on) atomicAdd(h_gt + g, 1u);
+      } else {
+        if (need_nnz) atomicAdd(gene_nnz + g, 1ULL);
+        if (on) atomicAdd(gene_gt + g, 1ULL);
       }
+      n += on ? 1 : 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     if (lane == 0) cell_gt[c] = n;
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) {
+      if (h_gt[g]) atomicAdd(gene_gt + g, (unsigned long long)h_gt[g]);
+      if (need_nnz && h_nz[g]) atomicAdd(gene_nnz + g, (unsigned long long)h_nz[g]);
+    }
   }
 }
 
@@ -63,8 +83,16 @@ int run_detect_genes(m3b_mat* m, double min_expr, long long* num_cells_expressed
   do {
     if ((e = cudaMemsetAsync(d_gt, 0, (size_t)std::max(2 * G, 1) * sizeof(unsigned long long), ctx->stream)) != cudaSuccess) break;
     if (C) {
-      const int blocks = (int)std::min<long long>((C + 7) / 8, (long long)ctx->sm_count * 8);
-      k_detect<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, C, min_expr, d_gt, d_nnz, d_cell);
+      // (the stored-entry counts are only needed when the implicit zeros qualify)
+      const size_t hist = 2 * (size_t)G * sizeof(unsigned int);
+      const int use_smem = hist <= 200 * 1024;
+      if (use_smem && hist > 48 * 1024 &&
+          (e = cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist)) != cudaSuccess)
+        break;
+      const int blocks = use_smem ? (int)std::min<long long>((C + 15) / 16, (long long)ctx->sm_count)
+                                  : (int)std::min<long long>((C + 15) / 16, (long long)ctx->sm_count * 4);
+      k_detect<<<blocks, 512, use_smem ? hist : 0, ctx->stream>>>(m->p, m->i, m->x, C, G, min_expr, min_expr < 0.0 ? 1 : 0,
+                                                                   use_smem, d_gt, d_nnz, d_cell);
       count_launch(ctx);
       if ((e = cudaGetLastError()) != cudaSuccess) break;
     }
@@ -139,15 +167,26 @@ __global__ void __launch_bounds__(32 * AG_WARPS) k_agg_cells(const long long* __
   }
 }
 
-// out[g, cg] = sum (or mean) over the cells of cell group cg, in cell order
-__global__ void k_agg_groups(const double* __restrict__ cells, long long ld, int n_groups, const long long* __restrict__ cg_ptr,
-                             const long long* __restrict__ cg_cells, int n_cell_groups, double* __restrict__ out) {
-  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (e >= (long long)n_groups * n_cell_groups) return;
-  const int g = (int)(e % n_groups), cg = (int)(e / n_groups);
+// out[g, cg] = sum over the cells of cell group cg.  Block = 32 gene groups x 16 slices: slice s
+// adds the cells q == s (mod 16) of the group's list in list order, the 16 slice sums are then
+// added in slice order -- a fixed summation order.  grid = (ceil(n_groups/32), n_cell_groups).
+__global__ void __launch_bounds__(512) k_agg_groups(const double* __restrict__ cells, long long ld, int n_groups,
+                                                    const long long* __restrict__ cg_ptr,
+                                                    const long long* __restrict__ cg_cells, double* __restrict__ out) {
+  __shared__ double part[16][33];
+  const int gl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int g = blockIdx.x * 32 + gl, cg = blockIdx.y;
   double a = 0.0;
-  for (long long q = cg_ptr[cg]; q < cg_ptr[cg + 1]; ++q) a += cells[(size_t)cg_cells[q] * ld + g];
-  out[e] = a;
+  if (g < n_groups)
+    for (long long q = cg_ptr[cg] + sl; q < cg_ptr[cg + 1]; q += 16) a += cells[(size_t)cg_cells[q] * ld + g];
+  part[sl][gl] = a;
+  __syncthreads();
+  if (sl == 0 && g < n_groups) {
+    double t = 0.0;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) t += part[s2][gl];
+    out[(size_t)cg * n_groups + g] = t;
+  }
 }
 
 int run_aggregate(m3b_mat* m, const int* gene_group, int n_groups, int gene_mean, const int* cell_group, int n_cell_groups,
@@ -226,7 +265,7 @@ int run_aggregate(m3b_mat* m, const int* gene_group, int n_groups, int gene_mean
           (e = cudaMemcpyAsync(d_list, cg_cells.data(), cg_cells.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         break;
       const long long ne = (long long)n_groups * n_cell_groups;
-      k_agg_groups<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(d_cells, n_groups, n_groups, d_ptr, d_list, n_cell_groups, d_out);
+      k_agg_groups<<<dim3((n_groups + 31) / 32, n_cell_groups), 512, 0, ctx->stream>>>(d_cells, n_groups, n_groups, d_ptr, d_list, d_out);
       count_launch(ctx);
       if ((e = cudaGetLastError()) != cudaSuccess) break;
       // group sizes ride behind the sums so that one allreduce covers both

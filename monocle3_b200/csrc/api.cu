@@ -150,6 +150,13 @@ int m3b_set_small_svd(m3b_ctx* ctx, m3b_small_svd_fn fn, void* user) {
   return M3B_OK;
 }
 
+int m3b_set_rnorm(m3b_ctx* ctx, m3b_rnorm_fn fn, void* user) {
+  if (!ctx) return M3B_E_DIMS;
+  ctx->rnorm = fn;
+  ctx->rnorm_user = user;
+  return M3B_OK;
+}
+
 int m3b_set_should_abort(m3b_ctx* ctx, m3b_should_abort_fn fn, void* user) {
   if (!ctx) return M3B_E_DIMS;
   ctx->should_abort = fn;

@@ -695,9 +695,11 @@ __global__ void __launch_bounds__(NT) k_scale_w(double* __restrict__ w, long lon
 }
 
 // single-rank fusion of k_reduce2 + k_scale_w: every block reduces the partials itself
+// force_zero (invariant-subspace recovery, irlb.c): w is a random replacement vector -- it is
+// normalised, but the recurrence coefficient it stands for is 0
 __global__ void __launch_bounds__(NT) k_scale_w_fused(double* __restrict__ w, long long rows, const double* __restrict__ pn,
                                                       const double* __restrict__ ps, int np, double* __restrict__ scal,
-                                                      int* __restrict__ ctl, double eps, int first) {
+                                                      int* __restrict__ ctl, double eps, int first, int force_zero) {
   __shared__ double sh[32];
   const double n2 = block_sum_partials(pn, np, sh);
   const double sm = block_sum_partials(ps, np, sh);
@@ -706,9 +708,9 @@ __global__ void __launch_bounds__(NT) k_scale_w_fused(double* __restrict__ w, lo
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
     w[r] *= SS;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    scal[SC_S] = S;
+    scal[SC_S] = force_zero ? 0.0 : S;
     scal[SC_SUMW] = sm * SS;
-    if (!(S >= eps)) ctl[CT_FLAG] |= first ? 1 : 2;
+    if (!(S >= eps) && !force_zero) ctl[CT_FLAG] |= first ? 1 : 2;
   }
 }
 
@@ -718,10 +720,12 @@ __global__ void __launch_bounds__(NT) k_finish_F(const double* __restrict__ F, c
                                                  const double* __restrict__ s, const double* __restrict__ ce, int n,
                                                  double* __restrict__ vnext, double* __restrict__ xs,
                                                  double* __restrict__ pb, double* __restrict__ Bm, int work, int j,
-                                                 double* __restrict__ scal, int* __restrict__ ctl, double eps) {
+                                                 double* __restrict__ scal, int* __restrict__ ctl, double eps,
+                                                 int force_zero) {
   __shared__ double sh[32];
-  const double rf = sqrt(block_sum_partials(pn, np, sh));
+  double rf = sqrt(block_sum_partials(pn, np, sh));
   const double R = 1.0 / rf;
+  if (force_zero) rf = 0.0;  // F is a random replacement vector: normalised, coefficient 0
   double acc = 0.0;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
     double v = F[g] * R;
@@ -737,7 +741,7 @@ __global__ void __launch_bounds__(NT) k_finish_F(const double* __restrict__ F, c
       scal[SC_RF] = rf;
       Bm[(long long)j * work + j] = scal[SC_S];
       Bm[(long long)(j + 1) * work + j] = rf;
-      if (!(rf >= eps)) ctl[CT_FLAG] |= 2;
+      if (!(rf >= eps) && !force_zero) ctl[CT_FLAG] |= 2;
     }
   }
 }
@@ -766,6 +770,7 @@ __global__ void k_restart_logic(int work, int nu, double tol, double svtol, cons
                                 double* __restrict__ Bm, const double* __restrict__ scal, int* __restrict__ ctl) {
   __shared__ int s_len;
   __shared__ int s_k;
+  if (ctl[CT_FLAG] & 2) return;  // the cycle broke down: leave svratio / B / k alone, the host re-runs it
   const double rf = scal[SC_RF];
   const double S = scal[SC_S];
   if (threadIdx.x == 0) s_len = 0;
@@ -1148,11 +1153,33 @@ struct Irlba {
   }
 
   // normalise W[:, jw] using pn/ps partials (cell side): S, sum(w)
-  int finish_w(int jw, bool first, int np) {
+  // ||y||^2 from the partials the last orthog / norm kernel left in pn (host value; slow path only)
+  int read_norm2(int np, double* out) {
+    k_reduce2<<<1, NT, 0, ctx->stream>>>(pn, ps, np, buf2);
+    count_launch(ctx);
+    CK(ctx, cudaMemcpyAsync(out, buf2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return M3B_OK;
+  }
+
+  // irlb.c's answer to an invariant subspace: y = rnorm(len) from the caller's stream, y -= X X^T y
+  int random_vector(double* X, long long ld, long long rows, int ncols, double* y, int chunk, int nblk, int nb) {
+    std::vector<double> h((size_t)rows);
+    if (ctx->rnorm((int64_t)rows, h.data(), ctx->rnorm_user) != 0) {
+      m3b_set_error(ctx, "rnorm callback failed");
+      return M3B_E_STATE;
+    }
+    CK(ctx, cudaMemcpyAsync(y, h.data(), (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += rows * 8;
+    return orthog(X, ld, rows, ncols, y, chunk, nblk, nb, false);
+  }
+
+  int finish_w(int jw, bool first, int np, bool force_zero = false) {
     if (ctx->comm.world == 1) {
       spmv_timer_begin(ctx, 5);
       k_scale_w_fused<<<nb_m, NT, 0, ctx->stream>>>(W + (long long)jw * mrows, mrows, pn, ps, np, scal, ctl, eps,
-                                                    first ? 1 : 0);
+                                                    first ? 1 : 0, force_zero ? 1 : 0);
       count_launch(ctx);
       spmv_timer_end(ctx);
       CK(ctx, cudaGetLastError());
@@ -1402,6 +1429,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     t_loop0 = now();
 
     bool pre_k4 = false;  // next cycle's first product already running on the side stream
+    bool careful = false; // this cycle is the re-run of one that hit an invariant subspace
     while (it < maxit) {
       int j = (it == 0) ? 0 : k;
       // W[:,j] = Ax(V[:,j])
@@ -1412,7 +1440,8 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         count_launch(ctx);
       }
       I.pb_n = I.nb_n;
-      const bool fz = I.fused;
+      const bool fz = I.fused && !careful;
+      const int mprod_cycle0 = mprod;
       IR(I.product_A(j, false, pre_k4, !(fz && it > 0)));
       pre_k4 = false;
       mprod++;
@@ -1447,13 +1476,33 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         mprod++;
         IR(I.orthog(I.V, n, n, j + 1, I.F, I.chunk_n, I.nblk_n, I.nbo_n, false));
         if (j + 1 < work) {
+          // careful mode (re-run of a cycle that broke down): look at every norm on the host and
+          // replace a vanished vector by a random one, as irlb.c does
+          bool rnd = false;
+          if (careful) {
+            double n2 = 0.0;
+            IR(I.read_norm2(I.nbo_n, &n2));
+            if (!(std::sqrt(n2) >= I.eps)) {
+              rnd = true;
+              IR(I.random_vector(I.V, n, n, j + 1, I.F, I.chunk_n, I.nblk_n, I.nbo_n));
+            }
+          }
           k_finish_F<<<I.nb_n, NT, 0, ctx->stream>>>(I.F, I.pn, I.nbo_n, I.s, I.ce, n, I.V + (long long)(j + 1) * n, I.xs,
-                                                     I.pb, I.Bm, work, j, I.scal, I.ctl, I.eps);
+                                                     I.pb, I.Bm, work, j, I.scal, I.ctl, I.eps, rnd ? 1 : 0);
           count_launch(ctx);
           IR(I.product_A(j + 1, true));
           mprod++;
           IR(I.orthog(I.W, mloc, mloc, j + 1, I.W + (long long)(j + 1) * mloc, I.chunk_m, I.nblk_m, I.nbo_m, true));
-          IR(I.finish_w(j + 1, false, I.nbo_m));
+          rnd = false;
+          if (careful) {
+            double n2 = 0.0;
+            IR(I.read_norm2(I.nbo_m, &n2));
+            if (!(std::sqrt(n2) >= I.eps)) {
+              rnd = true;
+              IR(I.random_vector(I.W, mloc, mloc, j + 1, I.W + (long long)(j + 1) * mloc, I.chunk_m, I.nblk_m, I.nbo_m));
+            }
+          }
+          IR(I.finish_w(j + 1, false, I.nbo_m, rnd));
         } else {
           k_finish_last<<<I.nb_n, NT, 0, ctx->stream>>>(I.F, I.pn, I.nbo_n, n, I.Bm, work, j, I.scal, I.eps);
           count_launch(ctx);
@@ -1519,6 +1568,21 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         status = M3B_E_CUDA;
         goto done;
       }
+      if ((hctl[CT_FLAG] & 2) && !careful && ctx->rnorm && ctx->comm.world == 1) {
+        // Invariant subspace (irlb.c: R_F < eps or S < eps).  The cycle only appended columns
+        // behind the restart state (V[:, :k+1], W[:, :k], the arrow part of B) and the restart
+        // logic left svratio / B / k alone, so the cycle is simply run again, this time looking
+        // at every norm on the host and drawing replacement vectors from the caller's stream.
+        ICK(cudaStreamSynchronize(ctx->stream2));
+        const int cleared = hctl[CT_FLAG] & ~2;
+        ICK(cudaMemcpyAsync(I.ctl + CT_FLAG, &cleared, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        ICK(cudaStreamSynchronize(ctx->stream));
+        mprod = mprod_cycle0;
+        pre_k4 = false;
+        careful = true;
+        continue;
+      }
+      careful = false;
       if (hctl[CT_FLAG] & 2) {
         m3b_set_error(ctx, "linear dependency encountered (invariant subspace) at restart %d", it);
         status = M3B_E_LINDEP;

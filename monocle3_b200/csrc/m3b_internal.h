@@ -85,6 +85,8 @@ struct m3b_ctx {
   void* small_svd_user = nullptr;
   m3b_should_abort_fn should_abort = nullptr;
   void* should_abort_user = nullptr;
+  m3b_rnorm_fn rnorm = nullptr;
+  void* rnorm_user = nullptr;
   m3b_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // m3b_timer_start / m3b_timer_stop
   cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // bracket the last K1 / K2 kernel

@@ -49,6 +49,24 @@ class Context:
         self.rank, self.world = 0, 1
         self.set_small_svd(small_svd)
 
+    def set_rnorm(self, fn):
+        """fn(n) -> n standard normals from the caller's stream (used only when the Lanczos process
+        hits an invariant subspace); None unregisters."""
+        if fn is None:
+            self._rnorm_cb = None
+            self.check(self.lib.m3b_set_rnorm(self.h, C.cast(None, L.RNORM_FN), None))
+            return
+
+        def cb(n, out, _user):
+            try:
+                v = np.asarray(fn(int(n)), dtype=np.float64)
+                C.memmove(out, v.ctypes.data, int(n) * 8)
+                return 0
+            except Exception:
+                return 1
+        self._rnorm_cb = L.RNORM_FN(cb)
+        self.check(self.lib.m3b_set_rnorm(self.h, self._rnorm_cb, None))
+
     def set_small_svd(self, mode):
         if mode == "lapack":
             self._cb = lapack_small_svd()

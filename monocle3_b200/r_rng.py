@@ -32,14 +32,24 @@ def _unif(raw):
     return np.where(1.0 - u <= 0.0, 1.0 - 0.5 * _I2_32M1, u)
 
 
+class RStream:
+    """`set.seed(seed)` followed by any number of `rnorm(n)` calls on the same stream (irlba draws
+    its start vector first and, on an invariant subspace, replacement vectors later)."""
+
+    def __init__(self, seed):
+        self.bg = np.random.MT19937()
+        st = self.bg.state
+        st["state"]["key"] = _r_seed_state(seed)
+        st["state"]["pos"] = 624
+        self.bg.state = st
+
+    def rnorm(self, n):
+        raw = self.bg.random_raw(2 * int(n)).astype(np.uint64) & np.uint64(0xFFFFFFFF)
+        u = _unif(raw)
+        a = np.floor(_BIG * u[0::2]) + u[1::2]
+        return ndtri(a / _BIG)
+
+
 def rnorm_after_seed(seed, n):
     """Equivalent of `set.seed(seed); rnorm(n)` in R (default RNG kinds)."""
-    bg = np.random.MT19937()
-    st = bg.state
-    st["state"]["key"] = _r_seed_state(seed)
-    st["state"]["pos"] = 624
-    bg.state = st
-    raw = bg.random_raw(2 * n).astype(np.uint64) & np.uint64(0xFFFFFFFF)
-    u = _unif(raw)
-    a = np.floor(_BIG * u[0::2]) + u[1::2]
-    return ndtri(a / _BIG)
+    return RStream(seed).rnorm(n)

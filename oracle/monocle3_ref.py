@@ -138,7 +138,9 @@ def sparse_prcomp_irlba(At, n, center=True, scale=False, v0=None, **irlba_args):
         sq = At.multiply(At) if sp.issparse(At) else At * At
         sc = np.sqrt(np.asarray(sq.sum(axis=0)).ravel() / max(1, C - 1))
     if v0 is None:
-        v0 = RRandom(2016).rnorm(G)  # set.seed(2016) at R/preprocess_cds.R:110, rnorm(n) inside irlba
+        rng = RRandom(2016)  # set.seed(2016) at R/preprocess_cds.R:110, rnorm(n) inside irlba
+        v0 = rng.rnorm(G)
+        irlba_args.setdefault("rng", rng)  # the same stream serves irlba's invariant-subspace restarts
     s = irlba_ref.irlba(At, n, v0, center=cen, scale=sc, **irlba_args)
     if s.err not in (0, -2):
         raise RuntimeError("irlba error %d" % s.err)

@@ -468,3 +468,41 @@ def test_aggregate_gene_expression(m3, worm_l2, kw):
     if use_g is not None:
         assert "solo" not in rn
     np.testing.assert_allclose(A, Ao, rtol=1e-10, atol=1e-12)
+
+
+def test_invariant_subspace_random_restart(m3):
+    """irlb.c replaces a Lanczos vector whose norm falls below eps (2.2e-16, absolute) by rnorm()
+    from R's stream.  A rank-4 matrix of norm ~1e-8 gets there after five steps; with the rnorm
+    callback the library follows irlba step for step (same stream, same iter / mprod, same
+    singular values), without it the call reports the linear dependency."""
+    from monocle3_b200 import engine, _lib as L
+    from monocle3_b200.r_rng import RStream
+    from oracle import irlba_ref
+    from oracle.r_rng import RRandom
+    rng = np.random.default_rng(5)
+    G, Cn, r = 40, 70, 4
+    dense = (rng.integers(1, 4, (G, r)) @ rng.integers(0, 3, (r, Cn))).astype(np.float64) * 1e-9
+    counts = sp.csc_matrix(dense)
+    ctx = engine.Context(device=0, small_svd="device")
+    dev = engine.DeviceMatrix.from_csc(ctx, counts)
+    dev.normalize(None, L.NORM_NONE, 0.0)
+    keep = dev.select_genes(None)
+    n = int(keep.sum())
+    stream = RStream(7)
+    v0 = stream.rnorm(n)
+    ctx.set_rnorm(stream.rnorm)
+    res = dev.pca_irlba(6, v0, center=False, scale=False)
+    ctx.set_rnorm(None)
+    orng = RRandom(7)
+    v0o = orng.rnorm(n)
+    assert np.array_equal(v0, v0o)
+    At = sp.csc_matrix(dense[keep, :].T)
+    o = irlba_ref.irlba(At, 6, v0o, rng=orng)
+    assert res["status"] == 0 and o.err == 0
+    assert (res["iter"], res["mprod"]) == (o.iter, o.mprod)
+    np.testing.assert_allclose(res["d"][:r], o.d[:r], rtol=1e-6)
+    assert np.all(res["d"][r:] < 1e-6 * res["d"][0])
+    assert subspace_angle(res["v"][:, :r], o.v[:, :r]) < ANGLE_TOL
+    # without a random stream the same input is reported as a linear dependency (irlba's -5)
+    with pytest.raises(Exception, match="linear dependency|invariant"):
+        dev.pca_irlba(6, v0, center=False, scale=False)
