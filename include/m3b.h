@@ -193,6 +193,14 @@ int m3b_aggregate_expression(m3b_mat* mat, const int32_t* gene_group, int32_t n_
                              const int32_t* cell_group, int32_t n_cell_groups, int cell_agg_mean,
                              double* out, int64_t ld_out);
 
+/* ---- Jaccard weights of a kNN graph ------------------ */
+/* Replaces the reference's native jaccard_coeff (src/clustering.cpp:13-58; registered as
+ * _monocle3_jaccard_coeff, src/RcppExports.cpp; called at R/cluster_cells.R:313 and
+ * R/graph_test.R:429,506), same argument and result layout: idx is an n x k matrix of 1-based
+ * neighbour ids as doubles, column-major (an R NumericMatrix); out is (n*k) x 3, column-major:
+ * (from, to, weight), row r = i*k + j, weights divided by their maximum.  k <= 64. */
+int m3b_jaccard_coeff(m3b_ctx* ctx, const double* idx, int64_t n, int32_t k, int weight, double* out);
+
 /* ---- IRLBA PCA (K4-K9) -------------------------------------------------- */
 /* nv: number of PCs; work: Lanczos subspace (0 => nv+7); v0: start vector (G').
  * center/scale: 0/1 flags (preprocess_cds passes scaling for both).

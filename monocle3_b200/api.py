@@ -156,6 +156,11 @@ def normalized_counts(cds, norm_method="log", pseudocount=1):
     return out
 
 
+def jaccard_coeff(R_idx, R_weight):
+    """R/RcppExports.R:4-6 -> src/clustering.cpp:49-54: Jaccard weights of a kNN graph."""
+    return engine.jaccard_coeff(get_context(), R_idx, bool(R_weight))
+
+
 def detect_genes(cds, min_expr=0):
     """R/utils.R:449-457: rowData$num_cells_expressed = rowSums(counts > min_expr) (over all
     ranks' cells), colData$num_genes_expressed = colSums(counts > min_expr)."""

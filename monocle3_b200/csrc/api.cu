@@ -507,6 +507,12 @@ int m3b_aggregate_expression(m3b_mat* m, const int32_t* gene_group, int32_t n_ge
   return run_aggregate(m, gene_group, n_gene_groups, gene_agg_mean, cell_group, n_cell_groups, cell_agg_mean, out, ld_out);
 }
 
+int m3b_jaccard_coeff(m3b_ctx* ctx, const double* idx, int64_t n, int32_t k, int weight, double* out) {
+  if (!ctx || !idx || !out) return M3B_E_DIMS;
+  cudaSetDevice(ctx->device);
+  return run_jaccard(ctx, idx, (long long)n, (int)k, weight, out);
+}
+
 int m3b_gene_nnz(m3b_mat* m, int64_t* nnz_per_sel_gene) {
   if (!m || !nnz_per_sel_gene) return M3B_E_DIMS;
   m3b_ctx* ctx = m->ctx;

@@ -252,6 +252,9 @@ int run_detect_genes(m3b_mat* m, double min_expr, long long* num_cells_expressed
 int run_aggregate(m3b_mat* m, const int* gene_group, int n_groups, int gene_mean, const int* cell_group, int n_cell_groups,
                   int cell_mean, double* out, long long ld_out);
 
+// jaccard.cu
+int run_jaccard(m3b_ctx* ctx, const double* idx, long long n, int k, int weight, double* out);
+
 // tfidf.cu (LSI branch)
 int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor, const double* row_sums_in,
               double num_cols, double* col_sums_out, double* row_sums_out);

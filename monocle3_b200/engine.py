@@ -134,6 +134,16 @@ class Context:
             pass
 
 
+def jaccard_coeff(ctx, idx, weight=True):
+    """(n*k) x 3 matrix (from, to, weight) of the kNN graph `idx` (n x k, 1-based ids)."""
+    a = np.asfortranarray(np.asarray(idx, dtype=np.float64))  # an R NumericMatrix: doubles, column-major
+    n, k = a.shape
+    out = np.zeros((3, n * k))  # column-major (n*k) x 3
+    ctx.check(ctx.lib.m3b_jaccard_coeff(ctx.h, a.ctypes.data_as(C.POINTER(C.c_double)), int(n), int(k),
+                                        int(bool(weight)), _dp(out)))
+    return out.T.copy()
+
+
 class DeviceMatrix:
     """The counts matrix (local cell shard) resident on the GPU (m3b_mat)."""
 

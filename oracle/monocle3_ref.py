@@ -345,3 +345,29 @@ def aggregate_gene_expression(counts, sf, gene_names, cell_names, gene_group_df=
         row_names = [row_names[k] for k in rk]
         col_names = [col_names[k] for k in ck]
     return agg, row_names, col_names
+
+
+def jaccard_coeff(idx, weight=True):
+    """src/clustering.cpp:13-46 (jaccard_coeff_cpp), loop for loop.  idx: n x k, 1-based neighbour
+    ids.  Returns the (n*k) x 3 matrix (from, to, weight / max weight).  Integer arithmetic and two
+    IEEE divisions: the device result must be bit-identical.  (The reference's tests hold no
+    expected values for this kernel either; the restatement is checked on hand-worked cases in
+    tests/test_oracle_aggregate.py.)"""
+    idx = np.asarray(idx)
+    n, k = idx.shape
+    out = np.zeros((n * k, 3))
+    sets = [set(int(v) for v in idx[i]) for i in range(n)]
+    r = 0
+    for i in range(n):
+        for j in range(k):
+            kk = int(idx[i, j]) - 1
+            w = 1.0
+            if weight:
+                u = len(sets[i] & sets[kk])          # intersect(nodei, nodej).size(): unique common values
+                v = 2 * k - u
+                if u > 0:
+                    w = float(u) / float(v)
+            out[r] = (i + 1, kk + 1, w)
+            r += 1
+    out[:, 2] = out[:, 2] / out[:, 2].max()
+    return out

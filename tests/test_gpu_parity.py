@@ -506,3 +506,17 @@ def test_invariant_subspace_random_restart(m3):
     # without a random stream the same input is reported as a linear dependency (irlba's -5)
     with pytest.raises(Exception, match="linear dependency|invariant"):
         dev.pca_irlba(6, v0, center=False, scale=False)
+
+
+@pytest.mark.parametrize("n,k", [(500, 20), (300, 33), (64, 64), (7, 1)])
+def test_jaccard_coeff_bit_exact(m3, n, k):
+    """The reference's native kernel (src/clustering.cpp:13-58): bit-identical to the restatement,
+    with repeated ids inside a row and asymmetric neighbourhoods."""
+    rng = np.random.default_rng(n + k)
+    idx = rng.integers(1, n + 1, (n, k))
+    idx[::7, : max(1, k // 3)] = idx[::7, :1]       # duplicates inside some rows
+    for weight in (True, False):
+        got = m3.jaccard_coeff(idx.astype(np.float64), weight)
+        assert np.array_equal(got, ref.jaccard_coeff(idx, weight))
+    with pytest.raises(Exception, match="1..n"):
+        m3.jaccard_coeff(np.array([[0.0, 2.0], [1.0, 2.0]]), True)

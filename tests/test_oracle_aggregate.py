@@ -31,3 +31,19 @@ def test_aggregate_dense(a549):
             np.testing.assert_allclose(A[i, j], N[np.ix_(rows, cols)].sum(axis=0).mean(), rtol=1e-12)
     Z, _, _ = ref.aggregate_gene_expression(counts, sf, genes, cells, gdf, cdf)
     assert np.abs(Z).max() <= 3 and np.allclose(Z.mean(axis=1), 0, atol=1e-12)
+
+
+def test_jaccard_hand_worked():
+    """src/clustering.cpp:13-46 on cases small enough to do by hand."""
+    # three nodes, every pair of neighbour sets shares exactly one id: u = 1, v = 2*2 - 1 = 3
+    w = ref.jaccard_coeff(np.array([[2, 3], [1, 3], [1, 2]]), True)
+    assert np.array_equal(w[:, 0], [1, 1, 2, 2, 3, 3]) and np.array_equal(w[:, 1], [2, 3, 1, 3, 1, 2])
+    assert np.array_equal(w[:, 2], np.ones(6))          # all 1/3, divided by the maximum 1/3
+    # node 1 and 2 share both neighbours (u = 2 -> 2/2 = 1); node 3's list has a duplicate and shares
+    # only id 4 with node 1 (unique values count once: u = 1 -> 1/3); no overlap keeps weight 1
+    idx = np.array([[3, 4], [3, 4], [4, 4], [1, 2]])
+    w = ref.jaccard_coeff(idx, True)
+    exp = {(1, 3): 1 / 3, (1, 4): 1.0, (2, 3): 1 / 3, (2, 4): 1.0, (3, 4): 1.0, (4, 1): 1.0, (4, 2): 1.0}
+    for r in range(8):
+        assert w[r, 2] == exp[(int(w[r, 0]), int(w[r, 1]))]
+    assert np.array_equal(ref.jaccard_coeff(idx, False)[:, 2], np.ones(8))

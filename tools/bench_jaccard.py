@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""SURVEY 8f row 3 timing: m3b_jaccard_coeff on a random kNN graph (n nodes, k neighbours), the
+call a user makes (host NumericMatrix in, (n*k) x 3 host matrix out), CUDA events around it, and
+the restated CPU loop (src/clustering.cpp:13-46 in Python) on a bounded sample for scale."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--k", type=int, default=20)
+    a = ap.parse_args()
+    import numpy as np
+    from monocle3_b200 import engine
+    from oracle import monocle3_ref as ref
+    rng = np.random.default_rng(0)
+    # neighbours drawn from a window around the node so that neighbourhoods overlap like a real kNN graph
+    base = np.arange(a.n)[:, None]
+    idx = ((base + rng.integers(-3 * a.k, 3 * a.k + 1, (a.n, a.k))) % a.n + 1).astype(np.float64)
+    ctx = engine.Context(0)
+    engine.jaccard_coeff(ctx, idx[:1000], True)
+    t = []
+    for _ in range(3):
+        ctx.timer_start()
+        w = engine.jaccard_coeff(ctx, idx, True)
+        t.append(ctx.timer_stop())
+    ms = float(np.median(t))
+    m = min(a.n, 20000)
+    sub = (np.arange(m)[:, None] + rng.integers(-3 * a.k, 3 * a.k + 1, (m, a.k))) % m + 1
+    t0 = time.time()
+    wo = ref.jaccard_coeff(sub, True)
+    cpu_s = time.time() - t0
+    assert np.array_equal(engine.jaccard_coeff(ctx, sub.astype(np.float64), True), wo)
+    print(json.dumps({"kernel": "m3b_jaccard_coeff", "n": a.n, "k": a.k, "ms_incl_copies": ms,
+                      "edges_per_s": a.n * a.k / (ms / 1e3), "h2d_bytes": a.n * a.k * 8, "d2h_bytes": 3 * a.n * a.k * 8,
+                      "cpu_port_edges_per_s": m * a.k / cpu_s, "cpu_sample_nodes": m, "bit_exact_on_sample": True,
+                      "mean_weight": float(w[:, 2].mean())}))
+
+
+if __name__ == "__main__":
+    main()
