@@ -134,14 +134,18 @@ class Context:
             pass
 
 
-def jaccard_coeff(ctx, idx, weight=True):
-    """(n*k) x 3 matrix (from, to, weight) of the kNN graph `idx` (n x k, 1-based ids)."""
-    a = np.asfortranarray(np.asarray(idx, dtype=np.float64))  # an R NumericMatrix: doubles, column-major
+def jaccard_coeff(ctx, idx, weight=True, out=None):
+    """(n*k) x 3 matrix (from, to, weight) of the kNN graph `idx` (n x k, 1-based ids).  `out`:
+    optional (3, n*k) C-ordered buffer (= the column-major result); then the transposed VIEW of it
+    is returned and nothing is allocated or copied on the host."""
+    a = np.asarray(idx, dtype=np.float64)
+    if not a.flags.f_contiguous:
+        a = np.asfortranarray(a)  # an R NumericMatrix: doubles, column-major
     n, k = a.shape
-    out = np.zeros((3, n * k))  # column-major (n*k) x 3
+    res = np.empty((3, n * k)) if out is None else out
     ctx.check(ctx.lib.m3b_jaccard_coeff(ctx.h, a.ctypes.data_as(C.POINTER(C.c_double)), int(n), int(k),
-                                        int(bool(weight)), _dp(out)))
-    return out.T.copy()
+                                        int(bool(weight)), _dp(res)))
+    return res.T.copy() if out is None else res.T
 
 
 class DeviceMatrix:

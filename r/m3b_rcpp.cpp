@@ -148,4 +148,13 @@ NumericMatrix m3b_aggregate_(S4 counts, NumericVector sf, int norm_method, Integ
   return out;
 }
 
+// drop-in body for the package's native kernel (src/clustering.cpp:49-54)
+// [[Rcpp::export]]
+NumericMatrix jaccard_coeff(SEXP R_idx, SEXP R_weight) {
+  NumericMatrix idx(R_idx);
+  NumericMatrix weights(idx.nrow() * idx.ncol(), 3);
+  m3b_check(the_ctx(), m3b_jaccard_coeff(the_ctx(), idx.begin(), idx.nrow(), idx.ncol(), as<bool>(R_weight), weights.begin()));
+  return weights;
+}
+
 // registration, as in src/RcppExports.cpp:38-47 (generated by Rcpp::compileAttributes() in practice)

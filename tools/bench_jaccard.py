@@ -24,12 +24,15 @@ def main():
     # neighbours drawn from a window around the node so that neighbourhoods overlap like a real kNN graph
     base = np.arange(a.n)[:, None]
     idx = ((base + rng.integers(-3 * a.k, 3 * a.k + 1, (a.n, a.k))) % a.n + 1).astype(np.float64)
+    idx = np.asfortranarray(idx)  # an R NumericMatrix is column-major already
     ctx = engine.Context(0)
-    engine.jaccard_coeff(ctx, np.minimum(idx[:1000], 1000.0), True)  # warm-up
+    buf = np.empty((3, a.n * a.k))
+    buf[:] = 0.0  # touch the pages once
+    engine.jaccard_coeff(ctx, idx, True, out=buf)  # warm-up
     t = []
     for _ in range(3):
         ctx.timer_start()
-        w = engine.jaccard_coeff(ctx, idx, True)
+        w = engine.jaccard_coeff(ctx, idx, True, out=buf)
         t.append(ctx.timer_stop())
     ms = float(np.median(t))
     m = min(a.n, 20000)
