@@ -435,7 +435,6 @@ struct FlatArgs {
   const double* x;
   const double* colscale;  // unit phase: tile *= colscale (layout B); nullptr on layout A
   double* partial;
-  int debug_skip;  // timing experiments only (M3B_FLAT_SKIP): 1 = no general phase, 2 = no unit phase
 };
 
 template <int K, int THREADS>
@@ -482,7 +481,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
       __syncthreads();
     }
     // ---- general stream: groups of 2 entries (u32 index pair + double2 values)
-    if (a.debug_skip != 1) {
+    {
       const int p0 = a.gp_ptr[vis * NWARPS + warp], p1 = a.gp_ptr[vis * NWARPS + warp + 1];
       for (int p = p0; p < p1; ++p) {
         const int4 pc = a.gp[p];
@@ -547,7 +546,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
       }
     }
     // ---- unit stream: groups of 8 indices, value applied on the dense side
-    if (a.uidx && a.debug_skip != 2) {
+    if (a.uidx) {
       if (a.colscale) {
         __syncthreads();
         const double* cs = a.colscale + off;
@@ -667,8 +666,6 @@ int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStr
   a.x = x;
   a.colscale = U ? U->colscale : nullptr;
   a.partial = L.partial;
-  static const int dbg_skip = getenv("M3B_FLAT_SKIP") ? atoi(getenv("M3B_FLAT_SKIP")) : 0;
-  a.debug_skip = dbg_skip;
   const size_t smem = ((size_t)L.tile_w + 2) * sizeof(double);
   cudaStream_t st = stream ? stream : ctx->stream;
   switch (fl_variant()) {
