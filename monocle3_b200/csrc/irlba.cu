@@ -519,13 +519,29 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
     const double* x2 = x0 + (nc > 2 ? 2 * a.ld : 0);
     const double* x3 = x0 + (nc > 3 ? 3 * a.ld : 0);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 2
-    for (int k = lane; k < len; k += 32) {
-      const double yv = ys[k];
-      a0 += x0[k] * yv;
-      a1 += x1[k] * yv;
-      a2 += x2[k] * yv;
-      a3 += x3[k] * yv;
+    // four row steps at a time with all sixteen loads issued before the first use (the chunk is
+    // a few hundred rows: the loop is pure load latency)
+    for (int k0 = lane; k0 < len; k0 += 128) {
+      double v0[4], v1[4], v2[4], v3[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        // unconditional loads from a clamped row (a per-lane "in range ? load : 0" makes the
+        // compiler select right behind every load, which waits for it); y is 0 past the end
+        const int k = min(k0 + 32 * u, len - 1);
+        v0[u] = x0[k];
+        v1[u] = x1[k];
+        v2[u] = x2[k];
+        v3[u] = x3[k];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u;
+        const double yv = (k < len) ? ys[k] : 0.0;
+        a0 += v0[u] * yv;
+        a1 += v1[u] * yv;
+        a2 += v2[u] * yv;
+        a3 += v3[u] * yv;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -569,14 +585,23 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       if (q < len) {
         const double* xr = a.X + r0 + q;
-        int c = cg;
-        for (; c + 24 < ncols; c += 32) {
-          a0 += xr[(long long)c * a.ld] * ts[c];
-          a1 += xr[(long long)(c + 8) * a.ld] * ts[c + 8];
-          a2 += xr[(long long)(c + 16) * a.ld] * ts[c + 16];
-          a3 += xr[(long long)(c + 24) * a.ld] * ts[c + 24];
+        // columns cg, cg+8, ...: sixteen loads (128 columns) issued together per round
+        for (int cb = cg; cb < ncols; cb += 128) {
+          double xv[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int c = min(cb + 8 * u, ncols - 1);  // clamped, unconditional (the factor is 0 past the end)
+            xv[u] = xr[(long long)c * a.ld];
+          }
+#pragma unroll
+          for (int u = 0; u < 16; u += 4) {
+            const int c = cb + 8 * u;
+            a0 += xv[u] * ((c < ncols) ? ts[c] : 0.0);
+            a1 += xv[u + 1] * ((c + 8 < ncols) ? ts[c + 8] : 0.0);
+            a2 += xv[u + 2] * ((c + 16 < ncols) ? ts[c + 16] : 0.0);
+            a3 += xv[u + 3] * ((c + 24 < ncols) ? ts[c + 24] : 0.0);
+          }
         }
-        for (; c < ncols; c += 8) a0 += xr[(long long)c * a.ld] * ts[c];
       }
       red[cg * 128 + rl] = (a0 + a1) + (a2 + a3);
       __syncthreads();
