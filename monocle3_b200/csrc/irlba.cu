@@ -872,11 +872,14 @@ __global__ void k_transpose_small(const double* __restrict__ in, int n, double* 
 // tensor pipe was 29% busy, profiles/).  kinp is padded to
 // kinp % 16 == 4 doubles so that the 8 rows (or columns) of a fragment land on disjoint banks.
 // --------------------------------------------------------------------------
-#define GEMM_RB 64
+#ifndef GEMM_RB
+#define GEMM_RB 32                 // rows per block (16 per row group)
+#endif
+#define GEMM_RG (GEMM_RB / 16)     // row groups
 #define GEMM_NF 13                 // B fragments (8 columns each) per pass
 #define GEMM_CPP (8 * GEMM_NF)     // columns per pass = 104
-#define GEMM_NCG 4                 // column groups: warps = 4 row groups x GEMM_NCG
-#define GEMM_THREADS (128 * GEMM_NCG)
+#define GEMM_NCG (32 / GEMM_RG)     // column groups: 32 warps = GEMM_RG row groups x GEMM_NCG
+#define GEMM_THREADS 1024
 #define GEMM_FPW ((GEMM_NF + GEMM_NCG - 1) / GEMM_NCG)  // fragments per warp (max)
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
@@ -941,7 +944,7 @@ k_restart_gemm(double* __restrict__ X, long long ld, long long rows, int kin, in
       cp_async_wait<0>();
     }
     __syncthreads();
-    const int rg = warp & 3, cg = warp >> 2;            // row group, column group
+    const int rg = warp % GEMM_RG, cg = warp / GEMM_RG;  // row group, column group
     const long long r0 = blk * GEMM_RB + rg * 16;       // this warp's 16 rows
     const double* xa0 = Xs + (size_t)(rg * 16 + gid) * kinp + tig;  // A fragment, rows 0-7
     const double* xa1 = xa0 + (size_t)8 * kinp;                     // rows 8-15
