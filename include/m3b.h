@@ -200,6 +200,13 @@ int m3b_aggregate_expression(m3b_mat* mat, const int32_t* gene_group, int32_t n_
  * neighbour ids as doubles, column-major (an R NumericMatrix); out is (n*k) x 3, column-major:
  * (from, to, weight), row r = i*k + j, weights divided by their maximum.  k <= 64. */
 int m3b_jaccard_coeff(m3b_ctx* ctx, const double* idx, int64_t n, int32_t k, int weight, double* out);
+/* Exact k nearest neighbours (Euclidean) of every row of X among the rows of X: what
+ * cluster_cells obtains from RANN::nn2(data, data, k, searchtype = "standard") with
+ * nn_control method "nn2" (R/cluster_cells.R:286-287; the caller passes k + 1 because the point
+ * itself is its own first neighbour).  X: n x d, column-major doubles (an R matrix, e.g.
+ * reducedDims(cds)[["PCA"]]).  nn_idx: n x k, column-major, 1-based ids sorted by distance (ties:
+ * smaller id first); nn_dists: n x k distances (not squared).  k <= 64. */
+int m3b_knn_self(m3b_ctx* ctx, const double* X, int64_t n, int32_t d, int32_t k, int32_t* nn_idx, double* nn_dists);
 
 /* ---- IRLBA PCA (K4-K9) -------------------------------------------------- */
 /* nv: number of PCs; work: Lanczos subspace (0 => nv+7); v0: start vector (G').

@@ -78,6 +78,7 @@ SIGNATURES = {
     "m3b_select_genes": (C.c_int, [_P, _ip, C.c_int32, C.POINTER(C.c_uint8), _ip]),
     "m3b_gene_nnz": (C.c_int, [_P, _lp]),
     "m3b_gene_moments": (C.c_int, [_P, _dp, _dp]),
+    "m3b_knn_self": (C.c_int, [_P, _dp, C.c_int64, C.c_int32, C.c_int32, _ip, _dp]),
     "m3b_jaccard_coeff": (C.c_int, [_P, _dp, C.c_int64, C.c_int32, C.c_int, _dp]),
     "m3b_detect_genes": (C.c_int, [_P, C.c_double, _lp, _lp]),
     "m3b_aggregate_expression": (C.c_int, [_P, _ip, C.c_int32, C.c_int, _ip, C.c_int32, C.c_int, _dp, C.c_int64]),

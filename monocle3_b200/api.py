@@ -161,6 +161,36 @@ def jaccard_coeff(R_idx, R_weight):
     return engine.jaccard_coeff(get_context(), R_idx, bool(R_weight))
 
 
+def cluster_cells_make_graph(data, weight, cell_names=None, k=20, nn_control=None, verbose=False):
+    """R/cluster_cells.R:255-336 up to the relations table, for nn_control method "nn2" (exact kNN;
+    the approximate annoy / hnsw indices are out of scope): kNN of the rows of `data` (e.g.
+    reducedDims(cds)[["PCA"]]) on the device, then the Jaccard weights on the device.  Returns
+    dict(relations=(from, to, weight), distMatrix=...); the igraph object is left to the caller."""
+    import warnings as _w
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim != 2:
+        raise ValueError("Wrong input data, should be a data frame or matrix!")
+    method = (nn_control or {}).get("method", "nn2")
+    if method != "nn2":
+        raise NotImplementedError("only nn_control method 'nn2' (exact search) is implemented on the device")
+    if k < 1:
+        raise ValueError("k must be a positive integer!")
+    if k > data.shape[0] - 2:
+        k = data.shape[0] - 2
+        _w.warn("The nearest neighbors includes the point itself, k must be smaller than\nthe total number of points - 1 "
+                "(all other points) - 1 (itself)! Total number of points is %d" % data.shape[0])
+    ctx = get_context()
+    idx, dist = engine.knn_self(ctx, data, k + 1)
+    neighbor, distm = idx[:, 1:], dist[:, 1:]
+    links = engine.jaccard_coeff(ctx, neighbor.astype(np.float64), bool(weight))
+    links = links[links[:, 0] > 0]
+    frm, to = links[:, 0].astype(np.int64), links[:, 1].astype(np.int64)
+    if cell_names is not None:
+        names = np.asarray(cell_names)
+        frm, to = names[frm - 1], names[to - 1]
+    return {"relations": (frm, to, links[:, 2]), "distMatrix": distm, "nn_idx": neighbor}
+
+
 def detect_genes(cds, min_expr=0):
     """R/utils.R:449-457: rowData$num_cells_expressed = rowSums(counts > min_expr) (over all
     ranks' cells), colData$num_genes_expressed = colSums(counts > min_expr)."""

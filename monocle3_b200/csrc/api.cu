@@ -513,6 +513,12 @@ int m3b_jaccard_coeff(m3b_ctx* ctx, const double* idx, int64_t n, int32_t k, int
   return run_jaccard(ctx, idx, (long long)n, (int)k, weight, out);
 }
 
+int m3b_knn_self(m3b_ctx* ctx, const double* X, int64_t n, int32_t d, int32_t k, int32_t* nn_idx, double* nn_dists) {
+  if (!ctx || !X || !nn_idx || !nn_dists) return M3B_E_DIMS;
+  cudaSetDevice(ctx->device);
+  return run_knn_self(ctx, X, (long long)n, (int)d, (int)k, nn_idx, nn_dists);
+}
+
 int m3b_gene_nnz(m3b_mat* m, int64_t* nnz_per_sel_gene) {
   if (!m || !nnz_per_sel_gene) return M3B_E_DIMS;
   m3b_ctx* ctx = m->ctx;

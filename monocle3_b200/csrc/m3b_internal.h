@@ -255,6 +255,9 @@ int run_aggregate(m3b_mat* m, const int* gene_group, int n_groups, int gene_mean
 // jaccard.cu
 int run_jaccard(m3b_ctx* ctx, const double* idx, long long n, int k, int weight, double* out);
 
+// knn.cu
+int run_knn_self(m3b_ctx* ctx, const double* X, long long n, int d, int k, int* idx_out, double* dist_out);
+
 // tfidf.cu (LSI branch)
 int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor, const double* row_sums_in,
               double num_cols, double* col_sums_out, double* row_sums_out);

@@ -134,6 +134,20 @@ class Context:
             pass
 
 
+def knn_self(ctx, X, k):
+    """Exact kNN of the rows of X among themselves: (nn_idx n x k, 1-based, nn_dists n x k), the
+    result layout of RANN::nn2(X, X, k)."""
+    a = np.asarray(X, dtype=np.float64)
+    if not a.flags.f_contiguous:
+        a = np.asfortranarray(a)
+    n, d = a.shape
+    idx = np.empty((k, n), dtype=np.int32)   # column-major n x k
+    dist = np.empty((k, n))
+    ctx.check(ctx.lib.m3b_knn_self(ctx.h, a.ctypes.data_as(C.POINTER(C.c_double)), int(n), int(d), int(k),
+                                   idx.ctypes.data_as(C.POINTER(C.c_int32)), _dp(dist)))
+    return idx.T, dist.T
+
+
 def jaccard_coeff(ctx, idx, weight=True, out=None):
     """(n*k) x 3 matrix (from, to, weight) of the kNN graph `idx` (n x k, 1-based ids).  `out`:
     optional (3, n*k) C-ordered buffer (= the column-major result); then the transposed VIEW of it

@@ -371,3 +371,36 @@ def jaccard_coeff(idx, weight=True):
             r += 1
     out[:, 2] = out[:, 2] / out[:, 2].max()
     return out
+
+
+def nn2_self(X, k):
+    """RANN::nn2(X, X, k, searchtype = "standard") as cluster_cells calls it (R/cluster_cells.R:286-287):
+    exact Euclidean k nearest neighbours of every row among all rows (the row itself included),
+    sorted by distance; returns (nn_idx 1-based, nn_dists).  RANN (a kd-tree over the same distances)
+    is not in /root/reference; the result is defined by the distances alone, ties (not defined by
+    RANN) go to the smaller index.  PARITY UNPINNED."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    idx = np.zeros((n, k), dtype=np.int64)
+    dist = np.zeros((n, k))
+    for i in range(n):
+        d2 = ((X - X[i]) ** 2).sum(axis=1)          # direct differences, like a kd-tree leaf scan
+        o = np.argsort(d2, kind="stable")[:k]
+        idx[i] = o + 1
+        dist[i] = np.sqrt(d2[o])
+    return idx, dist
+
+
+def cluster_cells_make_graph(data, weight, k):
+    """R/cluster_cells.R:255-336 with nn_control method "nn2", up to the relations table:
+    (relations (n*k) x 3 = from, to, weight; distMatrix n x k).  PARITY UNPINNED."""
+    data = np.asarray(data, dtype=np.float64)
+    if k < 1:
+        raise ValueError("k must be a positive integer!")
+    if k > data.shape[0] - 2:                         # :269-275
+        k = data.shape[0] - 2
+    idx, dist = nn2_self(data, k + 1)                 # :287
+    neighbor, distm = idx[:, 1:], dist[:, 1:]        # :303-304
+    links = jaccard_coeff(neighbor, weight)           # :313
+    links = links[links[:, 0] > 0]                    # :318
+    return links, distm

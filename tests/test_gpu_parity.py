@@ -520,3 +520,30 @@ def test_jaccard_coeff_bit_exact(m3, n, k):
         assert np.array_equal(got, ref.jaccard_coeff(idx, weight))
     with pytest.raises(Exception, match="1..n"):
         m3.jaccard_coeff(np.array([[0.0, 2.0], [1.0, 2.0]]), True)
+
+
+@pytest.mark.parametrize("n,d,k", [(1000, 50, 21), (130, 7, 5), (64, 100, 64), (257, 3, 1)])
+def test_knn_self_exact(m3, n, d, k):
+    """Exact kNN (what RANN::nn2 returns for cluster_cells, R/cluster_cells.R:286-287) against the
+    restatement: identical neighbour ids, distances to 1e-14 relative."""
+    from monocle3_b200 import engine
+    rng = np.random.default_rng(n * 7 + d)
+    X = rng.standard_normal((n, d)) * rng.uniform(0.5, 3.0, d)
+    idx, dist = engine.knn_self(m3.get_context(), X, k)
+    io, do = ref.nn2_self(X, k)
+    assert np.array_equal(idx, io)
+    np.testing.assert_allclose(dist, do, rtol=1e-13, atol=1e-300)
+    assert np.array_equal(idx[:, 0], np.arange(1, n + 1)) and np.all(dist[:, 0] == 0.0)
+
+
+def test_knn_jaccard_graph_on_pca(m3, worm_l2):
+    """The step after the path: kNN graph + Jaccard weights on the PCA embedding
+    (cluster_cells_make_graph, R/cluster_cells.R:255-336, nn2 method), device vs restatement."""
+    counts, extra = worm_l2
+    cds = m3.preprocess_cds(_cds(m3, counts[:, :1500], None), num_dim=20)
+    X = cds.reduced_dims["PCA"]
+    g = m3.cluster_cells_make_graph(X, True, k=20, nn_control={"method": "nn2"})
+    links, distm = ref.cluster_cells_make_graph(X, True, 20)
+    assert np.array_equal(g["relations"][0], links[:, 0]) and np.array_equal(g["relations"][1], links[:, 1])
+    assert np.array_equal(g["relations"][2], links[:, 2])
+    np.testing.assert_allclose(g["distMatrix"], distm, rtol=1e-13)
