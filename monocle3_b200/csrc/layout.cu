@@ -687,6 +687,113 @@ __global__ void __launch_bounds__(TB_THREADS) k_scatter_B(const long long* __res
   }
 }
 
+// ---- split matrices: both entry classes (general = raw count != 1, unit = raw count == 1) in ONE
+// pass.  The per-row state of the two classes shares a 32-bit word (general in the low half, unit
+// in the high half: counts inside a tile are <= 28672 < 2^16, the group mask has 16 bits), so the
+// shared-memory footprint is that of the single-class kernels and every entry is visited once per
+// phase instead of twice.
+__global__ void __launch_bounds__(TB_THREADS) k_count_B2(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                         const double* __restrict__ xraw,
+                                                         const int* __restrict__ sel_of_gene, int n_sel, int g0, int g1,
+                                                         int tile_w, int chunks_per_tile, int cells_per_chunk,
+                                                         long long n_cells, int* __restrict__ Hg, int* __restrict__ Hu) {
+  extern __shared__ int hist[];  // [2][ng]
+  const long long chunk = blockIdx.x;
+  const long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
+  const long long c0 = min(t * tile_w + s * (long long)cells_per_chunk, n_cells);
+  const long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
+  const int ng = g1 - g0;
+  for (int r = threadIdx.x; r < 2 * ng; r += blockDim.x) hist[r] = 0;
+  __syncthreads();
+  if (c0 < c1) {
+    const long long lo = p[c0], hi = p[c1];
+    for (long long k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+      const int r = sel_of_gene[ld_stream_s32(gi + k)];
+      if (r >= g0 && r < g1) atomicAdd(&hist[(ld_stream_f64(xraw + k) == 1.0 ? ng : 0) + r - g0], 1);
+    }
+  }
+  __syncthreads();
+  int* Hgc = Hg + chunk * n_sel + g0;
+  int* Huc = Hu + chunk * n_sel + g0;
+  for (int r = threadIdx.x; r < ng; r += blockDim.x) {
+    Hgc[r] = hist[r];
+    Huc[r] = hist[ng + r];
+  }
+}
+
+__global__ void __launch_bounds__(TB_THREADS) k_scatter_B2(
+    const long long* __restrict__ p, const int* __restrict__ gi, const double* __restrict__ y,
+    const double* __restrict__ xraw, const int* __restrict__ sel_of_gene, int n_sel, int g0, int g1, int tile_w,
+    int chunks_per_tile, int cells_per_chunk, long long n_cells, const int* __restrict__ Hg, const int* __restrict__ Hu,
+    const long long* __restrict__ base_g, const long long* __restrict__ base_u, unsigned short* __restrict__ idx_g,
+    double* __restrict__ val_g, unsigned short* __restrict__ idx_u) {
+  extern __shared__ int sm_tb[];
+  const int ng = g1 - g0;
+  unsigned int* cursor = reinterpret_cast<unsigned int*>(sm_tb);      // [ng] slot inside the run: general | unit << 16
+  unsigned int* mask = reinterpret_cast<unsigned int*>(sm_tb + ng);   // [ng] cells of the current group: general | unit << 16
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long chunk = blockIdx.x;
+  const long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
+  const long long c0 = min(t * tile_w + s * (long long)cells_per_chunk, n_cells);
+  const long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
+  const int* Hgc = Hg + chunk * n_sel + g0;
+  const int* Huc = Hu + chunk * n_sel + g0;
+  const long long* btg = base_g + t * n_sel + g0;
+  const long long* btu = base_u + t * n_sel + g0;
+  for (int r = threadIdx.x; r < ng; r += blockDim.x) {
+    cursor[r] = (unsigned)Hgc[r] | ((unsigned)Huc[r] << 16);
+    mask[r] = 0u;
+  }
+  __syncthreads();
+  const unsigned int below = (1u << w) - 1u;
+  for (long long cg = c0; cg < c1; cg += TB_WARPS) {
+    const long long c = cg + w;
+    const bool have = c < c1;
+    const long long lo = have ? p[c] : 0, hi = have ? p[c + 1] : 0;
+    // rr = selected row (or -1), sh = 0 (general) / 16 (unit)
+#define TB2_FOR_ROWS(BODY)                                                      \
+    for (long long k0 = lo; k0 < hi; k0 += 128) {                                \
+      int rr[4], sh4[4];                                                         \
+      long long kk[4];                                                           \
+      _Pragma("unroll") for (int u = 0; u < 4; ++u) {                            \
+        kk[u] = k0 + lane + 32 * u;                                              \
+        rr[u] = (kk[u] < hi) ? gi[kk[u]] : -1;                                   \
+        sh4[u] = (kk[u] < hi && ld_stream_f64(xraw + kk[u]) == 1.0) ? 16 : 0;    \
+      }                                                                          \
+      _Pragma("unroll") for (int u = 0; u < 4; ++u) rr[u] = (rr[u] >= 0) ? sel_of_gene[rr[u]] : -1; \
+      _Pragma("unroll") for (int u = 0; u < 4; ++u) {                            \
+        const int r = rr[u], sh = sh4[u];                                        \
+        const long long k = kk[u];                                               \
+        if (r >= g0 && r < g1) { BODY }                                          \
+      }                                                                          \
+    }
+    TB2_FOR_ROWS(atomicOr(&mask[r - g0], 1u << (w + sh)); (void)k;)  // A
+    __syncthreads();
+    const int local = (int)(c - t * tile_w);
+    TB2_FOR_ROWS(  // B
+        const int q = r - g0;
+        const unsigned int mq = (mask[q] >> sh) & 0xffffu;
+        const unsigned int cq = (cursor[q] >> sh) & 0xffffu;
+        const long long dst = (sh ? btu[q] : btg[q]) + cq + __popc(mq & below);
+        if (sh) {
+          idx_u[dst] = (unsigned short)local;
+        } else {
+          idx_g[dst] = (unsigned short)local;
+          val_g[dst] = ld_stream_f64(y + k);
+        })
+    __syncthreads();
+    TB2_FOR_ROWS(  // C
+        const int q = r - g0; (void)k;
+        const unsigned int mq = (mask[q] >> sh) & 0xffffu;
+        if ((mq & below) == 0u) {  // this warp's cell is the first of the group with this row and class
+          atomicAdd(&cursor[q], (unsigned)__popc(mq) << sh);
+          atomicAnd(&mask[q], ~(0xffffu << sh));
+        })
+#undef TB2_FOR_ROWS
+    __syncthreads();
+  }
+}
+
 // host copies kept for the re-map after the zero-gene filter
 struct BBuild {
   std::vector<int> cnt, cnt_u;  // per-(tile, selected row) entries of the general / unit layout
@@ -745,11 +852,34 @@ int build_layout_B(m3b_mat* m, bool split) {
   std::vector<int> cnt[2];
   HostTables T[2];
   TiledLayout* Ls[2] = {&L, L.unit};
+  static bool tb2_attr = false;
+  if (!tb2_attr) {
+    CK(ctx, cudaFuncSetAttribute(k_count_B2, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_GSEG_MAX * 8));
+    CK(ctx, cudaFuncSetAttribute(k_scatter_B2, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_GSEG_MAX * 8));
+    tb2_attr = true;
+  }
+  const bool both = split && m->n_cells && n_sel && getenv("M3B_COMBINED_BUILD") != nullptr;  // one pass for both classes (opt-in until verified on the GPU)
+  if (both) {
+    for (int q = 0; q < 2; ++q) {
+      RET(dev_alloc(ctx, &H[q], (size_t)n_chunks * n_sel));
+      RET(dev_alloc(ctx, &d_cnt[q], (size_t)n_tiles * n_sel));
+    }
+    for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG_MAX) {
+      const int g1 = std::min(n_sel, g0 + TB_GSEG_MAX);
+      k_count_B2<<<(unsigned)n_chunks, TB_THREADS, (size_t)(g1 - g0) * 8, ctx->stream>>>(
+          m->p, m->i, m->x, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[0], H[1]);
+      count_launch(ctx);
+    }
+  }
   for (int q = 0; q < n_cls; ++q) {
     const int cls = split ? q + 1 : 0;
-    RET(dev_alloc(ctx, &H[q], (size_t)n_chunks * std::max(n_sel, 1)));
-    RET(dev_alloc(ctx, &d_cnt[q], (size_t)n_tiles * std::max(n_sel, 1)));
-    if (m->n_cells && n_sel) {
+    if (!both) {
+      RET(dev_alloc(ctx, &H[q], (size_t)n_chunks * std::max(n_sel, 1)));
+      RET(dev_alloc(ctx, &d_cnt[q], (size_t)n_tiles * std::max(n_sel, 1)));
+    }
+    if (both) {
+      // counted above
+    } else if (m->n_cells && n_sel) {
       for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG_MAX) {  // counting has no write working set: big passes
         const int g1 = std::min(n_sel, g0 + TB_GSEG_MAX);
         k_count_B<<<(unsigned)n_chunks, TB_THREADS, (size_t)(g1 - g0) * 4, ctx->stream>>>(
@@ -784,7 +914,17 @@ int build_layout_B(m3b_mat* m, bool split) {
       k_fill_pads<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(d_cnt[q], d_base[q], n_runs, q == 1 ? 8 : 4,
                                                                             q == 1 ? Lq.tile_w : 0, Lq.idx, Lq.val);
       count_launch(ctx);
-      if (m->n_cells) {
+      if (both) {
+        if (q == 1) {  // both layouts allocated, both base tables uploaded: one scatter for the two classes
+          for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG) {
+            const int g1 = std::min(n_sel, g0 + TB_GSEG);
+            k_scatter_B2<<<(unsigned)n_chunks, TB_THREADS, std::max((size_t)(g1 - g0) * 8, scatter_smem_min), ctx->stream>>>(
+                m->p, m->i, m->y, m->x, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[0], H[1],
+                d_base[0], d_base[1], L.idx, L.val, L.unit->idx);
+            count_launch(ctx);
+          }
+        }
+      } else if (m->n_cells) {
         for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG) {
           const int g1 = std::min(n_sel, g0 + TB_GSEG);
           k_scatter_B<<<(unsigned)n_chunks, TB_THREADS, std::max((size_t)(g1 - g0) * 8, scatter_smem_min), ctx->stream>>>(
@@ -1100,6 +1240,85 @@ __global__ void __launch_bounds__(256) k_scatter_A(const long long* __restrict__
   }
 }
 
+// split matrices: both classes of layout A in one pass over the cell's entries
+__global__ void __launch_bounds__(256) k_count_A2(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                  const double* __restrict__ xraw, const int* __restrict__ kept_of_gene,
+                                                  long long n_cells, int tile_w, int n_tiles, int* __restrict__ cnt_g,
+                                                  int* __restrict__ cnt_u) {
+  const int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    for (int t = 0; t < n_tiles; ++t) {
+      int ng = 0, nu = 0;
+      for (long long k = lo + lane; k < hi; k += 32) {
+        const int g = kept_of_gene[ld_stream_s32(gi + k)];
+        if (g >= 0 && g / tile_w == t) {
+          if (ld_stream_f64(xraw + k) == 1.0) ++nu;
+          else ++ng;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ng += __shfl_xor_sync(0xffffffffu, ng, o);
+        nu += __shfl_xor_sync(0xffffffffu, nu, o);
+      }
+      if (lane == 0) {
+        cnt_g[(long long)t * n_cells + c] = ng;
+        cnt_u[(long long)t * n_cells + c] = nu;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_A2(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                    const double* __restrict__ y, const double* __restrict__ xraw,
+                                                    const int* __restrict__ kept_of_gene, long long n_cells, int tile_w,
+                                                    int n_tiles, const long long* __restrict__ base_g,
+                                                    const long long* __restrict__ base_u, unsigned short* __restrict__ idx_g,
+                                                    double* __restrict__ val_g, unsigned short* __restrict__ idx_u) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    for (int t = 0; t < n_tiles; ++t) {
+      const long long dg0 = base_g[(long long)t * n_cells + c], du0 = base_u[(long long)t * n_cells + c];
+      int rg = 0, ru = 0;
+      for (long long k0 = lo; k0 < hi; k0 += 32) {
+        const long long k = k0 + lane;
+        int g = -1;
+        bool one = false;
+        if (k < hi) {
+          g = kept_of_gene[ld_stream_s32(gi + k)];
+          if (g >= 0 && g / tile_w == t) one = ld_stream_f64(xraw + k) == 1.0;
+          else g = -1;
+        }
+        const unsigned mg = __ballot_sync(0xffffffffu, g >= 0 && !one), mu = __ballot_sync(0xffffffffu, g >= 0 && one);
+        if (g >= 0) {
+          if (one) {
+            idx_u[du0 + ru + __popc(mu & lt)] = (unsigned short)(g - t * tile_w);
+          } else {
+            const long long dst = dg0 + rg + __popc(mg & lt);
+            idx_g[dst] = (unsigned short)(g - t * tile_w);
+            val_g[dst] = ld_stream_f64(y + k);
+          }
+        }
+        rg += __popc(mg);
+        ru += __popc(mu);
+      }
+      const int pg = (rg + 3) & ~3, pu = (ru + 7) & ~7;
+      if (lane < pg - rg) {
+        idx_g[dg0 + rg + lane] = 0;
+        val_g[dg0 + rg + lane] = 0.0;
+      }
+      if (lane < pu - ru) idx_u[du0 + ru + lane] = (unsigned short)tile_w;
+    }
+  }
+}
+
 int build_layout_A(m3b_mat* m, bool split) {
   m3b_ctx* ctx = m->ctx;
   TiledLayout& L = m->A;
@@ -1130,9 +1349,16 @@ int build_layout_A(m3b_mat* m, bool split) {
   HostTables T[2];
   TiledLayout* Ls[2] = {&L, L.unit};
   int blocks = (int)std::max<long long>(1, std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8));
+  const bool both = split && m->n_cells && getenv("M3B_COMBINED_BUILD") != nullptr;  // one pass for both classes (opt-in until verified on the GPU)
+  if (both) {
+    for (int q = 0; q < 2; ++q) RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
+    k_count_A2<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, d_cnt[0],
+                                                d_cnt[1]);
+    count_launch(ctx);
+  }
   for (int q = 0; q < n_cls; ++q) {
-    RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
-    if (m->n_cells) {
+    if (!both) RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
+    if (m->n_cells && !both) {
       k_count_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, split ? q + 1 : 0, m->kept_of_gene, m->n_cells, L.tile_w,
                                                  L.n_tiles, d_cnt[q]);
       count_launch(ctx);
@@ -1151,9 +1377,17 @@ int build_layout_A(m3b_mat* m, bool split) {
     RET(dev_alloc(ctx, &d_base[q], (size_t)std::max<long long>(n_runs, 1)));
     if (n_runs) {
       CK(ctx, cudaMemcpyAsync(d_base[q], T[q].base.data(), n_runs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-      k_scatter_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, split ? q + 1 : 0, m->kept_of_gene, m->n_cells,
-                                                   L.tile_w, L.n_tiles, d_base[q], Lq.idx, Lq.val);
-      count_launch(ctx);
+      if (both) {
+        if (q == 1) {
+          k_scatter_A2<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles,
+                                                        d_base[0], d_base[1], L.idx, L.val, L.unit->idx);
+          count_launch(ctx);
+        }
+      } else {
+        k_scatter_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, split ? q + 1 : 0, m->kept_of_gene, m->n_cells,
+                                                     L.tile_w, L.n_tiles, d_base[q], Lq.idx, Lq.val);
+        count_launch(ctx);
+      }
     }
     CK(ctx, cudaGetLastError());
   }
