@@ -858,7 +858,7 @@ int build_layout_B(m3b_mat* m, bool split) {
     CK(ctx, cudaFuncSetAttribute(k_scatter_B2, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_GSEG_MAX * 8));
     tb2_attr = true;
   }
-  const bool both = split && m->n_cells && n_sel && getenv("M3B_COMBINED_BUILD") != nullptr;  // one pass for both classes (opt-in until verified on the GPU)
+  const bool both = split && m->n_cells && n_sel && !getenv("M3B_NO_COMBINED_BUILD");  // one pass for both classes
   if (both) {
     for (int q = 0; q < 2; ++q) {
       RET(dev_alloc(ctx, &H[q], (size_t)n_chunks * n_sel));
@@ -1349,7 +1349,7 @@ int build_layout_A(m3b_mat* m, bool split) {
   HostTables T[2];
   TiledLayout* Ls[2] = {&L, L.unit};
   int blocks = (int)std::max<long long>(1, std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8));
-  const bool both = split && m->n_cells && getenv("M3B_COMBINED_BUILD") != nullptr;  // one pass for both classes (opt-in until verified on the GPU)
+  const bool both = split && m->n_cells && !getenv("M3B_NO_COMBINED_BUILD");  // one pass for both classes
   if (both) {
     for (int q = 0; q < 2; ++q) RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
     k_count_A2<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, d_cnt[0],
