@@ -1,7 +1,9 @@
-// K4 / K5 (and the K3 row statistics): one kernel family over the tiled layout.
+// Per-item stream kernels over the tiled layout: the K3 row statistics (row sums, squared
+// deviations, positive counts), and the fallback for the two Lanczos products when a layout has no
+// flat plan (flat.cu holds the product kernel proper; M3B_NO_FLAT or > 2^31 groups per layout).
 //
-// Replaces CHOLMOD's cholmod_sdmult inside irlba (the two products per Lanczos
-// step behind R/utils.R:417) and the DelayedMatrixStats passes of R/utils.R:383,389.
+// Replaces the DelayedMatrixStats passes of R/utils.R:383,389 (and, as the fallback, CHOLMOD's
+// cholmod_sdmult inside irlba, the two products per Lanczos step behind R/utils.R:417).
 //
 // Shape of the kernel: persistent CTAs (one per SM, 512 threads).  The dense
 // operand of a CTA's tile (<= 28672 doubles = 224 KB) is staged in shared memory
@@ -10,6 +12,7 @@
 // from shared memory, reduces in a fixed shuffle tree and writes ONE partial per
 // item.  A second tiny kernel adds the partials of a row in a fixed order, so
 // results are bit-reproducible run to run and independent of the CTA schedule.
+// k_unit_stream is the same for the index-only unit layouts (count-1 entries).
 //
 // HBM traffic per launch is the 10 B/entry stream (8 B value + 2 B tile-local
 // index; the ALGORITHMIC figure of SURVEY.md section 8d stays 12 B/nnz for an
