@@ -423,7 +423,42 @@ struct OrthArgs {
   int* ctl;
   unsigned long long* bar;
   unsigned long long bar_base;
+  // cell-sharded runs (world > 1): peer-memory exchange buffers (Comm::xchg of every rank), see xchg_wait
+  double* const* peers;
+  int rank, world;
+  unsigned long long seq;  // number of the first exchange of this launch (F side uses 1, W side 2)
 };
+
+// ---- cross-rank exchange inside the fused kernel (one box, CUDA-IPC peer memory) ----
+// Every rank writes its contribution into its OWN buffer (slot seq & 1), one thread of the rank
+// then stores `seq` into its flag in EVERY rank's buffer (release, system scope); whoever needs the
+// sum spins on the world's flags in its own buffer (acquire) and reads the peers' slots directly.
+// Slots alternate, and a rank cannot start exchange s+2 before every peer has published s+1,
+// i.e. has finished reading s, so two slots suffice.  The spin is bounded (CT_FLAG bit 4).
+__device__ __forceinline__ double* xchg_slot(double* const* peers, int q, int world, unsigned long long seq) {
+  return peers[q] + (size_t)world * 2 * M3B_XCHG_FLAG_STRIDE + (size_t)(seq & 1ull) * M3B_XCHG_CAP;
+}
+__device__ __forceinline__ void xchg_publish(double* const* peers, int rank, int world, unsigned long long seq) {
+  __threadfence_system();
+  for (int q = 0; q < world; ++q)
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(peers[q] + ((size_t)rank * 2 + (seq & 1ull)) * M3B_XCHG_FLAG_STRIDE), seq);
+}
+// called by ONE thread; returns false on time-out
+__device__ __forceinline__ bool xchg_wait(double* const* peers, int rank, int world, unsigned long long seq, int* ctl) {
+  const long long t0 = clock64();
+  for (int q = 0; q < world; ++q) {
+    const unsigned long long* fl =
+        reinterpret_cast<const unsigned long long*>(peers[rank] + ((size_t)q * 2 + (seq & 1ull)) * M3B_XCHG_FLAG_STRIDE);
+    while (ld_acquire_sys_u64(fl) != seq) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicOr(ctl + CT_FLAG, 4);
+        return false;
+      }
+      __nanosleep(32);
+    }
+  }
+  return true;
+}
 
 // All CTAs are co-resident (cooperative launch).  The spin is bounded (~2 s) so that a lost CTA
 // turns into an error (CT_FLAG bit 8) instead of a hung device.
@@ -493,7 +528,9 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       for (int k = b + sub; k < e; k += 4) f += a.partial[k];
       f += __shfl_xor_sync(0xffffffffu, f, 2);
       f += __shfl_xor_sync(0xffffffffu, f, 1);
-      if (q < len && sub == 0) {
+      if (q < len && sub == 0 && a.world > 1 && a.mode != OF_W) {
+        xchg_slot(a.peers, a.rank, a.world, a.seq)[r] = f;  // raw local sum; summed over the ranks below
+      } else if (q < len && sub == 0) {
         if (a.mode == OF_W) {
           f -= beta;
           if (a.wprev) f -= rf * a.wprev[r];
@@ -510,7 +547,30 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       }
     }
     __syncthreads();
+    if (a.world > 1 && a.mode != OF_W) {
+      // every CTA of every rank has written its rows: publish, wait for the world, then this CTA
+      // sums its rows over the ranks (rank order => identical on every rank) and applies the fix-ups
+      __threadfence_system();
+      grid_barrier(a.bar, a.bar_base + gridDim.x, a.ctl);
+      if (blockIdx.x == 0 && tid == 0) xchg_publish(a.peers, a.rank, a.world, a.seq);
+      if (tid == 0) xchg_wait(a.peers, a.rank, a.world, a.seq, a.ctl);
+      __syncthreads();
+      for (int q = tid; q < len; q += OF_THREADS) {
+        const long long r = r0 + q;
+        double f = 0.0;
+        for (int rk = 0; rk < a.world; ++rk) f += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, a.seq) + r);
+        if (a.s) f = f / a.s[r];
+        if (a.ce) {
+          double c = sumw * a.ce[r];
+          if (a.s) c = c / a.s[r];
+          f = f - c;
+        }
+        ys[q] = f - S * a.vj[r];
+      }
+      __syncthreads();
+    }
   }
+  const unsigned long long nb0 = (a.world > 1 && a.mode != OF_W) ? 1ull : 0ull;  // local grid barriers used so far
   // ---- phase 1: partial dots of this chunk, a warp takes 4 columns at a time
   for (int c0 = warp * 4; c0 < ncols; c0 += (OF_THREADS / 32) * 4) {
     const int nc = min(4, ncols - c0);
@@ -558,7 +618,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       if (nc > 3) pp[3] = a3;
     }
   }
-  grid_barrier(a.bar, a.bar_base + gridDim.x, a.ctl);
+  grid_barrier(a.bar, a.bar_base + (nb0 + 1) * gridDim.x, a.ctl);
   // ---- phase 2a: t = sum over the CTAs' partial dots (group q of threads sums blocks q, q+G, ...)
   {
     const int G = OF_THREADS / max(ncols, 1);
@@ -575,6 +635,23 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       ts[tid] = v;
     }
     __syncthreads();
+    if (a.world > 1 && a.mode == OF_W) {
+      // the rows of W are sharded: t is the sum of the ranks' local coefficients (exchange a.seq)
+      if (blockIdx.x == 0) {
+        double* mine = xchg_slot(a.peers, a.rank, a.world, a.seq);
+        for (int c2 = tid; c2 < ncols; c2 += OF_THREADS) mine[c2] = ts[c2];
+        __syncthreads();
+        if (tid == 0) xchg_publish(a.peers, a.rank, a.world, a.seq);
+      }
+      if (tid == 0) xchg_wait(a.peers, a.rank, a.world, a.seq, a.ctl);
+      __syncthreads();
+      if (tid < ncols) {
+        double v = 0.0;
+        for (int rk = 0; rk < a.world; ++rk) v += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, a.seq) + tid);
+        ts[tid] = v;
+      }
+      __syncthreads();
+    }
   }
   // ---- phase 2b: y -= X t on this chunk (128 rows x 8 column groups per pass)
   double n2 = 0.0, sm = 0.0;
@@ -625,11 +702,35 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       a.ps[blockIdx.x] = r2;
     }
   }
-  grid_barrier(a.bar, a.bar_base + 2ULL * gridDim.x, a.ctl);
+  grid_barrier(a.bar, a.bar_base + (nb0 + 2) * gridDim.x, a.ctl);
   // ---- phase 3: norm, scaling, scalars
-  const double nn = block_sum_cg(a.pn, gridDim.x, sh, &bc);
+  double nn = block_sum_cg(a.pn, gridDim.x, sh, &bc);
   if (a.mode == OF_W) {
-    const double ssum = block_sum_cg(a.ps, gridDim.x, sh, &bc);
+    double ssum = block_sum_cg(a.ps, gridDim.x, sh, &bc);
+    if (a.world > 1) {
+      // ||w||^2 and sum(w) over the ranks (exchange a.seq + 1)
+      const unsigned long long s2 = a.seq + 1;
+      __shared__ double gx[2];
+      if (blockIdx.x == 0 && tid == 0) {
+        double* mine = xchg_slot(a.peers, a.rank, a.world, s2);
+        mine[0] = nn;
+        mine[1] = ssum;
+        xchg_publish(a.peers, a.rank, a.world, s2);
+      }
+      if (tid == 0) {
+        xchg_wait(a.peers, a.rank, a.world, s2, a.ctl);
+        double g0 = 0.0, g1 = 0.0;
+        for (int rk = 0; rk < a.world; ++rk) {
+          g0 += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, s2));
+          g1 += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, s2) + 1);
+        }
+        gx[0] = g0;
+        gx[1] = g1;
+      }
+      __syncthreads();
+      nn = gx[0];
+      ssum = gx[1];
+    }
     const double S = sqrt(nn), SS = 1.0 / S;
     for (int q = tid; q < len; q += OF_THREADS) a.y[r0 + q] = ys[q] * SS;
     if (blockIdx.x == 0 && tid == 0) {
@@ -1105,7 +1206,17 @@ struct Irlba {
     a.ctl = ctl;
     a.bar = bar;
     a.bar_base = bar_seq;
-    bar_seq += 2ULL * of_grid;
+    a.world = ctx->comm.world;
+    a.rank = ctx->comm.rank;
+    a.peers = ctx->comm.peers_dev;
+    int n_bar = 2;
+    if (a.world > 1) {
+      // exchanges of this launch: F side 1 (the gene vector), W side 2 (coefficients, then norm and sum)
+      a.seq = ctx->comm.xchg_seq + 1;
+      ctx->comm.xchg_seq += wside ? 2 : 1;
+      if (!wside) n_bar = 3;
+    }
+    bar_seq += (unsigned long long)n_bar * of_grid;
     void* args[] = {&a};
     const size_t smem = ((size_t)a.chunk + ((ncols + 1) & ~1) + 1024) * sizeof(double);
     spmv_timer_begin(ctx, 2);
@@ -1389,7 +1500,10 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     I.of_chunk_m = (int)((mloc + I.of_grid - 1) / I.of_grid);
     {
       const size_t smem = ((size_t)std::max(I.of_chunk_n, I.of_chunk_m) + work + 2 + 1024) * sizeof(double);
-      I.fused = ctx->comm.world == 1 && work <= 1024 && I.of_grid <= 1024 && I.of_grid <= MAX_PART &&
+      // sharded runs: only with the peer-memory exchange, and (until verified at scale) on request
+      const bool rank_ok = ctx->comm.world == 1 ||
+                           (ctx->comm.p2p && n <= M3B_XCHG_CAP && work <= M3B_XCHG_CAP && getenv("M3B_MR_FUSED") != nullptr);
+      I.fused = rank_ok && work <= 1024 && I.of_grid <= 1024 && I.of_grid <= MAX_PART &&
                 smem <= (size_t)M3B_OF_SMEM_MAX && !getenv("M3B_NO_FUSED_ORTH");
     }
     const size_t part_sz = (size_t)std::max(std::max(I.nblk_n, I.nblk_m), I.of_grid) * work;
