@@ -1500,9 +1500,10 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     I.of_chunk_m = (int)((mloc + I.of_grid - 1) / I.of_grid);
     {
       const size_t smem = ((size_t)std::max(I.of_chunk_n, I.of_chunk_m) + work + 2 + 1024) * sizeof(double);
-      // sharded runs: only with the peer-memory exchange, and (until verified at scale) on request
+      // sharded runs: only with the peer-memory exchange (verified on 2 and 4 GPUs; M3B_NO_MR_FUSED=1
+      // falls back to the separate kernels with NCCL between them)
       const bool rank_ok = ctx->comm.world == 1 ||
-                           (ctx->comm.p2p && n <= M3B_XCHG_CAP && work <= M3B_XCHG_CAP && getenv("M3B_MR_FUSED") != nullptr);
+                           (ctx->comm.p2p && n <= M3B_XCHG_CAP && work <= M3B_XCHG_CAP && !getenv("M3B_NO_MR_FUSED"));
       I.fused = rank_ok && work <= 1024 && I.of_grid <= 1024 && I.of_grid <= MAX_PART &&
                 smem <= (size_t)M3B_OF_SMEM_MAX && !getenv("M3B_NO_FUSED_ORTH");
     }
