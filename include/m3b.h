@@ -112,9 +112,10 @@ int         m3b_set_rnorm(m3b_ctx* ctx, m3b_rnorm_fn fn, void* user);
 int m3b_comm_unique_id(m3b_ctx* ctx, char id[M3B_COMM_ID_BYTES]);              /* rank 0 */
 int m3b_comm_init(m3b_ctx* ctx, int rank, int world, const char id[M3B_COMM_ID_BYTES]);
 int m3b_comm_world(const m3b_ctx* ctx);                                        /* 1 if unsharded */
-/* Optional, one box only: peer-memory exchange over NVLink for the per-step gene-vector
- * reduction (the K5 combine, the cross-rank sum and the centre/scale fix-ups then run as ONE
- * kernel that reads the peers' partials directly; NCCL stays the fallback).  After
+/* Optional, one box only: peer-memory exchange over NVLink for the per-step cross-rank sums of
+ * the Lanczos loop (the gene-length partial of A^T w, the Gram-Schmidt coefficients of the cell
+ * side and {||w||^2, sum w}): they then run INSIDE the fused vector kernel, which reads the peers'
+ * contributions directly; NCCL stays the fallback and serves the preparation passes.  After
  * m3b_comm_init every rank exports a 64-byte CUDA-IPC handle; the host gathers the world's
  * handles (rank order) and hands them back to every rank. */
 #define M3B_P2P_HANDLE_BYTES 64
