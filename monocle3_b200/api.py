@@ -44,6 +44,22 @@ def set_context(ctx):
     _default_ctx = ctx
 
 
+_DEFAULT_NAMES = {}
+
+
+def _default_names(n):
+    """Default dimnames "0".."n-1" (read-only, shared between data sets of the same size: building
+    tens of thousands of Python strings per call showed up in the end-to-end time)."""
+    a = _DEFAULT_NAMES.get(n)
+    if a is None:
+        a = np.arange(n).astype(str)
+        a.setflags(write=False)
+        if len(_DEFAULT_NAMES) > 8:
+            _DEFAULT_NAMES.clear()
+        _DEFAULT_NAMES[n] = a
+    return a
+
+
 class CellDataSet:
     """Minimal stand-in for the S4 `cell_data_set` (R/cell_data_set.R:28-34): the slots
     this path reads and writes.  `counts` is genes x cells CSC (the dgCMatrix).
@@ -57,8 +73,8 @@ class CellDataSet:
             counts = sp.csc_matrix(counts)  # methods::as(expression_data, "dgCMatrix")
         self.counts = counts
         G, C = counts.shape
-        self.gene_names = np.asarray(gene_names if gene_names is not None else [str(i) for i in range(G)])
-        self.cell_names = np.asarray(cell_names if cell_names is not None else [str(i) for i in range(C)])
+        self.gene_names = np.asarray(gene_names) if gene_names is not None else _default_names(G)
+        self.cell_names = np.asarray(cell_names) if cell_names is not None else _default_names(C)
         if len(self.gene_names) != G or len(self.cell_names) != C:
             raise ValueError("dimnames do not match the expression matrix")
         self.col_data = {}           # colData(cds): 'Size_Factor', 'num_genes_expressed'
