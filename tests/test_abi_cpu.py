@@ -114,3 +114,7 @@ def test_product_rng_matches_r_and_oracle():
     np.testing.assert_allclose(rnorm_after_seed(2016, 5),
                                [-0.91474184, 1.00124785, -0.05642291, 0.29664516, -2.79147086], atol=5e-9)
     assert np.array_equal(rnorm_after_seed(2016, 1500), RRandom(2016).rnorm(1500))
+    # one stream, several draws (start vector, then irlba's replacement vectors)
+    from monocle3_b200.r_rng import RStream
+    a, b = RStream(7), RRandom(7)
+    assert np.array_equal(a.rnorm(11), b.rnorm(11)) and np.array_equal(a.rnorm(5), b.rnorm(5))
