@@ -148,6 +148,16 @@ NumericMatrix m3b_aggregate_(S4 counts, NumericVector sf, int norm_method, Integ
   return out;
 }
 
+// exact kNN for cluster_cells_make_graph's "nn2" method (R/cluster_cells.R:286-287): the result list of
+// RANN::nn2(data, data, k, searchtype = "standard")
+// [[Rcpp::export]]
+List m3b_nn2_self(NumericMatrix data, int k) {
+  IntegerMatrix idx(data.nrow(), k);
+  NumericMatrix dists(data.nrow(), k);
+  m3b_check(the_ctx(), m3b_knn_self(the_ctx(), data.begin(), data.nrow(), data.ncol(), k, idx.begin(), dists.begin()));
+  return List::create(_["nn.idx"] = idx, _["nn.dists"] = dists);
+}
+
 // drop-in body for the package's native kernel (src/clustering.cpp:49-54)
 // [[Rcpp::export]]
 NumericMatrix jaccard_coeff(SEXP R_idx, SEXP R_weight) {
