@@ -4,10 +4,11 @@
 // R/utils.R:417).  The per-item kernels of spmv.cu pay one exposed DRAM latency per item, which
 // was invisible while items were ~1000 entries of a 10 B/entry stream but dominates once the
 // count-1 entries live in the 2 B/entry unit stream (items of a few hundred bytes; ncu: 1.7 TB/s,
-// long-scoreboard stalls).  Here the stream of a tile is cut ONCE, at build time, into one
-// contiguous, item-aligned piece per warp (equal bytes), and a warp streams its piece flat:
-//   * two register batches of FL_K rounds (32 lanes x one group each) keep 4-8 KB per warp in
-//     flight regardless of where items begin and end;
+// long-scoreboard stalls).  Here the stream of a tile is cut ONCE, at build time, into
+// item-aligned, memory-contiguous pieces of equal length for the warps of the CTAs that own the
+// tile (at cfg2 sizes: one piece per warp), and a warp streams its pieces flat:
+//   * two register batches of K rounds (32 lanes x one group each; K = 3 by default) keep a few KB
+//     per warp in flight regardless of where items begin and end;
 //   * bit 15 of the first index of a group marks "this group starts a new item" (tile-local
 //     indices are < 28672, so the bit is free): one ballot per round tells the warp whether an
 //     item boundary is inside the round.  No boundary: lanes just accumulate.  Boundary: the open
