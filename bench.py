@@ -1,25 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- preprocess_cds PCA throughput (cells/s) on B200, with roofline and CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
   torchrun ... bench.py --gpus N ...           (one rank per GPU, N > 1)
 
-A STEP is one full pass of the hot path over one synthetic matrix:
+Workloads are the named configurations of BASELINE.json (synthetic data):
+  cfg2  42 000 cells x 20 000 genes, ~8 % dense, preprocess_cds(num_dim=100)           configs[1]
+  cfg3  250 000 cells x 30 000 genes, ~6 % dense, preprocess_cds(num_dim=50, scaling=TRUE)  configs[2]  (DEFAULT)
+  cfg4  2 000 000 cells x 30 000 genes, ~5 % dense, preprocess_cds(num_dim=100)         configs[3]  (8 GPUs)
+  cfg5  preprocess_transform of 500 000 query cells onto saved loadings (30 000 x 100)  configs[4]
+The default is cfg3 at EVERY N: it is the configuration BASELINE.json quotes "at 1/2/4/8 B200", it
+fits one GPU, and ONE fixed matrix sharded by cells (contiguous ranges cut at nnz quantiles) is what
+makes the 1 -> 8 curve measure the machine: iter / mprod are identical at every N ("scaling":
+"strong").  Every run asserts on rank 0 that iter, mprod and the singular values equal the stored
+single-GPU run of the same matrix (profiles/expected_<workload>.json, which tools/fullsize_parity.py
+checked against the oracle at full size).
+
+A STEP is one full pass of the hot path over the matrix:
   normalize (K2) -> gene select/filter + dual layout build (K0) -> gene moments (K3) ->
-  IRLBA (K4-K9, num_dim=100) -> embedding.
+  IRLBA (K4-K9) -> embedding.
 `value`  : device-resident cells/s (raw CSC already in HBM when the clock starts).
 `e2e`    : the same through the public API (new_cell_data_set + preprocess_cds) from pinned
            HOST buffers, H2D/D2H inside the timed region.
-Workload : BASELINE.json configs[1] -- synthetic C. elegans L2 shape, 42k cells x 20k genes,
-           ~8% dense, num_dim=100, per GPU (weak scaling: N GPUs hold 42k*N cells of ONE matrix,
-           sharded by cells, one PCA over all of them).
 Timing   : CUDA events on the library's own stream (m3b_timer_*), barrier + synchronize on both
-           sides, max over ranks.  Inputs (0.8 GB per layout) are far larger than L2 (126 MB).
+           sides, max over ranks.  Inputs are far larger than L2 (126 MB).
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -30,9 +38,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CFG2 = dict(name="cfg2: synthetic C. elegans L2 shape", n_genes=20000, cells_per_gpu=42000, density=0.08,
-            num_dim=100, n_types=150, seed=1)
-CPU_SAMPLE_CELLS = 3000
+WORKLOADS = {
+    "cfg2": dict(name="cfg2 (BASELINE configs[1]): synthetic C. elegans L2 shape", n_genes=20000, cells=42000,
+                 density=0.08, num_dim=100, n_types=150, seed=1),
+    "cfg3": dict(name="cfg3 (BASELINE configs[2]): synthetic 250k cells x 30k genes", n_genes=30000, cells=250000,
+                 density=0.06, num_dim=50, n_types=75, seed=1),
+    "cfg4": dict(name="cfg4 (BASELINE configs[3]): synthetic MOCA-atlas shape", n_genes=30000, cells=2000000,
+                 density=0.05, num_dim=100, n_types=150, seed=1),
+    "cfg5": dict(name="cfg5 (BASELINE configs[4]): preprocess_transform of query cells onto saved loadings",
+                 n_genes=30000, cells=500000, density=0.05, num_dim=100, n_types=150, seed=2,
+                 model_cells=250000, model_seed=1),
+}
+METRIC = "cells/sec preprocess_cds PCA (num_dim=100)"
 
 
 def parse_args():
@@ -41,15 +58,30 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cells-per-gpu", type=int, default=CFG2["cells_per_gpu"])
-    ap.add_argument("--genes", type=int, default=CFG2["n_genes"])
-    ap.add_argument("--density", type=float, default=CFG2["density"])
-    ap.add_argument("--num-dim", type=int, default=CFG2["num_dim"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cells", type=int, default=0, help="override the workload's total cell count (experiments)")
+    ap.add_argument("--genes", type=int, default=0)
+    ap.add_argument("--density", type=float, default=0.0)
+    ap.add_argument("--num-dim", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-cells", type=int, default=CPU_SAMPLE_CELLS)
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (used for short ncu launch lists)")
     ap.add_argument("--no-roofline-pass", action="store_true", help="skip the instrumented step (short ncu launch lists)")
-    return ap.parse_args()
+    ap.add_argument("--ref-pairs", type=int, default=3, help="reference arm: product pairs timed per step")
+    ap.add_argument("--write-expected", default="", help="write iter/mprod/d of this run to the given JSON file")
+    a = ap.parse_args()
+    wl = dict(WORKLOADS[a.workload])
+    if a.cells:
+        wl["cells"] = a.cells
+    if a.genes:
+        wl["n_genes"] = a.genes
+    if a.density:
+        wl["density"] = a.density
+    if a.num_dim:
+        wl["num_dim"] = a.num_dim
+    wl["key"] = a.workload
+    wl["modified"] = bool(a.cells or a.genes or a.density or a.num_dim)
+    a.wl = wl
+    return a
 
 
 class ClockSampler:
@@ -116,62 +148,193 @@ def pinned(a):
     return t.numpy(), t
 
 
-def cpu_oracle_run(counts, num_dim):
-    """The restated reference algorithm (oracle/) on the host cores: full preprocess_cds."""
+def workload_config(wl, world, extra=None):
+    if wl["key"] == "cfg5":
+        text = "%s: %d query cells x %d genes, ~%.0f%% dense, onto loadings %d genes x %d PCs (model: PCA of %d reference cells)" % (
+            wl["name"], wl["cells"], wl["n_genes"], 100 * wl["density"], wl["n_genes"], wl["num_dim"], wl["model_cells"])
+    else:
+        text = "%s, %d cells x %d genes, ~%.0f%% dense, preprocess_cds(num_dim=%d, norm_method='log', scaling=TRUE)" % (
+            wl["name"], wl["cells"], wl["n_genes"], 100 * wl["density"], wl["num_dim"])
+    if wl.get("modified"):
+        text += " [shape overridden on the command line]"
+    cfg = {"workload": text, "cells_total": wl["cells"], "genes": wl["n_genes"], "density": wl["density"],
+           "num_dim": wl["num_dim"], "sharding": "ONE matrix, contiguous cell ranges cut at nnz quantiles x%d" % world,
+           "l2": "inputs larger than L2 (no flush needed)", "small_svd": "device"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def expected_path(wl):
+    return os.path.join(ROOT, "profiles", "expected_%s.json" % wl["key"])
+
+
+def load_expected(wl):
+    """iter / mprod / singular values of the single-GPU run of the SAME matrix (written by
+    tools/fullsize_parity.py, which also compared that run with the oracle at full size)."""
+    p = expected_path(wl)
+    if wl.get("modified") or not os.path.exists(p):
+        return None
+    try:
+        e = json.load(open(p))
+    except Exception:
+        return None
+    if e.get("cells") != wl["cells"] or e.get("genes") != wl["n_genes"] or e.get("num_dim") != wl["num_dim"]:
+        return None
+    return e
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU algorithm (oracle port) on the SAME matrix
+# ---------------------------------------------------------------------------------------------
+def reference_step(counts, wl, mprod, iters, n_pairs, scale_cells):
+    """One bounded sample of the CPU path on the workload's matrix.  Every component is run at the
+    matrix's full size; only the COUNT of Lanczos products / restarts is cut:
+      prep      estimate_size_factors + normalize_expr_data + zero-gene filter + Matrix::t + gene
+                moments, in full (one pass each over all nnz)
+      pair      n_pairs x { A x  (+ one Gram-Schmidt pass against work/2 vectors),  A^T w (+ GS) }
+      restart   one thick restart: dgesdd of the work x work B + the two restart GEMMs
+    and the step time is   prep + (mprod / 2) * pair + iters * restart   with mprod / iters of the
+    FULL run (the GPU run's, which equal the oracle's wherever both were run).  scale_cells > 1:
+    the matrix is a 1/scale_cells sample of the workload's cells (cfg4: not representable as one
+    dgCMatrix) and every component is scaled linearly in nnz."""
     from oracle import monocle3_ref as ref
+    import scipy.sparse as sp
     t0 = time.perf_counter()
     sf = ref.estimate_size_factors(counts)
-    r = ref.preprocess_cds(counts, sf, num_dim=num_dim)
-    dt = time.perf_counter() - t0
-    return dt, r
+    FM = ref.normalize_expr_data(counts, sf, "log")
+    FM, kept = ref.select_and_filter_genes(FM)
+    At = FM.T.tocsc()               # cells x genes, what irlba is handed (R/preprocess_cds.R:139)
+    cen, sd = ref.gene_moments(At)
+    A_ = At.tocsr()
+    AT = At.T.tocsr()
+    t_prep = time.perf_counter() - t0
+    m, n = At.shape
+    nv = min(wl["num_dim"], min(m, n) - 1)
+    work = nv + 7
+    rng = np.random.default_rng(0)
+    V = np.linalg.qr(rng.standard_normal((n, work)))[0]
+    W = np.linalg.qr(rng.standard_normal((m, work)))[0]
+    j = work // 2
+    t1 = time.perf_counter()
+    for _ in range(n_pairs):
+        xs = V[:, j] / sd
+        w = np.asarray(A_ @ xs).ravel() - np.dot(xs, cen)
+        w = w - W[:, :j] @ (W[:, :j].T @ w)
+        w *= 1.0 / np.linalg.norm(w)
+        f = np.asarray(AT @ w).ravel() / sd - np.sum(w) * cen / sd
+        f = f - V[:, :j + 1] @ (V[:, :j + 1].T @ f)
+        f *= 1.0 / np.linalg.norm(f)
+    t_pair = (time.perf_counter() - t1) / n_pairs
+    B = np.triu(rng.standard_normal((work, work)))
+    t2 = time.perf_counter()
+    BU, BS, BVt = np.linalg.svd(B)
+    k = max(1, work - 10)
+    V[:, :k] = V @ BVt.T[:, :k]
+    W[:, :k] = W @ BU[:, :k]
+    t_restart = time.perf_counter() - t2
+    total = scale_cells * (t_prep + (mprod / 2.0) * t_pair + iters * t_restart)
+    return total, dict(prep_s=t_prep, pair_s=t_pair, restart_s=t_restart, nnz=int(counts.nnz), cells=int(m), genes_kept=int(n))
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  R / irlba are not
     installable here (no R in the image), so this is the oracle port (oracle/): SciPy sparse
-    products (single-threaded, like CHOLMOD sdmult inside irlba) + NumPy/OpenBLAS dense ops
-    on all host threads.  Each step is a full preprocess_cds on a bounded sample of the
-    workload's cells."""
+    products (single-threaded, like CHOLMOD sdmult inside irlba) + NumPy/OpenBLAS dense ops on
+    all host threads -- on the SAME synthetic matrix as the GPU arm (same generator, same seed,
+    same device for the random streams), every component at full size, see reference_step."""
     if rank != 0:
         return
-    from monocle3_b200.synth import SynthSpec
     import scipy.sparse as sp
-    spec = SynthSpec(args.genes, args.cells_per_gpu * args.gpus, args.density, CFG2["n_types"], CFG2["seed"], device="cpu")
-    n = min(args.cpu_sample_cells, spec.C)
-    indptr, indices, data = spec.cells(0, n)
-    counts = sp.csc_matrix((data, indices, indptr), shape=(args.genes, n))
-    nd = min(args.num_dim, n - 1)
+    import torch
+    from monocle3_b200.synth import SynthSpec
+    wl = args.wl
+    if wl["key"] == "cfg5":
+        return run_reference_project(args)
+    gen_dev = "cuda" if torch.cuda.is_available() else "cpu"   # RNG engine only (the GPU arm's matrix needs the same stream)
+    spec = SynthSpec(wl["n_genes"], wl["cells"], wl["density"], wl["n_types"], wl["seed"], device=gen_dev)
+    # a dgCMatrix holds < 2^31 nnz: cfg4 is sampled (first 1/8 of the cells = the cfg3 shape) and scaled
+    scale_cells = 1
+    n_cells = wl["cells"]
+    while n_cells * wl["n_genes"] * wl["density"] > 1.5e9:
+        scale_cells *= 2
+        n_cells = wl["cells"] // scale_cells
+    indptr, indices, data = spec.cells(0, n_cells)
+    counts = sp.csc_matrix((data, indices, indptr), shape=(wl["n_genes"], n_cells))
+    del spec
+    exp = load_expected(wl)
+    if exp:
+        mprod, iters, src = exp["mprod"], exp["iter"], "profiles/expected_%s.json (GPU run == oracle)" % wl["key"]
+    else:
+        mprod, iters, src = {"cfg2": (1326, 185), "cfg3": (700, 100), "cfg4": (858, 120)}.get(wl["key"], (1000, 130)) + ("estimate",)
     for _ in range(args.warmup):
-        cpu_oracle_run(counts, nd)
-    t = []
+        reference_step(counts, wl, mprod, iters, max(1, args.ref_pairs // 2), scale_cells)
+    t, parts = [], None
     for _ in range(args.steps):
-        dt, r = cpu_oracle_run(counts, nd)
+        dt, parts = reference_step(counts, wl, mprod, iters, args.ref_pairs, scale_cells)
         t.append(dt)
     ms = 1e3 * float(np.mean(t))
-    val = n / (ms / 1e3)
+    val = wl["cells"] / (ms / 1e3)
     cores = os.cpu_count()
-    sample = "full preprocess_cds(num_dim=%d) on the first %d cells x %d genes of the workload (nnz %d, mprod %d)" % (
-        nd, n, args.genes, counts.nnz, r["mprod"])
+    sample = ("restated CPU path (irlba algorithm; SciPy SpMV single-threaded like CHOLMOD sdmult, NumPy/OpenBLAS dense ops "
+              "on %d threads) on the workload's own matrix%s: prep in full %.1f s + (mprod %d / 2) x product pair %.3f s "
+              "+ iter %d x restart %.3f s, mprod/iter from %s; %d product pairs timed per step at full size" % (
+                  cores, "" if scale_cells == 1 else " (first 1/%d of the cells, scaled x%d linearly in nnz)" % (scale_cells, scale_cells),
+                  parts["prep_s"], mprod, parts["pair_s"], iters, parts["restart_s"], src, args.ref_pairs))
     print(json.dumps({
-        "impl": "reference", "metric": "cells/sec preprocess_cds PCA (num_dim=100)", "value": val, "unit": "cells/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(wl, args.gpus, {"reference_extrapolation": dict(parts, mprod=mprod, iter=iters, source=src,
+                                                                                   cells_sampled=n_cells, scale=scale_cells)}),
         "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(args, world):
-    return {"workload": "%s, %d cells/GPU x %d genes, ~%.0f%% dense, preprocess_cds(num_dim=%d, norm_method='log', "
-                        "scaling=TRUE)" % (CFG2["name"], args.cells_per_gpu, args.genes, 100 * args.density, args.num_dim),
-            "cells_total": args.cells_per_gpu * world, "genes": args.genes, "density": args.density,
-            "num_dim": args.num_dim, "sharding": "cells x%d" % world,
-            "l2": "inputs larger than L2 (no flush needed)", "small_svd": "device"}
+def run_reference_project(args):
+    """cfg5 reference arm: preprocess_transform's block-wise dense multiply (R/projection.R:135-148,
+    R/utils.R:823-849) on a bounded block of the query, all host threads, scaled linearly in cells."""
+    import scipy.sparse as sp
+    import torch
+    from monocle3_b200.synth import SynthSpec
+    from oracle import monocle3_ref as ref
+    wl = args.wl
+    gen_dev = "cuda" if torch.cuda.is_available() else "cpu"
+    spec = SynthSpec(wl["n_genes"], wl["cells"], wl["density"], wl["n_types"], wl["seed"], device=gen_dev)
+    n = min(4096, wl["cells"])
+    indptr, indices, data = spec.cells(0, n)
+    counts = sp.csc_matrix((data, indices, indptr), shape=(wl["n_genes"], n))
+    rng = np.random.default_rng(1)
+    G, nv = wl["n_genes"], wl["num_dim"]
+    model = dict(norm_method="log", pseudo_count=1, svd_v=np.linalg.qr(rng.standard_normal((G, nv)))[0],
+                 svd_center=rng.random(G) + 0.1, svd_scale=rng.random(G) + 0.5)
+    sf = ref.estimate_size_factors(counts)
+    gidx = np.arange(G)
+    times = []
+    for k in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ref.preprocess_transform(counts, sf, model, gidx)
+        if k >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    val = n / dt
+    ms = 1e3 * dt * wl["cells"] / n
+    cores = os.cpu_count()
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(wl, args.gpus, {"cells_sampled": n}),
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port",
+                         "sample": "restated preprocess_transform (block densified like DelayedArray, then dgemm on %d threads) on "
+                                   "the first %d query cells; the block-wise algorithm is linear in cells" % (cores, n)},
+        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ---------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    wl = args.wl
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -183,7 +346,7 @@ def main():
     import scipy.sparse as sp
     import monocle3_b200 as m3
     from monocle3_b200 import engine, dist as m3dist, _lib as L
-    from monocle3_b200.synth import SynthSpec
+    from monocle3_b200.synth import SynthSpec, balanced_shard
     from monocle3_b200.r_rng import rnorm_after_seed
 
     if not torch.cuda.is_available():
@@ -199,35 +362,51 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        td.all_reduce(t, op=td.ReduceOp.MAX)
+        td.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x):
+        return reduce_ranks(x, td.ReduceOp.MAX)
+
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        td.all_reduce(t, op=td.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_ranks(x, td.ReduceOp.SUM)
 
     ctx = engine.Context(device=local_rank, small_svd="device")
     m3.set_context(ctx)
     if world > 1:
         m3dist.init_comm(ctx)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
-    # ---- synthetic shard (host, pinned) ----
-    C_total = args.cells_per_gpu * world
-    spec = SynthSpec(args.genes, C_total, args.density, CFG2["n_types"], CFG2["seed"])
-    lo, hi = rank * args.cells_per_gpu, (rank + 1) * args.cells_per_gpu
-    indptr, indices, data = spec.cells(lo, hi)
+    if wl["key"] == "cfg5":
+        from bench_project import run_project_bench
+        out = run_project_bench(args, wl, ctx, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks,
+                                ClockSampler, pinned, peak, peak_src, workload_config)
+        if rank == 0:
+            out["metric"] = METRIC
+            print(json.dumps(out))
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    # ---- this rank's shard of the ONE synthetic matrix (host, pinned), cut at nnz quantiles ----
+    C_total = wl["cells"]
+    spec = SynthSpec(wl["n_genes"], C_total, wl["density"], wl["n_types"], wl["seed"])
+    t_gen0 = time.perf_counter()
+    lo, hi, indptr, indices, data = balanced_shard(spec, rank, world, m3dist.make_allgather() if world > 1 else None)
+    gen_s = time.perf_counter() - t_gen0
     (indptr_p, k1), (indices_p, k2), (data_p, k3) = pinned(indptr.astype(np.int32)), pinned(indices), pinned(data)
-    counts = sp.csc_matrix((data_p, indices_p, indptr_p), shape=(args.genes, hi - lo), copy=False)
+    counts = sp.csc_matrix((data_p, indices_p, indptr_p), shape=(wl["n_genes"], hi - lo), copy=False)
     nnz_local = int(counts.nnz)
     shard = m3dist.make_shard(C_total) if world > 1 else None
-    del spec
+    del spec, indptr, indices, data
     torch.cuda.empty_cache()
 
     # ---- device-resident arm: counts + size factors already in HBM ----
@@ -244,7 +423,7 @@ def main():
         dev.select_genes(None)
         t2 = time.perf_counter()
         v0 = rnorm_after_seed(2016, dev.n_kept)
-        nv = min(args.num_dim, min(dev.n_kept, C_total) - 1)
+        nv = min(wl["num_dim"], min(dev.n_kept, C_total) - 1)
         t3 = time.perf_counter()
         r = dev.pca_irlba(nv, v0, center=True, scale=True, want_x=False)
         t4 = time.perf_counter()
@@ -259,70 +438,89 @@ def main():
     sampler.start()
     ctx.reset_stats()
     ctx.timer_start()
-    step_walls = []
     for _ in range(args.steps):
         res = device_step()
-        step_walls.append(dict(wall))
     ms_total = ctx.timer_stop()
     barrier()
     clocks = sampler.stop()
-    if os.environ.get("M3B_BENCH_DEBUG"):
-        print("DEBUG rank %d cpus=%s affinity=%d steps=%s host_ms=%s" % (
-            rank, os.cpu_count(), len(os.sched_getaffinity(0)),
-            [{k: round(v, 1) for k, v in w.items()} for w in step_walls],
-            [round(v, 1) for v in ctx.stats()["host_ms"]]), file=sys.stderr, flush=True)
     st = ctx.stats()
     ms_step = max_over_ranks(ms_total) / args.steps
     launches = int(sum_over_ranks(st["kernel_launches"]))
     value = C_total / (ms_step / 1e3)
+    irlba_ms_untimed = max_over_ranks(st["irlba_ms"])
+    select_ms = [max_over_ranks(v) for v in st["select_ms"]]
+
+    # ---- parity of this run against the stored single-GPU run of the same matrix ----
+    expected = load_expected(wl)
+    parity = None
+    if expected is not None:
+        d_exp = np.asarray(expected["d"])
+        rel = float(np.max(np.abs(res["d"] - d_exp) / d_exp)) if len(d_exp) == len(res["d"]) else float("inf")
+        parity = {"against": "profiles/expected_%s.json (1 GPU, oracle-checked)" % wl["key"],
+                  "iter": [res["iter"], expected["iter"]], "mprod": [res["mprod"], expected["mprod"]], "d_max_rel": rel,
+                  "ok": bool(res["iter"] == expected["iter"] and res["mprod"] == expected["mprod"] and rel < 1e-9)}
+        if rank == 0:
+            print("PARITY vs stored 1-GPU run of the same matrix: iter %d/%d mprod %d/%d d_max_rel %.2e -> %s" % (
+                res["iter"], expected["iter"], res["mprod"], expected["mprod"], rel, "OK" if parity["ok"] else "MISMATCH"),
+                file=sys.stderr, flush=True)
+            assert parity["ok"], "sharded run differs from the stored single-GPU run of the same matrix"
+    if args.write_expected and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.write_expected)), exist_ok=True)
+        json.dump({"workload": wl["key"], "cells": wl["cells"], "genes": wl["n_genes"], "num_dim": wl["num_dim"],
+                   "n_gpus": world, "iter": res["iter"], "mprod": res["mprod"], "d": [float(v) for v in res["d"]]},
+                  open(args.write_expected, "w"))
 
     roofline = None
     if not args.no_roofline_pass:
         # ---- roofline of the dominant kernel (k_flat_dot, the two SpMVs): one instrumented step ----
         ctx.set_flags(L.FLAG_TIME_SPMV)
         ctx.reset_stats()
-        res_i = device_step()
+        device_step()
         sti = ctx.stats()
         ctx.set_flags(0)
         nA, nB = sti["spmv_cells_out"], sti["spmv_genes_out"]
         bytes_total = nA * sti["spmv_bytes_cells_out"] + nB * sti["spmv_bytes_genes_out"]
+        stream_total = nA * sti["spmv_stream_bytes_cells_out"] + nB * sti["spmv_stream_bytes_genes_out"]
         spmv_ms = sti["spmv_cells_out_ms"] + sti["spmv_genes_out_ms"]
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = bytes_total / (spmv_ms / 1e3) / 1e9 if spmv_ms > 0 else 0.0
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-        if os.path.exists(tp):
+        physical = stream_total / (spmv_ms / 1e3) / 1e9 if spmv_ms > 0 else 0.0
+        n_launch = max(1, nA + nB)
+        # ncu DRAM bytes of one launch for this exact workload, when a capture was committed
+        traffic, traffic_src = stream_total / n_launch, "library: exact bytes of the streams the kernel reads/writes (m3b_stats)"
+        tp = os.path.join(ROOT, "profiles", "spmv_traffic_%s_n%d.json" % (wl["key"], world))
+        if os.path.exists(tp) and not wl.get("modified"):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp))["dram_bytes_per_launch"]
+                traffic_src = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum (%s)" % os.path.basename(tp)
             except Exception:
-                traffic = None
-        avg_us = 1e3 * spmv_ms / max(1, nA + nB)
+                pass
+        avg_us = 1e3 * spmv_ms / n_launch
         roofline = {"bound": "hbm", "kernel": "k_flat_dot (K4 cells-out + K5 genes-out SpMV)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                    "launches_timed": int(nA + nB), "avg_launch_us": 1e3 * spmv_ms / max(1, nA + nB),
-                    "algorithmic_bytes_per_launch": bytes_total / max(1, nA + nB),
+                    "traffic_source": traffic_src, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                    "launches_timed": int(nA + nB), "avg_launch_us": avg_us,
+                    "algorithmic_bytes_per_launch": bytes_total / n_launch,
+                    "stream_bytes_per_launch": stream_total / n_launch,
+                    "physical_gbs": physical, "physical_frac_of_peak": physical / peak,
+                    "physical_frac_of_nominal_8TBs": physical / 8000.0,
                     "cells_out": {"gbs": nA * sti["spmv_bytes_cells_out"] / max(sti["spmv_cells_out_ms"], 1e-9) / 1e6,
+                                  "physical_gbs": nA * sti["spmv_stream_bytes_cells_out"] / max(sti["spmv_cells_out_ms"], 1e-9) / 1e6,
                                   "avg_us": 1e3 * sti["spmv_cells_out_ms"] / max(1, nA)},
                     "genes_out": {"gbs": nB * sti["spmv_bytes_genes_out"] / max(sti["spmv_genes_out_ms"], 1e-9) / 1e6,
+                                  "physical_gbs": nB * sti["spmv_stream_bytes_genes_out"] / max(sti["spmv_genes_out_ms"], 1e-9) / 1e6,
                                   "avg_us": 1e3 * sti["spmv_genes_out_ms"] / max(1, nB)},
                     "spmv_share_of_irlba": spmv_ms / max(sti["irlba_ms"], 1e-9),
-                    "stream_note": "achieved = ALGORITHMIC bytes (12 B/nnz of an int32-indexed CSR, SURVEY 8d) / time; the "
-                                   "kernel streams less than that: 16-bit tile-local indices, and count-1 entries "
-                                   "(index only, 2 B) carry no value, so frac can exceed 1; dram_gbs is the measured "
-                                   "DRAM traffic of the ncu capture (traffic) over the same launch time",
-                    "dram_gbs": (traffic / (avg_us * 1e-6) / 1e9) if (traffic and avg_us > 0) else None,
-                    "dram_frac_of_peak": (traffic / (avg_us * 1e-6) / 1e9 / peak) if (traffic and avg_us > 0) else None,
+                    "stream_note": "achieved/frac = ALGORITHMIC bytes (12 B/nnz of an int32-indexed CSR, SURVEY 8d) / time; the "
+                                   "kernel streams a lossless compressed form (16-bit tile-local indices; count-1 entries "
+                                   "index-only, 2 B), so frac can exceed 1. physical_* = the exact bytes the kernel moves "
+                                   "(stream_bytes_per_launch) / the same time: that is the DRAM utilisation",
                     "irlba_phase_ms": dict(zip(["spmv_cells_out", "spmv_genes_out", "orthog", "small_svd", "restart_gemm",
                                                 "vector_epilogues", "allreduce"], [round(v, 3) for v in sti["phase_ms"][:7]])),
                     "irlba_ms": sti["irlba_ms"], "svd_sweeps": sti["svd_sweeps"], "svd_fallbacks": sti["svd_fallbacks"],
                     "host_wall_ms": {k: round(v, 2) for k, v in wall.items()},
-                    "irlba_host_ms": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in sti["host_ms"]])),
-                    "irlba_host_ms_untimed_step": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in st["host_ms"]]))}
+                    "select_genes_phase_ms": dict(zip(["layout_B", "row_sums_filter", "remap_plans_B", "layout_A"],
+                                                      [round(v, 2) for v in sti["select_ms"]])),
+                    "irlba_host_ms": dict(zip(["setup", "loop", "final", "release"], [round(v, 2) for v in sti["host_ms"]]))}
 
         # ---- the other HBM-bound passes of the path (K1 totals, K2 normalize), event-timed, 5 reps ----
         def timed(fn, reps=5):
@@ -349,7 +547,7 @@ def main():
         # ---- end-to-end arm: public API from pinned host buffers ----
         def e2e_step():
             c = m3.new_cell_data_set(counts, shard=shard)           # H2D of the CSC + size factors
-            c = m3.preprocess_cds(c, num_dim=args.num_dim)          # ... embedding + loadings back on the host
+            c = m3.preprocess_cds(c, num_dim=wl["num_dim"])         # ... embedding + loadings back on the host
             x = c.reduced_dims["PCA"]
             c._dev.free()
             return c, x
@@ -371,26 +569,37 @@ def main():
                "h2d_bytes_per_step": int(sum_over_ranks(ste["h2d_bytes"]) / args.steps),
                "d2h_bytes_per_step": int(sum_over_ranks(ste["d2h_bytes"]) / args.steps), "ms_per_step": ms_e2e}
 
-    # ---- CPU baseline (rank 0, N=1 only): oracle on a bounded sample ----
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on this very matrix, bounded product count ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = min(args.cpu_sample_cells, hi - lo)
-        sub = sp.csc_matrix((data[:indptr[n]], indices[:indptr[n]], indptr[:n + 1]), shape=(args.genes, n))
-        nd = min(args.num_dim, n - 1)
-        dt, r = cpu_oracle_run(sub, nd)
-        cpu_baseline = {"value": n / dt, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": "restated CPU path (irlba algorithm, SciPy SpMV + NumPy/OpenBLAS): full "
-                                  "preprocess_cds(num_dim=%d) on the first %d cells x %d genes (nnz %d, mprod %d, %.1f s)"
-                                  % (nd, n, args.genes, sub.nnz, r["mprod"], dt)}
+        sub = sp.csc_matrix((np.asarray(counts.data), np.asarray(counts.indices), np.asarray(counts.indptr).astype(np.int64)),
+                            shape=counts.shape)
+        dt, parts = reference_step(sub, wl, res["mprod"], res["iter"], 2, 1)
+        cpu_baseline = {"value": C_total / dt, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": "restated CPU path (irlba algorithm; SciPy SpMV single-threaded like CHOLMOD sdmult, "
+                                  "NumPy/OpenBLAS dense ops on all threads) on THIS run's full matrix (%d cells, nnz %d): prep in "
+                                  "full %.1f s + (mprod %d / 2) x product pair %.3f s + iter %d x restart %.3f s = %.1f s per step; "
+                                  "2 product pairs timed at full size, mprod/iter are this run's"
+                                  % (C_total, parts["nnz"], parts["prep_s"], res["mprod"], parts["pair_s"], res["iter"],
+                                     parts["restart_s"], dt)}
     nnz_total = int(sum_over_ranks(nnz_local))
+    nnz_max = int(max_over_ranks(nnz_local))
     if rank == 0:
-        out = {"metric": "cells/sec preprocess_cds PCA (num_dim=100)", "value": value, "unit": "cells/s",
+        out = {"metric": METRIC, "value": value, "unit": "cells/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": workload_config(wl, world), "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+               "mprod": res["mprod"], "iter": res["iter"],
+               "us_per_product": 1e3 * irlba_ms_untimed / max(1, res["mprod"]),
+               "us_per_product_note": "device time of m3b_pca_irlba (max over ranks) of the last timed step / mprod: products, "
+                                      "vector work, exchanges, restarts",
+               "parity_vs_single_gpu": parity,
                "roofline": roofline, "cpu_baseline": cpu_baseline,
+               "select_genes_phase_ms": dict(zip(["layout_B", "row_sums_filter", "remap_plans_B", "layout_A"],
+                                                 [round(v, 2) for v in select_ms])),
                "irlba": {"iter": res["iter"], "mprod": res["mprod"], "d1": float(res["d"][0]),
-                         "nnz_total": nnz_total, "status": res["status"]}}
+                         "nnz_total": nnz_total, "nnz_max_shard": nnz_max, "status": res["status"],
+                         "irlba_ms": irlba_ms_untimed, "generate_s": round(gen_s, 1)}}
         print(json.dumps(out))
     if world > 1:
         td.destroy_process_group()

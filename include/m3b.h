@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define M3B_ABI_VERSION 1
+#define M3B_ABI_VERSION 2
 
 /* status codes (negative = error; the first five mirror irlba's C path) */
 #define M3B_OK                0
@@ -127,7 +127,10 @@ int m3b_comm_p2p_open(m3b_ctx* ctx, const char* handles /* world x 64 bytes */);
  * cell count over all ranks (== n_cells_local when unsharded). */
 int  m3b_matrix_begin(m3b_ctx* ctx, int32_t n_genes, int64_t n_cells_local,
                       int64_t n_cells_total, int64_t nnz_hint, m3b_mat** out);
-/* p: chunk-local column pointers (n_cells_chunk+1, p[0]==0); i: row indices; x: values */
+/* p: chunk-local column pointers (n_cells_chunk+1, p[0]==0, non-decreasing); i: row indices in
+ * [0, n_genes), STRICTLY INCREASING inside every column (sorted and unique, as in a dgCMatrix);
+ * x: values.  The chunk is validated on the device; a violation returns M3B_E_DIMS and the chunk
+ * is not appended. */
 int  m3b_matrix_append_csc(m3b_mat* mat, int64_t n_cells_chunk, const int32_t* p,
                            const int32_t* i, const double* x);
 int  m3b_matrix_end(m3b_mat* mat);
@@ -260,6 +263,15 @@ typedef struct m3b_stats {
   double  k2_ms;               /* CUDA-event time of the last K2 (normalize) kernel     */
   int64_t svd_fallback_reasons;/* OR of the reasons: 1 size, 2 irregular poles/weights, 4 root not converged, 8 Loewner,
                                   16 right vectors B^T u / s not unit (tiny singular value) */
+  /* EXACT bytes one K4 / K5 launch moves to or from DRAM, counted from the layouts the kernel
+   * streams: 10 B per (padded) general entry + 2 B per (padded) unit entry + the work-plan
+   * descriptors + the dense operand (and the per-cell unit values on layout B) once + one 8-byte
+   * partial per item.  The physical counterpart of spmv_bytes_* (the SURVEY 8d figure). */
+  int64_t spmv_stream_bytes_cells_out;
+  int64_t spmv_stream_bytes_genes_out;
+  /* host wall clock of the phases of the last m3b_select_genes (ms): [0] layout B build
+   * [1] row sums + keep mask [2] re-map + plans of B [3] layout A build + plans */
+  double  select_ms[4];
 } m3b_stats;
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);
 int m3b_reset_stats(m3b_ctx* ctx);

@@ -103,6 +103,16 @@ int m3b_create(int device, int flags, m3b_ctx** out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  {
+    // bound of the in-kernel waits (peer exchange, grid barrier): seconds -> SM cycles.  Generous by
+    // default: ordinary rank skew (a host LAPACK callback, paging, a debugger) must not turn into a
+    // failure; M3B_XCHG_TIMEOUT_S overrides.
+    double secs = 30.0;
+    if (const char* e = getenv("M3B_XCHG_TIMEOUT_S")) secs = std::max(0.1, atof(e));
+    int khz = 1900000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    ctx->spin_timeout_cycles = (long long)(secs * 1e3 * (double)khz);
+  }
   if (const char* e = getenv("M3B_TILE_W")) {  // tuning knob (multiple of 32, <= 28672)
     int v = atoi(e);
     if (v >= 32 && v <= M3B_TILE_W_MAX) ctx->tile_w_max = v & ~31;
@@ -130,6 +140,7 @@ void m3b_destroy(m3b_ctx* ctx) {
   comm_destroy(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->sched) cudaFree(ctx->sched);
+  if (ctx->ingest_flag) cudaFree(ctx->ingest_flag);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->evk0) cudaEventDestroy(ctx->evk0);
@@ -474,9 +485,14 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
   RET(finish_selection(m, kp.data()));
   const double t3 = now();
   RET(build_layout_A(m, split));
+  const double t4 = now();
+  ctx->stats.select_ms[0] = t1 - t0;
+  ctx->stats.select_ms[1] = t2 - t1;
+  ctx->stats.select_ms[2] = t3 - t2;
+  ctx->stats.select_ms[3] = t4 - t3;
   if (dbg)
     fprintf(stderr, "m3b_select_genes: layout B %.2f ms, row sums %.2f ms, remap %.2f ms, layout A %.2f ms\n", t1 - t0,
-            t2 - t1, t3 - t2, now() - t3);
+            t2 - t1, t3 - t2, t4 - t3);
   if (keep) memcpy(keep, kp.data(), n_sel);
   if (n_kept) *n_kept = m->n_kept;
   m->selected = true;
@@ -484,6 +500,8 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
   m->tfidf_applied = false;
   ctx->stats.spmv_bytes_cells_out = spmv_algorithmic_bytes(m->A);
   ctx->stats.spmv_bytes_genes_out = spmv_algorithmic_bytes(m->B);
+  ctx->stats.spmv_stream_bytes_cells_out = spmv_stream_bytes(m->A);
+  ctx->stats.spmv_stream_bytes_genes_out = spmv_stream_bytes(m->B);
   return M3B_OK;
 }
 
@@ -623,9 +641,12 @@ int m3b_timer_stop(m3b_ctx* ctx, double* elapsed_ms) {
 int m3b_reset_stats(m3b_ctx* ctx) {
   if (!ctx) return M3B_E_DIMS;
   long long a = ctx->stats.spmv_bytes_cells_out, b = ctx->stats.spmv_bytes_genes_out;
+  long long c = ctx->stats.spmv_stream_bytes_cells_out, d = ctx->stats.spmv_stream_bytes_genes_out;
   ctx->stats = m3b_stats{};
   ctx->stats.spmv_bytes_cells_out = a;
   ctx->stats.spmv_bytes_genes_out = b;
+  ctx->stats.spmv_stream_bytes_cells_out = c;
+  ctx->stats.spmv_stream_bytes_genes_out = d;
   return M3B_OK;
 }
 

@@ -137,8 +137,38 @@ int comm_p2p_open(m3b_ctx* ctx, const char* handles) {
   }
   if (!c.peers_dev) CK(ctx, cudaMalloc((void**)&c.peers_dev, 16 * sizeof(double*)));
   CK(ctx, cudaMemcpy(c.peers_dev, ptrs.data(), c.world * sizeof(double*), cudaMemcpyHostToDevice));
+  // A second open on a live buffer must not see flags of the previous life: clear the flag area,
+  // then a barrier so that no rank publishes into a buffer its owner has not cleared yet.
+  CK(ctx, cudaMemset(c.xchg, 0, (size_t)c.world * 2 * M3B_XCHG_FLAG_STRIDE * sizeof(double)));
+  CK(ctx, cudaDeviceSynchronize());
   c.xchg_seq = 0;
   c.p2p = true;
+  return comm_xchg_resync(ctx);
+}
+
+// Every rank leaves with the same exchange counter (max over the ranks + 2: sequence numbers only
+// grow, so a flag of an abandoned exchange can never match a future one).  Called when the peer
+// buffers are opened and at the start of every IRLBA run: a rank-local error exit (linear
+// dependency, abort callback, allocation failure) leaves the counters apart, and without this
+// every later exchange would wait for its time-out.  The allreduce doubles as the barrier.
+int comm_xchg_resync(m3b_ctx* ctx) {
+  Comm& c = ctx->comm;
+  if (c.world == 1 || !c.p2p) return M3B_OK;
+  long long* d = nullptr;
+  CK(ctx, cudaMalloc((void**)&d, sizeof(long long)));
+  long long h = (long long)c.xchg_seq;
+  cudaError_t e = cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream);
+  int st = M3B_OK;
+  if (e == cudaSuccess) st = comm_allreduce_max_i64(ctx, d, 1);
+  if (e == cudaSuccess && st == M3B_OK) e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && st == M3B_OK) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (st != M3B_OK) return st;
+  if (e != cudaSuccess) {
+    m3b_set_error(ctx, "comm_xchg_resync: %s", cudaGetErrorString(e));
+    return M3B_E_CUDA;
+  }
+  c.xchg_seq = (unsigned long long)h + 2;
   return M3B_OK;
 }
 
@@ -167,6 +197,14 @@ int comm_allreduce_f64(m3b_ctx* ctx, double* dev, size_t n) {
   NcclApi* api = nccl_api(ctx);
   if (!api) return M3B_E_NCCL;
   NK(ctx, api, api->AllReduce(dev, dev, n, ncclDouble, ncclSum, (ncclComm_t)ctx->comm.comm, ctx->stream));
+  return M3B_OK;
+}
+
+int comm_allreduce_max_i64(m3b_ctx* ctx, long long* dev, size_t n) {
+  if (ctx->comm.world == 1 || n == 0) return M3B_OK;
+  NcclApi* api = nccl_api(ctx);
+  if (!api) return M3B_E_NCCL;
+  NK(ctx, api, api->AllReduce(dev, dev, n, ncclInt64, ncclMax, (ncclComm_t)ctx->comm.comm, ctx->stream));
   return M3B_OK;
 }
 

@@ -46,6 +46,7 @@ static int fl_variant() {
 
 struct FlatPlan {
   int n_cta = 0, n_visits = 0;
+  long long n_pieces = 0;        // descriptors in gp + up
   int* cta_visit_ptr = nullptr;  // [n_cta+1]
   int* visit_tile = nullptr;     // [n_visits]
   int* gp_ptr = nullptr;         // [n_visits*FL_WARPS+1] piece ranges of (visit, warp), general stream
@@ -53,6 +54,8 @@ struct FlatPlan {
   int* up_ptr = nullptr;         // the same for the unit stream (groups of 8 entries)
   int4* up = nullptr;
 };
+
+long long flat_plan_pieces(const FlatPlan* p) { return p ? p->n_pieces : 0; }
 
 void flat_plan_free(FlatPlan* p) {
   if (!p) return;
@@ -235,6 +238,7 @@ static int build_one_plan(m3b_ctx* ctx, const TiledLayout& L, const HostTables& 
   *out = P;
   P->n_cta = n_cta;
   P->n_visits = n_visits;
+  P->n_pieces = (long long)gp.size() + (long long)up.size();
   RET(upload_vec(ctx, &P->cta_visit_ptr, cta_visit_ptr));
   RET(upload_vec(ctx, &P->visit_tile, visit_tile));
   RET(upload_vec(ctx, &P->gp_ptr, gp_ptr));

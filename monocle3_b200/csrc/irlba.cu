@@ -204,7 +204,7 @@ k_combine_xchg_fix_F(const double* __restrict__ partial, const int* __restrict__
                      const double* __restrict__ s, const double* __restrict__ ce, const double* __restrict__ vj,
                      const double* __restrict__ scal, double* __restrict__ F, double* const* __restrict__ peers,
                      int rank, int world, unsigned long long seq, unsigned int* __restrict__ done_ctr,
-                     int* __restrict__ ctl) {
+                     int* __restrict__ ctl, long long timeout) {
   __shared__ int s_ok;
   if (*((volatile int*)(ctl + CT_FLAG)) & 4) return;  // an earlier exchange already timed out: do not wait again
   const int slot = (int)(seq & 1ull);
@@ -243,7 +243,7 @@ k_combine_xchg_fix_F(const double* __restrict__ partial, const int* __restrict__
       const unsigned long long* fl =
           reinterpret_cast<const unsigned long long*>(peers[rank] + ((size_t)q * 2 + slot) * M3B_XCHG_FLAG_STRIDE);
       while (ld_acquire_sys_u64(fl) != seq) {
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never arrived
+        if (clock64() - t0 > timeout) {  // a peer never arrived
           ok = 0;
           break;
         }
@@ -427,6 +427,7 @@ struct OrthArgs {
   double* const* peers;
   int rank, world;
   unsigned long long seq;  // number of the first exchange of this launch (F side uses 1, W side 2)
+  long long timeout;       // bound of the in-kernel waits, SM cycles
 };
 
 // ---- cross-rank exchange inside the fused kernel (one box, CUDA-IPC peer memory) ----
@@ -444,13 +445,14 @@ __device__ __forceinline__ void xchg_publish(double* const* peers, int rank, int
     st_release_sys_u64(reinterpret_cast<unsigned long long*>(peers[q] + ((size_t)rank * 2 + (seq & 1ull)) * M3B_XCHG_FLAG_STRIDE), seq);
 }
 // called by ONE thread; returns false on time-out
-__device__ __forceinline__ bool xchg_wait(double* const* peers, int rank, int world, unsigned long long seq, int* ctl) {
+__device__ __forceinline__ bool xchg_wait(double* const* peers, int rank, int world, unsigned long long seq, int* ctl,
+                                          long long timeout) {
   const long long t0 = clock64();
   for (int q = 0; q < world; ++q) {
     const unsigned long long* fl =
         reinterpret_cast<const unsigned long long*>(peers[rank] + ((size_t)q * 2 + (seq & 1ull)) * M3B_XCHG_FLAG_STRIDE);
     while (ld_acquire_sys_u64(fl) != seq) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > timeout) {
         atomicOr(ctl + CT_FLAG, 4);
         return false;
       }
@@ -462,7 +464,8 @@ __device__ __forceinline__ bool xchg_wait(double* const* peers, int rank, int wo
 
 // All CTAs are co-resident (cooperative launch).  The spin is bounded (~2 s) so that a lost CTA
 // turns into an error (CT_FLAG bit 8) instead of a hung device.
-__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target, int* ctl) {
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target, int* ctl,
+                                             long long timeout) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -472,7 +475,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
     for (;;) {
       asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
       if (v >= target) break;
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > timeout) {
         atomicOr(ctl + CT_FLAG, 8);
         break;
       }
@@ -551,9 +554,9 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       // every CTA of every rank has written its rows: publish, wait for the world, then this CTA
       // sums its rows over the ranks (rank order => identical on every rank) and applies the fix-ups
       __threadfence_system();
-      grid_barrier(a.bar, a.bar_base + gridDim.x, a.ctl);
+      grid_barrier(a.bar, a.bar_base + gridDim.x, a.ctl, a.timeout);
       if (blockIdx.x == 0 && tid == 0) xchg_publish(a.peers, a.rank, a.world, a.seq);
-      if (tid == 0) xchg_wait(a.peers, a.rank, a.world, a.seq, a.ctl);
+      if (tid == 0) xchg_wait(a.peers, a.rank, a.world, a.seq, a.ctl, a.timeout);
       __syncthreads();
       for (int q = tid; q < len; q += OF_THREADS) {
         const long long r = r0 + q;
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       if (nc > 3) pp[3] = a3;
     }
   }
-  grid_barrier(a.bar, a.bar_base + (nb0 + 1) * gridDim.x, a.ctl);
+  grid_barrier(a.bar, a.bar_base + (nb0 + 1) * gridDim.x, a.ctl, a.timeout);
   // ---- phase 2a: t = sum over the CTAs' partial dots (group q of threads sums blocks q, q+G, ...)
   {
     const int G = OF_THREADS / max(ncols, 1);
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
         __syncthreads();
         if (tid == 0) xchg_publish(a.peers, a.rank, a.world, a.seq);
       }
-      if (tid == 0) xchg_wait(a.peers, a.rank, a.world, a.seq, a.ctl);
+      if (tid == 0) xchg_wait(a.peers, a.rank, a.world, a.seq, a.ctl, a.timeout);
       __syncthreads();
       if (tid < ncols) {
         double v = 0.0;
@@ -702,7 +705,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       a.ps[blockIdx.x] = r2;
     }
   }
-  grid_barrier(a.bar, a.bar_base + (nb0 + 2) * gridDim.x, a.ctl);
+  grid_barrier(a.bar, a.bar_base + (nb0 + 2) * gridDim.x, a.ctl, a.timeout);
   // ---- phase 3: norm, scaling, scalars
   double nn = block_sum_cg(a.pn, gridDim.x, sh, &bc);
   if (a.mode == OF_W) {
@@ -718,7 +721,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
         xchg_publish(a.peers, a.rank, a.world, s2);
       }
       if (tid == 0) {
-        xchg_wait(a.peers, a.rank, a.world, s2, a.ctl);
+        xchg_wait(a.peers, a.rank, a.world, s2, a.ctl, a.timeout);
         double g0 = 0.0, g1 = 0.0;
         for (int rk = 0; rk < a.world; ++rk) {
           g0 += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, s2));
@@ -1209,6 +1212,7 @@ struct Irlba {
     a.world = ctx->comm.world;
     a.rank = ctx->comm.rank;
     a.peers = ctx->comm.peers_dev;
+    a.timeout = ctx->spin_timeout_cycles;
     int n_bar = 2;
     if (a.world > 1) {
       // exchanges of this launch: F side 1 (the gene vector), W side 2 (coefficients, then norm and sum)
@@ -1269,7 +1273,7 @@ struct Irlba {
       ctx->comm.xchg_seq++;
       k_combine_xchg_fix_F<<<std::max(1, std::min(XF_CTAS, (n + 31) / 32)), NT, 0, ctx->stream>>>(
           m->B.partial, m->B.row_slot_ptr, n, s, ce, V + (long long)j * n, scal, F, ctx->comm.peers_dev,
-          ctx->comm.rank, ctx->comm.world, ctx->comm.xchg_seq, xf_done, ctl);
+          ctx->comm.rank, ctx->comm.world, ctx->comm.xchg_seq, xf_done, ctl, ctx->spin_timeout_cycles);
       count_launch(ctx);
       spmv_timer_end(ctx);
       CK(ctx, cudaGetLastError());
@@ -1451,6 +1455,8 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
   const bool use_scale = scale != 0;
   const bool use_center = center != 0;
   if (use_scale || use_center) RET(compute_moments(m));
+  // an earlier run that ended in an error on one rank leaves the ranks' exchange counters apart
+  RET(comm_xchg_resync(ctx));
 
   Irlba I;
   I.ctx = ctx;

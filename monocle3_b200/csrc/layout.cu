@@ -157,9 +157,34 @@ __device__ __forceinline__ int ld_stream_s32(const int* p) {
 // ingest helpers
 // ---------------------------------------------------------------------------
 __global__ void k_offset_colptr(const int* __restrict__ p_chunk, long long n, long long base,
-                                long long* __restrict__ p_out) {
+                                long long* __restrict__ p_out, int* __restrict__ flag) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (k < n) p_out[k] = base + (long long)p_chunk[k];
+  if (k < n) {
+    p_out[k] = base + (long long)p_chunk[k];
+    if (k + 1 < n && p_chunk[k] > p_chunk[k + 1]) atomicOr(flag, 1);  // column pointers must not decrease
+  }
+}
+
+// Validation of an appended chunk (the kernels downstream index per-gene tables with these values
+// and rely on one entry per (gene, cell)): every row index in [0, n_genes), strictly increasing
+// inside a column -- what a dgCMatrix guarantees.  One warp per cell; offsets are clamped to the
+// chunk so that a bad column pointer cannot send the check itself out of bounds.
+__global__ void __launch_bounds__(256) k_validate_rows(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                       long long n_cells, long long lo_all, long long hi_all, int n_genes,
+                                                       int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  int bad = 0;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = min(max(p[c], lo_all), hi_all), hi = min(max(p[c + 1], lo_all), hi_all);
+    for (long long k = lo + lane; k < hi; k += 32) {
+      const int g = gi[k];
+      if (g < 0 || g >= n_genes) bad |= 2;
+      if (k + 1 < hi && gi[k + 1] <= g) bad |= 4;
+    }
+  }
+  if (bad) atomicOr(flag, bad);
 }
 
 int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* i, const double* x) {
@@ -201,11 +226,32 @@ int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* 
   CK(ctx, cudaMemcpyAsync(m->i + m->nnz, i, nnz_chunk * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaMemcpyAsync(m->x + m->nnz, x, nnz_chunk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   long long n = n_cells_chunk + 1;
-  k_offset_colptr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_pchunk, n, m->nnz, m->p + m->cells_appended);
+  if (!ctx->ingest_flag) {
+    CK(ctx, cudaMalloc((void**)&ctx->ingest_flag, sizeof(int)));
+    CK(ctx, cudaMemsetAsync(ctx->ingest_flag, 0, sizeof(int), ctx->stream));
+  }
+  k_offset_colptr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_pchunk, n, m->nnz, m->p + m->cells_appended,
+                                                                        ctx->ingest_flag);
   count_launch(ctx);
+  if (n_cells_chunk > 0 && nnz_chunk > 0) {
+    const int vblocks = (int)std::min<long long>((n_cells_chunk + 7) / 8, (long long)ctx->sm_count * 8);
+    k_validate_rows<<<vblocks, 256, 0, ctx->stream>>>(m->p + m->cells_appended, m->i, n_cells_chunk, m->nnz,
+                                                      m->nnz + nnz_chunk, m->n_genes, ctx->ingest_flag);
+    count_launch(ctx);
+  }
   CK(ctx, cudaGetLastError());
+  int bad = 0;
+  CK(ctx, cudaMemcpyAsync(&bad, ctx->ingest_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   dev_free(d_pchunk);
+  if (bad) {
+    cudaMemsetAsync(ctx->ingest_flag, 0, sizeof(int), ctx->stream);
+    m3b_set_error(ctx, "append: malformed CSC chunk (%s%s%s): the input must be a valid dgCMatrix slice -- non-decreasing "
+                       "column pointers, row indices in [0, n_genes) and strictly increasing inside every column",
+                  (bad & 1) ? "column pointers decrease; " : "", (bad & 2) ? "row index out of range; " : "",
+                  (bad & 4) ? "row indices not strictly increasing within a column" : "");
+    return M3B_E_DIMS;
+  }
   ctx->stats.h2d_bytes += (n_cells_chunk + 1) * 4 + nnz_chunk * 12;
   m->nnz += nnz_chunk;
   m->cells_appended += n_cells_chunk;

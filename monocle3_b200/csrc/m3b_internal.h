@@ -57,6 +57,9 @@ void comm_destroy(m3b_ctx* ctx);
 // in-place sum-allreduce of n doubles / int64 on the context stream (no-op if world==1)
 int comm_allreduce_f64(m3b_ctx* ctx, double* dev, size_t n);
 int comm_allreduce_i64(m3b_ctx* ctx, long long* dev, size_t n);
+int comm_allreduce_max_i64(m3b_ctx* ctx, long long* dev, size_t n);
+// all ranks agree on the next exchange sequence number (max over the ranks' counters + 2); a no-op when unsharded
+int comm_xchg_resync(m3b_ctx* ctx);
 int comm_p2p_handle(m3b_ctx* ctx, char* out64);
 int comm_p2p_open(m3b_ctx* ctx, const char* handles /* world x 64 bytes */);
 
@@ -96,6 +99,8 @@ struct m3b_ctx {
   size_t ev_used = 0;
   bool k1_timed = false, k2_timed = false;   // ev0/ev1 bracket the last K1 / K2 launch
   unsigned int* sched = nullptr;             // [2] dynamic unit counter + done counter (zeroed)
+  long long spin_timeout_cycles = 60000000000LL;  // bound of the in-kernel waits (m3b_create; M3B_XCHG_TIMEOUT_S)
+  int* ingest_flag = nullptr;                // device word raised by the ingest validation kernels
 };
 
 // ---------------------------------------------------------------------------
@@ -239,6 +244,7 @@ int launch_tile_stream(m3b_ctx* ctx, const TiledLayout& L, int op, const double*
 // out[row] = sum of the row's partials (fixed order: tile, then segment)
 int launch_combine_rows(m3b_ctx* ctx, const TiledLayout& L, double* out);
 long long spmv_algorithmic_bytes(const TiledLayout& L);
+long long spmv_stream_bytes(const TiledLayout& L);
 
 // flat.cu: the product kernel proper (OP_DOT) -- static, item-aligned partition of each tile's
 // entry stream over the warps, streamed flat with a register ring and reduced per item

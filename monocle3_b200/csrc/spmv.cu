@@ -496,3 +496,21 @@ long long spmv_algorithmic_bytes(const TiledLayout& L) {
   const long long nnz = L.nnz + (L.unit ? L.unit->nnz : 0);
   return 12LL * nnz + 8LL * (L.rows + L.cols) + 8LL * (L.rows + 1);
 }
+
+// EXACT DRAM bytes of one product launch over this layout (the physical counterpart of the
+// figure above): the two entry streams as stored (pads included), the plan descriptors, the
+// per-item slot / scale words, the dense operand (and the column scale of layout B) once --
+// re-reads by the other CTAs of a tile are served by L2 -- and one 8-byte partial per item.
+long long flat_plan_pieces(const struct FlatPlan* p);
+long long spmv_stream_bytes(const TiledLayout& L) {
+  const TiledLayout* U = L.unit;
+  long long b = 10LL * L.n_entries + 4LL * L.n_items + 8LL * L.n_items;
+  if (U) {
+    b += 2LL * U->n_entries + 4LL * U->n_items + 8LL * U->n_items;
+    if (U->item_scale) b += 8LL * U->n_items;
+    if (U->colscale) b += 8LL * L.cols;
+  }
+  b += 8LL * L.cols;
+  if (L.plan[0]) b += 16LL * flat_plan_pieces(L.plan[0]);
+  return b;
+}

@@ -106,6 +106,7 @@ class Context:
         out = {k: getattr(s, k) for k, _ in L.Stats._fields_}
         out["phase_ms"] = list(out["phase_ms"])
         out["host_ms"] = list(out["host_ms"])
+        out["select_ms"] = list(out["select_ms"])
         return out
 
     def set_flags(self, flags):
@@ -182,6 +183,9 @@ class DeviceMatrix:
         """counts: scipy.sparse.csc_matrix genes x (local) cells.  Appended in cell-range
         chunks whose nnz fits int32 (the dgCMatrix limit)."""
         G, Cn = counts.shape
+        if not counts.has_canonical_format:  # a dgCMatrix is sorted and duplicate-free; scipy need not be
+            counts = counts.copy()
+            counts.sum_duplicates()
         m = cls(ctx, G, Cn, n_cells_total, counts.nnz)
         indptr = np.asarray(counts.indptr)
         indices = np.ascontiguousarray(counts.indices, dtype=np.int32)

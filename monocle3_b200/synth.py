@@ -98,3 +98,41 @@ def synth_csc(n_genes, n_cells, density, n_types, seed=1, lo=0, hi=None, device=
     hi = n_cells if hi is None else hi
     indptr, indices, data = spec.cells(lo, hi)
     return sp.csc_matrix((data, indices, indptr), shape=(n_genes, hi - lo))
+
+
+def _concat_csc(parts):
+    """Concatenate cell ranges given as (indptr, indices, data) triples."""
+    parts = [p for p in parts if len(p[0]) > 1]
+    if not parts:
+        return np.zeros(1, dtype=np.int64), np.zeros(0, np.int32), np.zeros(0)
+    counts = np.concatenate([np.diff(p[0]) for p in parts])
+    indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return indptr, np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts])
+
+
+def balanced_shard(spec, rank, world, allgather=None):
+    """This rank's contiguous cell range of the ONE matrix `spec` describes, cut at nnz quantiles
+    of the global column pointer (dist.shard_ranges_by_nnz).  Every rank
+    generates its equal-cell range, the per-cell counts are all-gathered (`allgather`: see
+    dist.make_allgather), the cuts are computed identically everywhere, and the few cells that
+    moved across a cut are generated on top.  Returns (lo, hi, indptr, indices, data)."""
+    from .dist import shard_ranges_by_nnz, shard_ranges_even
+    if world == 1:
+        indptr, idx, val = spec.cells(0, spec.C)
+        return 0, spec.C, indptr, idx, val
+    lo0, hi0 = shard_ranges_even(spec.C, world)[rank]
+    indptr, idx, val = spec.cells(lo0, hi0)
+    all_counts = np.rint(allgather(np.diff(indptr).astype(np.float64))).astype(np.int64)
+    gptr = np.concatenate([[0], np.cumsum(all_counts)])
+    lo, hi = shard_ranges_by_nnz(gptr, world)[rank]
+    parts = []
+    if lo < lo0:
+        parts.append(spec.cells(lo, min(lo0, hi)))
+    a, z = max(lo, lo0), min(hi, hi0)
+    if a < z:
+        p0, p1 = int(indptr[a - lo0]), int(indptr[z - lo0])
+        parts.append((indptr[a - lo0:z - lo0 + 1] - p0, idx[p0:p1], val[p0:p1]))
+    if hi > hi0:
+        parts.append(spec.cells(max(hi0, lo), hi))
+    ip, ii, vv = _concat_csc(parts)
+    return lo, hi, ip, ii, vv
