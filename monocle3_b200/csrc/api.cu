@@ -260,6 +260,10 @@ void m3b_matrix_free(m3b_mat* m) {
   dev_free(m->scale);
   dev_free(m->Xdev);
   m3b_mat_set_bbuild(m, nullptr);
+  for (int q = 0; q < 2; ++q) {
+    dev_free(m->b_cnt[q]);
+    dev_free(m->b_base[q]);
+  }
   m->A.free_all();
   m->B.free_all();
   delete m;

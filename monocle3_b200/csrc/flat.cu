@@ -117,10 +117,14 @@ static long long env_ll(const char* name, long long dflt) {
 static long long fl_piece_general() { return env_ll("M3B_FLAT_PIECE_G", 8192); }
 static long long fl_piece_unit() { return env_ll("M3B_FLAT_PIECE_U", 32768); }
 
-static int build_one_plan(m3b_ctx* ctx, const TiledLayout& L, const HostTables& Tg, const HostTables* Tu, int n_cta,
-                          FlatPlan** out) {
-  const int n_tiles = L.n_tiles;
-  const long long rows = L.rows;
+// the plan as host vectors (pure host code: also what tools/host_tables_check.cu compares the
+// device builder with)
+struct HostPlan {
+  std::vector<int> cta_visit_ptr, visit_tile, gp_ptr, up_ptr;
+  std::vector<int4> gp, up;
+};
+static void plan_host(int n_tiles, long long rows, const HostTables& Tg, const HostTables* Tu, int n_cta, int warps,
+                      long long target_g, long long target_u, HostPlan& HP) {
   auto tile_items = [&](const HostTables& T, int t, int* i0, int* i1) {
     *i0 = T.row_item_ptr[(size_t)t * (rows + 1)];
     *i1 = T.row_item_ptr[(size_t)t * (rows + 1) + rows];
@@ -200,32 +204,38 @@ static int build_one_plan(m3b_ctx* ctx, const TiledLayout& L, const HostTables& 
   cta_visit_ptr[n_cta] = (int)visit_tile.size();
   const int n_visits = (int)visit_tile.size();
   // shares of every (visit, warp)
-  std::vector<std::vector<int4>> gshare((size_t)n_visits * FL_WARPS), ushare((size_t)n_visits * FL_WARPS);
+  std::vector<std::vector<int4>> gshare((size_t)n_visits * warps), ushare((size_t)n_visits * warps);
   for (int t = 0; t < n_tiles; ++t) {
     const int nc = (int)tile_ctas[t].size();
     if (nc == 0) continue;
-    const int W = nc * FL_WARPS;
+    const int W = nc * warps;
     for (int pass = 0; pass < (Tu ? 2 : 1); ++pass) {
       const HostTables& T = pass ? *Tu : Tg;
       int i0, i1;
       tile_items(T, t, &i0, &i1);
       std::vector<std::vector<int4>> sh;
-      split_tile(T.items, i0, i1, W, pass ? 8 : 2, pass ? fl_piece_unit() : fl_piece_general(), sh);
+      split_tile(T.items, i0, i1, W, pass ? 8 : 2, pass ? target_u : target_g, sh);
       for (int k = 0; k < nc; ++k) {
         const int c = tile_ctas[t][k];
         // the visit of CTA c that is tile t
         int v = -1;
         for (size_t q = 0; q < cta_tiles[c].size(); ++q)
           if (cta_tiles[c][q] == t) v = visit_of[c][q];
-        for (int w = 0; w < FL_WARPS; ++w) {
+        for (int w = 0; w < warps; ++w) {
           if (sh.empty()) continue;
-          (pass ? ushare : gshare)[(size_t)v * FL_WARPS + w] = sh[(size_t)k * FL_WARPS + w];
+          (pass ? ushare : gshare)[(size_t)v * warps + w] = sh[(size_t)k * warps + w];
         }
       }
     }
   }
-  std::vector<int> gp_ptr, up_ptr;
-  std::vector<int4> gp, up;
+  std::vector<int>& gp_ptr = HP.gp_ptr;
+  std::vector<int>& up_ptr = HP.up_ptr;
+  std::vector<int4>& gp = HP.gp;
+  std::vector<int4>& up = HP.up;
+  gp_ptr.clear();
+  up_ptr.clear();
+  gp.clear();
+  up.clear();
   for (size_t k = 0; k < gshare.size(); ++k) {
     gp_ptr.push_back((int)gp.size());
     gp.insert(gp.end(), gshare[k].begin(), gshare[k].end());
@@ -234,17 +244,25 @@ static int build_one_plan(m3b_ctx* ctx, const TiledLayout& L, const HostTables& 
   }
   gp_ptr.push_back((int)gp.size());
   up_ptr.push_back((int)up.size());
+  HP.cta_visit_ptr = cta_visit_ptr;
+  HP.visit_tile = visit_tile;
+}
+
+static int build_one_plan(m3b_ctx* ctx, const TiledLayout& L, const HostTables& Tg, const HostTables* Tu, int n_cta,
+                          FlatPlan** out) {
+  HostPlan HP;
+  plan_host(L.n_tiles, L.rows, Tg, Tu, n_cta, FL_WARPS, fl_piece_general(), fl_piece_unit(), HP);
   FlatPlan* P = new FlatPlan();
   *out = P;
   P->n_cta = n_cta;
-  P->n_visits = n_visits;
-  P->n_pieces = (long long)gp.size() + (long long)up.size();
-  RET(upload_vec(ctx, &P->cta_visit_ptr, cta_visit_ptr));
-  RET(upload_vec(ctx, &P->visit_tile, visit_tile));
-  RET(upload_vec(ctx, &P->gp_ptr, gp_ptr));
-  RET(upload_vec(ctx, &P->gp, gp));
-  RET(upload_vec(ctx, &P->up_ptr, up_ptr));
-  RET(upload_vec(ctx, &P->up, up));
+  P->n_visits = (int)HP.visit_tile.size();
+  P->n_pieces = (long long)HP.gp.size() + (long long)HP.up.size();
+  RET(upload_vec(ctx, &P->cta_visit_ptr, HP.cta_visit_ptr));
+  RET(upload_vec(ctx, &P->visit_tile, HP.visit_tile));
+  RET(upload_vec(ctx, &P->gp_ptr, HP.gp_ptr));
+  RET(upload_vec(ctx, &P->gp, HP.gp));
+  RET(upload_vec(ctx, &P->up_ptr, HP.up_ptr));
+  RET(upload_vec(ctx, &P->up, HP.up));
   CK(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
   return M3B_OK;
 }
@@ -271,6 +289,44 @@ int flat_build_plans(m3b_ctx* ctx, TiledLayout& L, const HostTables& Tg, const H
   RET(build_one_plan(ctx, L, Tg, Tu, ctx->sm_count, &L.plan[0]));
   if (L.n_tiles == 1 && ctx->sm_count > 2 * M3B_SIDE_CTA_RESERVE)
     RET(build_one_plan(ctx, L, Tg, Tu, ctx->sm_count - M3B_SIDE_CTA_RESERVE, &L.plan[1]));
+  if (L.n_items) {
+    k_mark_heads<<<(unsigned)((L.n_items + 255) / 256), 256, 0, ctx->stream>>>(L.idx, L.items, L.n_items);
+    count_launch(ctx);
+  }
+  if (L.unit && L.unit->n_items) {
+    TiledLayout& U = *L.unit;
+    k_mark_heads<<<(unsigned)((U.n_items + 255) / 256), 256, 0, ctx->stream>>>(U.idx, U.items, U.n_items);
+    count_launch(ctx);
+    dev_free(U.item_scale);
+    U.item_scale = nullptr;
+    if (U.rowscale) {
+      RET(dev_alloc(ctx, &U.item_scale, (size_t)U.n_items));
+      k_item_scale<<<(unsigned)((U.n_items + 255) / 256), 256, 0, ctx->stream>>>(U.items, U.n_items, U.rowscale, U.item_scale);
+      count_launch(ctx);
+    }
+  }
+  CK(ctx, cudaGetLastError());
+  return M3B_OK;
+}
+
+// Device-built plans (tables.cu): the same pieces as build_one_plan makes, computed per item on the
+// GPU.  Every (visit, warp) owns a fixed number of piece slots; a slot no item fell into has zero
+// groups and the kernel skips it.
+int flat_build_plans_device(m3b_ctx* ctx, TiledLayout& L) {
+  for (int k = 0; k < 2; ++k) {
+    flat_plan_free(L.plan[k]);
+    L.plan[k] = nullptr;
+  }
+  if (getenv("M3B_NO_FLAT")) return M3B_OK;
+  if (L.n_entries / 2 >= (1LL << 31) || (L.unit && L.unit->n_entries / 8 >= (1LL << 31))) return M3B_OK;  // 32-bit group offsets
+  const int n_plans = (L.n_tiles == 1 && ctx->sm_count > 2 * M3B_SIDE_CTA_RESERVE) ? 2 : 1;
+  for (int k = 0; k < n_plans; ++k) {
+    FlatPlan* P = new FlatPlan();
+    L.plan[k] = P;
+    P->n_cta = k == 0 ? ctx->sm_count : ctx->sm_count - M3B_SIDE_CTA_RESERVE;
+    RET(tables_build_plan(ctx, L, P->n_cta, FL_WARPS, fl_piece_general(), fl_piece_unit(), &P->cta_visit_ptr, &P->visit_tile,
+                          &P->gp_ptr, &P->gp, &P->up_ptr, &P->up, &P->n_visits, &P->n_pieces));
+  }
   if (L.n_items) {
     k_mark_heads<<<(unsigned)((L.n_items + 255) / 256), 256, 0, ctx->stream>>>(L.idx, L.items, L.n_items);
     count_launch(ctx);
@@ -493,6 +549,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
         const unsigned int* ip = reinterpret_cast<const unsigned int*>(a.gidx) + pc.x;
         const double2* vp = reinterpret_cast<const double2*>(a.gval) + pc.x;
         const int ng = pc.y, nr = (ng + 31) >> 5;
+        if (ng <= 0) continue;  // an empty slot of a device-built plan
         FlatState st;
         st.acc = 0.0;
         st.item = pc.z;
@@ -588,6 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
         const int4 pc = a.up[p];
         const uint4* ip = reinterpret_cast<const uint4*>(a.uidx) + pc.x;
         const int ng = pc.y, nr = (ng + 31) >> 5;
+        if (ng <= 0) continue;
         FlatState st;
         st.acc = 0.0;
         st.item = pc.z;

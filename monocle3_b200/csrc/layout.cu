@@ -124,6 +124,9 @@ void TiledLayout::free_all() {
   flat_plan_free(plan[0]);
   flat_plan_free(plan[1]);
   dev_free(item_scale);
+  dev_free(tile_len);
+  dev_free(item_tile);
+  dev_free(item_cum);
   dev_free(idx);
   dev_free(val);
   dev_free(items);
@@ -940,9 +943,63 @@ int build_layout_B(m3b_mat* m, bool split) {
       count_launch(ctx);
     }
     CK(ctx, cudaGetLastError());
-    cnt[q].resize((size_t)n_runs);
-    if (n_runs)
-      CK(ctx, cudaMemcpyAsync(cnt[q].data(), d_cnt[q], n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (use_host_tables()) {
+      cnt[q].resize((size_t)n_runs);
+      if (n_runs)
+        CK(ctx, cudaMemcpyAsync(cnt[q].data(), d_cnt[q], n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  if (!use_host_tables()) {
+    // ---- device tables: bases, streams, items / slots / chunks without leaving the GPU ----
+    for (int q = 0; q < n_cls; ++q) RET(dev_alloc(ctx, &d_base[q], (size_t)n_runs + 1));
+    long long n_ent[2] = {0, 0};
+    RET(tables_compute_bases(ctx, n_tiles, n_sel, d_cnt, n_cls, d_base, n_ent));
+    for (int q = 0; q < n_cls; ++q) {
+      TiledLayout& Lq = *Ls[q];
+      Lq.n_entries = n_ent[q];
+      RET(dev_alloc(ctx, &Lq.idx, (size_t)std::max<long long>(n_ent[q], 1)));
+      if (q == 0) RET(dev_alloc(ctx, &Lq.val, (size_t)std::max<long long>(n_ent[q], 1)));
+      if (n_runs) {
+        k_fill_pads<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(d_cnt[q], d_base[q], n_runs, q == 1 ? 8 : 4,
+                                                                              q == 1 ? Lq.tile_w : 0, Lq.idx, Lq.val);
+        count_launch(ctx);
+      }
+    }
+    if (n_runs && m->n_cells) {
+      for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG) {
+        const int g1 = std::min(n_sel, g0 + TB_GSEG);
+        const size_t smem = std::max((size_t)(g1 - g0) * 8, scatter_smem_min);
+        if (both) {
+          k_scatter_B2<<<(unsigned)n_chunks, TB_THREADS, smem, ctx->stream>>>(
+              m->p, m->i, m->y, m->x, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[0], H[1],
+              d_base[0], d_base[1], L.idx, L.val, L.unit->idx);
+          count_launch(ctx);
+        } else {
+          for (int q = 0; q < n_cls; ++q) {
+            k_scatter_B<<<(unsigned)n_chunks, TB_THREADS, smem, ctx->stream>>>(
+                m->p, m->i, m->y, m->x, split ? q + 1 : 0, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk,
+                m->n_cells, H[q], d_base[q], Ls[q]->idx, Ls[q]->val);
+            count_launch(ctx);
+          }
+        }
+      }
+    }
+    CK(ctx, cudaGetLastError());
+    RET(tables_build(ctx, L, n_sel, nullptr, d_cnt, d_base));
+    dev_free(m->sel_nnz);
+    RET(dev_alloc(ctx, &m->sel_nnz, (size_t)std::max(n_sel, 1)));
+    RET(tables_row_stats(ctx, n_tiles, n_sel, nullptr, d_cnt[0], split ? d_cnt[1] : nullptr, m->sel_nnz, nullptr));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    // the counts and run offsets stay on the device for the re-map after the zero-gene filter
+    for (int q = 0; q < 2; ++q) {
+      dev_free(m->b_cnt[q]);
+      dev_free(m->b_base[q]);
+      m->b_cnt[q] = d_cnt[q];
+      m->b_base[q] = d_base[q];
+      dev_free(H[q]);
+    }
+    if (dbg) fprintf(stderr, "  layout B (device tables): %.2f ms\n", now_ms() - tb0);
+    return M3B_OK;
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   const double tb1 = now_ms();
@@ -1024,8 +1081,49 @@ int build_layout_B(m3b_mat* m, bool split) {
 static int bank_reorder(m3b_ctx* ctx, TiledLayout& L);
 
 // After the keep mask is known: re-map B's items to kept rows (no data movement).
+static int finish_selection_device(m3b_mat* m, unsigned char* keep_host) {
+  m3b_ctx* ctx = m->ctx;
+  if (!m->b_cnt[0] || !m->b_base[0]) {
+    m3b_set_error(ctx, "internal: layout B tables missing");
+    return M3B_E_STATE;
+  }
+  const int n_sel = m->n_sel;
+  const bool split = m->B.unit != nullptr;
+  std::vector<int> kept_of_sel(std::max(n_sel, 1));
+  int nk = 0;
+  for (int s = 0; s < n_sel; ++s) kept_of_sel[s] = keep_host[s] ? nk++ : -1;
+  m->n_kept = nk;
+  dev_free(m->kept_of_sel);
+  RET(dev_alloc(ctx, &m->kept_of_sel, (size_t)std::max(n_sel, 1)));
+  if (n_sel) CK(ctx, cudaMemcpyAsync(m->kept_of_sel, kept_of_sel.data(), n_sel * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (nk != n_sel) {  // some rows dropped: re-map the tables (no data moves), turn their entries into pads
+    m->B.rows = nk;
+    if (split) m->B.unit->rows = nk;
+    RET(tables_build(ctx, m->B, n_sel, m->kept_of_sel, m->b_cnt, m->b_base));
+    RET(tables_neutralize_dropped(ctx, m->B, n_sel, m->kept_of_sel, m->b_cnt, m->b_base));
+  }
+  dev_free(m->kept_nnz);
+  dev_free(m->kept_padlen);
+  RET(dev_alloc(ctx, &m->kept_nnz, (size_t)std::max(nk, 1)));
+  RET(dev_alloc(ctx, &m->kept_padlen, (size_t)std::max(nk, 1)));
+  RET(tables_row_stats(ctx, m->B.n_tiles, n_sel, m->kept_of_sel, m->b_cnt[0], split ? m->b_cnt[1] : nullptr, m->kept_nnz,
+                       m->kept_padlen));
+  RET(bank_reorder(ctx, m->B));
+  if (split) RET(bank_reorder(ctx, *m->B.unit));
+  RET(flat_build_plans_device(ctx, m->B));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));  // kept_of_sel (host vector) goes out of scope
+  for (int q = 0; q < 2; ++q) {
+    dev_free(m->b_cnt[q]);
+    dev_free(m->b_base[q]);
+    m->b_cnt[q] = nullptr;
+    m->b_base[q] = nullptr;
+  }
+  return M3B_OK;
+}
+
 int finish_selection(m3b_mat* m, unsigned char* keep_host) {
   m3b_ctx* ctx = m->ctx;
+  if (!use_host_tables()) return finish_selection_device(m, keep_host);
   BBuild* bb = (BBuild*)m->b_host_tables;
   if (!bb) {
     m3b_set_error(ctx, "internal: layout B tables missing");
@@ -1410,8 +1508,46 @@ int build_layout_A(m3b_mat* m, bool split) {
       count_launch(ctx);
     }
     CK(ctx, cudaGetLastError());
-    cnt[q].resize((size_t)n_runs);
-    if (n_runs) CK(ctx, cudaMemcpyAsync(cnt[q].data(), d_cnt[q], n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (use_host_tables()) {
+      cnt[q].resize((size_t)n_runs);
+      if (n_runs) CK(ctx, cudaMemcpyAsync(cnt[q].data(), d_cnt[q], n_runs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  if (!use_host_tables()) {
+    for (int q = 0; q < n_cls; ++q) RET(dev_alloc(ctx, &d_base[q], (size_t)n_runs + 1));
+    if (!m->n_cells)
+      for (int q = 0; q < n_cls; ++q) CK(ctx, cudaMemsetAsync(d_cnt[q], 0, std::max<long long>(n_runs, 1) * sizeof(int), ctx->stream));
+    long long n_ent[2] = {0, 0};
+    RET(tables_compute_bases(ctx, L.n_tiles, L.rows, d_cnt, n_cls, d_base, n_ent));
+    for (int q = 0; q < n_cls; ++q) {
+      Ls[q]->n_entries = n_ent[q];
+      RET(dev_alloc(ctx, &Ls[q]->idx, (size_t)std::max<long long>(n_ent[q], 1)));
+      if (q == 0) RET(dev_alloc(ctx, &Ls[q]->val, (size_t)std::max<long long>(n_ent[q], 1)));
+    }
+    if (n_runs) {
+      if (both) {
+        k_scatter_A2<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles,
+                                                      d_base[0], d_base[1], L.idx, L.val, L.unit->idx);
+        count_launch(ctx);
+      } else {
+        for (int q = 0; q < n_cls; ++q) {
+          k_scatter_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, split ? q + 1 : 0, m->kept_of_gene, m->n_cells,
+                                                       L.tile_w, L.n_tiles, d_base[q], Ls[q]->idx, Ls[q]->val);
+          count_launch(ctx);
+        }
+      }
+    }
+    CK(ctx, cudaGetLastError());
+    RET(tables_build(ctx, L, L.rows, nullptr, d_cnt, d_base));
+    RET(bank_reorder(ctx, L));
+    if (split) RET(bank_reorder(ctx, *L.unit));
+    RET(flat_build_plans_device(ctx, L));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < 2; ++q) {
+      dev_free(d_cnt[q]);
+      dev_free(d_base[q]);
+    }
+    return M3B_OK;
   }
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   for (int q = 0; q < n_cls; ++q) compute_bases(cnt[q], L.n_tiles, L.rows, T[q], (q == 1) ? SHAPE_UNIT : SHAPE_GENERAL);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -165,6 +166,10 @@ struct TiledLayout {
   // grid of the side-stream launch (single-tile layouts only).  Owned by the general layout.
   struct FlatPlan* plan[2] = {nullptr, nullptr};
   double* item_scale = nullptr;  // unit layouts with a rowscale: rowscale[row of item], per item
+  // device-built tables only (tables.cu): kept entries per tile, tile and in-tile position of every item
+  long long* tile_len = nullptr;  // [n_tiles]
+  int* item_tile = nullptr;       // [n_items]
+  long long* item_cum = nullptr;  // [n_items]
   void free_all();
 };
 
@@ -207,7 +212,10 @@ struct m3b_mat {
   long long* kept_nnz = nullptr;// [n_kept] local nnz
   long long* kept_padlen = nullptr;  // [n_kept] local padded run length (>= nnz)
   double* mean_sparse = nullptr;     // [n_kept] mean of the stored sparse part (center - f0)
-  void* b_host_tables = nullptr;  // host copy of B's run counts between build and re-map
+  void* b_host_tables = nullptr;  // host copy of B's run counts between build and re-map (M3B_HOST_TABLES=1)
+  // device-side counterpart: per-(tile, selected row) entry counts and run offsets of B, general / unit
+  int* b_cnt[2] = {nullptr, nullptr};
+  long long* b_base[2] = {nullptr, nullptr};
   TiledLayout A;  // rows = local cells, cols = kept genes   (cells-out product, K4)
   TiledLayout B;  // rows = kept genes,  cols = local cells  (genes-out product, K5)
   double* center = nullptr;  // [n_kept] mean of the (implicit-dense) matrix
@@ -252,6 +260,22 @@ void flat_plan_free(struct FlatPlan* p);
 int flat_build_plans(m3b_ctx* ctx, TiledLayout& L, const HostTables& Tg, const HostTables* Tu);
 int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStream_t stream, int max_cta);
 int flat_init(m3b_ctx* ctx);
+int flat_build_plans_device(m3b_ctx* ctx, TiledLayout& L);
+
+// tables.cu: the layout tables and flat plans built on the device (default; M3B_HOST_TABLES=1 keeps
+// the host builders of layout.cu / flat.cu)
+int tables_compute_bases(m3b_ctx* ctx, int n_tiles, long long rows_in, const int* const cnt[2], int n_cls,
+                         long long* const base[2], long long n_entries[2]);
+int tables_build(m3b_ctx* ctx, TiledLayout& L, long long rows_in, const int* row_map, const int* const cnt[2],
+                 const long long* const base[2]);
+int tables_neutralize_dropped(m3b_ctx* ctx, TiledLayout& L, long long rows_in, const int* row_map, const int* const cnt[2],
+                              const long long* const base[2]);
+int tables_row_stats(m3b_ctx* ctx, int n_tiles, long long rows_in, const int* row_map, const int* cnt_g, const int* cnt_u,
+                     long long* nnz_out, long long* padlen_out);
+int tables_build_plan(m3b_ctx* ctx, const TiledLayout& L, int n_cta, int warps, long long target_g, long long target_u,
+                      int** cta_visit_ptr, int** visit_tile, int** gp_ptr, int4** gp, int** up_ptr, int4** up, int* n_visits,
+                      long long* n_pieces);
+static inline bool use_host_tables() { return getenv("M3B_HOST_TABLES") != nullptr; }
 
 // aggregate.cu
 int run_detect_genes(m3b_mat* m, double min_expr, long long* num_cells_expressed, long long* num_genes_expressed);
