@@ -332,6 +332,139 @@ def run_reference_project(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# cfg5: preprocess_transform of query cells onto saved loadings (K10)
+# ---------------------------------------------------------------------------------------------
+def run_project_bench(args, wl, ctx, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks, ClockSampler, pinned,
+                      peak, peak_src, workload_config):
+    """A STEP is preprocess_transform of the whole query (R/projection.R:102-149): normalize (K2) -> zero-gene
+    filter -> tiled sparse x dense projection (K10) -> embedding back on the host.  The model (loadings 30 000 x 100,
+    centre, scale) comes from preprocess_cds on `model_cells` reference cells of the same gene set, sharded like the
+    query (its cost is outside the timed region).  value: counts resident in HBM; e2e: new_cell_data_set +
+    preprocess_transform from pinned host buffers."""
+    import scipy.sparse as sp
+    import torch
+    import monocle3_b200 as m3
+    from monocle3_b200 import dist as m3dist
+    from monocle3_b200.synth import SynthSpec, balanced_shard
+    ag = m3dist.make_allgather() if world > 1 else None
+
+    def shard_of(cells, seed):
+        spec = SynthSpec(wl["n_genes"], cells, wl["density"], wl["n_types"], seed)
+        lo, hi, indptr, indices, data = balanced_shard(spec, rank, world, ag)
+        keepalive = [pinned(indptr.astype(np.int32)), pinned(indices), pinned(data)]
+        c = sp.csc_matrix((keepalive[2][0], keepalive[1][0], keepalive[0][0]), shape=(wl["n_genes"], hi - lo), copy=False)
+        return c, keepalive
+
+    # ---- the model: PCA of the reference cells (sharded like any other run) ----
+    ref_counts, ka_ref = shard_of(wl["model_cells"], wl["model_seed"])
+    shard_ref = m3dist.make_shard(wl["model_cells"]) if world > 1 else None
+    cds_ref = m3.new_cell_data_set(ref_counts, shard=shard_ref)
+    cds_ref = m3.preprocess_cds(cds_ref, num_dim=wl["num_dim"])
+    model = cds_ref.reduce_dim_aux["PCA"]
+    cds_ref._dev.free()
+    del cds_ref, ref_counts, ka_ref
+    torch.cuda.empty_cache()
+    nv = model["model"]["svd_v"].shape[1]
+
+    # ---- the query shard ----
+    counts, ka_q = shard_of(wl["cells"], wl["seed"])
+    shard_q = m3dist.make_shard(wl["cells"]) if world > 1 else None
+    nnz_local = int(counts.nnz)
+    cds = m3.new_cell_data_set(counts, shard=shard_q)
+    cds.reduce_dim_aux["PCA"] = model
+
+    def step():
+        m3.preprocess_transform(cds, "PCA")
+        return cds.reduced_dims["PCA"]
+
+    for _ in range(args.warmup):
+        Yq = step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ctx.reset_stats()
+    ctx.timer_start()
+    k10 = []
+    for _ in range(args.steps):
+        Yq = step()
+        k10.append(ctx.stats()["k10_ms"])
+    ms_total = ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    st = ctx.stats()
+    ms_step = max_over_ranks(ms_total) / args.steps
+    launches = int(sum_over_ranks(st["kernel_launches"]))
+    value = wl["cells"] / (ms_step / 1e3)
+    k10_ms = max_over_ranks(float(np.mean(k10)))
+    fp64_peak = ctx.measure_fp64_peak()
+    nnz_total = int(sum_over_ranks(nnz_local))
+    nnz_max = int(max_over_ranks(nnz_local))
+    flops_rank = 2.0 * nnz_max * nv
+    tfl = flops_rank / (k10_ms * 1e-3) / 1e12 if k10_ms > 0 else 0.0
+    hbm_bytes = 12.0 * nnz_max + 8.0 * counts.shape[1] * nv + 8.0 * wl["n_genes"] * nv
+    roofline = {"bound": "tensor", "bound_note": "fp64 FMA (CUDA-core DFMA; tcgen05 has no fp64 kind) -- SURVEY 8d names the fp64-FMA "
+                "roof for K10; the kernel's physical limit is the shared-memory pipe: 8 B x nv per non-zero at 128 B/clk/SM",
+                "kernel": "k_project_tiled (K10)", "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": tfl / fp64_peak if fp64_peak else None, "traffic": None,
+                "peak_source": "measured in this run (m3b_measure_fp64_peak: 8 DFMA chains/thread, 2x1024 threads/SM)",
+                "avg_launch_us": 1e3 * k10_ms, "flops_per_launch": flops_rank,
+                "algorithmic_hbm_bytes_per_launch": hbm_bytes, "hbm_gbs": hbm_bytes / (k10_ms * 1e-3) / 1e9 if k10_ms > 0 else None,
+                "smem_gather_bytes_per_launch": 8.0 * nv * nnz_max,
+                "smem_gather_tbs": 8.0 * nv * nnz_max / (k10_ms * 1e-3) / 1e12 if k10_ms > 0 else None,
+                "k10_share_of_step": k10_ms / ms_step}
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            c = m3.new_cell_data_set(counts, shard=shard_q)
+            c.reduce_dim_aux["PCA"] = model
+            m3.preprocess_transform(c, "PCA")
+            y = c.reduced_dims["PCA"]
+            c._dev.free()
+            return y
+        cds._dev.free()
+        cds._dev = None
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step()
+        barrier()
+        ctx.reset_stats()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            e2e_step()
+        ms_e2e_total = ctx.timer_stop()
+        barrier()
+        ste = ctx.stats()
+        ms_e2e = max_over_ranks(ms_e2e_total) / args.steps
+        e2e = {"value": wl["cells"] / (ms_e2e / 1e3), "unit": "cells/s",
+               "h2d_bytes_per_step": int(sum_over_ranks(ste["h2d_bytes"]) / args.steps),
+               "d2h_bytes_per_step": int(sum_over_ranks(ste["d2h_bytes"]) / args.steps), "ms_per_step": ms_e2e}
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import monocle3_ref as ref
+        n = min(2048, counts.shape[1])
+        sub = sp.csc_matrix((np.asarray(counts.data[:counts.indptr[n]]), np.asarray(counts.indices[:counts.indptr[n]]),
+                             np.asarray(counts.indptr[:n + 1]).astype(np.int64)), shape=(wl["n_genes"], n))
+        mdl = dict(model["model"])
+        names = np.asarray(mdl["svd_v_rownames"]).astype(np.int64)
+        gidx = np.full(wl["n_genes"], -1, dtype=np.int64)
+        gidx[names] = np.arange(len(names))
+        sf_sub = m3.size_factors(cds)[:n]
+        t0 = time.perf_counter()
+        Yo = ref.preprocess_transform(sub, sf_sub, mdl, gidx)
+        dt = time.perf_counter() - t0
+        err = float(np.max(np.abs(Yo - Yq[:n]))) if Yo.shape == Yq[:n].shape else float("nan")
+        cpu_baseline = {"value": n / dt, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": "restated preprocess_transform (block densified like DelayedArray, then dgemm on all threads) on the "
+                                  "first %d query cells (%.2f s; the block-wise algorithm is linear in cells); max |Y_gpu - Y_cpu| on "
+                                  "that block = %.2e" % (n, dt, err)}
+    return {"value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(wl, world), "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "project": {"nnz_total": nnz_total, "nnz_max_shard": nnz_max, "nv": int(nv), "k10_ms": k10_ms,
+                        "model_iter": model["irlba"]["iter"], "model_mprod": model["irlba"]["mprod"]}}
+
+
+# ---------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     wl = args.wl
@@ -386,7 +519,6 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
     if wl["key"] == "cfg5":
-        from bench_project import run_project_bench
         out = run_project_bench(args, wl, ctx, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks,
                                 ClockSampler, pinned, peak, peak_src, workload_config)
         if rank == 0:

@@ -165,6 +165,12 @@ int m3b_export_values(m3b_mat* mat, double* y /* nnz_local */);
  * (1 = kept), n_kept the number of kept genes G'.  Collective across ranks. */
 int m3b_select_genes(m3b_mat* mat, const int32_t* gene_order, int32_t n_sel,
                      uint8_t* keep, int32_t* n_kept);
+/* The same selection and zero-gene filter for the PROJECTION path (preprocess_transform,
+ * R/projection.R:117-133), without the two product layouts IRLBA needs: only m3b_project may
+ * follow.  Gene orders that are not increasing, negative values and the dense pseudo-count paths
+ * are handed to m3b_select_genes internally.  Collective across ranks. */
+int m3b_select_genes_for_transform(m3b_mat* mat, const int32_t* gene_order, int32_t n_sel,
+                                   uint8_t* keep, int32_t* n_kept);
 /* Exact per-selected-gene bookkeeping after m3b_select_genes (local shard). */
 int m3b_gene_nnz(m3b_mat* mat, int64_t* nnz_per_sel_gene /* n_sel */);
 
@@ -272,8 +278,12 @@ typedef struct m3b_stats {
   /* host wall clock of the phases of the last m3b_select_genes (ms): [0] layout B build
    * [1] row sums + keep mask [2] re-map + plans of B [3] layout A build + plans */
   double  select_ms[4];
+  double  k10_ms;              /* CUDA-event time of the last K10 (projection) kernel(s)  */
 } m3b_stats;
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);
+/* Measured fp64 FMA throughput of the device (TFLOP/s): the roof K10 (projection) is reported
+ * against; SURVEY 8(d) notes it is not among the driver's measured peaks. */
+int m3b_measure_fp64_peak(m3b_ctx* ctx, double* tflops);
 int m3b_reset_stats(m3b_ctx* ctx);
 /* flags for m3b_create / m3b_set_flags */
 #define M3B_FLAG_TIME_SPMV 1  /* bracket every SpMV launch with CUDA events (read back after the run) */

@@ -43,7 +43,7 @@ class Stats(C.Structure):
                 ("svd_sweeps", C.c_int64), ("host_ms", C.c_double * 4),
                 ("svd_fallbacks", C.c_int64), ("k1_ms", C.c_double), ("k2_ms", C.c_double),
                 ("svd_fallback_reasons", C.c_int64), ("spmv_stream_bytes_cells_out", C.c_int64),
-                ("spmv_stream_bytes_genes_out", C.c_int64), ("select_ms", C.c_double * 4)]
+                ("spmv_stream_bytes_genes_out", C.c_int64), ("select_ms", C.c_double * 4), ("k10_ms", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol include/m3b.h declares
@@ -77,6 +77,7 @@ SIGNATURES = {
     "m3b_normalize": (C.c_int, [_P, _dp, C.c_int, C.c_double]),
     "m3b_export_values": (C.c_int, [_P, _dp]),
     "m3b_select_genes": (C.c_int, [_P, _ip, C.c_int32, C.POINTER(C.c_uint8), _ip]),
+    "m3b_select_genes_for_transform": (C.c_int, [_P, _ip, C.c_int32, C.POINTER(C.c_uint8), _ip]),
     "m3b_gene_nnz": (C.c_int, [_P, _lp]),
     "m3b_gene_moments": (C.c_int, [_P, _dp, _dp]),
     "m3b_knn_self": (C.c_int, [_P, _dp, C.c_int64, C.c_int32, C.c_int32, _ip, _dp]),
@@ -90,6 +91,7 @@ SIGNATURES = {
                                        _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "m3b_project": (C.c_int, [_P, _ip, C.c_int32, _dp, _dp, _dp, C.c_int, _dp, C.c_int64]),
     "m3b_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "m3b_measure_fp64_peak": (C.c_int, [_P, _dp]),
     "m3b_reset_stats": (C.c_int, [_P]),
     "m3b_set_flags": (C.c_int, [_P, C.c_int]),
     "m3b_timer_start": (C.c_int, [_P]),

@@ -430,13 +430,22 @@ def preprocess_transform(cds, reduction_method="PCA", block_size=None, cores=1):
     dev = _normalize_on_device(cds, model["norm_method"], model["pseudo_count"])  # :109
     if cds.counts.shape[0] == 0:
         raise ValueError("all rows have standard deviation zero")
-    keep = dev.select_genes(None)  # :117-118
+    light = reduction_method == "PCA"  # the LSI branch rewrites the product layouts (TF-IDF): it needs them
+    keep = dev.select_genes(None, for_transform=light)  # :117-118
     kept_names = cds.gene_names[keep]
-    lut = {g: k for k, g in enumerate(model["svd_v_rownames"])}
     # intersect(rownames(rotation), rownames(FM)) is in the MODEL's order (:121-122); every kept
     # query gene must be in the model, otherwise FM[intersect_genes,] would silently drop rows --
     # R stops when match() yields NA.
-    model_row = np.array([lut.get(g, -1) for g in kept_names], dtype=np.int32)
+    model_names = np.asarray(model["svd_v_rownames"])
+    if len(model_names) == len(kept_names) and np.array_equal(model_names, kept_names):
+        model_row = np.arange(len(kept_names), dtype=np.int32)  # the usual case: same gene set, same order
+    else:  # match(kept_names, model_names) with sorted look-ups (no Python-level loop over 30k names)
+        order = np.argsort(model_names, kind="stable")
+        pos = np.searchsorted(model_names, kept_names, sorter=order)
+        pos = np.clip(pos, 0, max(len(model_names) - 1, 0))
+        cand = order[pos] if len(model_names) else np.zeros(len(kept_names), dtype=np.int64)
+        hit = (model_names[cand] == kept_names) if len(model_names) else np.zeros(len(kept_names), dtype=bool)
+        model_row = np.where(hit, cand, -1).astype(np.int32)
     n_common = int(np.sum(model_row >= 0))
     if len(kept_names) and n_common / len(kept_names) < 0.5:  # :128-130
         warnings.warn("fewer than half the genes in the subject matrix are also in the reference matrix: "
@@ -444,7 +453,7 @@ def preprocess_transform(cds, reduction_method="PCA", block_size=None, cores=1):
     if np.any(model_row < 0):
         # genes of the query that the model does not know are dropped by the intersect (:121,133)
         qidx = np.nonzero(keep)[0][model_row >= 0]
-        keep2 = dev.select_genes(qidx.astype(np.int32))
+        keep2 = dev.select_genes(qidx.astype(np.int32), for_transform=light)
         if not np.all(keep2):
             raise RuntimeError("internal: filter changed between passes")
         model_row = model_row[model_row >= 0]

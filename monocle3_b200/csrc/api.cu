@@ -451,6 +451,10 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
     }
     sel_of_gene[g] = s;
   }
+  m->sel_monotone = true;
+  if (gene_order)
+    for (int s = 1; s < n_sel; ++s)
+      if (gene_order[s] <= gene_order[s - 1]) m->sel_monotone = false;
   const bool dbg = getenv("M3B_DEBUG_TIMING") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
@@ -500,12 +504,28 @@ int m3b_select_genes(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8
   if (keep) memcpy(keep, kp.data(), n_sel);
   if (n_kept) *n_kept = m->n_kept;
   m->selected = true;
+  m->layouts_built = true;
   m->moments_done = false;
   m->tfidf_applied = false;
   ctx->stats.spmv_bytes_cells_out = spmv_algorithmic_bytes(m->A);
   ctx->stats.spmv_bytes_genes_out = spmv_algorithmic_bytes(m->B);
   ctx->stats.spmv_stream_bytes_cells_out = spmv_stream_bytes(m->A);
   ctx->stats.spmv_stream_bytes_genes_out = spmv_stream_bytes(m->B);
+  return M3B_OK;
+}
+
+int m3b_select_genes_for_transform(m3b_mat* m, const int32_t* gene_order, int32_t n_sel, uint8_t* keep, int32_t* n_kept) {
+  if (!m) return M3B_E_DIMS;
+  m3b_ctx* ctx = m->ctx;
+  if (!m->normalized) {
+    m3b_set_error(ctx, "m3b_select_genes_for_transform before m3b_normalize");
+    return M3B_E_STATE;
+  }
+  cudaSetDevice(ctx->device);
+  int fallback = 0, nk = 0;
+  RET(run_select_for_transform(m, gene_order, n_sel, keep, &nk, &fallback));
+  if (fallback) return m3b_select_genes(m, gene_order, n_sel, keep, n_kept);
+  if (n_kept) *n_kept = nk;
   return M3B_OK;
 }
 
@@ -544,7 +564,7 @@ int m3b_knn_self(m3b_ctx* ctx, const double* X, int64_t n, int32_t d, int32_t k,
 int m3b_gene_nnz(m3b_mat* m, int64_t* nnz_per_sel_gene) {
   if (!m || !nnz_per_sel_gene) return M3B_E_DIMS;
   m3b_ctx* ctx = m->ctx;
-  if (!m->selected) {
+  if (!m->selected || !m->layouts_built) {
     m3b_set_error(ctx, "m3b_gene_nnz before m3b_select_genes");
     return M3B_E_STATE;
   }
@@ -559,7 +579,7 @@ int m3b_gene_nnz(m3b_mat* m, int64_t* nnz_per_sel_gene) {
 int m3b_gene_moments(m3b_mat* m, double* center, double* scale) {
   if (!m) return M3B_E_DIMS;
   m3b_ctx* ctx = m->ctx;
-  if (!m->selected) {
+  if (!m->selected || !m->layouts_built) {
     m3b_set_error(ctx, "m3b_gene_moments before m3b_select_genes");
     return M3B_E_STATE;
   }
@@ -584,7 +604,7 @@ int m3b_pca_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double sv
                   int scale, double* d, double* V, double* X, int64_t ldx, double* center_out, double* scale_out,
                   int* iter, int* mprod) {
   if (!m || !v0 || !d) return M3B_E_DIMS;
-  if (!m->selected) {
+  if (!m->selected || !m->layouts_built) {
     m3b_set_error(m->ctx, "m3b_pca_irlba before m3b_select_genes");
     return M3B_E_STATE;
   }
@@ -596,7 +616,7 @@ int m3b_pca_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double sv
 int m3b_pca_irlba_device(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol, const double* v0,
                          int center, int scale, double* d, int* iter, int* mprod) {
   if (!m || !v0 || !d) return M3B_E_DIMS;
-  if (!m->selected) {
+  if (!m->selected || !m->layouts_built) {
     m3b_set_error(m->ctx, "m3b_pca_irlba_device before m3b_select_genes");
     return M3B_E_STATE;
   }
@@ -610,6 +630,53 @@ int m3b_project(m3b_mat* q, const int32_t* model_row, int32_t n_model, const dou
   if (!q || !model_row || !V || !Y) return M3B_E_DIMS;
   cudaSetDevice(q->ctx->device);
   return run_project(q, model_row, n_model, V, center, scale, nv, Y, ldy);
+}
+
+// fp64 FMA peak of this device, measured: the roof the projection kernel (K10) is reported against
+// (MEASURED_PEAKS.json has no fp64 figure).  8 independent DFMA chains per thread, 2 x 1024-thread
+// CTAs per SM, CUDA events; best of 5.
+__global__ void __launch_bounds__(1024) k_fp64_peak(double* __restrict__ out, int iters, double x, double y) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1e-3 * (threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = fma(a[k], x, y);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
+
+int m3b_measure_fp64_peak(m3b_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return M3B_E_DIMS;
+  cudaSetDevice(ctx->device);
+  const int grid = ctx->sm_count * 2, threads = 1024, iters = 4096;
+  double* d = nullptr;
+  RET(dev_alloc(ctx, &d, (size_t)grid * threads));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(ctx->evk0, ctx->stream);
+    k_fp64_peak<<<grid, threads, 0, ctx->stream>>>(d, iters, 0.999999, 1e-7);
+    cudaEventRecord(ctx->evk1, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1);
+    const double fl = 2.0 * 32.0 * (double)iters * (double)grid * (double)threads;
+    if (rep > 0 && ms > 0.f) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  count_launch(ctx, 6);
+  dev_free(d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || best == 0.0) {
+    m3b_set_error(ctx, "m3b_measure_fp64_peak: %s", cudaGetErrorString(e));
+    return M3B_E_CUDA;
+  }
+  *tflops = best;
+  return M3B_OK;
 }
 
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out) {

@@ -56,6 +56,7 @@ struct FlatPlan {
 };
 
 long long flat_plan_pieces(const FlatPlan* p) { return p ? p->n_pieces : 0; }
+bool flat_has_plan(const TiledLayout& L, int n_cta) { return L.plan[1] && L.plan[1]->n_cta == n_cta; }
 
 void flat_plan_free(FlatPlan* p) {
   if (!p) return;
@@ -319,7 +320,8 @@ int flat_build_plans_device(m3b_ctx* ctx, TiledLayout& L) {
   }
   if (getenv("M3B_NO_FLAT")) return M3B_OK;
   if (L.n_entries / 2 >= (1LL << 31) || (L.unit && L.unit->n_entries / 8 >= (1LL << 31))) return M3B_OK;  // 32-bit group offsets
-  const int n_plans = (L.n_tiles == 1 && ctx->sm_count > 2 * M3B_SIDE_CTA_RESERVE) ? 2 : 1;
+  // [1]: the reduced grid of the side-stream launch (the next cycle's first product under the restart SVD)
+  const int n_plans = (ctx->sm_count > 2 * M3B_SIDE_CTA_RESERVE) ? 2 : 1;
   for (int k = 0; k < n_plans; ++k) {
     FlatPlan* P = new FlatPlan();
     L.plan[k] = P;

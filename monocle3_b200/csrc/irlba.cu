@@ -1663,7 +1663,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       // final before the SVD: run it on the side stream underneath the (latency-bound, few-SM)
       // restart SVD.  It takes all but 28 SMs so that the SVD kernels find free ones.  If this
       // restart turns out to be the last one the product is simply not used.
-      if (!ctx->small_svd && m->A.n_tiles == 1 && ctx->sm_count > 56 && it + 1 < maxit) {
+      if (!ctx->small_svd && flat_has_plan(m->A, ctx->sm_count - M3B_SIDE_CTA_RESERVE) && ctx->sm_count > 56 && it + 1 < maxit) {
         ICK(cudaEventRecord(evF, ctx->stream));
         ICK(cudaStreamWaitEvent(ctx->stream2, evF, 0));
         k_make_xs<<<I.nb_n, NT, 0, ctx->stream2>>>(I.F, I.s, I.ce, n, I.xs, I.pb);

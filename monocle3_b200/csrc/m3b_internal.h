@@ -99,6 +99,7 @@ struct m3b_ctx {
   std::vector<int> ev_kind;  // 0 = cells-out (K4), 1 = genes-out (K5)
   size_t ev_used = 0;
   bool k1_timed = false, k2_timed = false;   // ev0/ev1 bracket the last K1 / K2 launch
+  bool k10_timed = false;                    // ... the K10 (projection) kernel
   unsigned int* sched = nullptr;             // [2] dynamic unit counter + done counter (zeroed)
   long long spin_timeout_cycles = 60000000000LL;  // bound of the in-kernel waits (m3b_create; M3B_XCHG_TIMEOUT_S)
   int* ingest_flag = nullptr;                // device word raised by the ingest validation kernels
@@ -200,6 +201,8 @@ struct m3b_mat {
   std::vector<unsigned char> keep_mask;  // zero-gene filter of the last selection (per selected gene)
   bool ended = false, normalized = false, selected = false, moments_done = false;
   bool tfidf_applied = false;  // the layouts hold TF-IDF values (LSI branch), not the normalised ones
+  bool sel_monotone = true;    // kept index grows with the gene id (no use_genes re-ordering)
+  bool layouts_built = false;  // A / B exist (m3b_select_genes); false after m3b_select_genes_for_transform
   int norm_method = -1;
   double pseudo_count = 0, f0 = 0;  // f0 = implicit value of the non-stored entries
   // gene selection
@@ -260,6 +263,7 @@ void flat_plan_free(struct FlatPlan* p);
 int flat_build_plans(m3b_ctx* ctx, TiledLayout& L, const HostTables& Tg, const HostTables* Tu);
 int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStream_t stream, int max_cta);
 int flat_init(m3b_ctx* ctx);
+bool flat_has_plan(const TiledLayout& L, int n_cta);  // a plan for exactly n_cta CTAs exists (side-stream launch)
 int flat_build_plans_device(m3b_ctx* ctx, TiledLayout& L);
 
 // tables.cu: the layout tables and flat plans built on the device (default; M3B_HOST_TABLES=1 keeps
@@ -299,6 +303,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
 int compute_moments(m3b_mat* m);
 
 // project.cu
+int run_select_for_transform(m3b_mat* m, const int* gene_order, int n_sel, unsigned char* keep, int* n_kept, int* fallback);
 int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, const double* center,
                 const double* scale, int nv, double* Y, long long ldy);
 

@@ -78,6 +78,329 @@ __global__ void __launch_bounds__(256) k_project(const unsigned short* __restric
   }
 }
 
+// ---------------------------------------------------------------------------
+// K10, tiled: the scaled loadings are staged in SHARED memory, gene tile by gene tile.
+//
+// The warp-per-cell kernel above pulls one 800-byte row of Vs out of L2 per non-zero: at the cfg5
+// shape that is 600 GB of L2 gathers (L2 serves ~12 TB/s chip-wide => >= 50 ms on one GPU) against
+// 1.5e11 fp64 flops (~4 ms of DFMA).  Here a CTA owns a block of 128 query cells (16 warps x 8
+// cells, accumulators in registers: 4 doubles per lane and cell) and walks the kept genes in tiles
+// of ~128 rows of Vs (100 KB), double-buffered in shared memory with one bulk async copy
+// (cp.async.bulk + mbarrier; a tile of the row-major Vs is ONE contiguous range) per tile, so the
+// per-entry gather becomes two LDS.128 per lane.  The raw CSC is sorted by gene inside a cell, so a
+// cell's entries that fall into the current tile are a prefix of what is left of the cell: each
+// warp keeps one cursor per cell and fetches 4 entries of each of its 8 cells per round.
+// The bound is now the shared-memory pipe (800 B per non-zero at 128 B/clk/SM); the Vs tiles cost
+// n_blocks x 24 MB of L2 -> SM traffic, overlapped with the arithmetic.
+// Requires: kept index monotone in the gene id (no use_genes re-ordering) and values taken from
+// the normalised CSC (not after TF-IDF, which rewrites the layouts only) -- otherwise k_project.
+// ---------------------------------------------------------------------------
+#define PT_WARPS 16
+#define PT_CPW 8                      // cells per warp
+#define PT_CELLS (PT_WARPS * PT_CPW)  // cells per CTA
+#define PT_SMEM_TILE (110 * 1024)     // bytes per Vs tile buffer (two buffers)
+
+__device__ __forceinline__ void pt_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void pt_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pt_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PT_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PT_WAIT_DONE;\n"
+      "bra PT_WAIT_LOOP;\n"
+      "PT_WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void pt_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(PT_WARPS * 32, 1)
+k_project_tiled(const long long* __restrict__ p, const int* __restrict__ gi, const double* __restrict__ y,
+                const int* __restrict__ kept_of_gene, long long n_cells, int n_kept, const double* __restrict__ Vs, int nvp,
+                int ncols, int tg, const double* __restrict__ b, double* __restrict__ Y, long long ldy) {
+  extern __shared__ __align__(128) unsigned char pt_smem[];
+  double* buf0 = reinterpret_cast<double*>(pt_smem);
+  double* buf1 = reinterpret_cast<double*>(pt_smem + PT_SMEM_TILE);
+  __shared__ __align__(8) unsigned long long mbar[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&mbar[0]), bar1 = (unsigned)__cvta_generic_to_shared(&mbar[1]);
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      pt_mbar_init(bar0, 1);
+      pt_mbar_init(bar1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  unsigned ph0 = 0, ph1 = 0;  // parity of the next completion of each buffer's barrier
+  const int n_gt = (n_kept + tg - 1) / tg;
+  const size_t row_bytes = (size_t)nvp * sizeof(double);
+  const long long n_blocks = (n_cells + PT_CELLS - 1) / PT_CELLS;
+  const bool second = 64 + 2 * lane < nvp;  // this lane also owns columns 64 + 2 lane, + 1
+  const bool first = 2 * lane < nvp;
+  auto load_tile = [&](int gt, int which) {
+    const int g0 = gt * tg, rows = min(tg, n_kept - g0);
+    const unsigned bytes = (unsigned)(rows * row_bytes);
+    double* dst = which ? buf1 : buf0;
+    const double* src = Vs + (size_t)g0 * nvp;
+    if (TMA) {
+      if (threadIdx.x == 0) {
+        const unsigned bar = which ? bar1 : bar0;
+        pt_mbar_expect_tx(bar, bytes);
+        pt_bulk_g2s((unsigned)__cvta_generic_to_shared(dst), src, bytes, bar);
+      }
+    } else {
+      const double2* s2 = reinterpret_cast<const double2*>(src);
+      double2* d2 = reinterpret_cast<double2*>(dst);
+      for (int k = threadIdx.x; k < (int)(bytes / 16); k += blockDim.x) d2[k] = s2[k];
+    }
+  };
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const long long c0 = blk * PT_CELLS + (long long)warp * PT_CPW;
+    long long cur = 0, end = 0;  // lanes 0..7: cursor / end of cell c0 + lane
+    if (lane < PT_CPW && c0 + lane < n_cells) {
+      cur = p[c0 + lane];
+      end = p[c0 + lane + 1];
+    }
+    double acc[PT_CPW][4];
+#pragma unroll
+    for (int j = 0; j < PT_CPW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+    load_tile(0, 0);
+    for (int gt = 0; gt < n_gt; ++gt) {
+      const int which = gt & 1;
+      if (gt + 1 < n_gt) load_tile(gt + 1, which ^ 1);  // that buffer was released by the barrier below
+      if (TMA) {
+        if (which) {
+          pt_mbar_wait(bar1, ph1);
+          ph1 ^= 1u;
+        } else {
+          pt_mbar_wait(bar0, ph0);
+          ph0 ^= 1u;
+        }
+      } else {
+        __syncthreads();
+      }
+      const double* tile = which ? buf1 : buf0;
+      const int g0 = gt * tg, g1 = min(n_kept, g0 + tg);
+      const int j_of = lane & 7, sub = lane >> 3;
+      for (;;) {
+        const long long cj = __shfl_sync(0xffffffffu, cur, j_of), ej = __shfl_sync(0xffffffffu, end, j_of);
+        const long long k = cj + sub;
+        const bool have = k < ej;
+        int kq = -1;
+        double val = 0.0;
+        if (have) {
+          kq = kept_of_gene[gi[k]];
+          val = y[k];
+        }
+        // consumable: a dropped gene (kq < 0) or a kept gene of this or an earlier tile; a cell's
+        // consumable entries must form a prefix of the four fetched ones
+        const unsigned m = __ballot_sync(0xffffffffu, have && kq < g1);
+        const unsigned need = ((1u << (8 * sub + 1)) - 1u) & 0x01010101u;
+        const bool cons = (((m >> j_of) & 0x01010101u) & need) == need;
+        const unsigned mc = __ballot_sync(0xffffffffu, cons);
+        if (mc == 0u) break;
+        const unsigned mv = __ballot_sync(0xffffffffu, cons && kq >= g0);
+        const int local = kq - g0;
+#pragma unroll
+        for (int j = 0; j < PT_CPW; ++j) {
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int ql = s4 * 8 + j;
+            if ((mv >> ql) & 1u) {  // warp-uniform
+              const int g = __shfl_sync(0xffffffffu, local, ql);
+              const double v = __shfl_sync(0xffffffffu, val, ql);
+              const double* row = tile + (size_t)g * nvp;
+              if (first) {
+                const double2 a = *reinterpret_cast<const double2*>(row + 2 * lane);
+                acc[j][0] = fma(v, a.x, acc[j][0]);
+                acc[j][1] = fma(v, a.y, acc[j][1]);
+              }
+              if (second) {
+                const double2 c = *reinterpret_cast<const double2*>(row + 64 + 2 * lane);
+                acc[j][2] = fma(v, c.x, acc[j][2]);
+                acc[j][3] = fma(v, c.y, acc[j][3]);
+              }
+            }
+          }
+        }
+        if (lane < PT_CPW) cur += __popc((mc >> lane) & 0x01010101u);
+      }
+      __syncthreads();  // every warp is done with this tile: its buffer may be refilled
+    }
+    // Y[c, col] = acc - b[col]
+#pragma unroll
+    for (int j = 0; j < PT_CPW; ++j) {
+      const long long c = c0 + j;
+      if (c < n_cells) {
+        if (first) {
+          const int col = 2 * lane;
+          if (col < ncols) Y[(long long)col * ldy + c] = acc[j][0] - b[col];
+          if (col + 1 < ncols) Y[(long long)(col + 1) * ldy + c] = acc[j][1] - b[col + 1];
+        }
+        if (second) {
+          const int col = 64 + 2 * lane;
+          if (col < ncols) Y[(long long)col * ldy + c] = acc[j][2] - b[col];
+          if (col + 1 < ncols) Y[(long long)(col + 1) * ldy + c] = acc[j][3] - b[col + 1];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Gene selection for the projection path (m3b_select_genes_for_transform): the zero-gene filter of
+// R/projection.R:117-118 WITHOUT the two product layouts m3b_select_genes builds for IRLBA -- the
+// tiled projection kernel reads the normalised CSC directly.  One pass over the stored entries
+// with integer atomics (order-free, exact): per selected gene the number of positive entries, and
+// flags for negative / non-finite values.  For non-negative data (every size-factor based
+// norm_method on counts) "row sum finite and != 0" is exactly "no non-finite entry and at least
+// one positive entry"; anything else falls back to the exact row sums of m3b_select_genes.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gene_flags(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                    const double* __restrict__ y, const int* __restrict__ sel_of_gene,
+                                                    long long n_cells, long long* __restrict__ npos, long long* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  int bad = 0;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    for (long long k = lo + lane; k < hi; k += 32) {
+      const int s = sel_of_gene[gi[k]];
+      if (s < 0) continue;
+      const double v = y[k];
+      if (!isfinite(v)) {
+        bad |= 2;
+        atomicAdd(reinterpret_cast<unsigned long long*>(flags + 2 + s), 1ULL);
+      } else if (v > 0.0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(npos + s), 1ULL);
+      } else if (v < 0.0) {
+        bad |= 1;
+      }
+    }
+  }
+  if (bad & 1) atomicOr(reinterpret_cast<unsigned long long*>(flags), 1ULL);
+  if (bad & 2) atomicOr(reinterpret_cast<unsigned long long*>(flags + 1), 1ULL);
+}
+
+__global__ void k_compose_kept(const int* __restrict__ sel_of_gene, const int* __restrict__ kept_of_sel, int n_genes,
+                               int* __restrict__ kept_of_gene) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_genes) {
+    int s = sel_of_gene[g];
+    kept_of_gene[g] = (s >= 0) ? kept_of_sel[s] : -1;
+  }
+}
+
+// returns M3B_OK with *fallback = 1 when the exact path is needed (negative values, dense pseudo-count path)
+int run_select_for_transform(m3b_mat* m, const int* gene_order, int n_sel, unsigned char* keep, int* n_kept, int* fallback) {
+  m3b_ctx* ctx = m->ctx;
+  *fallback = 0;
+  if (m->f0 != 0.0) {
+    *fallback = 1;
+    return M3B_OK;
+  }
+  if (!gene_order) n_sel = m->n_genes;
+  std::vector<int> sel_of_gene(std::max(m->n_genes, 1), -1);
+  bool mono = true;
+  for (int s = 0; s < n_sel; ++s) {
+    const int g = gene_order ? gene_order[s] : s;
+    if (g < 0 || g >= m->n_genes) {
+      m3b_set_error(ctx, "use_genes index %d out of range", g);
+      return M3B_E_DIMS;
+    }
+    if (sel_of_gene[g] != -1) {
+      m3b_set_error(ctx, "use_genes lists gene %d twice", g);
+      return M3B_E_DIMS;
+    }
+    sel_of_gene[g] = s;
+    if (s > 0 && gene_order && gene_order[s] <= gene_order[s - 1]) mono = false;
+  }
+  long long *d_npos = nullptr, *d_flags = nullptr;
+  int status = M3B_OK;
+  std::vector<long long> npos(std::max(n_sel, 1), 0), flags(2 + std::max(n_sel, 1), 0);
+  std::vector<int> kept_of_sel(std::max(n_sel, 1), -1);
+  cudaError_t e = cudaSuccess;
+  dev_free(m->sel_of_gene);
+  m->sel_of_gene = nullptr;
+  RET(dev_alloc(ctx, &m->sel_of_gene, sel_of_gene.size()));
+  RET(dev_alloc(ctx, &d_npos, npos.size()));
+  if (dev_alloc(ctx, &d_flags, flags.size()) != M3B_OK) {
+    dev_free(d_npos);
+    return M3B_E_NOMEM;
+  }
+  do {
+    if ((e = cudaMemcpyAsync(m->sel_of_gene, sel_of_gene.data(), sel_of_gene.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(d_npos, 0, npos.size() * sizeof(long long), ctx->stream)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(d_flags, 0, flags.size() * sizeof(long long), ctx->stream)) != cudaSuccess) break;
+    if (m->n_cells && n_sel) {
+      const int blocks = (int)std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8);
+      k_gene_flags<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->sel_of_gene, m->n_cells, d_npos, d_flags);
+      count_launch(ctx);
+    }
+    if ((status = comm_allreduce_i64(ctx, d_npos, npos.size())) != M3B_OK) break;
+    if ((status = comm_allreduce_i64(ctx, d_flags, flags.size())) != M3B_OK) break;
+    if ((e = cudaMemcpyAsync(npos.data(), d_npos, npos.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(flags.data(), d_flags, flags.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) break;
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) break;
+    if (flags[0]) {  // negative values somewhere: the sign of a row sum needs the exact sums
+      *fallback = 1;
+      break;
+    }
+    int nk = 0;
+    for (int s = 0; s < n_sel; ++s) {
+      const bool kp = npos[s] > 0 && flags[2 + s] == 0;  // finite and non-zero row sum (R/projection.R:117-118)
+      if (keep) keep[s] = kp ? 1 : 0;
+      kept_of_sel[s] = kp ? nk++ : -1;
+    }
+    m->n_sel = n_sel;
+    m->n_kept = nk;
+    m->keep_mask.assign(std::max(n_sel, 1), 0);
+    for (int s = 0; s < n_sel; ++s) m->keep_mask[s] = kept_of_sel[s] >= 0;
+    dev_free(m->kept_of_sel);
+    dev_free(m->kept_of_gene);
+    m->kept_of_sel = m->kept_of_gene = nullptr;
+    if ((status = dev_alloc(ctx, &m->kept_of_sel, kept_of_sel.size())) != M3B_OK) break;
+    if ((status = dev_alloc(ctx, &m->kept_of_gene, (size_t)std::max(m->n_genes, 1))) != M3B_OK) break;
+    if ((e = cudaMemcpyAsync(m->kept_of_sel, kept_of_sel.data(), kept_of_sel.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
+    if (m->n_genes) {
+      k_compose_kept<<<(m->n_genes + 255) / 256, 256, 0, ctx->stream>>>(m->sel_of_gene, m->kept_of_sel, m->n_genes, m->kept_of_gene);
+      count_launch(ctx);
+    }
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) break;
+    // no product layouts: only m3b_project (tiled kernel) may follow
+    m->A.free_all();
+    m->B.free_all();
+    m->layouts_built = false;
+    m->sel_monotone = mono;
+    m->selected = true;
+    m->moments_done = false;
+    m->tfidf_applied = false;
+    m->split = false;
+    if (n_kept) *n_kept = nk;
+  } while (0);
+  dev_free(d_npos);
+  dev_free(d_flags);
+  if (e != cudaSuccess) {
+    m3b_set_error(ctx, "m3b_select_genes_for_transform: %s", cudaGetErrorString(e));
+    return M3B_E_CUDA;
+  }
+  return status;
+}
+
 int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, const double* center,
                 const double* scale, int nv, double* Y, long long ldy) {
   m3b_ctx* ctx = q->ctx;
@@ -96,8 +419,20 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
       m3b_set_error(ctx, "gene sets differ: genes in the subject matrix are not in the reference matrix");
       return M3B_E_DIMS;
     }
-  // scaled loadings (row-major) and the constant row b, built on the host: G'q x nv is tiny
-  std::vector<double> Vs((size_t)std::max(n, 1) * nv), b(nv, 0.0);
+  // The tiled kernel reads the normalised CSC (sorted by gene inside a cell): it needs the kept index
+  // to grow with the gene id and the values of m3b_normalize (TF-IDF rewrites the layouts only).
+  const bool tiled = q->sel_monotone && !q->tfidf_applied && (!q->layouts_built || !getenv("M3B_PROJECT_OLD")) && n > 0;
+  if (!tiled && !q->layouts_built) {
+    m3b_set_error(ctx, "m3b_project: this selection (re-ordered genes) needs the product layouts: call m3b_select_genes, "
+                       "not m3b_select_genes_for_transform");
+    return M3B_E_STATE;
+  }
+  // scaled loadings (row-major, rows padded to an even number of columns for the tiled kernel) and
+  // the constant row b, built on the host: G'q x nv is tiny
+  const int pass_cols = tiled ? 128 : 32 * PJ_CPL;
+  const int nvp = tiled ? ((std::min(nv, pass_cols) + 1) & ~1) : nv;
+  const int n_pass = (nv + pass_cols - 1) / pass_cols;
+  std::vector<double> Vs((size_t)std::max(n, 1) * nvp * (tiled ? n_pass : 1), 0.0), b(nv, 0.0);
   std::vector<long double> bacc(nv, 0.0L);
   for (int g = 0; g < n; ++g) {
     const int r = model_row[g];
@@ -105,7 +440,8 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
     const double ce = (center ? center[r] : 0.0) - q->f0;
     for (int c = 0; c < nv; ++c) {
       const double v = V[(size_t)c * n_model + r];
-      Vs[(size_t)g * nv + c] = v / s;
+      if (tiled) Vs[((size_t)(c / pass_cols) * n + g) * nvp + (c % pass_cols)] = v / s;  // one [n][nvp] block per pass
+      else Vs[(size_t)g * nv + c] = v / s;
       bacc[c] += (long double)(ce / s) * v;
     }
   }
@@ -120,8 +456,34 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
     if ((e = cudaMemcpyAsync(dVs, Vs.data(), Vs.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
     if ((e = cudaMemcpyAsync(db, b.data(), nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) break;
     ctx->stats.h2d_bytes += (long long)Vs.size() * 8 + nv * 8;
-    if (rows) {
+    if (rows && tiled) {
+      static bool attr = false;
+      if (!attr) {
+        if ((e = cudaFuncSetAttribute(k_project_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
+        if ((e = cudaFuncSetAttribute(k_project_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
+        attr = true;
+      }
+      const int tg = std::max(8, (int)(PT_SMEM_TILE / (nvp * sizeof(double))));
+      const long long n_blocks = (rows + PT_CELLS - 1) / PT_CELLS;
+      const int grid = (int)std::min<long long>(n_blocks, ctx->sm_count);
+      const bool tma = !getenv("M3B_PROJECT_NO_TMA");
+      cudaEventRecord(ctx->evk0, ctx->stream);
+      for (int ps = 0; ps < n_pass; ++ps) {
+        const int col0 = ps * pass_cols, ncols = std::min(pass_cols, nv - col0);
+        const double* vs = dVs + (size_t)ps * n * nvp;
+        if (tma)
+          k_project_tiled<true><<<grid, PT_WARPS * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
+                                                                                  ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
+        else
+          k_project_tiled<false><<<grid, PT_WARPS * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs,
+                                                                                   nvp, ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
+        count_launch(ctx);
+      }
+      cudaEventRecord(ctx->evk1, ctx->stream);
+      ctx->k10_timed = true;
+    } else if (rows) {
       int blocks = (int)std::min<long long>((rows + 7) / 8, (long long)ctx->sm_count * 8);
+      cudaEventRecord(ctx->evk0, ctx->stream);
       for (int col0 = 0; col0 < nv; col0 += 32 * PJ_CPL) {
         const TiledLayout* U = q->A.unit;
         k_project<<<blocks, 256, 0, ctx->stream>>>(q->A.idx, q->A.val, q->A.items, q->A.row_item_ptr,
@@ -130,6 +492,10 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
                                                    q->A.n_tiles, q->A.tile_w, dVs, db, nv, col0, dY, rows);
         count_launch(ctx);
       }
+      cudaEventRecord(ctx->evk1, ctx->stream);
+      ctx->k10_timed = true;
+    }
+    if (rows) {
       if ((e = cudaGetLastError()) != cudaSuccess) break;
       if ((e = cudaMemcpy2DAsync(Y, ldy * sizeof(double), dY, rows * sizeof(double), rows * sizeof(double), nv,
                                  cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess)
@@ -137,6 +503,11 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
       ctx->stats.d2h_bytes += rows * nv * 8;
     }
     e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && ctx->k10_timed) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1) == cudaSuccess) ctx->stats.k10_ms = ms;
+      ctx->k10_timed = false;
+    }
   } while (0);
   if (e != cudaSuccess) {
     m3b_set_error(ctx, "m3b_project: %s", cudaGetErrorString(e));

@@ -59,7 +59,7 @@ static int item_tiles(m3b_ctx* ctx, const TiledLayout& L, int** out) {
 int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor, const double* row_sums_in,
               double num_cols, double* col_sums_out, double* row_sums_out) {
   m3b_ctx* ctx = m->ctx;
-  if (!m->selected) {
+  if (!m->selected || !m->layouts_built) {
     m3b_set_error(ctx, "m3b_tfidf before m3b_select_genes");
     return M3B_E_STATE;
   }

@@ -109,6 +109,12 @@ class Context:
         out["select_ms"] = list(out["select_ms"])
         return out
 
+    def measure_fp64_peak(self):
+        """Measured fp64 FMA peak of this GPU in TFLOP/s (the roof of the projection kernel)."""
+        v = C.c_double()
+        self.check(self.lib.m3b_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
     def set_flags(self, flags):
         self.check(self.lib.m3b_set_flags(self.h, int(flags)))
 
@@ -227,7 +233,8 @@ class DeviceMatrix:
         self.ctx.check(self.lib.m3b_export_values(self.h, _dp(y)))
         return y[:self.nnz]
 
-    def select_genes(self, gene_order=None):
+    def select_genes(self, gene_order=None, for_transform=False):
+        """for_transform: the light variant (m3b_select_genes_for_transform), only project() may follow."""
         if gene_order is None:
             n_sel, go = self.n_genes, None
         else:
@@ -235,7 +242,8 @@ class DeviceMatrix:
             n_sel = len(go)
         keep = np.zeros(max(n_sel, 1), dtype=np.uint8)
         nk = C.c_int32()
-        self.ctx.check(self.lib.m3b_select_genes(self.h, _ip(go), n_sel, keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nk)))
+        fn = self.lib.m3b_select_genes_for_transform if for_transform else self.lib.m3b_select_genes
+        self.ctx.check(fn(self.h, _ip(go), n_sel, keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(nk)))
         self.n_sel, self.n_kept = n_sel, nk.value
         return keep[:n_sel].astype(bool)
 
