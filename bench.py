@@ -449,7 +449,9 @@ def run_project_bench(args, wl, ctx, rank, world, local_rank, barrier, max_over_
         gidx[names] = np.arange(len(names))
         sf_sub = m3.size_factors(cds)[:n]
         t0 = time.perf_counter()
-        Yo = ref.preprocess_transform(sub, sf_sub, mdl, gidx)
+        keep_full = np.zeros(wl["n_genes"], dtype=bool)   # the zero-gene filter of the WHOLE query (all its genes are model genes here)
+        keep_full[names] = True
+        Yo = ref.preprocess_transform(sub, sf_sub, mdl, gidx, keep_override=keep_full)
         dt = time.perf_counter() - t0
         err = float(np.max(np.abs(Yo - Yq[:n]))) if Yo.shape == Yq[:n].shape else float("nan")
         cpu_baseline = {"value": n / dt, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",

@@ -218,6 +218,19 @@ int m3b_jaccard_coeff(m3b_ctx* ctx, const double* idx, int64_t n, int32_t k, int
  * smaller id first); nn_dists: n x k distances (not squared).  k <= 64. */
 int m3b_knn_self(m3b_ctx* ctx, const double* X, int64_t n, int32_t d, int32_t k, int32_t* nn_idx, double* nn_dists);
 
+/* ---- align_cds residual regression ------------------- */
+/* Replaces limma::lmFit(t(preproc_res), X.model_mat) and the subtraction that follows
+ * (R/alignment.R:106-117): ordinary least squares of every column of X (cells x nv, the PCA or
+ * LSI coordinates, column-major with leading dimension ldx, local cells) on the design M (cells x p,
+ * column-major, leading dimension n, INTERCEPT FIRST -- what sparse.model.matrix returns for the
+ * formula), with lm.fit's aliasing rule (collinear column -> NA -> 0).  beta receives
+ * fit$coefficients[, -1] (nv x (p-1), column-major) and X is overwritten with
+ * X - M[, -1] %*% t(beta).  Collective across ranks (the cells are sharded, beta is replicated).
+ * p <= 64, p + nv <= 216. */
+int m3b_align_residuals(m3b_ctx* ctx, double* X, int64_t n, int nv, int64_t ldx, const double* M, int p, double* beta);
+/* align_beta_transform (R/projection.R:468-478): subtract the effects of a SAVED beta. */
+int m3b_align_apply_beta(m3b_ctx* ctx, double* X, int64_t n, int nv, int64_t ldx, const double* M, int p, const double* beta);
+
 /* ---- IRLBA PCA (K4-K9) -------------------------------------------------- */
 /* nv: number of PCs; work: Lanczos subspace (0 => nv+7); v0: start vector (G').
  * center/scale: 0/1 flags (preprocess_cds passes scaling for both).

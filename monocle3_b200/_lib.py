@@ -84,6 +84,8 @@ SIGNATURES = {
     "m3b_jaccard_coeff": (C.c_int, [_P, _dp, C.c_int64, C.c_int32, C.c_int, _dp]),
     "m3b_detect_genes": (C.c_int, [_P, C.c_double, _lp, _lp]),
     "m3b_aggregate_expression": (C.c_int, [_P, _ip, C.c_int32, C.c_int, _ip, C.c_int32, C.c_int, _dp, C.c_int64]),
+    "m3b_align_residuals": (C.c_int, [_P, _dp, C.c_int64, C.c_int, C.c_int64, _dp, C.c_int, _dp]),
+    "m3b_align_apply_beta": (C.c_int, [_P, _dp, C.c_int64, C.c_int, C.c_int64, _dp, C.c_int, _dp]),
     "m3b_tfidf": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _dp, C.c_double, _dp, _dp]),
     "m3b_pca_irlba": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp, C.c_int, C.c_int,
                                 _dp, _dp, _dp, C.c_int64, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

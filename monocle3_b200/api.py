@@ -466,3 +466,131 @@ def preprocess_transform(cds, reduction_method="PCA", block_size=None, cores=1):
         Y = dev.project(model_row, model["svd_v"], model["svd_center"], model["svd_scale"])
     cds.reduced_dims[reduction_method] = Y
     return cds
+
+
+# ------------------------------------------------------------------------------------------------
+# align_cds (residual regression part) and the transform-model hand-off
+# ------------------------------------------------------------------------------------------------
+def _parse_formula(formula):
+    """'~ a + b' -> ['a', 'b'] (main effects only: what align_cds is used with in the reference's
+    tests and vignette; interactions / functions are left to R's model.matrix)."""
+    f = formula.strip()
+    if not f.startswith("~"):
+        raise ValueError("residual_model_formula_str must be a one-sided formula such as '~ batch'")
+    terms = [t.strip() for t in f[1:].split("+") if t.strip() not in ("", "1")]
+    for t in terms:
+        if any(ch in t for ch in "*:()^|/ -"):
+            raise NotImplementedError("only main effects are supported in the formula (term '%s')" % t)
+    return terms
+
+
+def model_matrix(cds, formula):
+    """Matrix::sparse.model.matrix(as.formula(formula), colData(cds), drop.unused.levels = TRUE)
+    for main-effect formulas: intercept, numeric columns as they are, factors with treatment
+    contrasts (levels sorted like as.factor, first level dropped).  Returns (M, column names).
+    On a cell-sharded cds the factor levels are agreed on across the ranks."""
+    terms = _parse_formula(formula)
+    n = cds.counts.shape[1]
+    cols, names = [np.ones(n)], ["(Intercept)"]
+    for t in terms:
+        if t not in cds.col_data or cds.col_data[t] is None:
+            raise ValueError("object '%s' not found in colData(cds)" % t)
+        v = np.asarray(cds.col_data[t])
+        if v.dtype.kind in "fiub":
+            cols.append(v.astype(np.float64))
+            names.append(t)
+            continue
+        levels = sorted(set(v.tolist()))
+        if cds.shard:  # every rank must build the same columns
+            import torch.distributed as td
+            allv = [None] * cds.shard[1]
+            td.all_gather_object(allv, levels)
+            levels = sorted(set(x for l in allv for x in l))
+        for lv in levels[1:]:
+            cols.append((v == lv).astype(np.float64))
+            names.append("%s%s" % (t, lv))
+    return np.stack(cols, axis=1), names
+
+
+def align_cds(cds, preprocess_method="PCA", alignment_group=None, alignment_k=20, residual_model_formula_str=None,
+              verbose=False, build_nn_index=False, nn_control=None):
+    """R/alignment.R:66-160.  The residual regression (limma::lmFit on the PCA / LSI coordinates,
+    :106-117) runs on the device (m3b_align_residuals); the mutual-nearest-neighbour correction
+    (alignment_group, batchelor::reducedMNN) is outside this build's scope."""
+    if preprocess_method not in ("PCA", "LSI"):
+        raise ValueError("preprocess_method must be one of 'PCA' or 'LSI'")
+    X = cds.reduced_dims.get(preprocess_method)
+    if X is None:
+        raise ValueError("Preprocessing for '%s' does not exist. Please make sure you have run preprocess_cds with"
+                         "preprocess_method = '%s' before calling align_cds." % (preprocess_method, preprocess_method))
+    if build_nn_index:
+        raise NotImplementedError("nearest-neighbour indices are outside this build's scope (SURVEY.md section 8f)")
+    if alignment_group is not None:
+        raise NotImplementedError("alignment_group (batchelor::reducedMNN) is outside this build's scope; use "
+                                  "residual_model_formula_str for linear effects")
+    model = {"alignment_group": alignment_group, "alignment_k": alignment_k,
+             "residual_model_formula_str": residual_model_formula_str, "beta": None}
+    if residual_model_formula_str is not None:
+        if verbose:
+            print("Removing residual effects")
+        M, names = model_matrix(cds, residual_model_formula_str)
+        X, beta = engine.align_residuals(get_context(), X, M)
+        model["beta"] = beta
+        model["beta_colnames"] = names[1:]
+    cds.reduced_dims["Aligned"] = np.asarray(X)
+    cds.reduce_dim_aux["Aligned"] = {"model": model}
+    return cds
+
+
+def align_beta_transform(cds, preprocess_method="PCA"):
+    """R/projection.R:468-494: subtract the effects of the SAVED beta from the projected coordinates."""
+    X = cds.reduced_dims.get(preprocess_method)
+    model = (cds.reduce_dim_aux.get("Aligned") or {}).get("model")
+    if X is None or model is None or model.get("beta") is None:
+        raise ValueError("align_beta_transform needs reducedDims '%s' and an 'Aligned' model with beta" % preprocess_method)
+    M, _ = model_matrix(cds, model["residual_model_formula_str"])
+    if M.shape[1] - 1 != np.asarray(model["beta"]).shape[1]:
+        raise ValueError("the design has %d columns, the saved beta %d" % (M.shape[1] - 1, np.asarray(model["beta"]).shape[1]))
+    Xa, _ = engine.align_residuals(get_context(), X, M, beta=model["beta"])
+    cds.reduced_dims["Aligned"] = Xa
+    return cds
+
+
+_MODEL_ARRAYS = ("svd_v", "svd_v_rownames", "svd_sdev", "svd_center", "svd_scale", "prop_var_expl", "col_sums", "row_sums",
+                 "beta")
+
+
+def save_transform_models(cds, directory_path):
+    """The model hand-off of R/io.R:819-996 for the reductions this build produces (PCA, LSI,
+    Aligned): everything preprocess_transform / align_beta_transform read, one .npz per method plus
+    a small index.  (The reference writes RDS files and the nn indices; RDS stays in R.)"""
+    import json
+    os.makedirs(directory_path, exist_ok=True)
+    index = {}
+    for method, aux in cds.reduce_dim_aux.items():
+        model = (aux or {}).get("model")
+        if model is None:
+            continue
+        arrays = {k: np.asarray(v) for k, v in model.items() if k in _MODEL_ARRAYS and v is not None}
+        scalars = {k: v for k, v in model.items() if k not in _MODEL_ARRAYS}
+        np.savez(os.path.join(directory_path, "rdd_%s_transform_model.npz" % method.lower()), **arrays)
+        index[method] = {"scalars": scalars, "arrays": sorted(arrays)}
+    with open(os.path.join(directory_path, "file_index.json"), "w") as f:
+        json.dump(index, f, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o))
+    return cds
+
+
+def load_transform_models(cds, directory_path):
+    """R/io.R:1025-1146: put the saved models back into cds@reduce_dim_aux."""
+    import json
+    with open(os.path.join(directory_path, "file_index.json")) as f:
+        index = json.load(f)
+    for method, rec in index.items():
+        z = np.load(os.path.join(directory_path, "rdd_%s_transform_model.npz" % method.lower()), allow_pickle=False)
+        model = dict(rec["scalars"])
+        for k in rec["arrays"]:
+            model[k] = z[k]
+        for k in _MODEL_ARRAYS:
+            model.setdefault(k, None)
+        cds.reduce_dim_aux[method] = {"model": model}
+    return cds

@@ -561,6 +561,18 @@ int m3b_knn_self(m3b_ctx* ctx, const double* X, int64_t n, int32_t d, int32_t k,
   return run_knn_self(ctx, X, (long long)n, (int)d, (int)k, nn_idx, nn_dists);
 }
 
+int m3b_align_residuals(m3b_ctx* ctx, double* X, int64_t n, int nv, int64_t ldx, const double* M, int p, double* beta) {
+  if (!ctx || !X || !M || !beta) return M3B_E_DIMS;
+  cudaSetDevice(ctx->device);
+  return run_align_residuals(ctx, X, (long long)n, nv, (long long)ldx, M, p, beta, true);
+}
+
+int m3b_align_apply_beta(m3b_ctx* ctx, double* X, int64_t n, int nv, int64_t ldx, const double* M, int p, const double* beta) {
+  if (!ctx || !X || !M || !beta) return M3B_E_DIMS;
+  cudaSetDevice(ctx->device);
+  return run_align_residuals(ctx, X, (long long)n, nv, (long long)ldx, M, p, const_cast<double*>(beta), false);
+}
+
 int m3b_gene_nnz(m3b_mat* m, int64_t* nnz_per_sel_gene) {
   if (!m || !nnz_per_sel_gene) return M3B_E_DIMS;
   m3b_ctx* ctx = m->ctx;

@@ -292,6 +292,10 @@ int run_jaccard(m3b_ctx* ctx, const double* idx, long long n, int k, int weight,
 // knn.cu
 int run_knn_self(m3b_ctx* ctx, const double* X, long long n, int d, int k, int* idx_out, double* dist_out);
 
+// align.cu
+int run_align_residuals(m3b_ctx* ctx, double* X, long long n, int nv, long long ldx, const double* M, int p, double* beta,
+                        bool fit);
+
 // tfidf.cu (LSI branch)
 int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor, const double* row_sums_in,
               double num_cols, double* col_sums_out, double* row_sums_out);

@@ -169,6 +169,25 @@ def jaccard_coeff(ctx, idx, weight=True, out=None):
     return res.T.copy() if out is None else res.T
 
 
+def align_residuals(ctx, X, M, beta=None):
+    """align_cds residual regression on the device: X (cells x nv) and the design M (cells x p,
+    intercept first) -> (X_aligned, beta nv x (p-1)).  With `beta` given, only subtracts its effects
+    (align_beta_transform)."""
+    Xf = np.array(X, dtype=np.float64, order="F", copy=True)
+    Mf = np.asfortranarray(M, dtype=np.float64)
+    n, nv = Xf.shape
+    p = Mf.shape[1]
+    if beta is None:
+        b = np.zeros((nv, max(p - 1, 0)), order="F")
+        bb = b if b.size else np.zeros(1)
+        ctx.check(ctx.lib.m3b_align_residuals(ctx.h, _dp(Xf), n, nv, max(n, 1), _dp(Mf), p, _dp(bb)))
+    else:
+        b = np.asfortranarray(beta, dtype=np.float64)
+        bb = b if b.size else np.zeros(1)
+        ctx.check(ctx.lib.m3b_align_apply_beta(ctx.h, _dp(Xf), n, nv, max(n, 1), _dp(Mf), p, _dp(bb)))
+    return Xf, b
+
+
 class DeviceMatrix:
     """The counts matrix (local cell shard) resident on the GPU (m3b_mat)."""
 

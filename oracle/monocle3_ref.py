@@ -239,15 +239,19 @@ def preprocess_transform_lsi(counts, sf, model, gene_index_in_model):
     return np.asarray(X @ model["svd_v"][m_rows, :])
 
 
-def preprocess_transform(counts, sf, model, gene_index_in_model):
+def preprocess_transform(counts, sf, model, gene_index_in_model, keep_override=None):
     """PCA branch of R/projection.R:102-149.
 
     gene_index_in_model[g] = row of model['svd_v'] for query gene g, or -1 if the
     query gene is not in the model (R does this by rowname intersect, :121-122).
+    keep_override: the zero-gene filter of a LARGER query this block of cells belongs to (the filter
+    is a property of the whole query matrix; bench.py checks a block of cells of a big query).
     """
     FM = normalize_expr_data(counts, sf, model["norm_method"], model.get("pseudo_count"))
     rs = np.asarray(FM.sum(axis=1)).ravel()
     keep = np.isfinite(rs) & (rs != 0)  # :117-118
+    if keep_override is not None:
+        keep = np.asarray(keep_override, dtype=bool)
     gidx = np.asarray(gene_index_in_model)
     # R: intersect(rownames(rotation), rownames(FM)) keeps the MODEL's order (:121)
     q_rows = np.nonzero(keep & (gidx >= 0))[0]
@@ -404,3 +408,68 @@ def cluster_cells_make_graph(data, weight, k):
     links = jaccard_coeff(neighbor, weight)           # :313
     links = links[links[:, 0] > 0]                    # :318
     return links, distm
+
+
+# ------------------------------------------------------------------------------------------------
+# align_cds residual regression (R/alignment.R:106-117) and align_beta_transform
+# (R/projection.R:468-478).  limma::lmFit(t(X), design) without weights / blocking fits every row of
+# t(X) (every PC) by ordinary least squares through lm.fit's pivoted QR (LINPACK dqrdc2, tolerance
+# 1e-7: a design column whose residual norm after projecting out the columns before it falls below
+# tol x its norm is aliased -> coefficient NA); align_cds zeroes the NAs, drops the intercept and
+# subtracts the fitted effects.  limma is not in /root/reference (DESCRIPTION: Imports), so this is
+# restated from the published lm.fit semantics; the reference pins one value, beta[[1]] = 2.071
+# (tests/testthat/test-alignment.R:100,139), on data drawn with R's rmultinom, which cannot be
+# reproduced without R -- tests/test_oracle_align.py checks it statistically.
+# ------------------------------------------------------------------------------------------------
+def lm_fit_coefficients(Y, M, tol=1e-7):
+    """Coefficients (p x q, NaN for aliased design columns) of the least-squares fits of the columns
+    of Y (n x q) on the design M (n x p), with lm.fit's limited column pivoting."""
+    Y = np.asarray(Y, dtype=np.float64)
+    M = np.asarray(M, dtype=np.float64)
+    n, p = M.shape
+    Q = np.zeros((n, 0))
+    used = []
+    for j in range(p):
+        col = M[:, j]
+        r = col - Q @ (Q.T @ col)
+        r = r - Q @ (Q.T @ r)  # second pass: Householder-grade orthogonality
+        nrm0 = np.linalg.norm(col)
+        if nrm0 == 0 or np.linalg.norm(r) < tol * nrm0:
+            continue  # aliased: moved to the end by dqrdc2, coefficient NA
+        Q = np.hstack([Q, (r / np.linalg.norm(r))[:, None]])
+        used.append(j)
+    coef = np.full((p, Y.shape[1]), np.nan)
+    if used:
+        sol, *_ = np.linalg.lstsq(M[:, used], Y, rcond=None)
+        coef[used, :] = sol
+    return coef
+
+
+def align_residuals(X, M):
+    """R/alignment.R:112-116: beta = fit$coefficients[, -1] (PCs x terms, NA -> 0);
+    X_aligned = t(t(X) - beta %*% t(M[, -1])).  X: cells x PCs, M: cells x p with the intercept first.
+    Returns (X_aligned, beta)."""
+    coef = lm_fit_coefficients(X, M)          # p x nv
+    beta = coef[1:, :].T.copy()               # nv x (p - 1)
+    beta[np.isnan(beta)] = 0.0
+    return np.asarray(X) - np.asarray(M)[:, 1:] @ beta.T, beta
+
+
+def model_matrix(columns, terms):
+    """The subset of stats::model.matrix / Matrix::sparse.model.matrix this path needs: main effects
+    of numeric columns and of factors with treatment contrasts (first level dropped, levels sorted
+    like as.factor), intercept first.  columns: dict name -> sequence; terms: list of names.
+    Returns (M, column_names)."""
+    n = len(next(iter(columns.values()))) if columns else 0
+    cols, names = [np.ones(n)], ["(Intercept)"]
+    for t in terms:
+        v = np.asarray(columns[t])
+        if v.dtype.kind in "fiub":
+            cols.append(v.astype(np.float64))
+            names.append(t)
+        else:
+            levels = sorted(set(v.tolist()))
+            for lv in levels[1:]:
+                cols.append((v == lv).astype(np.float64))
+                names.append("%s%s" % (t, lv))
+    return np.stack(cols, axis=1), names
