@@ -439,26 +439,40 @@ struct OrthArgs {
 __device__ __forceinline__ double* xchg_slot(double* const* peers, int q, int world, unsigned long long seq) {
   return peers[q] + (size_t)world * 2 * M3B_XCHG_FLAG_STRIDE + (size_t)(seq & 1ull) * M3B_XCHG_CAP;
 }
+// Publishing costs ONE system-scope fence: the first version issued a st.release.sys per peer, i.e. a
+// fence per peer (each waits for every outstanding write to be acknowledged over NVLink: 8 of them
+// in a row at 8 GPUs), and polled the world's flags with one ld.acquire.sys each.  Now: fence once,
+// then relaxed flag stores to all peers back to back; the waiter polls all flags with relaxed loads
+// and fences once when the last one has arrived.
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void xchg_publish(double* const* peers, int rank, int world, unsigned long long seq) {
   __threadfence_system();
   for (int q = 0; q < world; ++q)
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(peers[q] + ((size_t)rank * 2 + (seq & 1ull)) * M3B_XCHG_FLAG_STRIDE), seq);
+    st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(peers[q] + ((size_t)rank * 2 + (seq & 1ull)) * M3B_XCHG_FLAG_STRIDE), seq);
 }
 // called by ONE thread; returns false on time-out
 __device__ __forceinline__ bool xchg_wait(double* const* peers, int rank, int world, unsigned long long seq, int* ctl,
                                           long long timeout) {
   const long long t0 = clock64();
-  for (int q = 0; q < world; ++q) {
-    const unsigned long long* fl =
-        reinterpret_cast<const unsigned long long*>(peers[rank] + ((size_t)q * 2 + (seq & 1ull)) * M3B_XCHG_FLAG_STRIDE);
-    while (ld_acquire_sys_u64(fl) != seq) {
-      if (clock64() - t0 > timeout) {
-        atomicOr(ctl + CT_FLAG, 4);
-        return false;
-      }
-      __nanosleep(32);
+  const unsigned long long* fl0 = reinterpret_cast<const unsigned long long*>(peers[rank] + (seq & 1ull) * M3B_XCHG_FLAG_STRIDE);
+  for (;;) {
+    int arrived = 0;
+    for (int q = 0; q < world; ++q)
+      arrived += ld_relaxed_sys_u64(fl0 + (size_t)q * 2 * M3B_XCHG_FLAG_STRIDE) == seq;
+    if (arrived == world) break;
+    if (clock64() - t0 > timeout) {
+      atomicOr(ctl + CT_FLAG, 4);
+      return false;
     }
   }
+  __threadfence_system();  // acquire: the peers' data published before their flags is visible from here on
   return true;
 }
 
@@ -1404,22 +1418,30 @@ int compute_moments(m3b_mat* m) {
   RET(dev_alloc(ctx, &m->mean_sparse, (size_t)std::max(n, 1)));
   double* tmp = nullptr;
   RET(dev_alloc(ctx, &tmp, (size_t)std::max(n, 1)));
+  int st = M3B_OK;
   if (n) {
     const int nb = (n + 255) / 256;
-    RET(launch_tile_stream(ctx, m->B, OP_SUM, nullptr));
-    RET(launch_combine_rows(ctx, m->B, tmp));
-    RET(comm_allreduce_f64(ctx, tmp, n));
-    k_mean_from_sum<<<nb, 256, 0, ctx->stream>>>(tmp, n, 1.0 / (double)m->n_cells_total, m->f0, m->mean_sparse, m->center);
-    RET(launch_tile_stream(ctx, m->B, OP_SQDEV, m->mean_sparse));
-    RET(launch_combine_rows(ctx, m->B, tmp));
-    k_ss_local<<<nb, 256, 0, ctx->stream>>>(tmp, m->mean_sparse, m->kept_padlen, m->n_cells, n);
-    RET(comm_allreduce_f64(ctx, tmp, n));
-    k_sd_from_ss<<<nb, 256, 0, ctx->stream>>>(tmp, n, (double)(m->n_cells_total - 1), m->scale);
-    count_launch(ctx, 3);
-    CK(ctx, cudaGetLastError());
+    do {  // (tmp is released on every exit)
+      if ((st = launch_tile_stream(ctx, m->B, OP_SUM, nullptr)) != M3B_OK) break;
+      if ((st = launch_combine_rows(ctx, m->B, tmp)) != M3B_OK) break;
+      if ((st = comm_allreduce_f64(ctx, tmp, n)) != M3B_OK) break;
+      k_mean_from_sum<<<nb, 256, 0, ctx->stream>>>(tmp, n, 1.0 / (double)m->n_cells_total, m->f0, m->mean_sparse, m->center);
+      if ((st = launch_tile_stream(ctx, m->B, OP_SQDEV, m->mean_sparse)) != M3B_OK) break;
+      if ((st = launch_combine_rows(ctx, m->B, tmp)) != M3B_OK) break;
+      k_ss_local<<<nb, 256, 0, ctx->stream>>>(tmp, m->mean_sparse, m->kept_padlen, m->n_cells, n);
+      if ((st = comm_allreduce_f64(ctx, tmp, n)) != M3B_OK) break;
+      k_sd_from_ss<<<nb, 256, 0, ctx->stream>>>(tmp, n, (double)(m->n_cells_total - 1), m->scale);
+      count_launch(ctx, 3);
+    } while (0);
   }
-  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
   dev_free(tmp);
+  if (st != M3B_OK) return st;
+  if (e != cudaSuccess) {
+    m3b_set_error(ctx, "gene moments: %s", cudaGetErrorString(e));
+    return M3B_E_CUDA;
+  }
   m->moments_done = true;
   return M3B_OK;
 }
@@ -1440,6 +1462,15 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     m3b_set_error(ctx, "max(nu, nv) must be strictly less than min(nrow(A), ncol(A)) (nv=%d, min dim=%lld)", nv, minmn);
     return M3B_E_DIMS;
   }
+  if (scale && !center) {
+    // sparse_prcomp_irlba scales by the root mean square sqrt(colSums(x^2) / (n - 1)) when center = FALSE
+    // (R/utils.R:396-400); preprocess_cds never asks for that (it passes scaling for both), and the
+    // standard deviation about the mean would be a silently different answer
+    m3b_set_error(ctx, "m3b_pca_irlba: scale without center is not supported (preprocess_cds passes `scaling` for both)");
+    return M3B_E_DIMS;
+  }
+  if (minmn < 6)  // irlba: "Tiny problem detected, using standard `svd` function" 
+    return run_irlba_tiny(m, nv, center, scale, d_out, V_out, X_out, ldx, center_out, scale_out, iter_out, mprod_out, copy_x);
   if (work <= 0) work = nv + 7;
   if (work <= nv) work = nv + 1;
   if (work > minmn) work = (int)minmn;

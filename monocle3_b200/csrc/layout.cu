@@ -781,6 +781,52 @@ __global__ void __launch_bounds__(TB_THREADS) k_count_B2(const long long* __rest
   }
 }
 
+// the same count with both classes packed into one 32-bit word per row (general low half, unit high
+// half; a chunk has at most tile_w <= 28 672 cells, so a half never overflows): twice as many rows
+// fit the shared-memory histogram, i.e. one pass over the CSC instead of two for 30 000 genes
+#define TB_GSEG_PACKED 49152
+__global__ void __launch_bounds__(TB_THREADS) k_count_B3(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                         const double* __restrict__ xraw,
+                                                         const int* __restrict__ sel_of_gene, int n_sel, int g0, int g1,
+                                                         int tile_w, int chunks_per_tile, int cells_per_chunk,
+                                                         long long n_cells, int* __restrict__ Hg, int* __restrict__ Hu) {
+  extern __shared__ unsigned int hist32[];  // [ng]
+  const long long chunk = blockIdx.x;
+  const long long t = chunk / chunks_per_tile, s = chunk % chunks_per_tile;
+  const long long c0 = min(t * tile_w + s * (long long)cells_per_chunk, n_cells);
+  const long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
+  const int ng = g1 - g0;
+  for (int r = threadIdx.x; r < ng; r += blockDim.x) hist32[r] = 0u;
+  __syncthreads();
+  if (c0 < c1) {
+    const long long lo = p[c0], hi = p[c1];
+    // four independent index / value loads in flight per thread
+    for (long long k0 = lo + threadIdx.x; k0 < hi; k0 += 4LL * blockDim.x) {
+      int g[4];
+      double x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long k = k0 + (long long)u * blockDim.x;
+        g[u] = (k < hi) ? ld_stream_s32(gi + k) : -1;
+        x[u] = (k < hi) ? ld_stream_f64(xraw + k) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = (g[u] >= 0) ? sel_of_gene[g[u]] : -1;
+        if (r >= g0 && r < g1) atomicAdd(&hist32[r - g0], x[u] == 1.0 ? 0x10000u : 1u);
+      }
+    }
+  }
+  __syncthreads();
+  int* Hgc = Hg + chunk * n_sel + g0;
+  int* Huc = Hu + chunk * n_sel + g0;
+  for (int r = threadIdx.x; r < ng; r += blockDim.x) {
+    const unsigned int v = hist32[r];
+    Hgc[r] = (int)(v & 0xffffu);
+    Huc[r] = (int)(v >> 16);
+  }
+}
+
 __global__ void __launch_bounds__(TB_THREADS) k_scatter_B2(
     const long long* __restrict__ p, const int* __restrict__ gi, const double* __restrict__ y,
     const double* __restrict__ xraw, const int* __restrict__ sel_of_gene, int n_sel, int g0, int g1, int tile_w,
@@ -854,6 +900,132 @@ __global__ void __launch_bounds__(TB_THREADS) k_scatter_B2(
   }
 }
 
+// ---------------------------------------------------------------------------
+// Stable scatter, third version: SEGMENT-major and read-once.
+//
+// ncu on k_scatter_B2 at the cfg3 shape (profiles/r02e_full_k_scatter_B2.txt): 16 warps per SM (the
+// cursors of 24 576 rows take the whole shared memory), every entry read three times -- once per
+// phase, 19.8 GB of DRAM reads for a 5.7 GB input -- 9 % issue utilisation, the top stalls
+// `barrier` and `long_scoreboard`: latency-bound.  The rows of a dgCMatrix column are sorted, so the
+// entries of a cell that belong to a block of 2 048 consecutive selected rows are ONE contiguous
+// piece of the cell.  Here the CTA walks the row segments in the outer loop and keeps one read
+// cursor per cell: a warp loads (at most) 128 entries of its cell, keeps row and class in
+// registers through the three phases (mark, write, advance) and never reads them again; the
+// write cursors of a segment take 16 KB, so three to four CTAs (48-64 warps) share an SM.
+// Needs the selected row to grow with the gene id (no use_genes re-ordering): otherwise k_scatter_B2.
+// Inside a row the entries stay ordered by cell unless a cell has more than 128 entries in one
+// segment (extra rounds); the order is a fixed function of the input either way.
+// ---------------------------------------------------------------------------
+#define TB3_SEG 2048
+#define TB3_CELLS_MAX 4096  // cells per chunk the read cursors are sized for
+
+__global__ void __launch_bounds__(TB_THREADS, 3) k_scatter_B3(
+    const long long* __restrict__ p, const int* __restrict__ gi, const double* __restrict__ y,
+    const double* __restrict__ xraw, const int* __restrict__ sel_of_gene, int n_sel, int tile_w, int chunks_per_tile,
+    int cells_per_chunk, long long n_cells, const int* __restrict__ Hg, const int* __restrict__ Hu,
+    const long long* __restrict__ base_g, const long long* __restrict__ base_u, unsigned short* __restrict__ idx_g,
+    double* __restrict__ val_g, unsigned short* __restrict__ idx_u, int split) {
+  __shared__ unsigned int cursor[TB3_SEG];  // slot inside the (tile, row) run: general | unit << 16
+  __shared__ unsigned int mask[TB3_SEG];    // cells of the current group that hold the row: general | unit << 16
+  extern __shared__ long long ccur[];       // [cells of the chunk] read cursor into the cell's entries
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long chunk = blockIdx.x;
+  const long long t = chunk / chunks_per_tile, sc = chunk % chunks_per_tile;
+  const long long c0 = min(t * tile_w + sc * (long long)cells_per_chunk, n_cells);
+  const long long c1 = min(min(c0 + cells_per_chunk, (t + 1) * (long long)tile_w), n_cells);
+  const int n_loc = (int)(c1 - c0);
+  for (int i = threadIdx.x; i < n_loc; i += blockDim.x) ccur[i] = p[c0 + i];
+  const int* Hgc = Hg + chunk * n_sel;
+  const int* Huc = split ? Hu + chunk * n_sel : nullptr;
+  const long long* btg = base_g + t * n_sel;
+  const long long* btu = split ? base_u + t * n_sel : nullptr;
+  const unsigned int below = (1u << w) - 1u;
+  for (int seg0 = 0; seg0 < n_sel; seg0 += TB3_SEG) {
+    const int seg1 = min(n_sel, seg0 + TB3_SEG), ng = seg1 - seg0;
+    __syncthreads();  // the previous segment is finished (and the read cursors are initialised)
+    for (int r = threadIdx.x; r < ng; r += blockDim.x) {
+      cursor[r] = (unsigned)Hgc[seg0 + r] | (split ? ((unsigned)Huc[seg0 + r] << 16) : 0u);
+      mask[r] = 0u;
+    }
+    __syncthreads();
+    for (int cg = 0; cg < n_loc; cg += TB_WARPS) {
+      const int ci = cg + w;
+      const bool have = ci < n_loc;
+      const long long c = c0 + ci;
+      long long lo = have ? ccur[ci] : 0;
+      const long long hi = have ? p[c + 1] : 0;
+      const int local = (int)(c - t * tile_w);
+      for (;;) {  // rounds of <= 128 entries; almost always one
+        int rr[4], sh4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long k = lo + lane + 32 * u;
+          rr[u] = (k < hi) ? gi[k] : -2;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rr[u] = (rr[u] >= 0) ? sel_of_gene[rr[u]] : rr[u];  // -1: gene not selected, -2: past the end
+        // the entries of this segment (or of unselected genes) form a prefix of the 128 in entry order 32 u + lane
+        int ncons = 0;
+        bool open = true;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned m = __ballot_sync(0xffffffffu, rr[u] != -2 && rr[u] < seg1);
+          if (open) {
+            if (m == 0xffffffffu) {
+              ncons += 32;
+            } else {
+              ncons += __ffs(~m) - 1;
+              open = false;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = 32 * u + lane;
+          sh4[u] = 0;
+          if (e < ncons && rr[u] >= seg0) {
+            rr[u] -= seg0;
+            if (split && ld_stream_f64(xraw + lo + e) == 1.0) sh4[u] = 16;
+          } else {
+            rr[u] = -1;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)  // A: which cells of the group hold the row
+          if (rr[u] >= 0) atomicOr(&mask[rr[u]], 1u << (w + sh4[u]));
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u)  // B: slot = cursor + number of earlier cells of the group with the row
+          if (rr[u] >= 0) {
+            const int q = rr[u], sh = sh4[u];
+            const unsigned int mq = (mask[q] >> sh) & 0xffffu, cq = (cursor[q] >> sh) & 0xffffu;
+            const long long dst = (sh ? btu[seg0 + q] : btg[seg0 + q]) + cq + __popc(mq & below);
+            if (sh) {
+              idx_u[dst] = (unsigned short)local;
+            } else {
+              idx_g[dst] = (unsigned short)local;
+              val_g[dst] = ld_stream_f64(y + lo + 32 * u + lane);
+            }
+          }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u)  // C: the first cell of the group with the row advances its cursor
+          if (rr[u] >= 0) {
+            const int q = rr[u], sh = sh4[u];
+            const unsigned int mq = (mask[q] >> sh) & 0xffffu;
+            if ((mq & below) == 0u) {
+              atomicAdd(&cursor[q], (unsigned)__popc(mq) << sh);
+              atomicAnd(&mask[q], ~(0xffffu << sh));
+            }
+          }
+        lo += ncons;
+        if (!__syncthreads_or(ncons == 128)) break;  // (also the barrier that ends phase C)
+      }
+      if (have && lane == 0) ccur[ci] = lo;
+    }
+  }
+}
+
 // host copies kept for the re-map after the zero-gene filter
 struct BBuild {
   std::vector<int> cnt, cnt_u;  // per-(tile, selected row) entries of the general / unit layout
@@ -891,6 +1063,14 @@ int build_layout_B(m3b_mat* m, bool split) {
   // ~2 chunks per SM in total (one CTA each), never fewer than 16 cells per chunk
   int cpt = (int)std::max<long long>(1, std::min<long long>((2LL * ctx->sm_count + n_tiles - 1) / n_tiles,
                                                              (L.tile_w + TB_WARPS - 1) / TB_WARPS));
+  {
+    // One wave of CTAs per tile: the scatter's partial-sector writes then all fall into ONE tile's output
+    // block, which L2 mostly holds, instead of ~6 tiles at once (cfg3 shape: 52 -> 38 ms for layout B).  Bounded
+    // by the size of the per-(chunk, row) count tables (two classes, 4 B each).
+    const long long table_cap = (512LL << 20) / (8LL * std::max(n_sel, 1) * n_tiles);
+    const long long want = std::min<long long>(ctx->sm_count, std::max<long long>(table_cap, cpt));
+    cpt = (int)std::max<long long>(cpt, std::min<long long>(want, (L.tile_w + TB_WARPS - 1) / TB_WARPS));
+  }
   if (const char* e = getenv("M3B_CPT")) cpt = std::max(1, std::min(atoi(e), (L.tile_w + TB_WARPS - 1) / TB_WARPS));  // sweep knob
   const int cells_per_chunk = (L.tile_w + cpt - 1) / cpt;
   const long long n_chunks = (long long)n_tiles * cpt;
@@ -925,11 +1105,25 @@ int build_layout_B(m3b_mat* m, bool split) {
       RET(dev_alloc(ctx, &H[q], (size_t)n_chunks * n_sel));
       RET(dev_alloc(ctx, &d_cnt[q], (size_t)n_tiles * n_sel));
     }
-    for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG_MAX) {
-      const int g1 = std::min(n_sel, g0 + TB_GSEG_MAX);
-      k_count_B2<<<(unsigned)n_chunks, TB_THREADS, (size_t)(g1 - g0) * 8, ctx->stream>>>(
-          m->p, m->i, m->x, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[0], H[1]);
-      count_launch(ctx);
+    if (!getenv("M3B_OLD_SCATTER")) {
+      static bool attr3 = false;
+      if (!attr3) {
+        CK(ctx, cudaFuncSetAttribute(k_count_B3, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_GSEG_PACKED * 4));
+        attr3 = true;
+      }
+      for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG_PACKED) {
+        const int g1 = std::min(n_sel, g0 + TB_GSEG_PACKED);
+        k_count_B3<<<(unsigned)n_chunks, TB_THREADS, (size_t)(g1 - g0) * 4, ctx->stream>>>(
+            m->p, m->i, m->x, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[0], H[1]);
+        count_launch(ctx);
+      }
+    } else {
+      for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG_MAX) {
+        const int g1 = std::min(n_sel, g0 + TB_GSEG_MAX);
+        k_count_B2<<<(unsigned)n_chunks, TB_THREADS, (size_t)(g1 - g0) * 8, ctx->stream>>>(
+            m->p, m->i, m->x, m->sel_of_gene, n_sel, g0, g1, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[0], H[1]);
+        count_launch(ctx);
+      }
     }
   }
   for (int q = 0; q < n_cls; ++q) {
@@ -977,6 +1171,13 @@ int build_layout_B(m3b_mat* m, bool split) {
         count_launch(ctx);
       }
     }
+    const bool seg_scatter = (both || !split) && m->sel_monotone && cells_per_chunk <= TB3_CELLS_MAX && !getenv("M3B_OLD_SCATTER");
+    if (n_runs && m->n_cells && seg_scatter) {
+      k_scatter_B3<<<(unsigned)n_chunks, TB_THREADS, (size_t)cells_per_chunk * sizeof(long long), ctx->stream>>>(
+          m->p, m->i, m->y, m->x, m->sel_of_gene, n_sel, L.tile_w, cpt, cells_per_chunk, m->n_cells, H[0], split ? H[1] : nullptr,
+          d_base[0], split ? d_base[1] : nullptr, L.idx, L.val, split ? L.unit->idx : nullptr, split ? 1 : 0);
+      count_launch(ctx);
+    } else
     if (n_runs && m->n_cells) {
       for (int g0 = 0; g0 < n_sel; g0 += TB_GSEG) {
         const int g1 = std::min(n_sel, g0 + TB_GSEG);
@@ -1210,31 +1411,49 @@ int finish_selection(m3b_mat* m, unsigned char* keep_host) {
 // for the index-only unit stream, whose lanes gather component j of their 16-byte load together),
 // so position p belongs to lane class (p / S) mod 16.
 // ---------------------------------------------------------------------------
-#define BR_WARPS 3
-#define BR_MAX M3B_UITEM_MAX  // >= M3B_ITEM_MAX
+// The pass is memory-latency bound (a warp walks its item in 32-entry steps), so what counts is
+// warps per SM and bytes per load: the staging per warp is cut to what the layout kind needs (no
+// value arrays for the index-only unit layouts) and the item is read and written back with
+// 16-byte accesses through a second shared-memory copy.  (First version: 3 warps per SM and one
+// 2-byte load per lane and step -- 33 ms of a 100 ms m3b_select_genes at the cfg3 shape.)
+template <bool HAS_VAL, int MAXE>
+struct BrSmem {
+  // per warp: source idx, destination position, hole list, permuted idx (+ source / permuted values)
+  static constexpr int bytes = MAXE * (2 + 2 + 2 + 2) + (HAS_VAL ? MAXE * 16 : 0) + 256;
+};
 
-__global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* __restrict__ idx, double* __restrict__ val,
-                                                               const ItemDesc* __restrict__ items, long long n_items,
-                                                               int S /* 2 or 8 */, int lgS) {
-  extern __shared__ unsigned char br_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // per-warp staging: source idx/val, destination position of every entry, hole list
-  unsigned char* base = br_smem + (size_t)warp * (BR_MAX * (2 + 8 + 2 + 2) + 256);
-  double* sval = reinterpret_cast<double*>(base);
-  unsigned short* sidx = reinterpret_cast<unsigned short*>(base + BR_MAX * 8);
-  unsigned short* dpos = sidx + BR_MAX;   // destination position of source entry e
-  unsigned short* hole = dpos + BR_MAX;   // positions of the holes, in class order
-  int* cnt = reinterpret_cast<int*>(hole + BR_MAX);  // [16] entries per class, then scratch [16..63]
+template <bool HAS_VAL, int MAXE>
+__global__ void __launch_bounds__(256) k_bank_reorder(unsigned short* __restrict__ idx, double* __restrict__ val,
+                                                      const ItemDesc* __restrict__ items, long long n_items,
+                                                      int S /* 2 or 8 */, int lgS) {
+  extern __shared__ __align__(16) unsigned char br_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  unsigned char* base = br_smem + (size_t)warp * BrSmem<HAS_VAL, MAXE>::bytes;
+  unsigned short* sidx = reinterpret_cast<unsigned short*>(base);
+  unsigned short* dpos = sidx + MAXE;   // destination position of source entry e
+  unsigned short* hole = dpos + MAXE;   // positions of the holes, in class order
+  unsigned short* sout = hole + MAXE;   // permuted indices
+  double* sval = reinterpret_cast<double*>(sout + MAXE);                       // HAS_VAL only
+  double* vout = sval + MAXE;                                                  // HAS_VAL only
+  int* cnt = reinterpret_cast<int*>(base + BrSmem<HAS_VAL, MAXE>::bytes - 256);  // [16] per class, then scratch [16..63]
   const unsigned lt = (1u << lane) - 1u;
-  for (long long it = (long long)blockIdx.x * BR_WARPS + warp; it < n_items; it += (long long)gridDim.x * BR_WARPS) {
+  for (long long it = (long long)blockIdx.x * nwarps + warp; it < n_items; it += (long long)gridDim.x * nwarps) {
     const ItemDesc d = items[it];
     const int len = d.len;
-    if (len < 64 || len > BR_MAX) continue;  // too short to matter (or unexpected)
-    for (int e = lane; e < len; e += 32) {
-      sidx[e] = idx[d.start + e];
-      if (val) sval[e] = val[d.start + e];
+    if (len < 64 || len > MAXE) continue;  // too short to matter (or unexpected)
+    // items start on a multiple of 4 entries (general) / 8 entries (unit) and have such a length:
+    // 8-byte / 16-byte accesses on idx, 16-byte accesses on val
+    if (HAS_VAL) {
+      const uint2* g2 = reinterpret_cast<const uint2*>(idx + d.start);
+      for (int q = lane; q < (len >> 2); q += 32) reinterpret_cast<uint2*>(sidx)[q] = g2[q];
+      const double2* v2 = reinterpret_cast<const double2*>(val + d.start);
+      for (int q = lane; q < (len >> 1); q += 32) reinterpret_cast<double2*>(sval)[q] = v2[q];
+    } else {
+      const uint4* g4 = reinterpret_cast<const uint4*>(idx + d.start);
+      for (int q = lane; q < (len >> 3); q += 32) reinterpret_cast<uint4*>(sidx)[q] = g4[q];
     }
-    if (lane < 32) cnt[lane] = 0, cnt[32 + lane] = 0;
+    cnt[lane] = 0;
+    cnt[32 + lane] = 0;
     __syncwarp();
     // stable rank of every entry inside its class
     for (int e0 = 0; e0 < len; e0 += 32) {
@@ -1266,9 +1485,9 @@ __global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* 
     int po = over, ph = holes;
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, po, o), h = __shfl_up_sync(0xffffffffu, ph, o);
+      const int a2 = __shfl_up_sync(0xffffffffu, po, o), h = __shfl_up_sync(0xffffffffu, ph, o);
       if (lane >= o) {
-        po += a;
+        po += a2;
         ph += h;
       }
     }
@@ -1287,13 +1506,18 @@ __global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* 
       int p;
       if (r < nb) p = period * (r >> lgS) + S * b + (r & (S - 1));
       else p = hole[cnt[32 + b] + (r - nb)];
-      dpos[e] = (unsigned short)p;
+      sout[p] = sidx[e];
+      if (HAS_VAL) vout[p] = sval[e];
     }
     __syncwarp();
-    for (int e = lane; e < len; e += 32) {
-      const int p = dpos[e];
-      idx[d.start + p] = sidx[e];
-      if (val) val[d.start + p] = sval[e];
+    if (HAS_VAL) {
+      uint2* g2 = reinterpret_cast<uint2*>(idx + d.start);
+      for (int q = lane; q < (len >> 2); q += 32) g2[q] = reinterpret_cast<const uint2*>(sout)[q];
+      double2* v2 = reinterpret_cast<double2*>(val + d.start);
+      for (int q = lane; q < (len >> 1); q += 32) v2[q] = reinterpret_cast<const double2*>(vout)[q];
+    } else {
+      uint4* g4 = reinterpret_cast<uint4*>(idx + d.start);
+      for (int q = lane; q < (len >> 3); q += 32) g4[q] = reinterpret_cast<const uint4*>(sout)[q];
     }
     __syncwarp();
   }
@@ -1301,15 +1525,20 @@ __global__ void __launch_bounds__(32 * BR_WARPS) k_bank_reorder(unsigned short* 
 
 static int bank_reorder(m3b_ctx* ctx, TiledLayout& L) {
   if (L.n_items == 0 || getenv("M3B_NO_BANK_REORDER")) return M3B_OK;
-  const size_t smem = (size_t)BR_WARPS * (BR_MAX * (2 + 8 + 2 + 2) + 256);
   static bool attr = false;
+  constexpr int SM_U = BrSmem<false, M3B_UITEM_MAX>::bytes, SM_G = BrSmem<true, M3B_ITEM_MAX>::bytes;
+  constexpr int W_U = 6, W_G = 4;  // warps per CTA: 6 x 33 KB / 4 x 48 KB of staging, one CTA per SM
   if (!attr) {
-    CK(ctx, cudaFuncSetAttribute(k_bank_reorder, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(ctx, cudaFuncSetAttribute(k_bank_reorder<false, M3B_UITEM_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_U * SM_U));
+    CK(ctx, cudaFuncSetAttribute(k_bank_reorder<true, M3B_ITEM_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_G * SM_G));
     attr = true;
   }
-  const unsigned grid = (unsigned)std::min<long long>((L.n_items + BR_WARPS - 1) / BR_WARPS, (long long)ctx->sm_count * 4);
-  k_bank_reorder<<<grid, 32 * BR_WARPS, smem, ctx->stream>>>(L.idx, L.val, L.items, L.n_items, L.is_unit ? 8 : 2,
-                                                             L.is_unit ? 3 : 1);
+  const int w = L.is_unit ? W_U : W_G;
+  const unsigned grid = (unsigned)std::min<long long>((L.n_items + w - 1) / w, (long long)ctx->sm_count);
+  if (L.is_unit)
+    k_bank_reorder<false, M3B_UITEM_MAX><<<grid, 32 * w, W_U * SM_U, ctx->stream>>>(L.idx, nullptr, L.items, L.n_items, 8, 3);
+  else
+    k_bank_reorder<true, M3B_ITEM_MAX><<<grid, 32 * w, W_G * SM_G, ctx->stream>>>(L.idx, L.val, L.items, L.n_items, 2, 1);
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
   return M3B_OK;
@@ -1475,6 +1704,123 @@ __global__ void __launch_bounds__(256) k_scatter_A2(const long long* __restrict_
   }
 }
 
+// Layout A in ONE pass over the cell's entries for all (<= 4) gene tiles and both classes
+// (k_count_A2 / k_scatter_A2 read the cell once per tile: 11.8 GB of DRAM reads for a 5.7 GB input
+// at the cfg3 shape, and one dependent load chain per 32 entries).  Four batches of 32 entries are
+// loaded up front; positions come from one ballot per (tile, class).
+template <int NT>
+__global__ void __launch_bounds__(256) k_count_A3(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                  const double* __restrict__ xraw, const int* __restrict__ kept_of_gene,
+                                                  long long n_cells, int tile_w, int n_tiles, int split,
+                                                  int* __restrict__ cnt_g, int* __restrict__ cnt_u) {
+  const int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    int ng[NT], nu[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) ng[t] = nu[t] = 0;
+    for (long long k0 = lo; k0 < hi; k0 += 128) {
+      int g[4];
+      double x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long k = k0 + lane + 32 * u;
+        g[u] = (k < hi) ? ld_stream_s32(gi + k) : -1;
+        x[u] = (split && k < hi) ? ld_stream_f64(xraw + k) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) g[u] = (g[u] >= 0) ? kept_of_gene[g[u]] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tl = (g[u] >= 0) ? g[u] / tile_w : -1;
+        const bool one = split && x[u] == 1.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          ng[t] += __popc(__ballot_sync(0xffffffffu, tl == t && !one));
+          if (split) nu[t] += __popc(__ballot_sync(0xffffffffu, tl == t && one));
+        }
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        if (t < n_tiles) {
+          cnt_g[(long long)t * n_cells + c] = ng[t];
+          if (split) cnt_u[(long long)t * n_cells + c] = nu[t];
+        }
+    }
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256) k_scatter_A3(const long long* __restrict__ p, const int* __restrict__ gi,
+                                                    const double* __restrict__ y, const double* __restrict__ xraw,
+                                                    const int* __restrict__ kept_of_gene, long long n_cells, int tile_w,
+                                                    int n_tiles, int split, const long long* __restrict__ base_g,
+                                                    const long long* __restrict__ base_u, unsigned short* __restrict__ idx_g,
+                                                    double* __restrict__ val_g, unsigned short* __restrict__ idx_u) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = warp; c < n_cells; c += nwarps) {
+    const long long lo = p[c], hi = p[c + 1];
+    long long dg[NT], du[NT];
+    int rg[NT], ru[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      dg[t] = (t < n_tiles) ? base_g[(long long)t * n_cells + c] : 0;
+      du[t] = (split && t < n_tiles) ? base_u[(long long)t * n_cells + c] : 0;
+      rg[t] = ru[t] = 0;
+    }
+    for (long long k0 = lo; k0 < hi; k0 += 128) {
+      int g[4];
+      double x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long k = k0 + lane + 32 * u;
+        g[u] = (k < hi) ? ld_stream_s32(gi + k) : -1;
+        x[u] = (split && k < hi) ? ld_stream_f64(xraw + k) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) g[u] = (g[u] >= 0) ? kept_of_gene[g[u]] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long k = k0 + lane + 32 * u;
+        const int tl = (g[u] >= 0) ? g[u] / tile_w : -1;
+        const bool one = split && x[u] == 1.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const unsigned mg = __ballot_sync(0xffffffffu, tl == t && !one);
+          if (tl == t && !one) {
+            const long long dst = dg[t] + rg[t] + __popc(mg & lt);
+            idx_g[dst] = (unsigned short)(g[u] - t * tile_w);
+            val_g[dst] = ld_stream_f64(y + k);
+          }
+          rg[t] += __popc(mg);
+          if (split) {
+            const unsigned mu = __ballot_sync(0xffffffffu, tl == t && one);
+            if (tl == t && one) idx_u[du[t] + ru[t] + __popc(mu & lt)] = (unsigned short)(g[u] - t * tile_w);
+            ru[t] += __popc(mu);
+          }
+        }
+      }
+    }
+    // pads: general runs to 4 entries (idx 0, val 0), unit runs to 8 (idx = tile_w, the zero slot behind the tile)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int pg = (rg[t] + 3) & ~3, pu = (ru[t] + 7) & ~7;
+      if (lane < pg - rg[t]) {
+        idx_g[dg[t] + rg[t] + lane] = 0;
+        val_g[dg[t] + rg[t] + lane] = 0.0;
+      }
+      if (split && lane < pu - ru[t]) idx_u[du[t] + ru[t] + lane] = (unsigned short)tile_w;
+    }
+  }
+}
+
 int build_layout_A(m3b_mat* m, bool split) {
   m3b_ctx* ctx = m->ctx;
   TiledLayout& L = m->A;
@@ -1506,15 +1852,27 @@ int build_layout_A(m3b_mat* m, bool split) {
   TiledLayout* Ls[2] = {&L, L.unit};
   int blocks = (int)std::max<long long>(1, std::min<long long>((m->n_cells + 7) / 8, (long long)ctx->sm_count * 8));
   const bool both = split && m->n_cells && !getenv("M3B_NO_COMBINED_BUILD");  // one pass for both classes
-  if (both) {
+  // one pass over the cells for all tiles and both classes (<= 4 gene tiles; device tables only)
+  const bool one_pass = !use_host_tables() && (both || !split) && m->n_cells && L.n_tiles <= 4 && !getenv("M3B_OLD_SCATTER");
+  if (one_pass) {
+    for (int q = 0; q < n_cls; ++q) RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
+    const int sp = split ? 1 : 0;
+    if (L.n_tiles == 1)
+      k_count_A3<1><<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, sp, d_cnt[0], d_cnt[1]);
+    else if (L.n_tiles == 2)
+      k_count_A3<2><<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, sp, d_cnt[0], d_cnt[1]);
+    else
+      k_count_A3<4><<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, sp, d_cnt[0], d_cnt[1]);
+    count_launch(ctx);
+  } else if (both) {
     for (int q = 0; q < 2; ++q) RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
     k_count_A2<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, d_cnt[0],
                                                 d_cnt[1]);
     count_launch(ctx);
   }
   for (int q = 0; q < n_cls; ++q) {
-    if (!both) RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
-    if (m->n_cells && !both) {
+    if (!both && !one_pass) RET(dev_alloc(ctx, &d_cnt[q], (size_t)std::max<long long>(n_runs, 1)));
+    if (m->n_cells && !both && !one_pass) {
       k_count_A<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->x, split ? q + 1 : 0, m->kept_of_gene, m->n_cells, L.tile_w,
                                                  L.n_tiles, d_cnt[q]);
       count_launch(ctx);
@@ -1536,7 +1894,20 @@ int build_layout_A(m3b_mat* m, bool split) {
       RET(dev_alloc(ctx, &Ls[q]->idx, (size_t)std::max<long long>(n_ent[q], 1)));
       if (q == 0) RET(dev_alloc(ctx, &Ls[q]->val, (size_t)std::max<long long>(n_ent[q], 1)));
     }
-    if (n_runs) {
+    if (n_runs && one_pass) {
+      const int sp = split ? 1 : 0;
+      unsigned short* iu = split ? L.unit->idx : nullptr;
+      if (L.n_tiles == 1)
+        k_scatter_A3<1><<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, sp,
+                                                         d_base[0], d_base[1], L.idx, L.val, iu);
+      else if (L.n_tiles == 2)
+        k_scatter_A3<2><<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, sp,
+                                                         d_base[0], d_base[1], L.idx, L.val, iu);
+      else
+        k_scatter_A3<4><<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles, sp,
+                                                         d_base[0], d_base[1], L.idx, L.val, iu);
+      count_launch(ctx);
+    } else if (n_runs) {
       if (both) {
         k_scatter_A2<<<blocks, 256, 0, ctx->stream>>>(m->p, m->i, m->y, m->x, m->kept_of_gene, m->n_cells, L.tile_w, L.n_tiles,
                                                       d_base[0], d_base[1], L.idx, L.val, L.unit->idx);

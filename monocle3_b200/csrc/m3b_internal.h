@@ -305,6 +305,9 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
               int center, int scale, double* d, double* V, double* X, long long ldx,
               double* center_out, double* scale_out, int* iter, int* mprod, bool copy_x);
 int compute_moments(m3b_mat* m);
+// tiny.cu: irlba's dense branch for min(cells, genes) < 6
+int run_irlba_tiny(m3b_mat* m, int nv, int center, int scale, double* d, double* V, double* X, long long ldx, double* center_out,
+                   double* scale_out, int* iter, int* mprod, bool copy_x);
 
 // project.cu
 int run_select_for_transform(m3b_mat* m, const int* gene_order, int n_sel, unsigned char* keep, int* n_kept, int* fallback);

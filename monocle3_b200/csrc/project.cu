@@ -212,23 +212,20 @@ k_project_tiled(const long long* __restrict__ p, const int* __restrict__ gi, con
         const bool cons = (((m >> j_of) & 0x01010101u) & need) == need;
         const unsigned mc = __ballot_sync(0xffffffffu, cons);
         if (mc == 0u) break;
-        const bool contrib = cons && kq >= g0;
-        const unsigned mv = __ballot_sync(0xffffffffu, contrib);
-        // Branch-free inside a group of 8 slots (one per cell): a slot without a contribution reads row 0
-        // with the value 0, so the eight shuffle / LDS.128 / DFMA chains of a group are independent
-        // and the compiler overlaps their latencies (the first version branched per slot: every
-        // step waited for its own shuffle and shared-memory load, 24 k cycles per tile).
-        const int off = contrib ? (kq - g0) * nvp : 0;  // doubles into the tile
-        const double vv = contrib ? val : 0.0;
+        // (a branch-free variant -- slots without a contribution read row 0 with the value 0 so that the
+        // eight chains of a group overlap -- was SLOWER, 89 vs 73 ms at the cfg5 shape: the kernel is
+        // bound by the shared-memory pipe, and the dummy slots add LDS traffic)
+        const unsigned mv = __ballot_sync(0xffffffffu, cons && kq >= g0);
+        const int local = kq - g0;
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-          if ((mv >> (8 * s4)) & 0xffu) {  // warp-uniform: any of the 8 cells has a slot-s4 entry
+        for (int j = 0; j < PT_CPW; ++j) {
 #pragma unroll
-            for (int j = 0; j < PT_CPW; ++j) {
-              const int ql = s4 * 8 + j;
-              const int o = __shfl_sync(0xffffffffu, off, ql);
-              const double v = __shfl_sync(0xffffffffu, vv, ql);
-              const double* row = tile + o;
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int ql = s4 * 8 + j;
+            if ((mv >> ql) & 1u) {  // warp-uniform
+              const int g = __shfl_sync(0xffffffffu, local, ql);
+              const double v = __shfl_sync(0xffffffffu, val, ql);
+              const double* row = tile + (size_t)g * nvp;
               if (first) {
                 const double2 a = *reinterpret_cast<const double2*>(row + 2 * lane);
                 acc[j][0] = fma(v, a.x, acc[j][0]);

@@ -59,6 +59,15 @@ def irlba(A, nv, v0, center=None, scale=None, work=None, maxit=1000, tol=1e-5,
         work = nv + 7
     if nv >= min(m, n):
         raise ValueError("max(nu, nv) must be strictly less than min(nrow(A), ncol(A))")
+    if min(m, n) < 6:
+        # irlba R/irlba.R: "Tiny problem detected, using standard `svd` function" 
+        D = A.toarray() if hasattr(A, "toarray") else np.asarray(A, dtype=np.float64)
+        if center is not None:
+            D = D - center[None, :]
+        if scale is not None:
+            D = D / scale[None, :]
+        U, S, Vt = np.linalg.svd(D, full_matrices=False)
+        return IrlbaResult(d=S[:nu].copy(), u=U[:, :nu].copy(), v=Vt.T[:, :nv].copy(), iter=0, mprod=0, err=0)
     if work <= nv:
         work = nv + 1
     work = min(work, min(m, n))

@@ -35,6 +35,49 @@ estimate_sf_sparse <- function(counts, round_exprs=TRUE, method="mean-geometric-
   pc <- model$pseudo_count; if (is.null(pc)) pc <- if (model$norm_method == "log") 1 else 0
   y <- m3b_preprocess_transform(SingleCellExperiment::counts(cds), size_factors(cds),
                                 match(model$norm_method, c("log", "size_only", "none")) - 1L, pc,
-                                row_of_gene, model$svd_v, model$svd_center, model$svd_scale)
+                                row_of_gene, model$svd_v, model$svd_center, model$svd_scale,
+                                model$row_sums, if (is.null(model$num_cols)) 0 else model$num_cols)  # LSI: the MODEL's idf
   rownames(y) <- colnames(cds); y
+}
+
+# replaces the LSI branch body of preprocess_cds, R/preprocess_cds.R:185-241 (tfidf() + irlba without centre / scale)
+.m3b_lsi <- function(cds, num_dim, norm_method, use_genes, pseudo_count) {
+  if (is.null(pseudo_count)) pseudo_count <- if (norm_method == "log") 1 else 0
+  gene_order <- if (is.null(use_genes)) NULL else match(use_genes, rownames(cds)) - 1L
+  set.seed(2016)
+  v0 <- rnorm(nrow(cds))
+  res <- m3b_preprocess_lsi(SingleCellExperiment::counts(cds), size_factors(cds),
+                            match(norm_method, c("log", "size_only", "none")) - 1L, pseudo_count, gene_order, num_dim, v0)
+  kept <- (if (is.null(use_genes)) rownames(cds) else use_genes)[as.logical(res$keep)]
+  x <- res$x; rownames(x) <- colnames(cds)                                                   # :196-197
+  v <- res$v; rownames(v) <- kept                                                            # :199-200
+  list(x = x, v = v, d = res$d, col_sums = res$col_sums, row_sums = res$row_sums, num_cols = res$num_cols,
+       sdev = res$d / sqrt(max(1, res$num_cols - 1)))                                        # :213
+}
+
+# replaces the sparse branch of normalized_counts, R/utils.R:488-503
+.m3b_normalized_counts <- function(cds, norm_method = c("log", "binary", "size_only"), pseudocount = 1) {
+  norm_method <- match.arg(norm_method)
+  norm_mat <- SingleCellExperiment::counts(cds)
+  if (norm_method == "log" && pseudocount != 1) stop("Pseudocount must equal 1 with sparse expression matrices")
+  code <- c(log = 3L, size_only = 1L, binary = 4L)[[norm_method]]        # M3B_NORM_LOG10 / SIZE_ONLY / BINARY
+  norm_mat@x <- m3b_normalized_counts_x(norm_mat, size_factors(cds), code, if (norm_method == "log") 1 else 0)
+  if (norm_method == "binary") norm_mat <- Matrix::drop0(norm_mat)
+  norm_mat
+}
+
+# replaces lmFit + the subtraction in align_cds, R/alignment.R:112-117
+.m3b_align_residuals <- function(preproc_res, X.model_mat) {
+  res <- m3b_align_residuals_(as.matrix(preproc_res), as.matrix(X.model_mat))
+  beta <- res$beta
+  rownames(beta) <- colnames(preproc_res); colnames(beta) <- colnames(X.model_mat)[-1]
+  aligned <- res$aligned; dimnames(aligned) <- dimnames(preproc_res)
+  list(preproc_res = aligned, beta = beta)
+}
+
+# replaces the subtraction in align_beta_transform, R/projection.R:477-478
+.m3b_align_beta_transform <- function(preproc_res, X.model_mat, beta) {
+  out <- m3b_align_apply_beta_(as.matrix(preproc_res), as.matrix(X.model_mat), as.matrix(beta))
+  dimnames(out) <- dimnames(preproc_res)
+  out
 }

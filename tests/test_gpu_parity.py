@@ -547,3 +547,24 @@ def test_knn_jaccard_graph_on_pca(m3, worm_l2):
     assert np.array_equal(g["relations"][0], links[:, 0]) and np.array_equal(g["relations"][1], links[:, 1])
     assert np.array_equal(g["relations"][2], links[:, 2])
     np.testing.assert_allclose(g["distMatrix"], distm, rtol=1e-13)
+
+
+@pytest.mark.parametrize("shape", [(5, 300), (300, 5), (4, 4000)])
+def test_irlba_tiny_problem_dense_branch(m3, shape):
+    """min(cells, kept genes) < 6: irlba switches to a dense svd (irlba R/irlba.R, SURVEY.md Appendix A.2);
+    iter = mprod = 0."""
+    G, C = shape
+    rng = np.random.default_rng(7)
+    dense = rng.poisson(1.5, size=(G, C)).astype(np.float64)
+    dense[:, dense.sum(axis=0) == 0] = 1.0
+    dense[dense.sum(axis=1) == 0, 0] = 1.0
+    counts = sp.csc_matrix(dense)
+    nd = min(G, C) - 2
+    for scaling in (True, False):
+        cds = m3.preprocess_cds(_cds(m3, counts), num_dim=nd, scaling=scaling)
+        o = ref.preprocess_cds(counts, ref.estimate_size_factors(counts), num_dim=nd, scaling=scaling)
+        ir = cds.reduce_dim_aux["PCA"]["irlba"]
+        assert ir["iter"] == 0 and ir["mprod"] == 0 and o["iter"] == 0
+        assert sv_rel_err(ir["d"], o["d"]) < SV_TOL
+        assert subspace_angle(cds.reduce_dim_aux["PCA"]["model"]["svd_v"], o["svd_v"]) < ANGLE_TOL
+        assert subspace_angle(cds.reduced_dims["PCA"], o["PCA"]) < ANGLE_TOL

@@ -36,11 +36,13 @@ def main():
         dev = cds.device_matrix()
         sf = m3.size_factors(cds)
         res = {}
-        for mode in ("device", "host"):
+        for mode in ("device", "host", "oldscatter"):
+            os.environ.pop("M3B_HOST_TABLES", None)
+            os.environ.pop("M3B_OLD_SCATTER", None)
             if mode == "host":
                 os.environ["M3B_HOST_TABLES"] = "1"
-            else:
-                os.environ.pop("M3B_HOST_TABLES", None)
+            if mode == "oldscatter":      # device tables, but the round-1 scatter / count kernels
+                os.environ["M3B_OLD_SCATTER"] = "1"
             dev.normalize(sf, L.NORM_LOG2, 1.0)
             dev.select_genes(None)          # warm
             dev.normalize(sf, L.NORM_LOG2, 1.0)
@@ -51,17 +53,25 @@ def main():
             r = dev.pca_irlba(nd, v0, center=True, scale=True)
             res[mode] = (r, keep, t_sel, ctx.stats()["select_ms"])
         os.environ.pop("M3B_HOST_TABLES", None)
+        os.environ.pop("M3B_OLD_SCATTER", None)
         a, b = res["device"][0], res["host"][0]
+        c_old = res["oldscatter"][0]
         rec = dict(case=name, kept=int(dev.n_kept), iter=(a["iter"], b["iter"]), mprod=(a["mprod"], b["mprod"]),
                    d_identical=bool(np.array_equal(a["d"], b["d"])), v_identical=bool(np.array_equal(a["v"], b["v"])),
                    x_identical=bool(np.array_equal(a["x"], b["x"])), keep_identical=bool(np.array_equal(res["device"][1], res["host"][1])),
                    d_max_rel=float(np.max(np.abs(a["d"] - b["d"]) / b["d"])),
+                   new_vs_old_scatter_identical=bool(np.array_equal(a["d"], c_old["d"]) and np.array_equal(a["x"], c_old["x"])),
+                   new_vs_old_scatter_d_max_rel=float(np.max(np.abs(a["d"] - c_old["d"]) / c_old["d"])),
+                   select_ms_oldscatter=round(1e3 * res["oldscatter"][2], 2),
                    select_ms_device=round(1e3 * res["device"][2], 2), select_ms_host=round(1e3 * res["host"][2], 2),
                    select_phases_device=[round(v, 2) for v in res["device"][3]], select_phases_host=[round(v, 2) for v in res["host"][3]])
         print("AB_TABLES " + json.dumps(rec), flush=True)
         out.append(rec)
         dev.free()
-    ok = all(r["d_identical"] and r["v_identical"] and r["x_identical"] and r["keep_identical"] for r in out)
+    # bit-identical wherever the two builders produce the same plans; the host builder makes no side-stream
+    # plan for multi-tile layouts (case a), where the first product of a cycle is then summed in another order
+    ok = all((r["d_identical"] and r["v_identical"] and r["x_identical"] or r["d_max_rel"] < 1e-13) and r["keep_identical"]
+             and r["new_vs_old_scatter_d_max_rel"] < 1e-13 for r in out)
     print("AB_TABLES_OK %s" % ok)
     return 0 if ok else 1
 
