@@ -50,6 +50,7 @@ WORKLOADS = {
                  model_cells=250000, model_seed=1),
 }
 METRIC = "cells/sec preprocess_cds PCA (num_dim=100)"
+BLOCK_CELLS = 262144   # cells per CSC block when one rank's matrix exceeds a dgCMatrix (multiple of synth.BLOCK)
 
 
 def parse_args():
@@ -559,13 +560,28 @@ def main():
     C_total = wl["cells"]
     spec = SynthSpec(wl["n_genes"], C_total, wl["density"], wl["n_types"], wl["seed"])
     t_gen0 = time.perf_counter()
-    lo, hi, indptr, indices, data = balanced_shard(spec, rank, world, m3dist.make_allgather() if world > 1 else None)
-    gen_s = time.perf_counter() - t_gen0
-    (indptr_p, k1), (indices_p, k2), (data_p, k3) = pinned(indptr.astype(np.int32)), pinned(indices), pinned(data)
-    counts = sp.csc_matrix((data_p, indices_p, indptr_p), shape=(wl["n_genes"], hi - lo), copy=False)
+    keep_alive = []
+    if world == 1 and C_total * wl["n_genes"] * wl["density"] > 1.5e9:
+        # beyond one dgCMatrix (< 2^31 stored entries): consecutive cell blocks, each a CSC of its own,
+        # appended in order through m3b_matrix_append_csc (monocle3_b200.CSCBlocks)
+        blocks, lo, hi = [], 0, C_total
+        for b0 in range(0, C_total, BLOCK_CELLS):
+            ip_b, ii_b, vv_b = spec.cells(b0, min(C_total, b0 + BLOCK_CELLS))
+            (ip_p, q1), (ii_p, q2), (vv_p, q3) = pinned(ip_b.astype(np.int32)), pinned(ii_b), pinned(vv_b)
+            keep_alive += [q1, q2, q3]
+            blocks.append(sp.csc_matrix((vv_p, ii_p, ip_p), shape=(wl["n_genes"], len(ip_b) - 1), copy=False))
+            del ip_b, ii_b, vv_b
+        counts = m3.CSCBlocks(blocks)
+        gen_s = time.perf_counter() - t_gen0
+    else:
+        lo, hi, indptr, indices, data = balanced_shard(spec, rank, world, m3dist.make_allgather() if world > 1 else None)
+        gen_s = time.perf_counter() - t_gen0
+        (indptr_p, k1), (indices_p, k2), (data_p, k3) = pinned(indptr.astype(np.int32)), pinned(indices), pinned(data)
+        counts = sp.csc_matrix((data_p, indices_p, indptr_p), shape=(wl["n_genes"], hi - lo), copy=False)
+        del indptr, indices, data
     nnz_local = int(counts.nnz)
     shard = m3dist.make_shard(C_total) if world > 1 else None
-    del spec, indptr, indices, data
+    del spec
     torch.cuda.empty_cache()
 
     # ---- device-resident arm: counts + size factors already in HBM ----
@@ -607,6 +623,16 @@ def main():
     launches = int(sum_over_ranks(st["kernel_launches"]))
     value = C_total / (ms_step / 1e3)
     irlba_ms_untimed = max_over_ranks(st["irlba_ms"])
+    xd = st.get("xchg_diag", [0.0] * 8)
+    xchg = None
+    if world > 1 and xd[5] + xd[6] > 0:
+        # in-kernel exchange cost of the LAST timed step on rank 0 (clock64 on CTA 0 of the fused vector kernel)
+        nF, nW = max(1.0, xd[5]), max(1.0, xd[6])
+        xchg = {"rank": 0, "launches_gene_side": int(xd[5]), "launches_cell_side": int(xd[6]),
+                "wait_us_per_launch": {"gene_vector_rows": round(xd[0] / nF, 2), "gs_coefficients": round(xd[1] / nW, 2),
+                                       "norm_partials": round(xd[2] / nW, 2)},
+                "kernel_us_per_launch": {"gene_side": round(xd[3] / nF, 2), "cell_side": round(xd[4] / nW, 2)},
+                "note": "waits include rank skew; cycles at the nominal SM clock"}
     select_ms = [max_over_ranks(v) for v in st["select_ms"]]
 
     # ---- parity of this run against the stored single-GPU run of the same matrix ----
@@ -731,16 +757,20 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on this very matrix, bounded product count ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sub = sp.csc_matrix((np.asarray(counts.data), np.asarray(counts.indices), np.asarray(counts.indptr).astype(np.int64)),
-                            shape=counts.shape)
-        dt, parts = reference_step(sub, wl, res["mprod"], res["iter"], 2, 1)
+        blk = counts.blocks[0] if isinstance(counts, m3.CSCBlocks) else counts
+        scale = nnz_local / max(1, int(blk.nnz))   # > 1 only beyond the dgCMatrix limit (first cell block, scaled in nnz)
+        sub = sp.csc_matrix((np.asarray(blk.data), np.asarray(blk.indices), np.asarray(blk.indptr).astype(np.int64)),
+                            shape=blk.shape)
+        dt, parts = reference_step(sub, wl, res["mprod"], res["iter"], 2, scale)
         cpu_baseline = {"value": C_total / dt, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
                         "sample": "restated CPU path (irlba algorithm; SciPy SpMV single-threaded like CHOLMOD sdmult, "
-                                  "NumPy/OpenBLAS dense ops on all threads) on THIS run's full matrix (%d cells, nnz %d): prep in "
-                                  "full %.1f s + (mprod %d / 2) x product pair %.3f s + iter %d x restart %.3f s = %.1f s per step; "
-                                  "2 product pairs timed at full size, mprod/iter are this run's"
-                                  % (C_total, parts["nnz"], parts["prep_s"], res["mprod"], parts["pair_s"], res["iter"],
-                                     parts["restart_s"], dt)}
+                                  "NumPy/OpenBLAS dense ops on all threads) on %s (%d cells, nnz %d): prep in "
+                                  "full %.1f s + (mprod %d / 2) x product pair %.3f s + iter %d x restart %.3f s%s = %.1f s per step; "
+                                  "2 product pairs timed at that size, mprod/iter are this run's"
+                                  % ("THIS run's full matrix" if scale == 1 else
+                                     "the first cell block of this run's matrix (a dgCMatrix holds < 2^31 entries)",
+                                     blk.shape[1], parts["nnz"], parts["prep_s"], res["mprod"], parts["pair_s"], res["iter"],
+                                     parts["restart_s"], "" if scale == 1 else ", all x %.2f (linear in nnz)" % scale, dt)}
     nnz_total = int(sum_over_ranks(nnz_local))
     nnz_max = int(max_over_ranks(nnz_local))
     if rank == 0:
@@ -752,7 +782,7 @@ def main():
                "us_per_product": 1e3 * irlba_ms_untimed / max(1, res["mprod"]),
                "us_per_product_note": "device time of m3b_pca_irlba (max over ranks) of the last timed step / mprod: products, "
                                       "vector work, exchanges, restarts",
-               "parity_vs_single_gpu": parity,
+               "parity_vs_single_gpu": parity, "exchange": xchg,
                "roofline": roofline, "cpu_baseline": cpu_baseline,
                "select_genes_phase_ms": dict(zip(["layout_B", "row_sums_filter", "remap_plans_B", "layout_A"],
                                                  [round(v, 2) for v in select_ms])),

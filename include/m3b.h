@@ -292,6 +292,12 @@ typedef struct m3b_stats {
    * [1] row sums + keep mask [2] re-map + plans of B [3] layout A build + plans */
   double  select_ms[4];
   double  k10_ms;              /* CUDA-event time of the last K10 (projection) kernel(s)  */
+  /* cell-sharded runs, last m3b_pca_irlba: what the in-kernel cross-rank exchanges of the fused
+   * vector kernel cost, measured with clock64 on CTA 0 and summed over the launches (us at the
+   * nominal SM clock): [0] wait for the peers' gene-vector rows  [1] wait for the peers'
+   * Gram-Schmidt coefficients  [2] wait for the world's norm partials  [3] whole kernel, gene side
+   * [4] whole kernel, cell side  [5] launches, gene side  [6] launches, cell side  [7] clock (kHz) */
+  double  xchg_diag[8];
 } m3b_stats;
 int m3b_get_stats(const m3b_ctx* ctx, m3b_stats* out);
 /* Measured fp64 FMA throughput of the device (TFLOP/s): the roof K10 (projection) is reported

@@ -43,7 +43,8 @@ class Stats(C.Structure):
                 ("svd_sweeps", C.c_int64), ("host_ms", C.c_double * 4),
                 ("svd_fallbacks", C.c_int64), ("k1_ms", C.c_double), ("k2_ms", C.c_double),
                 ("svd_fallback_reasons", C.c_int64), ("spmv_stream_bytes_cells_out", C.c_int64),
-                ("spmv_stream_bytes_genes_out", C.c_int64), ("select_ms", C.c_double * 4), ("k10_ms", C.c_double)]
+                ("spmv_stream_bytes_genes_out", C.c_int64), ("select_ms", C.c_double * 4), ("k10_ms", C.c_double),
+                ("xchg_diag", C.c_double * 8)]
 
 
 # name -> (restype, argtypes); every symbol include/m3b.h declares

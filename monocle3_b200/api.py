@@ -69,7 +69,7 @@ class CellDataSet:
     returns the concatenation over ranks in rank order (see dist.py)."""
 
     def __init__(self, counts, gene_names=None, cell_names=None, shard=None):
-        if not sp.isspmatrix_csc(counts):
+        if not isinstance(counts, engine.CSCBlocks) and not sp.isspmatrix_csc(counts):
             counts = sp.csc_matrix(counts)  # methods::as(expression_data, "dgCMatrix")
         self.counts = counts
         G, C = counts.shape
@@ -157,6 +157,8 @@ def normalized_counts(cds, norm_method="log", pseudocount=1):
     """R/utils.R:477-509 (sparse branch): returns a CSC with the input's pattern."""
     if norm_method not in ("log", "binary", "size_only"):
         raise ValueError("'arg' should be one of 'log', 'binary', 'size_only'")
+    if isinstance(cds.counts, engine.CSCBlocks):
+        raise ValueError("normalized_counts: the result would exceed a dgCMatrix; call it per block")
     dev = cds.device_matrix()
     if norm_method == "binary":
         dev.normalize(None, L.NORM_BINARY, 0.0)
@@ -375,7 +377,8 @@ def preprocess_cds(cds, method="PCA", num_dim=50, norm_method="log", use_genes=N
     # from the same stream if the Lanczos process hits an invariant subspace
     stream = RStream(2016)
     v0 = stream.rnorm(len(kept_idx))
-    dev.ctx.set_rnorm(stream.rnorm if not cds.shard else None)
+    # (cell-sharded runs: every rank continues the same stream; the library slices cell-length draws)
+    dev.ctx.set_rnorm(stream.rnorm)
     try:
         res = dev.pca_irlba(n, v0, center=scaling, scale=scaling, **(_irlba_args or {}))
     finally:

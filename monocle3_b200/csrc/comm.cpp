@@ -94,7 +94,8 @@ int comm_init(m3b_ctx* ctx, int rank, int world, const char* id) {
 }
 
 static size_t xchg_bytes(int world) {
-  return ((size_t)world * 2 * M3B_XCHG_FLAG_STRIDE + 2 * (size_t)M3B_XCHG_CAP) * sizeof(double);
+  return ((size_t)world * 2 * M3B_XCHG_FLAG_STRIDE + 2 * (size_t)M3B_XCHG_CAP) * sizeof(double) +
+         2 * M3B_LL_ENTRIES(world) * 16;
 }
 
 // Peer-memory exchange buffer: allocate + export (step 1), import everybody's (step 2).
@@ -139,7 +140,7 @@ int comm_p2p_open(m3b_ctx* ctx, const char* handles) {
   CK(ctx, cudaMemcpy(c.peers_dev, ptrs.data(), c.world * sizeof(double*), cudaMemcpyHostToDevice));
   // A second open on a live buffer must not see flags of the previous life: clear the flag area,
   // then a barrier so that no rank publishes into a buffer its owner has not cleared yet.
-  CK(ctx, cudaMemset(c.xchg, 0, (size_t)c.world * 2 * M3B_XCHG_FLAG_STRIDE * sizeof(double)));
+  CK(ctx, cudaMemset(c.xchg, 0, xchg_bytes(c.world)));  // flags AND the flag-in-data areas
   CK(ctx, cudaDeviceSynchronize());
   c.xchg_seq = 0;
   c.p2p = true;
@@ -169,6 +170,7 @@ int comm_xchg_resync(m3b_ctx* ctx) {
     return M3B_E_CUDA;
   }
   c.xchg_seq = (unsigned long long)h + 2;
+  c.ll_launch[0] = c.ll_launch[1] = 0;  // the allreduce above was a barrier: nobody is inside an exchange
   return M3B_OK;
 }
 

@@ -32,10 +32,11 @@
 struct FlatVariant {
   int k, threads;
 };
-static const FlatVariant FL_VARIANTS[] = {{6, 512}, {3, 1024}, {2, 1024}};
+static const FlatVariant FL_VARIANTS[] = {{6, 512}, {3, 1024}, {2, 1024}, {1, 1024}, {2, 1024}};  // 3, 4: ring, R = k
 static int fl_variant() {
   static int v = -1;
-  if (v < 0) {
+  static const bool dynamic = getenv("M3B_FLAT_DYNAMIC") != nullptr;  // sweeps: re-read the variant on every call
+  if (v < 0 || dynamic) {
     const char* e = getenv("M3B_FLAT_VARIANT");
     v = e ? atoi(e) : 1;
     if (v < 0 || v >= (int)(sizeof(FL_VARIANTS) / sizeof(FL_VARIANTS[0]))) v = 0;
@@ -692,6 +693,340 @@ __global__ void __launch_bounds__(THREADS, 1) k_flat_dot(const FlatArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Ring variant (M3B_FLAT_VARIANT=3 / 4): same plan, same item bookkeeping, same results per item
+// up to the order of the adds -- but the stream travels global -> SHARED memory with bulk async
+// copies (cp.async.bulk + mbarrier complete_tx, the 1-D TMA path) into a small ring that every warp
+// owns, instead of through register-resident batches.  Why: with the batches a warp has at most
+// one batch (1.5-1.9 KB) in flight and only while it is busy with the other one; ncu on the batch
+// kernel shows long_scoreboard as the top stall (6.6 warps per issue), issue slots 50 % busy, DRAM
+// 48 %.  With the ring the copies are issued by one lane, cost no registers, and a stage is refilled
+// the moment it has been read, so the whole ring (2-3 KB per warp, 64-96 KB per SM) stays in flight
+// whatever the consumer is doing.  A stage is R rounds: 512 R bytes of the unit stream, or
+// 128 R (+16: the index pairs of a piece start on a 4-byte boundary, the copy on a 16-byte one)
+// + 512 R bytes of the general stream.  Shared memory: tile | ring (NWARPS x RB) | mbarriers.
+// ---------------------------------------------------------------------------
+#define FR_NS_MAX 8
+__device__ __forceinline__ void fr_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fr_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fr_bulk(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fr_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ uint4 fr_lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned fr_lds32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 fr_lds_d2(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+// walks the chunks (<= 32 R groups, never across a piece boundary) of a warp's pieces of one phase
+struct FrIter {
+  int p, p1;  // current piece, end of the warp's range
+  int g0, ng, item0;
+  int off;    // groups of the current piece already handed out
+};
+__device__ __forceinline__ void fr_iter_load(FrIter& it, const int4* __restrict__ pieces) {
+  it.ng = 0;
+  while (it.p < it.p1) {
+    const int4 pc = pieces[it.p];
+    if (pc.y > 0) {
+      it.g0 = pc.x;
+      it.ng = pc.y;
+      it.item0 = pc.z;
+      break;
+    }
+    ++it.p;  // an empty slot of a device-built plan
+  }
+  it.off = 0;
+}
+__device__ __forceinline__ void fr_iter_next(FrIter& it, int n, const int4* __restrict__ pieces) {
+  it.off += n;
+  if (it.off >= it.ng) {
+    ++it.p;
+    fr_iter_load(it, pieces);
+  }
+}
+
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_flat_dot_ring(const FlatArgs a, const int ring_off, const int rb) {
+  constexpr int NWARPS = THREADS / 32;
+  constexpr int GPC = 32 * R;                                // groups per chunk
+  constexpr int SBU = 512 * R;                               // stage bytes, unit stream
+  constexpr int IDXR = (128 * R + 16 + 15) & ~15;            // index region of a general stage
+  constexpr int SBG = IDXR + 512 * R;                        // stage bytes, general stream
+  extern __shared__ double sx[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile_w = a.tile_w;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sx);
+  const unsigned ring = sbase + (unsigned)ring_off + (unsigned)(warp * rb);
+  const unsigned bars = sbase + (unsigned)ring_off + (unsigned)(NWARPS * rb) + (unsigned)(warp * FR_NS_MAX * 8);
+  const int nsu = min(FR_NS_MAX, rb / SBU), nsg = min(FR_NS_MAX, rb / SBG);
+  if (lane < FR_NS_MAX) fr_mbar_init(bars + 8u * lane, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  unsigned phase = 0u;  // bit s: parity the next wait on barrier s uses
+  const int v0 = a.cta_visit_ptr[blockIdx.x], v1 = a.cta_visit_ptr[blockIdx.x + 1];
+  for (int vis = v0; vis < v1; ++vis) {
+    const int tile = a.visit_tile[vis];
+    const long long off = (long long)tile * tile_w;
+    const int len = (int)min((long long)tile_w, a.cols - off);
+    if (vis > v0) __syncthreads();  // the previous tile is still being read
+    // ---- general stream: the first stages go out before the tile is staged (they only touch the ring)
+    FrIter gi_is, gi_co;
+    gi_is.p = gi_co.p = a.gp_ptr[vis * NWARPS + warp];
+    gi_is.p1 = gi_co.p1 = a.gp_ptr[vis * NWARPS + warp + 1];
+    fr_iter_load(gi_is, a.gp);
+    gi_co = gi_is;
+#define FR_GISSUE(S)                                                                              \
+  {                                                                                               \
+    const int n_ = min(GPC, gi_is.ng - gi_is.off);                                                \
+    const long long g_ = (long long)gi_is.g0 + gi_is.off;                                         \
+    const unsigned m_ = (unsigned)((4 * g_) & 15);                                                \
+    const unsigned bi_ = (m_ + 4u * n_ + 15u) & ~15u, bv_ = 16u * n_;                             \
+    if (lane == 0) {                                                                              \
+      const unsigned st_ = ring + (unsigned)((S) * SBG), bar_ = bars + 8u * (S);                  \
+      fr_expect_tx(bar_, bi_ + bv_);                                                              \
+      fr_bulk(st_, reinterpret_cast<const char*>(a.gidx) + 4 * g_ - m_, bi_, bar_);               \
+      fr_bulk(st_ + IDXR, reinterpret_cast<const char*>(a.gval) + 16 * g_, bv_, bar_);            \
+    }                                                                                             \
+    fr_iter_next(gi_is, n_, a.gp);                                                                \
+  }
+    for (int s = 0; s < nsg; ++s)
+      if (gi_is.p < gi_is.p1) FR_GISSUE(s)
+    {
+      // stage the tile of the dense operand (coalesced 16-byte loads; x is L2-resident); the
+      // slots [len, tile_w] read as 0 (tile_w is where the unit stream's pads point)
+      const double* xs0 = a.x + off;
+      if ((reinterpret_cast<unsigned long long>(xs0) & 15ull) == 0ull) {
+        const double2* src = reinterpret_cast<const double2*>(xs0);
+        double2* dst = reinterpret_cast<double2*>(sx);
+        const int n2 = len >> 1;
+        for (int k0 = threadIdx.x; k0 < n2; k0 += 5 * THREADS) {
+          double2 v[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int k = k0 + u * THREADS;
+            v[u] = (k < n2) ? src[k] : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int k = k0 + u * THREADS;
+            if (k < n2) dst[k] = v[u];
+          }
+        }
+        if ((len & 1) && threadIdx.x == 0) sx[len - 1] = xs0[len - 1];
+      } else {
+        for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] = xs0[k];
+      }
+      for (int k = len + threadIdx.x; k <= tile_w; k += blockDim.x) sx[k] = 0.0;
+      __syncthreads();
+    }
+    {
+      FlatState st;
+      st.acc = 0.0;
+      st.item = 0;
+      st.open = false;
+      st.wbase = 0;
+      st.wslot = 0;
+      st.wscale = 1.0;
+      bool any_piece = false;
+      int s = 0;
+      while (gi_co.p < gi_co.p1) {
+        if (gi_co.off == 0) {
+          if (any_piece) fl_finish(st, lane, a.gslot, nullptr, a.g_items, a.partial);
+          any_piece = true;
+          st.acc = 0.0;
+          st.item = gi_co.item0;
+          st.open = false;
+          fl_window(st, gi_co.item0, a.gslot, nullptr, a.g_items, lane);
+        }
+        const int n = min(GPC, gi_co.ng - gi_co.off);
+        const unsigned m = (unsigned)((4 * ((long long)gi_co.g0 + gi_co.off)) & 15);
+        const unsigned stg = ring + (unsigned)(s * SBG);
+        fr_wait(bars + 8u * s, (phase >> s) & 1u);
+        phase ^= 1u << s;
+        double v[R];
+        unsigned mk[R], any = 0u;
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const int g = 32 * u + lane;
+          const bool valid = g < n;
+          const int gc = min(g, n - 1);
+          const unsigned pair = fr_lds32(stg + m + 4u * gc);
+          const double2 w = fr_lds_d2(stg + IDXR + 16u * gc);
+          mk[u] = __ballot_sync(0xffffffffu, valid && ((pair >> 15) & 1u));
+          any |= mk[u];
+          unsigned ga, gb;
+          fl_addr2(pair & 0xffff7fffu, sbase, ga, gb);
+          const double t = fma(w.y, fl_lds(gb), w.x * fl_lds(ga));
+          v[u] = valid ? t : 0.0;
+        }
+        if (any == 0u) {
+          st.acc += fl_tree<R>(v);
+        } else {
+#pragma unroll
+          for (int u = 0; u < R; ++u)
+            if (32 * u < n) fl_round(st, v[u], mk[u], lane, a.gslot, nullptr, a.g_items, a.partial);
+        }
+        __syncwarp();
+        if (gi_is.p < gi_is.p1) FR_GISSUE(s)
+        fr_iter_next(gi_co, n, a.gp);
+        s = (s + 1 == nsg) ? 0 : s + 1;
+      }
+      if (any_piece) fl_finish(st, lane, a.gslot, nullptr, a.g_items, a.partial);
+    }
+#undef FR_GISSUE
+    // ---- unit stream: groups of 8 indices, value applied on the dense side
+    if (a.uidx) {
+      FrIter ui_is, ui_co;
+      ui_is.p = a.up_ptr[vis * NWARPS + warp];
+      ui_is.p1 = a.up_ptr[vis * NWARPS + warp + 1];
+      fr_iter_load(ui_is, a.up);
+      ui_co = ui_is;
+#define FR_UISSUE(S)                                                                              \
+  {                                                                                               \
+    const int n_ = min(GPC, ui_is.ng - ui_is.off);                                                \
+    const long long g_ = (long long)ui_is.g0 + ui_is.off;                                         \
+    if (lane == 0) {                                                                              \
+      const unsigned bar_ = bars + 8u * (S);                                                      \
+      fr_expect_tx(bar_, 16u * n_);                                                               \
+      fr_bulk(ring + (unsigned)((S) * SBU), reinterpret_cast<const char*>(a.uidx) + 16 * g_, 16u * n_, bar_); \
+    }                                                                                             \
+    fr_iter_next(ui_is, n_, a.up);                                                                \
+  }
+      // (the general phase has drained the ring: every copy it issued has been waited for and read)
+      for (int s = 0; s < nsu; ++s)
+        if (ui_is.p < ui_is.p1) FR_UISSUE(s)
+      if (a.colscale) {
+        __syncthreads();
+        const double* cs = a.colscale + off;
+        if ((reinterpret_cast<unsigned long long>(cs) & 15ull) == 0ull) {
+          const double2* cs2 = reinterpret_cast<const double2*>(cs);
+          double2* d2 = reinterpret_cast<double2*>(sx);
+          const int n2 = len >> 1;
+          for (int k0 = threadIdx.x; k0 < n2; k0 += 5 * THREADS) {
+            double2 v[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+              const int k = k0 + u * THREADS;
+              v[u] = (k < n2) ? cs2[k] : make_double2(1.0, 1.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+              const int k = k0 + u * THREADS;
+              if (k < n2) {
+                double2 t = d2[k];
+                t.x *= v[u].x;
+                t.y *= v[u].y;
+                d2[k] = t;
+              }
+            }
+          }
+          if ((len & 1) && threadIdx.x == 0) sx[len - 1] *= cs[len - 1];
+        } else {
+          for (int k = threadIdx.x; k < len; k += blockDim.x) sx[k] *= cs[k];
+        }
+        __syncthreads();
+      }
+      FlatState st;
+      st.acc = 0.0;
+      st.item = 0;
+      st.open = false;
+      st.wbase = 0;
+      st.wslot = 0;
+      st.wscale = 1.0;
+      bool any_piece = false;
+      int s = 0;
+      while (ui_co.p < ui_co.p1) {
+        if (ui_co.off == 0) {
+          if (any_piece) fl_finish(st, lane, a.uslot, a.uscale, a.u_items, a.partial);
+          any_piece = true;
+          st.acc = 0.0;
+          st.item = ui_co.item0;
+          st.open = false;
+          fl_window(st, ui_co.item0, a.uslot, a.uscale, a.u_items, lane);
+        }
+        const int n = min(GPC, ui_co.ng - ui_co.off);
+        const unsigned stg = ring + (unsigned)(s * SBU);
+        fr_wait(bars + 8u * s, (phase >> s) & 1u);
+        phase ^= 1u << s;
+        double v[R];
+        unsigned mk[R], any = 0u;
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const int g = 32 * u + lane;
+          const bool valid = g < n;
+          const uint4 b = fr_lds128(stg + 16u * min(g, n - 1));
+          mk[u] = __ballot_sync(0xffffffffu, valid && ((b.x >> 15) & 1u));
+          any |= mk[u];
+          const double t = (fl_gsum(sbase, b.x & 0xffff7fffu) + fl_gsum(sbase, b.y)) +
+                           (fl_gsum(sbase, b.z) + fl_gsum(sbase, b.w));
+          v[u] = valid ? t : 0.0;
+        }
+        if (any == 0u) {
+          st.acc += fl_tree<R>(v);
+        } else {
+#pragma unroll
+          for (int u = 0; u < R; ++u)
+            if (32 * u < n) fl_round(st, v[u], mk[u], lane, a.uslot, a.uscale, a.u_items, a.partial);
+        }
+        __syncwarp();
+        if (ui_is.p < ui_is.p1) FR_UISSUE(s)
+        fr_iter_next(ui_co, n, a.up);
+        s = (s + 1 == nsu) ? 0 : s + 1;
+      }
+      if (any_piece) fl_finish(st, lane, a.uslot, a.uscale, a.u_items, a.partial);
+#undef FR_UISSUE
+    }
+  }
+}
+
+// shared-memory carve of the ring variant for a tile width; false when the ring would be too small
+static bool fr_carve(int tile_w, int warps, int rounds, int* ring_off, int* rb, int* total) {
+  const int tile_bytes = (int)(((size_t)tile_w + 2) * sizeof(double) + 127) & ~127;
+  const int bar_bytes = warps * FR_NS_MAX * 8;
+  const int avail = 232448 - tile_bytes - bar_bytes;  // 227 KB per CTA
+  if (avail <= 0) return false;
+  int per = (avail / warps) & ~127;
+  per = std::min(per, 4096);
+  const int sbg = ((128 * rounds + 16 + 15) & ~15) + 512 * rounds;
+  if (per / sbg < 2) return false;
+  *ring_off = tile_bytes;
+  *rb = per;
+  *total = tile_bytes + warps * per + bar_bytes;
+  return true;
+}
+
 template <int K, int THREADS>
 static int fl_init_one(m3b_ctx* ctx) {
   CK(ctx, cudaFuncSetAttribute(k_flat_dot<K, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -703,6 +1038,8 @@ int flat_init(m3b_ctx* ctx) {
   RET((fl_init_one<6, 512>(ctx)));
   RET((fl_init_one<3, 1024>(ctx)));
   RET((fl_init_one<2, 1024>(ctx)));
+  CK(ctx, cudaFuncSetAttribute(k_flat_dot_ring<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  CK(ctx, cudaFuncSetAttribute(k_flat_dot_ring<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   return M3B_OK;
 }
 
@@ -733,7 +1070,12 @@ int flat_launch_dot(m3b_ctx* ctx, const TiledLayout& L, const double* x, cudaStr
   a.partial = L.partial;
   const size_t smem = ((size_t)L.tile_w + 2) * sizeof(double);
   cudaStream_t st = stream ? stream : ctx->stream;
-  switch (fl_variant()) {
+  int variant = fl_variant();
+  int ring_off = 0, rb = 0, ring_total = 0;
+  if (variant >= 3 && !fr_carve(L.tile_w, 32, FL_VARIANTS[variant].k, &ring_off, &rb, &ring_total)) variant = 1;  // tile too wide for a ring
+  switch (variant) {
+    case 3: k_flat_dot_ring<1, 1024><<<P->n_cta, 1024, ring_total, st>>>(a, ring_off, rb); break;
+    case 4: k_flat_dot_ring<2, 1024><<<P->n_cta, 1024, ring_total, st>>>(a, ring_off, rb); break;
     case 1: k_flat_dot<3, 1024><<<P->n_cta, 1024, smem, st>>>(a); break;
     case 2: k_flat_dot<2, 1024><<<P->n_cta, 1024, smem, st>>>(a); break;
     default: k_flat_dot<6, 512><<<P->n_cta, 512, smem, st>>>(a); break;

@@ -428,7 +428,11 @@ struct OrthArgs {
   int rank, world;
   unsigned long long seq;  // number of the first exchange of this launch (F side uses 1, W side 2)
   long long timeout;       // bound of the in-kernel waits, SM cycles
+  int xpar;                // parity of the flag-in-data areas this launch uses (alternates per launch and side)
+  unsigned long long* diag;  // [8] cycle counters of CTA 0 (see XD_*), or nullptr
 };
+// diag slots: cycles CTA 0 spent waiting for the peers in the three exchanges, whole-kernel cycles and launch counts
+enum { XD_WAIT_F = 0, XD_WAIT_W1 = 1, XD_WAIT_W2 = 2, XD_KERNEL_F = 3, XD_KERNEL_W = 4, XD_N_F = 5, XD_N_W = 6, XD_COUNT = 8 };
 
 // ---- cross-rank exchange inside the fused kernel (one box, CUDA-IPC peer memory) ----
 // Every rank writes its contribution into its OWN buffer (slot seq & 1), one thread of the rank
@@ -474,6 +478,50 @@ __device__ __forceinline__ bool xchg_wait(double* const* peers, int rank, int wo
   }
   __threadfence_system();  // acquire: the peers' data published before their flags is visible from here on
   return true;
+}
+
+// ---- flag-in-data exchange ("LL": every 16-byte entry carries its own validity flag) ----
+// The pull protocol above costs, per exchange, a local grid barrier (the slot must be complete before
+// it is published), a system-scope fence, a flag store, and then a dependent round trip over NVLink
+// for the data.  Here the data is PUSHED: a value travels as {lo32, flag, hi32, flag} in one 16-byte
+// store into the receiver's own memory (8-byte halves are single-copy atomic, so a half whose flag
+// matches is valid; the flag is the exchange's sequence number, which only grows), the receiver polls
+// its local copy.  No fence, no barrier, one one-way trip; every CTA exchanges its own rows.
+// Parity: an area is reused by the launch after next of the same side, which a rank can only reach
+// after every peer has pushed the launch in between, i.e. has finished reading this one.
+__device__ __forceinline__ double* ll_area(double* const* peers, int q, int world, int par) {
+  return peers[q] + (size_t)world * 2 * M3B_XCHG_FLAG_STRIDE + 2 * (size_t)M3B_XCHG_CAP +
+         (size_t)par * 2 * M3B_LL_ENTRIES(world);
+}
+__device__ __forceinline__ double* ll_entry_f(double* area, int src, long long row) {
+  return area + 2 * ((size_t)src * M3B_LL_CAPF + (size_t)row);
+}
+__device__ __forceinline__ double* ll_entry_w1(double* area, int world, int src, int c) {
+  return area + 2 * ((size_t)world * M3B_LL_CAPF + (size_t)src * M3B_LL_CAPW + c);
+}
+__device__ __forceinline__ double* ll_entry_w2(double* area, int world, int src, int blk, int k) {
+  return area + 2 * ((size_t)world * (M3B_LL_CAPF + M3B_LL_CAPW) + ((size_t)src * M3B_LL_CAPG + blk) * 2 + k);
+}
+__device__ __forceinline__ void ll_store(double* e, double v, unsigned flag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(e), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+// spins (bounded) until the entry carries `flag`; on time-out raises CT_FLAG bit 4 and returns 0
+__device__ __forceinline__ double ll_wait(const double* e, unsigned flag, int* ctl, long long timeout) {
+  unsigned a, b, c, d;
+  long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(e) : "memory");
+    if (b == flag && d == flag) break;
+    if ((spin & 1023u) == 1023u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > timeout) {
+        atomicOr(ctl + CT_FLAG, 4);
+        return 0.0;
+      }
+    }
+  }
+  return __hiloint2double((int)c, (int)a);
 }
 
 // All CTAs are co-resident (cooperative launch).  The spin is bounded (~2 s) so that a lost CTA
@@ -522,6 +570,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
   const long long r0 = (long long)blockIdx.x * a.chunk;
   const int len = (int)max(0LL, min((long long)a.chunk, a.rows - r0));
   const int ncols = a.ncols;
+  const long long t_kernel0 = clock64();
   // ---- phase 0: combine (4 lanes per row)
   {
     double beta = 0.0, rf = 0.0, sumw = 0.0, S = 0.0;
@@ -546,7 +595,7 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       f += __shfl_xor_sync(0xffffffffu, f, 2);
       f += __shfl_xor_sync(0xffffffffu, f, 1);
       if (q < len && sub == 0 && a.world > 1 && a.mode != OF_W) {
-        xchg_slot(a.peers, a.rank, a.world, a.seq)[r] = f;  // raw local sum; summed over the ranks below
+        ys[q] = f;  // raw local sum; pushed to the peers and summed over the ranks below
       } else if (q < len && sub == 0) {
         if (a.mode == OF_W) {
           f -= beta;
@@ -565,17 +614,25 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
     }
     __syncthreads();
     if (a.world > 1 && a.mode != OF_W) {
-      // every CTA of every rank has written its rows: publish, wait for the world, then this CTA
-      // sums its rows over the ranks (rank order => identical on every rank) and applies the fix-ups
-      __threadfence_system();
-      grid_barrier(a.bar, a.bar_base + gridDim.x, a.ctl, a.timeout);
-      if (blockIdx.x == 0 && tid == 0) xchg_publish(a.peers, a.rank, a.world, a.seq);
-      if (tid == 0) xchg_wait(a.peers, a.rank, a.world, a.seq, a.ctl, a.timeout);
-      __syncthreads();
+      // this CTA pushes the raw sums of ITS rows into every peer's area (consecutive threads ->
+      // consecutive 16-byte entries of one peer), then adds its rows over the ranks in rank order
+      // (=> identical on every rank) out of its own area and applies the fix-ups.  No grid barrier:
+      // the same CTA of every rank owns the same rows.
+      const unsigned flag = (unsigned)a.seq;
+      const int npush = len * (a.world - 1);
+      for (int k = tid; k < npush; k += OF_THREADS) {
+        const int pr = k / len, q = k - pr * len;
+        const int peer = pr + (pr >= a.rank ? 1 : 0);
+        ll_store(ll_entry_f(ll_area(a.peers, peer, a.world, a.xpar), a.rank, r0 + q), ys[q], flag);
+      }
+      __syncthreads();  // ys is rewritten below
+      const long long tw0 = clock64();
+      double* mine = ll_area(a.peers, a.rank, a.world, a.xpar);
       for (int q = tid; q < len; q += OF_THREADS) {
         const long long r = r0 + q;
         double f = 0.0;
-        for (int rk = 0; rk < a.world; ++rk) f += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, a.seq) + r);
+        for (int rk = 0; rk < a.world; ++rk)
+          f += (rk == a.rank) ? ys[q] : ll_wait(ll_entry_f(mine, rk, r), flag, a.ctl, a.timeout);
         if (a.s) f = f / a.s[r];
         if (a.ce) {
           double c = sumw * a.ce[r];
@@ -585,9 +642,10 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
         ys[q] = f - S * a.vj[r];
       }
       __syncthreads();
+      if (a.diag && blockIdx.x == 0 && tid == 0) atomicAdd(a.diag + XD_WAIT_F, (unsigned long long)(clock64() - tw0));
     }
   }
-  const unsigned long long nb0 = (a.world > 1 && a.mode != OF_W) ? 1ull : 0ull;  // local grid barriers used so far
+  const unsigned long long nb0 = 0ull;  // local grid barriers used so far
   // ---- phase 1: partial dots of this chunk, a warp takes 4 columns at a time
   for (int c0 = warp * 4; c0 < ncols; c0 += (OF_THREADS / 32) * 4) {
     const int nc = min(4, ncols - c0);
@@ -653,21 +711,28 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
     }
     __syncthreads();
     if (a.world > 1 && a.mode == OF_W) {
-      // the rows of W are sharded: t is the sum of the ranks' local coefficients (exchange a.seq)
+      // the rows of W are sharded: t is the sum of the ranks' local coefficients (exchange a.seq).
+      // CTA 0 pushes the local sums to every peer; every CTA adds them in rank order out of its
+      // own rank's area (its own rank's term it has just computed itself).
+      const unsigned flag = (unsigned)a.seq;
       if (blockIdx.x == 0) {
-        double* mine = xchg_slot(a.peers, a.rank, a.world, a.seq);
-        for (int c2 = tid; c2 < ncols; c2 += OF_THREADS) mine[c2] = ts[c2];
-        __syncthreads();
-        if (tid == 0) xchg_publish(a.peers, a.rank, a.world, a.seq);
+        const int npush = ncols * (a.world - 1);
+        for (int k = tid; k < npush; k += OF_THREADS) {
+          const int pr = k / ncols, c2 = k - pr * ncols;
+          const int peer = pr + (pr >= a.rank ? 1 : 0);
+          ll_store(ll_entry_w1(ll_area(a.peers, peer, a.world, a.xpar), a.world, a.rank, c2), ts[c2], flag);
+        }
       }
-      if (tid == 0) xchg_wait(a.peers, a.rank, a.world, a.seq, a.ctl, a.timeout);
+      const long long tw0 = clock64();
+      double* mine = ll_area(a.peers, a.rank, a.world, a.xpar);
+      double v = 0.0;
+      if (tid < ncols)
+        for (int rk = 0; rk < a.world; ++rk)
+          v += (rk == a.rank) ? ts[tid] : ll_wait(ll_entry_w1(mine, a.world, rk, tid), flag, a.ctl, a.timeout);
       __syncthreads();
-      if (tid < ncols) {
-        double v = 0.0;
-        for (int rk = 0; rk < a.world; ++rk) v += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, a.seq) + tid);
-        ts[tid] = v;
-      }
+      if (tid < ncols) ts[tid] = v;
       __syncthreads();
+      if (a.diag && blockIdx.x == 0 && tid == 0) atomicAdd(a.diag + XD_WAIT_W1, (unsigned long long)(clock64() - tw0));
     }
   }
   // ---- phase 2b: y -= X t on this chunk (128 rows x 8 column groups per pass)
@@ -711,43 +776,59 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       __syncthreads();
     }
   }
+  const bool ll_norms = a.world > 1 && a.mode == OF_W;
+  double nn, ssum = 0.0;
   {
     const double r1 = block_sum(n2, sh);
     const double r2 = block_sum(sm, sh);
-    if (tid == 0) {
-      a.pn[blockIdx.x] = r1;
-      a.ps[blockIdx.x] = r2;
-    }
-  }
-  grid_barrier(a.bar, a.bar_base + (nb0 + 2) * gridDim.x, a.ctl, a.timeout);
-  // ---- phase 3: norm, scaling, scalars
-  double nn = block_sum_cg(a.pn, gridDim.x, sh, &bc);
-  if (a.mode == OF_W) {
-    double ssum = block_sum_cg(a.ps, gridDim.x, sh, &bc);
-    if (a.world > 1) {
-      // ||w||^2 and sum(w) over the ranks (exchange a.seq + 1)
-      const unsigned long long s2 = a.seq + 1;
-      __shared__ double gx[2];
-      if (blockIdx.x == 0 && tid == 0) {
-        double* mine = xchg_slot(a.peers, a.rank, a.world, s2);
-        mine[0] = nn;
-        mine[1] = ssum;
-        xchg_publish(a.peers, a.rank, a.world, s2);
-      }
+    if (!ll_norms) {
       if (tid == 0) {
-        xchg_wait(a.peers, a.rank, a.world, s2, a.ctl, a.timeout);
-        double g0 = 0.0, g1 = 0.0;
-        for (int rk = 0; rk < a.world; ++rk) {
-          g0 += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, s2));
-          g1 += ld_relaxed_sys_f64(xchg_slot(a.peers, rk, a.world, s2) + 1);
-        }
-        gx[0] = g0;
-        gx[1] = g1;
+        a.pn[blockIdx.x] = r1;
+        a.ps[blockIdx.x] = r2;
+      }
+      grid_barrier(a.bar, a.bar_base + (nb0 + 2) * gridDim.x, a.ctl, a.timeout);
+      nn = block_sum_cg(a.pn, gridDim.x, sh, &bc);
+      if (a.mode == OF_W) ssum = block_sum_cg(a.ps, gridDim.x, sh, &bc);
+    } else {
+      // exchange a.seq + 1: every CTA pushes its {|w|^2, sum w} partial to EVERY rank (its own
+      // included); having received all world x grid partials IS the barrier, so the local grid
+      // barrier and the separate cross-rank exchange of the pull protocol collapse into one one-way
+      // trip.  Every CTA of every rank adds the same values in the same order (thread t takes the
+      // entries t, t + 1024, ... of the rank-major list, then the fixed block tree).
+      const unsigned flag = (unsigned)(a.seq + 1);
+      __shared__ double pr2[2];
+      if (tid == 0) {
+        pr2[0] = r1;
+        pr2[1] = r2;
       }
       __syncthreads();
-      nn = gx[0];
-      ssum = gx[1];
+      if (tid < 2 * a.world) {
+        const int peer = tid >> 1, k = tid & 1;
+        ll_store(ll_entry_w2(ll_area(a.peers, peer, a.world, a.xpar), a.world, a.rank, blockIdx.x, k), pr2[k], flag);
+      }
+      const long long tw0 = clock64();
+      double* mine = ll_area(a.peers, a.rank, a.world, a.xpar);
+      const int ntot = a.world * (int)gridDim.x;
+      double v1 = 0.0, v2 = 0.0;
+      for (int e = tid; e < ntot; e += OF_THREADS) {
+        const int rk = e / (int)gridDim.x, b = e - rk * (int)gridDim.x;
+        v1 += ll_wait(ll_entry_w2(mine, a.world, rk, b, 0), flag, a.ctl, a.timeout);
+        v2 += ll_wait(ll_entry_w2(mine, a.world, rk, b, 1), flag, a.ctl, a.timeout);
+      }
+      const double g1 = block_sum(v1, sh);
+      const double g2 = block_sum(v2, sh);
+      if (tid == 0) {
+        pr2[0] = g1;
+        pr2[1] = g2;
+      }
+      __syncthreads();
+      nn = pr2[0];
+      ssum = pr2[1];
+      if (a.diag && blockIdx.x == 0 && tid == 0) atomicAdd(a.diag + XD_WAIT_W2, (unsigned long long)(clock64() - tw0));
     }
+  }
+  // ---- phase 3: norm, scaling, scalars
+  if (a.mode == OF_W) {
     const double S = sqrt(nn), SS = 1.0 / S;
     for (int q = tid; q < len; q += OF_THREADS) a.y[r0 + q] = ys[q] * SS;
     if (blockIdx.x == 0 && tid == 0) {
@@ -784,6 +865,10 @@ __global__ void __launch_bounds__(OF_THREADS, 1) k_orth_fused(const OrthArgs a) 
       a.scal[SC_RF] = (rf < a.eps) ? 0.0 : rf;
       a.Bm[(long long)a.j * a.work + a.j] = a.scal[SC_S];
     }
+  }
+  if (a.diag && blockIdx.x == 0 && tid == 0) {
+    atomicAdd(a.diag + (a.mode == OF_W ? XD_KERNEL_W : XD_KERNEL_F), (unsigned long long)(clock64() - t_kernel0));
+    atomicAdd(a.diag + (a.mode == OF_W ? XD_N_W : XD_N_F), 1ULL);
   }
 }
 
@@ -825,15 +910,15 @@ __global__ void __launch_bounds__(NT) k_reduce2(const double* __restrict__ pn, c
 // W side: S = sqrt(buf2[0]); w *= 1/S; scal[S], scal[SUMW] = buf2[1]/S
 __global__ void __launch_bounds__(NT) k_scale_w(double* __restrict__ w, long long rows, const double* __restrict__ buf2,
                                                 double* __restrict__ scal, int* __restrict__ ctl, double eps,
-                                                int first) {
+                                                int first, int force_zero) {
   const double S = sqrt(buf2[0]);
   const double SS = 1.0 / S;
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
     w[r] *= SS;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    scal[SC_S] = S;
+    scal[SC_S] = force_zero ? 0.0 : S;  // force_zero: a random replacement vector (see k_scale_w_fused)
     scal[SC_SUMW] = buf2[1] * SS;
-    if (!(S >= eps)) ctl[CT_FLAG] |= first ? 1 : 2;  // 1: start vector in null space, 2: breakdown
+    if (!(S >= eps) && !force_zero) ctl[CT_FLAG] |= first ? 1 : 2;  // 1: start vector in null space, 2: breakdown
   }
 }
 
@@ -1141,6 +1226,7 @@ struct Irlba {
   int pb_n = 0;  // valid entries of pb (k_make_xs: nb_n, k_orth_fused: of_grid)
   unsigned long long* bar = nullptr;
   unsigned long long bar_seq = 0;
+  unsigned long long* xdiag = nullptr;  // [XD_COUNT] in-kernel exchange timing of the sharded fused kernel
   int nb_n, nb_m;        // blocks of the vector kernels (gene side / cell side)
   int nb_ca;             // blocks of k_combine_A (32 rows per block)
   int nbo_n, nbo_m;      // blocks of k_apply_orth (= number of pn/ps partials it writes)
@@ -1229,10 +1315,13 @@ struct Irlba {
     a.timeout = ctx->spin_timeout_cycles;
     int n_bar = 2;
     if (a.world > 1) {
-      // exchanges of this launch: F side 1 (the gene vector), W side 2 (coefficients, then norm and sum)
+      // exchanges of this launch: F side 1 (the gene vector), W side 2 (coefficients, then norm and sum);
+      // the W side's second grid barrier is the all-to-all of the norm partials itself
       a.seq = ctx->comm.xchg_seq + 1;
       ctx->comm.xchg_seq += wside ? 2 : 1;
-      if (!wside) n_bar = 3;
+      a.xpar = (int)(ctx->comm.ll_launch[wside ? 1 : 0]++ & 1u);
+      a.diag = xdiag;
+      if (wside) n_bar = 1;
     }
     bar_seq += (unsigned long long)n_bar * of_grid;
     void* args[] = {&a};
@@ -1311,25 +1400,57 @@ struct Irlba {
 
   // normalise W[:, jw] using pn/ps partials (cell side): S, sum(w)
   // ||y||^2 from the partials the last orthog / norm kernel left in pn (host value; slow path only)
-  int read_norm2(int np, double* out) {
+  int read_norm2(int np, double* out, bool sharded_rows = false) {
     k_reduce2<<<1, NT, 0, ctx->stream>>>(pn, ps, np, buf2);
     count_launch(ctx);
+    if (sharded_rows) RET(comm_allreduce_f64(ctx, buf2, 2));  // cell side of a sharded run: sum over the ranks
     CK(ctx, cudaMemcpyAsync(out, buf2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return M3B_OK;
   }
 
   // irlb.c's answer to an invariant subspace: y = rnorm(len) from the caller's stream, y -= X X^T y
-  int random_vector(double* X, long long ld, long long rows, int ncols, double* y, int chunk, int nblk, int nb) {
-    std::vector<double> h((size_t)rows);
-    if (ctx->rnorm((int64_t)rows, h.data(), ctx->rnorm_user) != 0) {
+  // Sharded runs: every rank's callback continues the SAME stream (they all drew the start vector
+  // from it), so a gene-length vector is simply drawn everywhere (replicas stay identical), and for
+  // a cell-length vector every rank draws all n_cells_total values and keeps its own cell range --
+  // the streams stay in step and the result is the unsharded run's vector, sliced.
+  long long cell_offset = -1;  // first global cell of this rank (lazily: one allreduce)
+  int find_cell_offset() {
+    if (cell_offset >= 0) return M3B_OK;
+    cell_offset = 0;
+    const int world = ctx->comm.world;
+    if (world == 1) return M3B_OK;
+    long long* d = nullptr;
+    RET(dev_alloc(ctx, &d, (size_t)world));
+    std::vector<long long> h((size_t)world, 0);
+    h[ctx->comm.rank] = mrows;
+    cudaError_t e = cudaMemcpyAsync(d, h.data(), world * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+    int st = e == cudaSuccess ? comm_allreduce_i64(ctx, d, (size_t)world) : M3B_E_CUDA;
+    if (st == M3B_OK) e = cudaMemcpyAsync(h.data(), d, world * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (st == M3B_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(d);
+    if (st != M3B_OK) return st;
+    CK(ctx, e);
+    for (int q = 0; q < ctx->comm.rank; ++q) cell_offset += h[q];
+    return M3B_OK;
+  }
+  int random_vector(double* X, long long ld, long long rows, int ncols, double* y, int chunk, int nblk, int nb,
+                    bool sharded_rows = false) {
+    long long total = rows, off = 0;
+    if (sharded_rows && ctx->comm.world > 1) {
+      RET(find_cell_offset());
+      total = m->n_cells_total;
+      off = cell_offset;
+    }
+    std::vector<double> h((size_t)std::max<long long>(total, 1));
+    if (ctx->rnorm((int64_t)total, h.data(), ctx->rnorm_user) != 0) {
       m3b_set_error(ctx, "rnorm callback failed");
       return M3B_E_STATE;
     }
-    CK(ctx, cudaMemcpyAsync(y, h.data(), (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (rows) CK(ctx, cudaMemcpyAsync(y, h.data() + off, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.h2d_bytes += rows * 8;
-    return orthog(X, ld, rows, ncols, y, chunk, nblk, nb, false);
+    return orthog(X, ld, rows, ncols, y, chunk, nblk, nb, sharded_rows && ctx->comm.world > 1);
   }
 
   int finish_w(int jw, bool first, int np, bool force_zero = false) {
@@ -1346,7 +1467,8 @@ struct Irlba {
     k_reduce2<<<1, NT, 0, ctx->stream>>>(pn, ps, np, buf2);
     count_launch(ctx);
     RET(comm_allreduce_f64(ctx, buf2, 2));
-    k_scale_w<<<nb_m, NT, 0, ctx->stream>>>(W + (long long)jw * mrows, mrows, buf2, scal, ctl, eps, first ? 1 : 0);
+    k_scale_w<<<nb_m, NT, 0, ctx->stream>>>(W + (long long)jw * mrows, mrows, buf2, scal, ctl, eps, first ? 1 : 0,
+                                            force_zero ? 1 : 0);
     count_launch(ctx);
     spmv_timer_end(ctx);
     CK(ctx, cudaGetLastError());
@@ -1540,7 +1662,8 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       // sharded runs: only with the peer-memory exchange (verified on 2 and 4 GPUs; M3B_NO_MR_FUSED=1
       // falls back to the separate kernels with NCCL between them)
       const bool rank_ok = ctx->comm.world == 1 ||
-                           (ctx->comm.p2p && n <= M3B_XCHG_CAP && work <= M3B_XCHG_CAP && !getenv("M3B_NO_MR_FUSED"));
+                           (ctx->comm.p2p && n <= M3B_LL_CAPF && work <= M3B_LL_CAPW && I.of_grid <= M3B_LL_CAPG &&
+                            !getenv("M3B_NO_MR_FUSED"));
       I.fused = rank_ok && work <= 1024 && I.of_grid <= 1024 && I.of_grid <= MAX_PART &&
                 smem <= (size_t)M3B_OF_SMEM_MAX && !getenv("M3B_NO_FUSED_ORTH");
     }
@@ -1575,6 +1698,8 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     ICK(cudaMemsetAsync(I.pb, 0, 1024 * sizeof(double), ctx->stream));
     IR(I.alloc(&I.bar, (size_t)2));
     ICK(cudaMemsetAsync(I.bar, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    IR(I.alloc(&I.xdiag, (size_t)XD_COUNT));
+    ICK(cudaMemsetAsync(I.xdiag, 0, XD_COUNT * sizeof(unsigned long long), ctx->stream));
     // operator vectors
     I.s = use_scale ? m->scale : nullptr;
     if (use_center) {
@@ -1676,10 +1801,10 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
           rnd = false;
           if (careful) {
             double n2 = 0.0;
-            IR(I.read_norm2(I.nbo_m, &n2));
+            IR(I.read_norm2(I.nbo_m, &n2, true));
             if (!(std::sqrt(n2) >= I.eps)) {
               rnd = true;
-              IR(I.random_vector(I.W, mloc, mloc, j + 1, I.W + (long long)(j + 1) * mloc, I.chunk_m, I.nblk_m, I.nbo_m));
+              IR(I.random_vector(I.W, mloc, mloc, j + 1, I.W + (long long)(j + 1) * mloc, I.chunk_m, I.nblk_m, I.nbo_m, true));
             }
           }
           IR(I.finish_w(j + 1, false, I.nbo_m, rnd));
@@ -1748,7 +1873,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
         status = M3B_E_CUDA;
         goto done;
       }
-      if ((hctl[CT_FLAG] & 2) && !careful && ctx->rnorm && ctx->comm.world == 1) {
+      if ((hctl[CT_FLAG] & 2) && !careful && ctx->rnorm) {  // (the flag derives from replicated scalars: every rank takes this branch)
         // Invariant subspace (irlb.c: R_F < eps or S < eps).  The cycle only appended columns
         // behind the restart state (V[:, :k+1], W[:, :k], the arrow part of B) and the restart
         // logic left svratio / B / k alone, so the cycle is simply run again, this time looking
@@ -1810,7 +1935,17 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       ICK(cudaMemcpyAsync(center_out, m->center, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (scale_out && use_scale)
       ICK(cudaMemcpyAsync(scale_out, m->scale, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    ICK(cudaStreamSynchronize(ctx->stream));
+    {
+      unsigned long long hd[XD_COUNT];
+      ICK(cudaMemcpyAsync(hd, I.xdiag, sizeof(hd), cudaMemcpyDeviceToHost, ctx->stream));
+      ICK(cudaStreamSynchronize(ctx->stream));
+      int khz = 1;
+      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+      for (int q = 0; q < 5; ++q) ctx->stats.xchg_diag[q] = (double)hd[q] / ((double)khz * 1e-3);  // cycles -> us (nominal clock)
+      ctx->stats.xchg_diag[5] = (double)hd[XD_N_F];
+      ctx->stats.xchg_diag[6] = (double)hd[XD_N_W];
+      ctx->stats.xchg_diag[7] = (double)khz;
+    }
     spmv_timer_collect(ctx);
     ctx->stats.d2h_bytes += nv * 8 + (V_out ? (long long)n * nv * 8 : 0);
     {

@@ -1163,7 +1163,7 @@ int build_layout_B(m3b_mat* m, bool split) {
     for (int q = 0; q < n_cls; ++q) {
       TiledLayout& Lq = *Ls[q];
       Lq.n_entries = n_ent[q];
-      RET(dev_alloc(ctx, &Lq.idx, (size_t)std::max<long long>(n_ent[q], 1)));
+      RET(dev_alloc(ctx, &Lq.idx, (size_t)std::max<long long>(n_ent[q], 1) + 16));
       if (q == 0) RET(dev_alloc(ctx, &Lq.val, (size_t)std::max<long long>(n_ent[q], 1)));
       if (n_runs) {
         k_fill_pads<<<(unsigned)((n_runs + 255) / 256), 256, 0, ctx->stream>>>(d_cnt[q], d_base[q], n_runs, q == 1 ? 8 : 4,
@@ -1222,7 +1222,7 @@ int build_layout_B(m3b_mat* m, bool split) {
     TiledLayout& Lq = *Ls[q];
     const int cls = split ? q + 1 : 0;
     Lq.n_entries = T[q].n_entries;
-    RET(dev_alloc(ctx, &Lq.idx, (size_t)T[q].n_entries));
+    RET(dev_alloc(ctx, &Lq.idx, (size_t)T[q].n_entries + 16));
     if (q == 0) RET(dev_alloc(ctx, &Lq.val, (size_t)T[q].n_entries));
     RET(dev_alloc(ctx, &d_base[q], (size_t)std::max<long long>(n_runs, 1)));
     if (n_runs) {
@@ -1937,7 +1937,7 @@ int build_layout_A(m3b_mat* m, bool split) {
   for (int q = 0; q < n_cls; ++q) {
     TiledLayout& Lq = *Ls[q];
     Lq.n_entries = T[q].n_entries;
-    RET(dev_alloc(ctx, &Lq.idx, (size_t)T[q].n_entries));
+    RET(dev_alloc(ctx, &Lq.idx, (size_t)T[q].n_entries + 16));
     if (q == 0) RET(dev_alloc(ctx, &Lq.val, (size_t)T[q].n_entries));
     RET(dev_alloc(ctx, &d_base[q], (size_t)std::max<long long>(n_runs, 1)));
     if (n_runs) {

@@ -40,6 +40,13 @@ void m3b_set_error(m3b_ctx* ctx, const char* fmt, ...);
 struct NcclApi;
 #define M3B_XCHG_CAP 131072      // doubles per exchange slot (kept genes <= 131072 for the fused path)
 #define M3B_XCHG_FLAG_STRIDE 16  // doubles (128 B) between two flags
+// flag-in-data ("LL") areas behind the two slots, used by the fused vector kernel (k_orth_fused):
+// 16-byte entries {lo32, flag, hi32, flag}; per parity: [world][CAPF] gene-vector rows,
+// [world][CAPW] Gram-Schmidt coefficients, [world][CAPG][2] per-CTA {|w|^2, sum w} partials
+#define M3B_LL_CAPF 65536
+#define M3B_LL_CAPW 512
+#define M3B_LL_CAPG 256
+#define M3B_LL_ENTRIES(world) ((size_t)(world) * (M3B_LL_CAPF + M3B_LL_CAPW + 2 * M3B_LL_CAPG))
 struct Comm {
   int rank = 0, world = 1;
   void* comm = nullptr;  // ncclComm_t
@@ -50,6 +57,7 @@ struct Comm {
   double** peers_dev = nullptr;    // [world] device array of the ranks' buffers (own included)
   void* peer_base[16] = {nullptr}; // opened IPC mappings (to close)
   unsigned long long xchg_seq = 0; // use counter (same on every rank)
+  unsigned int ll_launch[2] = {0, 0};  // fused launches so far, gene side / cell side (parity of the LL areas)
   bool p2p = false;
 };
 int comm_get_unique_id(m3b_ctx* ctx, char* id);

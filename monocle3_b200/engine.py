@@ -107,6 +107,7 @@ class Context:
         out["phase_ms"] = list(out["phase_ms"])
         out["host_ms"] = list(out["host_ms"])
         out["select_ms"] = list(out["select_ms"])
+        out["xchg_diag"] = list(out["xchg_diag"])
         return out
 
     def measure_fp64_peak(self):
@@ -188,6 +189,23 @@ def align_residuals(ctx, X, M, beta=None):
     return Xf, b
 
 
+class CSCBlocks:
+    """A genes x cells count matrix given as consecutive CELL BLOCKS, each a scipy csc_matrix (a
+    dgCMatrix: < 2^31 stored entries).  This is how a matrix beyond the dgCMatrix limit reaches the
+    library (the 2M-cell target has 3.2e9 entries): the R shim appends the
+    blocks in order through m3b_matrix_append_csc, exactly like the chunks of one dgCMatrix."""
+
+    def __init__(self, blocks):
+        self.blocks = list(blocks)
+        if not self.blocks:
+            raise ValueError("CSCBlocks needs at least one block")
+        G = self.blocks[0].shape[0]
+        if any(b.shape[0] != G for b in self.blocks):
+            raise ValueError("all blocks must have the same number of genes")
+        self.shape = (G, int(sum(b.shape[1] for b in self.blocks)))
+        self.nnz = int(sum(int(b.nnz) for b in self.blocks))
+
+
 class DeviceMatrix:
     """The counts matrix (local cell shard) resident on the GPU (m3b_mat)."""
 
@@ -208,10 +226,27 @@ class DeviceMatrix:
         """counts: scipy.sparse.csc_matrix genes x (local) cells.  Appended in cell-range
         chunks whose nnz fits int32 (the dgCMatrix limit)."""
         G, Cn = counts.shape
+        if isinstance(counts, CSCBlocks):
+            m = cls(ctx, G, Cn, n_cells_total, counts.nnz)
+            for blk in counts.blocks:
+                if not blk.has_canonical_format:
+                    blk = blk.copy()
+                    blk.sum_duplicates()
+                cls._append_ranges(m, blk, chunk_cells)
+            m.end()
+            return m
         if not counts.has_canonical_format:  # a dgCMatrix is sorted and duplicate-free; scipy need not be
             counts = counts.copy()
             counts.sum_duplicates()
         m = cls(ctx, G, Cn, n_cells_total, counts.nnz)
+        cls._append_ranges(m, counts, chunk_cells)
+        m.end()
+        return m
+
+    @staticmethod
+    def _append_ranges(m, counts, chunk_cells=None):
+        """Append one CSC block in cell ranges whose nnz fits int32."""
+        Cn = counts.shape[1]
         indptr = np.asarray(counts.indptr)
         indices = np.ascontiguousarray(counts.indices, dtype=np.int32)
         data = np.ascontiguousarray(counts.data, dtype=np.float64)
@@ -223,10 +258,6 @@ class DeviceMatrix:
                 hi = lo + max(1, (hi - lo) // 2)
             m.append_csc(indptr[lo:hi + 1] - indptr[lo], indices[indptr[lo]:indptr[hi]], data[indptr[lo]:indptr[hi]])
             lo = hi
-        if Cn == 0:
-            pass
-        m.end()
-        return m
 
     def append_csc(self, p, i, x):
         p = np.ascontiguousarray(p, dtype=np.int32)

@@ -32,7 +32,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("case,num_dim", [("worm_l2", 50), ("synth20k", 50)])
+@pytest.mark.parametrize("case,num_dim", [("worm_l2", 50), ("synth20k", 50), ("invariant", 6)])
 def test_sharded_parity(world, case, num_dim):
     if _n_gpus() < world:
         pytest.skip("needs %d GPUs, this box has %d" % (world, _n_gpus()))

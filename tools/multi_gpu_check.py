@@ -35,6 +35,8 @@ def main():
     torch.cuda.set_device(lr)
     td.init_process_group("nccl", device_id=torch.device("cuda", lr))
     rank, world = td.get_rank(), td.get_world_size()
+    if name == "invariant":
+        return invariant_case(td, lr)
     if name == "synth20k":
         from monocle3_b200.synth import synth_csc
         # generated on the CPU so that every rank (and the oracle) sees the same matrix
@@ -72,6 +74,56 @@ def main():
     v = np.ascontiguousarray(model["svd_v"]).ravel()
     vs = ag(np.array([float(np.sum(v)), float(np.sum(np.abs(v))), float(v[0]), float(v[-1])]))
     same = all(np.array_equal(vs[:4], vs[4 * r:4 * r + 4]) for r in range(world))
+    if rank == 0:
+        print("REPLICAS_IDENTICAL %s" % same, flush=True)
+    td.destroy_process_group()
+    sys.exit(0 if (ok and same) else 1)
+
+
+def invariant_case(td, lr):
+    """irlba's answer to an exact invariant subspace (a vanished Lanczos vector is replaced by rnorm()
+    from R's stream), cell-sharded: every rank continues the same stream, cell-length draws are
+    sliced by the library.  Same iter / mprod / singular values as the restatement on the whole
+    matrix (the single-GPU twin is tests/test_gpu_parity.py::test_invariant_subspace_random_restart)."""
+    import scipy.sparse as sp
+    from monocle3_b200 import engine, dist, _lib as L
+    from monocle3_b200.r_rng import RStream
+    from tests.parity import subspace_angle
+    rank, world = td.get_rank(), td.get_world_size()
+    rng = np.random.default_rng(5)
+    G, Cn, r = 40, 70, 4
+    dense = (rng.integers(1, 4, (G, r)) @ rng.integers(0, 3, (r, Cn))).astype(np.float64) * 1e-9
+    counts = sp.csc_matrix(dense)
+    lo, hi = dist.shard_ranges_even(Cn, world)[rank]
+    ctx = engine.Context(device=lr, small_svd="device")
+    dist.init_comm(ctx)
+    dev = engine.DeviceMatrix.from_csc(ctx, counts[:, lo:hi], n_cells_total=Cn)
+    dev.normalize(None, L.NORM_NONE, 0.0)
+    keep = dev.select_genes(None)
+    n = int(keep.sum())
+    stream = RStream(7)
+    v0 = stream.rnorm(n)
+    ctx.set_rnorm(stream.rnorm)
+    res = dev.pca_irlba(6, v0, center=False, scale=False)
+    ctx.set_rnorm(None)
+    ok = True
+    if rank == 0:
+        from oracle import irlba_ref
+        from oracle.r_rng import RRandom
+        orng = RRandom(7)
+        v0o = orng.rnorm(n)
+        o = irlba_ref.irlba(sp.csc_matrix(dense[keep, :].T), 6, v0o, rng=orng)
+        out = dict(world=world, fixture="invariant", status=int(res["status"]), iter=(res["iter"], o.iter), mprod=(res["mprod"], o.mprod),
+                   sv_rel=float(np.max(np.abs(res["d"][:r] - o.d[:r]) / o.d[:r])),
+                   angle_v=subspace_angle(res["v"][:, :r], o.v[:, :r]))
+        ok = (res["status"] == 0 and o.err == 0 and (res["iter"], res["mprod"]) == (o.iter, o.mprod)
+              and out["sv_rel"] < 1e-6 and out["angle_v"] < 1e-4)
+        out["ok"] = bool(ok)
+        print("MULTI_GPU_CHECK " + json.dumps(out), flush=True)
+    ag = dist.make_allgather()
+    v = np.ascontiguousarray(res["v"]).ravel()
+    vs = ag(np.array([float(np.sum(v)), float(np.sum(np.abs(v))), float(v[0]), float(v[-1])]))
+    same = all(np.array_equal(vs[:4], vs[4 * q:4 * q + 4]) for q in range(world))
     if rank == 0:
         print("REPLICAS_IDENTICAL %s" % same, flush=True)
     td.destroy_process_group()
