@@ -1227,6 +1227,7 @@ struct Irlba {
   unsigned long long* bar = nullptr;
   unsigned long long bar_seq = 0;
   unsigned long long* xdiag = nullptr;  // [XD_COUNT] in-kernel exchange timing of the sharded fused kernel
+  double* s_rms = nullptr;              // scale for center = FALSE, scale = TRUE (k_rms_scale)
   int nb_n, nb_m;        // blocks of the vector kernels (gene side / cell side)
   int nb_ca;             // blocks of k_combine_A (32 rows per block)
   int nbo_n, nbo_m;      // blocks of k_apply_orth (= number of pn/ps partials it writes)
@@ -1568,6 +1569,18 @@ int compute_moments(m3b_mat* m) {
   return M3B_OK;
 }
 
+// sparse_prcomp_irlba with center = FALSE, scale. = TRUE (R/utils.R:395-397): the scale is the root mean
+// square about ZERO, sqrt(colSums(x^2) / max(1, nrow - 1)), not the standard deviation.  From the
+// moments already on the device: sum x^2 = (C - 1) sd^2 + C mean^2.
+__global__ void k_rms_scale(const double* __restrict__ mean, const double* __restrict__ sd, int n, double C,
+                            double* __restrict__ out) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) {
+    const double d = fmax(1.0, C - 1.0);
+    out[g] = sqrt(((C - 1.0) * sd[g] * sd[g] + C * mean[g] * mean[g]) / d);
+  }
+}
+
 __global__ void k_fill(double* p, int n, double v) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < n) p[g] = v;
@@ -1702,6 +1715,12 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     ICK(cudaMemsetAsync(I.xdiag, 0, XD_COUNT * sizeof(unsigned long long), ctx->stream));
     // operator vectors
     I.s = use_scale ? m->scale : nullptr;
+    if (use_scale && !use_center) {
+      IR(I.alloc(&I.s_rms, (size_t)n));
+      k_rms_scale<<<(n + 255) / 256, 256, 0, ctx->stream>>>(m->center, m->scale, n, (double)m->n_cells_total, I.s_rms);
+      count_launch(ctx);
+      I.s = I.s_rms;
+    }
     if (use_center) {
       I.ce = m->mean_sparse;  // mean(D) - f0 = mean of the stored sparse part
     } else if (m->f0 != 0.0) {
@@ -1934,7 +1953,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     if (center_out && use_center)
       ICK(cudaMemcpyAsync(center_out, m->center, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (scale_out && use_scale)
-      ICK(cudaMemcpyAsync(scale_out, m->scale, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      ICK(cudaMemcpyAsync(scale_out, I.s, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     {
       unsigned long long hd[XD_COUNT];
       ICK(cudaMemcpyAsync(hd, I.xdiag, sizeof(hd), cudaMemcpyDeviceToHost, ctx->stream));

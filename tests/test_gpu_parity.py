@@ -2,6 +2,8 @@
 oracle on the committed fixtures.  Bars (BASELINE.json north_star): size factors and nnz
 bookkeeping exact; singular values 1e-6 relative; sign-aligned loadings / embeddings
 subspace angle < 1e-4 rad; iter/mprod equal to the oracle's."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -522,6 +524,22 @@ def test_jaccard_coeff_bit_exact(m3, n, k):
         m3.jaccard_coeff(np.array([[0.0, 2.0], [1.0, 2.0]]), True)
 
 
+@pytest.mark.parametrize("n,k", [(500, 20), (64, 64), (2000, 15)])
+def test_jaccard_coeff_vs_reference_native(m3, n, k):
+    """m3b_jaccard_coeff against the REFERENCE'S OWN code: oracle/_ref/libm3ref.so is
+    src/clustering.cpp compiled unmodified against a shim of the Rcpp containers (oracle/Makefile).
+    Bit-identical (ids, row order, weights)."""
+    from tests.test_oracle_ref_native import LIB, native_jaccard
+    if not os.path.exists(LIB):
+        pytest.skip("oracle/_ref/libm3ref.so not built")
+    rng = np.random.default_rng(3 * n + k)
+    idx = rng.integers(1, n + 1, (n, k))
+    idx[::7, : max(1, k // 3)] = idx[::7, :1]
+    for weight in (True, False):
+        got = m3.jaccard_coeff(idx.astype(np.float64), weight)
+        assert np.array_equal(got, native_jaccard(idx, weight))
+
+
 @pytest.mark.parametrize("n,d,k", [(1000, 50, 21), (130, 7, 5), (64, 100, 64), (257, 3, 1)])
 def test_knn_self_exact(m3, n, d, k):
     """Exact kNN (what RANN::nn2 returns for cluster_cells, R/cluster_cells.R:286-287) against the
@@ -568,3 +586,27 @@ def test_irlba_tiny_problem_dense_branch(m3, shape):
         assert sv_rel_err(ir["d"], o["d"]) < SV_TOL
         assert subspace_angle(cds.reduce_dim_aux["PCA"]["model"]["svd_v"], o["svd_v"]) < ANGLE_TOL
         assert subspace_angle(cds.reduced_dims["PCA"], o["PCA"]) < ANGLE_TOL
+
+
+def test_abi_scale_without_center_is_root_mean_square(m3, worm_l2):
+    """m3b_pca_irlba(center=0, scale=1): sparse_prcomp_irlba scales by sqrt(colSums(x^2) / (n - 1)) when
+    it does not centre (R/utils.R:395-397), not by the standard deviation.  preprocess_cds never asks
+    for this combination (center == scale == scaling), the C ABI can."""
+    from monocle3_b200 import engine, _lib as L
+    from monocle3_b200.r_rng import rnorm_after_seed
+    counts, _ = worm_l2
+    sf = ref.estimate_size_factors(counts)
+    FM = ref.normalize_expr_data(counts, sf, "log")
+    FM, kept = ref.select_and_filter_genes(FM)
+    At = FM.T.tocsc()
+    v0 = rnorm_after_seed(2016, At.shape[1])
+    o = ref.sparse_prcomp_irlba(At, 20, center=False, scale=True, v0=v0)
+    ctx = m3.get_context()
+    dev = engine.DeviceMatrix.from_csc(ctx, counts)
+    dev.normalize(sf, L.NORM_LOG2, 1.0)
+    dev.select_genes(None)
+    r = dev.pca_irlba(20, v0, center=False, scale=True)
+    np.testing.assert_allclose(r["scale"], o["svd_scale"], rtol=1e-12)
+    assert (r["iter"], r["mprod"]) == (o["iter"], o["mprod"])
+    assert sv_rel_err(r["d"], o["d"]) < SV_TOL
+    assert subspace_angle(r["v"], o["rotation"]) < ANGLE_TOL and subspace_angle(r["x"], o["x"]) < ANGLE_TOL
