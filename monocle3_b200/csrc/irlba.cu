@@ -1199,7 +1199,161 @@ k_restart_gemm(double* __restrict__ X, long long ld, long long rows, int kin, in
   cp_async_wait<0>();
 }
 
+// --------------------------------------------------------------------------
+// K9, second version: the same in-place X[:, :kout] = X[:, :kin] Q^T with DMMA, re-tiled.
+//
+// What the first version (above) left on the table, measured at the 2M-cell shape where X no longer
+// sits in L2: 4.1 ms per cell-side GEMM = 10 TFLOP/s and 0.8 TB/s -- neither the tensor pipe nor
+// DRAM.  (a) A 32-row block is staged with 8-byte cp.async, one per element and thread: 256-byte
+// runs scattered over kin DRAM pages; (b) with 16 column groups per 16 rows every warp re-reads the
+// same A fragments: 3 LDS per 2 DMMA, 20 KB of shared-memory traffic per row.
+// Here: a STAGE is 64 rows, kept COLUMN-major in shared memory (stride 72 doubles: the four k of a
+// fragment land on disjoint bank halves), so a column of a stage is ONE contiguous 512-byte run in
+// global memory and is fetched with ONE bulk async copy (cp.async.bulk + mbarrier complete_tx,
+// issued by a single thread; two stages double-buffered); a CTA walks a CONTIGUOUS range of
+// stages.  16 warps = 4 row groups (16 rows) x 4 column groups (4/3/3/3 fragments of 8 columns): 6 LDS
+// per 8 DMMA, 6.5 KB of shared-memory traffic per row.  Requires kout <= 104 (one pass) and the
+// tile to fit; otherwise the first version runs.
+// Column starts that are only 8-byte aligned (odd ld): the copy starts one element early and the
+// fragment loads of that column are shifted by one row.
+// --------------------------------------------------------------------------
+#define G2_ROWS 64
+#define G2_RS 72
+#define G2_THREADS 512
+__device__ __forceinline__ void g2_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void g2_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g2_bulk(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void g2_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__global__ void __launch_bounds__(G2_THREADS, 1)
+k_restart_gemm2(double* __restrict__ X, long long ld, long long rows, int kin, int kinp, int kout,
+                const double* __restrict__ Q, long long stages_per_cta) {
+  extern __shared__ __align__(128) double smg2[];
+  const int k4 = ((kin + 3) >> 2) << 2;
+  double* Qs = smg2;                                   // [104][kinp]
+  double* Xs0 = smg2 + (size_t)GEMM_CPP * kinp;        // [2][k4][G2_RS]
+  __shared__ __align__(8) unsigned long long mbar[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int rg = warp & 3, cg = warp >> 2;
+  const int f0 = (cg == 0) ? 0 : 1 + 3 * cg, nf = (cg == 0) ? 4 : 3;   // fragments 0-3 | 4-6 | 7-9 | 10-12
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&mbar[0]);
+  const long long n_stages = (rows + G2_ROWS - 1) / G2_ROWS;
+  const long long s_begin = (long long)blockIdx.x * stages_per_cta, s_end = min(n_stages, s_begin + stages_per_cta);
+  if (s_begin >= s_end) return;
+  const int odd = (int)(ld & 1);
+  if (threadIdx.x == 0) {
+    g2_mbar_init(bar0, 1);
+    g2_mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // Q (zero-padded in k and in the columns past kout) and the k padding of both stage buffers
+  for (int e = threadIdx.x; e < GEMM_CPP * kinp; e += G2_THREADS) {
+    const int c = e / kinp, k = e - c * kinp;
+    Qs[e] = (c < kout && k < kin) ? Q[(long long)c * kin + k] : 0.0;
+  }
+  for (int e = threadIdx.x; e < 2 * (k4 - kin) * G2_RS; e += G2_THREADS) {
+    const int b = e / ((k4 - kin) * G2_RS), q = e - b * (k4 - kin) * G2_RS;
+    Xs0[(size_t)b * k4 * G2_RS + (size_t)kin * G2_RS + q] = 0.0;
+  }
+  __syncthreads();
+  // issue the copies of a FULL stage (one thread); a partial last stage is copied by everybody at use
+  auto prefetch = [&](long long st, int buf) {
+    const long long r0 = st * G2_ROWS;
+    if (r0 + G2_ROWS > rows) return;  // partial
+    if (warp == 0) {  // the lanes of warp 0 share the columns; lane 0 announces the byte count first
+      const unsigned bar = bar0 + 8u * buf;
+      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(Xs0 + (size_t)buf * k4 * G2_RS);
+      const int n_odd = odd ? (kin >> 1) : 0;   // columns 1, 3, 5, ... start on an 8-byte boundary only
+      if (lane == 0) g2_expect_tx(bar, (unsigned)((kin - n_odd) * (G2_ROWS * 8) + n_odd * (G2_ROWS * 8 + 16)));
+      __syncwarp();
+      for (int c = lane; c < kin; c += 32) {
+        const double* src = X + (long long)c * ld + r0;
+        if (odd && (c & 1)) g2_bulk(dst0 + (unsigned)(c * G2_RS * 8), src - 1, G2_ROWS * 8 + 16, bar);
+        else g2_bulk(dst0 + (unsigned)(c * G2_RS * 8), src, G2_ROWS * 8, bar);
+      }
+    }
+  };
+  unsigned ph = 0u;  // bit b: parity of the next completion of buffer b's barrier
+  prefetch(s_begin, 0);
+  const int oa = (odd && (tig & 1)) ? 1 : 0;   // row shift of this lane's k columns (k = 4 ks + tig)
+  for (long long st = s_begin; st < s_end; ++st) {
+    const int buf = (int)((st - s_begin) & 1);
+    if (st + 1 < s_end) prefetch(st + 1, buf ^ 1);
+    const long long r0 = st * G2_ROWS;
+    double* Xs = Xs0 + (size_t)buf * k4 * G2_RS;
+    if (r0 + G2_ROWS > rows) {
+      // partial stage: plain copies, same (possibly shifted) placement
+      const int nr = (int)(rows - r0);
+      for (int e = threadIdx.x; e < kin * G2_ROWS; e += G2_THREADS) {
+        const int c = e / G2_ROWS, r = e - c * G2_ROWS;
+        Xs[(size_t)c * G2_RS + r + ((odd && (c & 1)) ? 1 : 0)] = (r < nr) ? X[(long long)c * ld + r0 + r] : 0.0;
+      }
+      __syncthreads();
+    } else {
+      g2_wait(bar0 + 8u * buf, (ph >> buf) & 1u);
+      ph ^= 1u << buf;
+    }
+    double c[2][4][2];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) c[0][f][0] = c[0][f][1] = c[1][f][0] = c[1][f][1] = 0.0;
+    const double* xa = Xs + (size_t)tig * G2_RS + 16 * rg + gid + oa;
+    const double* qb = Qs + (size_t)(8 * f0 + gid) * kinp + tig;
+    const int ksteps = k4 >> 2;
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const double a0 = xa[(size_t)(4 * ks) * G2_RS], a1 = xa[(size_t)(4 * ks) * G2_RS + 8];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        if (f < nf) {  // warp-uniform
+          const double b = qb[(size_t)f * 8 * kinp + 4 * ks];
+          dmma_m8n8k4(c[0][f][0], c[0][f][1], a0, b);
+          dmma_m8n8k4(c[1][f][0], c[1][f][1], a1, b);
+        }
+      }
+    }
+    __syncthreads();  // every warp has read its fragments of this stage: the rows may be overwritten,
+                      // and the buffer refilled by the prefetch of the next iteration
+    const long long rr = r0 + 16 * rg + gid;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if (f < nf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = 8 * (f0 + f) + 2 * tig + h;
+          if (col < kout) {
+            if (rr < rows) X[(long long)col * ld + rr] = c[0][f][h];
+            if (rr + 8 < rows) X[(long long)col * ld + rr + 8] = c[1][f][h];
+          }
+        }
+      }
+    }
+  }
+}
+
 int irlba_init(m3b_ctx* ctx) {
+  CK(ctx, cudaFuncSetAttribute(k_restart_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   CK(ctx, cudaFuncSetAttribute(k_restart_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   CK(ctx, cudaFuncSetAttribute(k_orth_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, M3B_OF_SMEM_MAX));
   return M3B_OK;
@@ -1481,6 +1635,21 @@ struct Irlba {
     const size_t budget = 224 * 1024;
     int kinp = ((kin + 3) & ~3);
     while ((kinp & 15) != 4) kinp += 4;  // kinp % 16 == 4: the 8 rows of a fragment hit disjoint banks
+    {
+      // second version (bulk-copied 64-row stages, 4 x 4 warp grid) whenever it applies
+      static const bool no_v2 = getenv("M3B_GEMM_V1") != nullptr;
+      const int k4 = (kin + 3) & ~3;
+      const size_t smem2 = ((size_t)GEMM_CPP * kinp + 2 * (size_t)k4 * G2_RS) * sizeof(double);
+      if (!no_v2 && kout <= GEMM_CPP && smem2 <= (size_t)226 * 1024 - 64 && rows >= G2_ROWS) {
+        const long long n_stages = (rows + G2_ROWS - 1) / G2_ROWS;
+        const long long per = (n_stages + ctx->sm_count - 1) / ctx->sm_count;
+        const unsigned grid = (unsigned)((n_stages + per - 1) / per);
+        k_restart_gemm2<<<grid, G2_THREADS, smem2, ctx->stream>>>(X, ld, rows, kin, kinp, kout, Qd, per);
+        count_launch(ctx);
+        CK(ctx, cudaGetLastError());
+        return M3B_OK;
+      }
+    }
     int nbuf = 2;
     size_t smem = (size_t)(GEMM_CPP + nbuf * GEMM_RB) * kinp * sizeof(double);
     if (smem > budget) {
@@ -1681,8 +1850,8 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
                 smem <= (size_t)M3B_OF_SMEM_MAX && !getenv("M3B_NO_FUSED_ORTH");
     }
     const size_t part_sz = (size_t)std::max(std::max(I.nblk_n, I.nblk_m), I.of_grid) * work;
-    IR(I.alloc(&I.V, (size_t)n * work));
-    IR(I.alloc(&I.W, (size_t)std::max<long long>(mloc, 1) * work));
+    IR(I.alloc(&I.V, (size_t)n * work + 8));
+    IR(I.alloc(&I.W, (size_t)std::max<long long>(mloc, 1) * work + 8));  // + slack: see k_restart_gemm2 (odd ld)
     IR(I.alloc(&I.F, (size_t)n));
     IR(I.alloc(&I.Fraw, (size_t)n + 2));
     IR(I.alloc(&I.xs, (size_t)n));
