@@ -247,6 +247,11 @@ def aggregate_gene_expression(cds, gene_group_df=None, cell_group_df=None, norm_
         raise ValueError("'arg' should be one of 'log', 'binary', 'size_only'")
     if gene_agg_fun not in ("sum", "mean") or cell_agg_fun not in ("sum", "mean"):
         raise ValueError("aggregation functions must be 'sum' or 'mean'")
+    if cds.shard and cell_group_df is None:
+        # without cell groups the result has one column per cell: on a cell-sharded cds that would be
+        # this rank's columns only, silently -- the caller gathers per-cell results itself
+        raise ValueError("aggregate_gene_expression on a cell-sharded cds needs cell_group_df "
+                         "(per-cell columns stay with their rank)")
     dev = cds.device_matrix()
     if norm_method == "binary":
         dev.normalize(None, L.NORM_BINARY, 0.0)

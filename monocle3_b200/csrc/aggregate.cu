@@ -75,6 +75,9 @@ int run_detect_genes(m3b_mat* m, double min_expr, long long* num_cells_expressed
   const long long C = m->n_cells;
   unsigned long long *d_gt = nullptr, *d_nnz = nullptr;
   long long* d_cell = nullptr;
+  DevScope guard;
+  guard.own(&d_gt);
+  guard.own(&d_cell);
   RET(dev_alloc(ctx, &d_gt, (size_t)std::max(2 * G, 1)));
   d_nnz = d_gt + G;
   RET(dev_alloc(ctx, &d_cell, (size_t)std::max<long long>(C, 1)));
@@ -111,8 +114,6 @@ int run_detect_genes(m3b_mat* m, double min_expr, long long* num_cells_expressed
       for (long long c = 0; c < C; ++c) num_genes_expressed[c] += G - (hp[c + 1] - hp[c]);
     }
   } while (0);
-  dev_free(d_gt);
-  dev_free(d_cell);
   if (e != cudaSuccess) {
     m3b_set_error(ctx, "m3b_detect_genes: %s", cudaGetErrorString(e));
     return M3B_E_CUDA;
@@ -232,6 +233,13 @@ int run_aggregate(m3b_mat* m, const int* gene_group, int n_groups, int gene_mean
   int *d_gg = nullptr, *d_gs = nullptr;
   double *d_cells = nullptr, *d_out = nullptr;
   long long *d_ptr = nullptr, *d_list = nullptr;
+  DevScope guard;
+  guard.own(&d_gg);
+  guard.own(&d_gs);
+  guard.own(&d_cells);
+  guard.own(&d_out);
+  guard.own(&d_ptr);
+  guard.own(&d_list);
   RET(dev_alloc(ctx, &d_gg, (size_t)std::max(G, 1)));
   RET(dev_alloc(ctx, &d_gs, (size_t)n_groups));
   RET(dev_alloc(ctx, &d_cells, (size_t)std::max<long long>(C, 1) * n_groups));
@@ -286,12 +294,6 @@ int run_aggregate(m3b_mat* m, const int* gene_group, int n_groups, int gene_mean
     }
     e = cudaStreamSynchronize(ctx->stream);
   } while (0);
-  dev_free(d_gg);
-  dev_free(d_gs);
-  dev_free(d_cells);
-  dev_free(d_out);
-  dev_free(d_ptr);
-  dev_free(d_list);
   if (e != cudaSuccess) {
     m3b_set_error(ctx, "m3b_aggregate_expression: %s", cudaGetErrorString(e));
     return M3B_E_CUDA;

@@ -1766,11 +1766,11 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     m3b_set_error(ctx, "max(nu, nv) must be strictly less than min(nrow(A), ncol(A)) (nv=%d, min dim=%lld)", nv, minmn);
     return M3B_E_DIMS;
   }
-  if (scale && !center) {
-    // sparse_prcomp_irlba scales by the root mean square sqrt(colSums(x^2) / (n - 1)) when center = FALSE
-    // (R/utils.R:396-400); preprocess_cds never asks for that (it passes scaling for both), and the
-    // standard deviation about the mean would be a silently different answer
-    m3b_set_error(ctx, "m3b_pca_irlba: scale without center is not supported (preprocess_cds passes `scaling` for both)");
+  // scale without center: sparse_prcomp_irlba scales by the root mean square sqrt(colSums(x^2) / (n - 1))
+  // (R/utils.R:396-400), not by the standard deviation -- see k_rms_scale.  preprocess_cds never asks
+  // for that (it passes `scaling` for both); the dense tiny-problem branch does not implement it.
+  if (scale && !center && minmn < 6) {
+    m3b_set_error(ctx, "m3b_pca_irlba: scale without center is not supported on the dense branch (min dimension < 6)");
     return M3B_E_DIMS;
   }
   if (minmn < 6)  // irlba: "Tiny problem detected, using standard `svd` function" 

@@ -94,6 +94,11 @@ int run_jaccard(m3b_ctx* ctx, const double* idx, long long n, int k, int weight,
   double *d_idx = nullptr, *d_out = nullptr;
   int* d_nb = nullptr;
   unsigned long long* d_max = nullptr;
+  DevScope guard;
+  guard.own(&d_idx);
+  guard.own(&d_out);
+  guard.own(&d_nb);
+  guard.own(&d_max);
   RET(dev_alloc(ctx, &d_idx, (size_t)total));
   RET(dev_alloc(ctx, &d_out, (size_t)3 * total));
   RET(dev_alloc(ctx, &d_nb, (size_t)total + 2));
@@ -125,10 +130,6 @@ int run_jaccard(m3b_ctx* ctx, const double* idx, long long n, int k, int weight,
     ctx->stats.d2h_bytes += 3 * total * 8;
     e = cudaStreamSynchronize(ctx->stream);
   } while (0);
-  dev_free(d_idx);
-  dev_free(d_out);
-  dev_free(d_nb);
-  dev_free(d_max);
   if (e != cudaSuccess) {
     m3b_set_error(ctx, "m3b_jaccard_coeff: %s", cudaGetErrorString(e));
     return M3B_E_CUDA;

@@ -115,6 +115,10 @@ int run_knn_self(m3b_ctx* ctx, const double* X, long long n, int d, int k, int* 
   }
   double *d_X = nullptr, *d_dist = nullptr;
   int* d_idx = nullptr;
+  DevScope guard;
+  guard.own(&d_X);
+  guard.own(&d_dist);
+  guard.own(&d_idx);
   RET(dev_alloc(ctx, &d_X, (size_t)n * d));
   RET(dev_alloc(ctx, &d_dist, (size_t)n * k));
   RET(dev_alloc(ctx, &d_idx, (size_t)n * k));
@@ -131,9 +135,6 @@ int run_knn_self(m3b_ctx* ctx, const double* X, long long n, int d, int k, int* 
     ctx->stats.d2h_bytes += n * k * 12;
     e = cudaStreamSynchronize(ctx->stream);
   } while (0);
-  dev_free(d_X);
-  dev_free(d_dist);
-  dev_free(d_idx);
   if (e != cudaSuccess) {
     m3b_set_error(ctx, "m3b_knn_self: %s", cudaGetErrorString(e));
     return M3B_E_CUDA;

@@ -219,8 +219,11 @@ int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* 
   }
   if (m->nnz + nnz_chunk > m->nnz_cap) {  // grow
     long long cap = std::max(m->nnz + nnz_chunk, (long long)(m->nnz_cap * 1.5) + 1024);
-    int* ni;
-    double* nx;
+    int* ni = nullptr;
+    double* nx = nullptr;
+    DevScope grow;  // the new arrays, until they replace the old ones
+    grow.own(&ni);
+    grow.own(&nx);
     RET(dev_alloc(ctx, &ni, (size_t)cap));
     RET(dev_alloc(ctx, &nx, (size_t)cap));
     if (m->nnz) {
@@ -232,9 +235,13 @@ int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* 
     dev_free(m->x);
     m->i = ni;
     m->x = nx;
+    ni = nullptr;  // handed over
+    nx = nullptr;
     m->nnz_cap = cap;
   }
-  int* d_pchunk;
+  int* d_pchunk = nullptr;
+  DevScope guard;  // d_pchunk goes back to the pool on every exit
+  guard.own(&d_pchunk);
   RET(dev_alloc(ctx, &d_pchunk, (size_t)n_cells_chunk + 1));
   CK(ctx, cudaMemcpyAsync(d_pchunk, p, (n_cells_chunk + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaMemcpyAsync(m->i + m->nnz, i, nnz_chunk * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -257,7 +264,6 @@ int ingest_append(m3b_mat* m, long long n_cells_chunk, const int* p, const int* 
   int bad = 0;
   CK(ctx, cudaMemcpyAsync(&bad, ctx->ingest_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));
-  dev_free(d_pchunk);
   if (bad) {
     cudaMemsetAsync(ctx->ingest_flag, 0, sizeof(int), ctx->stream);
     m3b_set_error(ctx, "append: malformed CSC chunk (%s%s%s): the input must be a valid dgCMatrix slice -- non-decreasing "

@@ -243,6 +243,23 @@ template <typename T>
 int dev_alloc(m3b_ctx* ctx, T** p, size_t n);
 void dev_free(void* p);
 void dev_pool_release(int device);  // return the cached blocks of a device to the driver
+// Frees the registered device blocks when the scope is left -- on EVERY path: CK() / RET() return
+// early, and a block that is not given back stays in the pool's live map for good.  Register the
+// pointer VARIABLE before allocating into it; a block handed on to the caller is taken out by
+// setting the variable to nullptr.
+struct DevScope {
+  std::vector<void**> slots;
+  template <typename T>
+  void own(T** p) {
+    slots.push_back(reinterpret_cast<void**>(p));
+  }
+  ~DevScope() {
+    for (void** q : slots) {
+      dev_free(*q);
+      *q = nullptr;
+    }
+  }
+};
 
 // layout.cu
 int k1_cell_totals(m3b_mat* m, int round_exprs, double* d_tot);

@@ -450,6 +450,10 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
   }
   for (int c = 0; c < nv; ++c) b[c] = (double)bacc[c];
   double *dVs = nullptr, *db = nullptr, *dY = nullptr;
+  DevScope guard;
+  guard.own(&dVs);
+  guard.own(&db);
+  guard.own(&dY);
   RET(dev_alloc(ctx, &dVs, Vs.size()));
   RET(dev_alloc(ctx, &db, (size_t)nv));
   RET(dev_alloc(ctx, &dY, (size_t)std::max<long long>(rows, 1) * nv));
@@ -516,8 +520,5 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
     m3b_set_error(ctx, "m3b_project: %s", cudaGetErrorString(e));
     status = M3B_E_CUDA;
   }
-  dev_free(dVs);
-  dev_free(db);
-  dev_free(dY);
   return status;
 }

@@ -79,6 +79,12 @@ int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor
   if (num_cols <= 0) num_cols = (double)m->n_cells_total;
   double *d_colsum = nullptr, *d_rowpos = nullptr, *d_idf = nullptr;
   int *tileA = nullptr, *tileB = nullptr;
+  DevScope guard;
+  guard.own(&d_colsum);
+  guard.own(&d_rowpos);
+  guard.own(&d_idf);
+  guard.own(&tileA);
+  guard.own(&tileB);
   RET(dev_alloc(ctx, &d_colsum, (size_t)std::max<long long>(C, 1)));
   RET(dev_alloc(ctx, &d_rowpos, (size_t)std::max(n, 1)));
   RET(dev_alloc(ctx, &d_idf, (size_t)std::max(n, 1)));
@@ -120,10 +126,5 @@ int run_tfidf(m3b_mat* m, int frequencies, int log_scale_tf, double scale_factor
     m->tfidf_applied = true;
     m->moments_done = false;
   } while (0);
-  dev_free(d_colsum);
-  dev_free(d_rowpos);
-  dev_free(d_idf);
-  dev_free(tileA);
-  dev_free(tileB);
   return st;
 }

@@ -610,3 +610,21 @@ def test_abi_scale_without_center_is_root_mean_square(m3, worm_l2):
     assert (r["iter"], r["mprod"]) == (o["iter"], o["mprod"])
     assert sv_rel_err(r["d"], o["d"]) < SV_TOL
     assert subspace_angle(r["v"], o["rotation"]) < ANGLE_TOL and subspace_angle(r["x"], o["x"]) < ANGLE_TOL
+
+
+def test_csc_blocks_equal_one_matrix(m3, worm_l2):
+    """A matrix handed over as consecutive cell blocks (monocle3_b200.CSCBlocks: how a matrix beyond
+    the dgCMatrix limit of 2^31 entries reaches the library) gives bit for bit the
+    result of the same matrix as one CSC, through the public API."""
+    counts, _ = worm_l2
+    C = counts.shape[1]
+    cuts = [0, 1000, 1001, 3500, C]
+    blocks = m3.CSCBlocks([counts[:, a:b] for a, b in zip(cuts[:-1], cuts[1:])])
+    assert blocks.shape == counts.shape and blocks.nnz == counts.nnz
+    a = m3.preprocess_cds(m3.new_cell_data_set(counts), num_dim=20)
+    b = m3.preprocess_cds(m3.new_cell_data_set(blocks), num_dim=20)
+    assert np.array_equal(m3.size_factors(a), m3.size_factors(b))
+    assert np.array_equal(a.reduced_dims["PCA"], b.reduced_dims["PCA"])
+    assert np.array_equal(a.reduce_dim_aux["PCA"]["model"]["svd_v"], b.reduce_dim_aux["PCA"]["model"]["svd_v"])
+    with pytest.raises(ValueError, match="per block"):
+        m3.normalized_counts(b)
