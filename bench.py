@@ -467,7 +467,8 @@ def run_project_bench(args, wl, ctx, rank, world, local_rank, barrier, max_over_
         ms_e2e = max_over_ranks(ms_e2e_total) / args.steps
         e2e = {"value": wl["cells"] / (ms_e2e / 1e3), "unit": "cells/s",
                "h2d_bytes_per_step": int(sum_over_ranks(ste["h2d_bytes"]) / args.steps),
-               "d2h_bytes_per_step": int(sum_over_ranks(ste["d2h_bytes"]) / args.steps), "ms_per_step": ms_e2e}
+               "d2h_bytes_per_step": int(sum_over_ranks(ste["d2h_bytes"]) / args.steps), "ms_per_step": ms_e2e,
+               "host_wall_ms_rank0_last_step": dict(e2e_wall)}
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import monocle3_ref as ref
@@ -739,11 +740,18 @@ def main():
     e2e = None
     if not args.no_e2e:
         # ---- end-to-end arm: public API from pinned host buffers ----
+        e2e_wall = {}
+
         def e2e_step():
+            t0 = time.perf_counter()
             c = m3.new_cell_data_set(counts, shard=shard)           # H2D of the CSC + size factors
+            t1 = time.perf_counter()
             c = m3.preprocess_cds(c, num_dim=wl["num_dim"])         # ... embedding + loadings back on the host
             x = c.reduced_dims["PCA"]
+            t2 = time.perf_counter()
             c._dev.free()
+            e2e_wall.update(new_cell_data_set_ms=round(1e3 * (t1 - t0), 1), preprocess_cds_ms=round(1e3 * (t2 - t1), 1),
+                            free_ms=round(1e3 * (time.perf_counter() - t2), 1))
             return c, x
 
         dev.free()

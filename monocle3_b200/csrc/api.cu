@@ -111,6 +111,7 @@ int m3b_create(int device, int flags, m3b_ctx** out) {
     if (const char* e = getenv("M3B_XCHG_TIMEOUT_S")) secs = std::max(0.1, atof(e));
     int khz = 1900000;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    ctx->clock_khz = khz;  // (queried ONCE: the attribute goes to the driver and can take milliseconds)
     ctx->spin_timeout_cycles = (long long)(secs * 1e3 * (double)khz);
   }
   if (const char* e = getenv("M3B_TILE_W")) {  // tuning knob (multiple of 32, <= 28672)

@@ -2127,8 +2127,7 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
       unsigned long long hd[XD_COUNT];
       ICK(cudaMemcpyAsync(hd, I.xdiag, sizeof(hd), cudaMemcpyDeviceToHost, ctx->stream));
       ICK(cudaStreamSynchronize(ctx->stream));
-      int khz = 1;
-      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+      const int khz = std::max(1, ctx->clock_khz);
       for (int q = 0; q < 5; ++q) ctx->stats.xchg_diag[q] = (double)hd[q] / ((double)khz * 1e-3);  // cycles -> us (nominal clock)
       ctx->stats.xchg_diag[5] = (double)hd[XD_N_F];
       ctx->stats.xchg_diag[6] = (double)hd[XD_N_W];

@@ -109,6 +109,7 @@ struct m3b_ctx {
   bool k1_timed = false, k2_timed = false;   // ev0/ev1 bracket the last K1 / K2 launch
   bool k10_timed = false;                    // ... the K10 (projection) kernel
   unsigned int* sched = nullptr;             // [2] dynamic unit counter + done counter (zeroed)
+  int clock_khz = 1900000;                        // nominal SM clock (m3b_create)
   long long spin_timeout_cycles = 60000000000LL;  // bound of the in-kernel waits (m3b_create; M3B_XCHG_TIMEOUT_S)
   int* ingest_flag = nullptr;                // device word raised by the ingest validation kernels
 };

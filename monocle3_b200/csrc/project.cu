@@ -264,6 +264,171 @@ k_project_tiled(const long long* __restrict__ p, const int* __restrict__ gi, con
 }
 
 // ---------------------------------------------------------------------------
+// K10, tiled, second version.  What ncu showed on the first one (profiles/r02e_k_project_tiled*):
+// 25 % of the stall samples sit in the block barrier at the end of every gene tile (235 tiles per
+// cell block, 16 warps in lockstep, a cell has ~6 entries per tile: whoever has a heavy tile makes
+// everybody wait), 17 % wait for the two dependent loads kept_of_gene[gi[k]] that EVERY round
+// repeats for its four entries per cell, consumed or not; shared-memory pipe 32 % busy.
+//   * a 17th warp is the producer: it alone issues the bulk copies of the Vs tiles and waits for the
+//     "empty" mbarrier of a buffer (one arrival per consumer warp) before refilling it; consumer
+//     warps wait for the "full" barrier of the tile they need and arrive on "empty" when done with
+//     it.  No block barrier: a warp may run one tile ahead of the slowest one;
+//   * the four fetched entries of a cell live in registers ACROSS rounds and tiles: after a round
+//     that consumed c entries of a cell, the remaining ones move up by c lanes (three shuffles) and
+//     only the c vacated slots are loaded -- every entry is loaded exactly once.
+// Same arithmetic and summation order per cell as the first version (entries in CSC order).
+// ---------------------------------------------------------------------------
+#define PT2_CWARPS 15                        // consumer warps (+ 1 producer warp = 512 threads: a whole number of 4-warp register allocation units)
+#define PT2_CELLS (PT2_CWARPS * PT_CPW)      // cells per CTA
+#define PT2_THREADS ((PT2_CWARPS + 1) * 32)
+__device__ __forceinline__ void pt_mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(PT2_THREADS, 1)
+k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, const double* __restrict__ y,
+                 const int* __restrict__ kept_of_gene, long long n_cells, int n_kept, const double* __restrict__ Vs, int nvp,
+                 int ncols, int tg, const double* __restrict__ b, double* __restrict__ Y, long long ldy) {
+  extern __shared__ __align__(128) unsigned char pt_smem[];
+  double* buf0 = reinterpret_cast<double*>(pt_smem);
+  double* buf1 = reinterpret_cast<double*>(pt_smem + PT_SMEM_TILE);
+  __shared__ __align__(8) unsigned long long mbar[4];  // full[0], full[1], empty[0], empty[1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bar_full = (unsigned)__cvta_generic_to_shared(&mbar[0]);
+  const unsigned bar_empty = (unsigned)__cvta_generic_to_shared(&mbar[2]);
+  if (threadIdx.x == 0) {
+    pt_mbar_init(bar_full, 1);
+    pt_mbar_init(bar_full + 8, 1);
+    pt_mbar_init(bar_empty, PT2_CWARPS);
+    pt_mbar_init(bar_empty + 8, PT2_CWARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int n_gt = (n_kept + tg - 1) / tg;
+  const size_t row_bytes = (size_t)nvp * sizeof(double);
+  const long long n_blocks = (n_cells + PT2_CELLS - 1) / PT2_CELLS;
+  if (warp == PT2_CWARPS) {
+    // ---- producer: one lane streams the tiles of every cell block this CTA owns
+    if (lane == 0) {
+      long long it = 0;
+      for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x)
+        for (int gt = 0; gt < n_gt; ++gt, ++it) {
+          const int sb = (int)(it & 1);
+          if (it >= 2) pt_mbar_wait(bar_empty + 8u * sb, (unsigned)(((it >> 1) - 1) & 1));
+          const int g0 = gt * tg, rows = min(tg, n_kept - g0);
+          const unsigned bytes = (unsigned)(rows * row_bytes);
+          pt_mbar_expect_tx(bar_full + 8u * sb, bytes);
+          pt_bulk_g2s((unsigned)__cvta_generic_to_shared(sb ? buf1 : buf0), Vs + (size_t)g0 * nvp, bytes, bar_full + 8u * sb);
+        }
+    }
+    return;
+  }
+  // ---- consumers
+  const bool second = 64 + 2 * lane < nvp;  // this lane also owns columns 64 + 2 lane, + 1
+  const bool first = 2 * lane < nvp;
+  const int j_of = lane & 7, sub = lane >> 3;
+  const int NONE = 0x7fffffff;
+  long long it = 0;
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const long long c0 = blk * PT2_CELLS + (long long)warp * PT_CPW;
+    long long cur = 0, end = 0;  // lanes 0..7: cursor / end of cell c0 + lane
+    if (lane < PT_CPW && c0 + lane < n_cells) {
+      cur = p[c0 + lane];
+      end = p[c0 + lane + 1];
+    }
+    // this lane's slot of the register queue: entry number `sub` of cell j_of behind its cursor
+    int kq = NONE;
+    double val = 0.0;
+    {
+      const long long k = __shfl_sync(0xffffffffu, cur, j_of) + sub, ej = __shfl_sync(0xffffffffu, end, j_of);
+      if (k < ej) {
+        kq = kept_of_gene[gi[k]];
+        val = y[k];
+      }
+    }
+    double acc[PT_CPW][4];
+#pragma unroll
+    for (int j = 0; j < PT_CPW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+    for (int gt = 0; gt < n_gt; ++gt, ++it) {
+      const int sb = (int)(it & 1);
+      pt_mbar_wait(bar_full + 8u * sb, (unsigned)((it >> 1) & 1));
+      const double* tile = sb ? buf1 : buf0;
+      const int g0 = gt * tg, g1 = min(n_kept, g0 + tg);
+      for (;;) {
+        // consumable: a dropped gene (kq < 0) or a kept gene of this or an earlier tile; a cell's
+        // consumable entries must form a prefix of the four queued ones
+        const unsigned m = __ballot_sync(0xffffffffu, kq < g1);
+        const unsigned need = ((1u << (8 * sub + 1)) - 1u) & 0x01010101u;
+        const bool cons = (((m >> j_of) & 0x01010101u) & need) == need;
+        const unsigned mc = __ballot_sync(0xffffffffu, cons);
+        if (mc == 0u) break;
+        const unsigned mv = __ballot_sync(0xffffffffu, cons && kq >= g0);
+        const int local = kq - g0;
+#pragma unroll
+        for (int j = 0; j < PT_CPW; ++j) {
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int ql = s4 * 8 + j;
+            if ((mv >> ql) & 1u) {  // warp-uniform
+              const int g = __shfl_sync(0xffffffffu, local, ql);
+              const double v = __shfl_sync(0xffffffffu, val, ql);
+              const double* row = tile + (size_t)g * nvp;
+              if (first) {
+                const double2 a = *reinterpret_cast<const double2*>(row + 2 * lane);
+                acc[j][0] = fma(v, a.x, acc[j][0]);
+                acc[j][1] = fma(v, a.y, acc[j][1]);
+              }
+              if (second) {
+                const double2 c = *reinterpret_cast<const double2*>(row + 64 + 2 * lane);
+                acc[j][2] = fma(v, c.x, acc[j][2]);
+                acc[j][3] = fma(v, c.y, acc[j][3]);
+              }
+            }
+          }
+        }
+        // advance the cursors and shift the queue: slot (cell, sub) takes what slot (cell, sub + c)
+        // held, c = entries of the cell consumed in this round; vacated slots are loaded
+        if (lane < PT_CPW) cur += __popc((mc >> lane) & 0x01010101u);
+        const int c = __popc((mc >> j_of) & 0x01010101u);
+        const int src = sub + c;
+        const int kq_s = __shfl_sync(0xffffffffu, kq, ((src & 3) << 3) | j_of);
+        const double val_s = __shfl_sync(0xffffffffu, val, ((src & 3) << 3) | j_of);
+        const long long k = __shfl_sync(0xffffffffu, cur, j_of) + sub, ej = __shfl_sync(0xffffffffu, end, j_of);
+        if (src < 4) {
+          kq = kq_s;
+          val = val_s;
+        } else if (k < ej) {
+          kq = kept_of_gene[gi[k]];
+          val = y[k];
+        } else {
+          kq = NONE;
+          val = 0.0;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) pt_mbar_arrive(bar_empty + 8u * sb);  // this warp is done with the tile
+    }
+    // Y[c, col] = acc - b[col]
+#pragma unroll
+    for (int j = 0; j < PT_CPW; ++j) {
+      const long long c = c0 + j;
+      if (c < n_cells) {
+        if (first) {
+          const int col = 2 * lane;
+          if (col < ncols) Y[(long long)col * ldy + c] = acc[j][0] - b[col];
+          if (col + 1 < ncols) Y[(long long)(col + 1) * ldy + c] = acc[j][1] - b[col + 1];
+        }
+        if (second) {
+          const int col = 64 + 2 * lane;
+          if (col < ncols) Y[(long long)col * ldy + c] = acc[j][2] - b[col];
+          if (col + 1 < ncols) Y[(long long)(col + 1) * ldy + c] = acc[j][3] - b[col + 1];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Gene selection for the projection path (m3b_select_genes_for_transform): the zero-gene filter of
 // R/projection.R:117-118 WITHOUT the two product layouts m3b_select_genes builds for IRLBA -- the
 // tiled projection kernel reads the normalised CSC directly.  One pass over the stored entries
@@ -468,17 +633,23 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
       if (!attr) {
         if ((e = cudaFuncSetAttribute(k_project_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
         if ((e = cudaFuncSetAttribute(k_project_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
+        if ((e = cudaFuncSetAttribute(k_project_tiled2, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
         attr = true;
       }
       const int tg = std::max(8, (int)(PT_SMEM_TILE / (nvp * sizeof(double))));
-      const long long n_blocks = (rows + PT_CELLS - 1) / PT_CELLS;
-      const int grid = (int)std::min<long long>(n_blocks, ctx->sm_count);
       const bool tma = !getenv("M3B_PROJECT_NO_TMA");
+      const bool v1 = getenv("M3B_PROJECT_V1") != nullptr;  // first tiled version (block barrier per tile), for A/B runs
+      const int cells_per_cta = (tma && !v1) ? PT2_CELLS : PT_CELLS;
+      const long long n_blocks = (rows + cells_per_cta - 1) / cells_per_cta;
+      const int grid = (int)std::min<long long>(n_blocks, ctx->sm_count);
       cudaEventRecord(ctx->evk0, ctx->stream);
       for (int ps = 0; ps < n_pass; ++ps) {
         const int col0 = ps * pass_cols, ncols = std::min(pass_cols, nv - col0);
         const double* vs = dVs + (size_t)ps * n * nvp;
-        if (tma)
+        if (tma && !v1)
+          k_project_tiled2<<<grid, PT2_THREADS, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp, ncols,
+                                                                                tg, db + col0, dY + (size_t)col0 * rows, rows);
+        else if (tma)
           k_project_tiled<true><<<grid, PT_WARPS * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
                                                                                   ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
         else
