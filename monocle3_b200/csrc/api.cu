@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "m3b_internal.h"
@@ -324,18 +325,42 @@ static double r_mean(const double* x, int64_t n) {
 int m3b_size_factors_from_totals(const double* tot, int64_t n, int method, double* sf, int* any_zero) {
   if (!tot || !sf || n < 0) return M3B_E_DIMS;
   if (method != M3B_SF_MEAN_GEOMETRIC_MEAN_TOTAL && method != M3B_SF_MEAN_GEOMETRIC_MEAN_LOG_TOTAL) return M3B_E_DIMS;
-  int az = 0;
   std::vector<double> lg((size_t)n);
-  for (int64_t k = 0; k < n; ++k) {
-    if (tot[k] == 0.0) az = 1;
-    lg[k] = (method == M3B_SF_MEAN_GEOMETRIC_MEAN_TOTAL) ? log(tot[k]) : log(log(tot[k]));
-  }
+  // The element-wise parts (one or two libm logs per cell: ~50 ms for 2M cells on one core, on EVERY
+  // rank of a sharded run) are spread over a few host threads; the mean itself stays the strictly
+  // sequential long-double loop of R's mean(), so the result does not depend on the thread count.
+  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(8, n / 65536));
+  std::vector<int> zero_seen((size_t)n_thr, 0);
+  auto span = [&](int t, int64_t* lo, int64_t* hi) {
+    *lo = n * t / n_thr;
+    *hi = n * (t + 1) / n_thr;
+  };
+  auto run = [&](auto&& body) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_thr; ++t) th.emplace_back(body, t);
+    body(0);
+    for (auto& x : th) x.join();
+  };
+  run([&](int t) {
+    int64_t lo, hi;
+    span(t, &lo, &hi);
+    for (int64_t k = lo; k < hi; ++k) {
+      if (tot[k] == 0.0) zero_seen[t] = 1;
+      lg[k] = (method == M3B_SF_MEAN_GEOMETRIC_MEAN_TOTAL) ? log(tot[k]) : log(log(tot[k]));
+    }
+  });
+  int az = 0;
+  for (int t = 0; t < n_thr; ++t) az |= zero_seen[t];
   const double denom = n ? exp(r_mean(lg.data(), n)) : NAN;
-  for (int64_t k = 0; k < n; ++k) {
-    double num = (method == M3B_SF_MEAN_GEOMETRIC_MEAN_TOTAL) ? tot[k] : log(tot[k]);
-    double v = num / denom;
-    sf[k] = (v != v) ? 1.0 : v;  // sfs[is.na(sfs)] <- 1   (R/utils.R:68)
-  }
+  run([&](int t) {
+    int64_t lo, hi;
+    span(t, &lo, &hi);
+    for (int64_t k = lo; k < hi; ++k) {
+      double num = (method == M3B_SF_MEAN_GEOMETRIC_MEAN_TOTAL) ? tot[k] : log(tot[k]);
+      double v = num / denom;
+      sf[k] = (v != v) ? 1.0 : v;  // sfs[is.na(sfs)] <- 1   (R/utils.R:68)
+    }
+  });
   if (any_zero) *any_zero = az;
   return M3B_OK;
 }

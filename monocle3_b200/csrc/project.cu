@@ -278,14 +278,16 @@ k_project_tiled(const long long* __restrict__ p, const int* __restrict__ gi, con
 //     only the c vacated slots are loaded -- every entry is loaded exactly once.
 // Same arithmetic and summation order per cell as the first version (entries in CSC order).
 // ---------------------------------------------------------------------------
-#define PT2_CWARPS 15                        // consumer warps (+ 1 producer warp = 512 threads: a whole number of 4-warp register allocation units)
-#define PT2_CELLS (PT2_CWARPS * PT_CPW)      // cells per CTA
-#define PT2_THREADS ((PT2_CWARPS + 1) * 32)
+// <CPW cells per warp, CW consumer warps> (+ 1 producer warp; CW + 1 a multiple of 4 = the register
+// allocation unit): <8, 15> keeps 4 queued entries per cell and 64 accumulator registers, <4, 23>
+// 8 queued entries per cell (a tile's ~6 entries of a cell in ONE round) and 32 accumulator
+// registers, which lets 24 warps fit.
 __device__ __forceinline__ void pt_mbar_arrive(unsigned bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(PT2_THREADS, 1)
+template <int CPW, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, const double* __restrict__ y,
                  const int* __restrict__ kept_of_gene, long long n_cells, int n_kept, const double* __restrict__ Vs, int nvp,
                  int ncols, int tg, const double* __restrict__ b, double* __restrict__ Y, long long ldy) {
@@ -299,15 +301,18 @@ k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, co
   if (threadIdx.x == 0) {
     pt_mbar_init(bar_full, 1);
     pt_mbar_init(bar_full + 8, 1);
-    pt_mbar_init(bar_empty, PT2_CWARPS);
-    pt_mbar_init(bar_empty + 8, PT2_CWARPS);
+    pt_mbar_init(bar_empty, CW);
+    pt_mbar_init(bar_empty + 8, CW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int n_gt = (n_kept + tg - 1) / tg;
   const size_t row_bytes = (size_t)nvp * sizeof(double);
-  const long long n_blocks = (n_cells + PT2_CELLS - 1) / PT2_CELLS;
-  if (warp == PT2_CWARPS) {
+  constexpr int CELLS = CPW * CW;            // cells per CTA
+  constexpr int NSUB = 32 / CPW;             // queued entries per cell
+  constexpr unsigned CMASK = (CPW == 8) ? 0x01010101u : 0x11111111u;  // one bit per queue slot of a cell
+  const long long n_blocks = (n_cells + CELLS - 1) / CELLS;
+  if (warp == CW) {
     // ---- producer: one lane streams the tiles of every cell block this CTA owns
     if (lane == 0) {
       long long it = 0;
@@ -326,13 +331,13 @@ k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, co
   // ---- consumers
   const bool second = 64 + 2 * lane < nvp;  // this lane also owns columns 64 + 2 lane, + 1
   const bool first = 2 * lane < nvp;
-  const int j_of = lane & 7, sub = lane >> 3;
+  const int j_of = lane & (CPW - 1), sub = lane / CPW;
   const int NONE = 0x7fffffff;
   long long it = 0;
   for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-    const long long c0 = blk * PT2_CELLS + (long long)warp * PT_CPW;
+    const long long c0 = blk * CELLS + (long long)warp * CPW;
     long long cur = 0, end = 0;  // lanes 0..7: cursor / end of cell c0 + lane
-    if (lane < PT_CPW && c0 + lane < n_cells) {
+    if (lane < CPW && c0 + lane < n_cells) {
       cur = p[c0 + lane];
       end = p[c0 + lane + 1];
     }
@@ -346,9 +351,9 @@ k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, co
         val = y[k];
       }
     }
-    double acc[PT_CPW][4];
+    double acc[CPW][4];
 #pragma unroll
-    for (int j = 0; j < PT_CPW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+    for (int j = 0; j < CPW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
     for (int gt = 0; gt < n_gt; ++gt, ++it) {
       const int sb = (int)(it & 1);
       pt_mbar_wait(bar_full + 8u * sb, (unsigned)((it >> 1) & 1));
@@ -358,17 +363,17 @@ k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, co
         // consumable: a dropped gene (kq < 0) or a kept gene of this or an earlier tile; a cell's
         // consumable entries must form a prefix of the four queued ones
         const unsigned m = __ballot_sync(0xffffffffu, kq < g1);
-        const unsigned need = ((1u << (8 * sub + 1)) - 1u) & 0x01010101u;
-        const bool cons = (((m >> j_of) & 0x01010101u) & need) == need;
+        const unsigned need = ((2u << (CPW * sub)) - 1u) & CMASK;
+        const bool cons = (((m >> j_of) & CMASK) & need) == need;
         const unsigned mc = __ballot_sync(0xffffffffu, cons);
         if (mc == 0u) break;
         const unsigned mv = __ballot_sync(0xffffffffu, cons && kq >= g0);
         const int local = kq - g0;
 #pragma unroll
-        for (int j = 0; j < PT_CPW; ++j) {
+        for (int j = 0; j < CPW; ++j) {
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {
-            const int ql = s4 * 8 + j;
+          for (int s4 = 0; s4 < NSUB; ++s4) {
+            const int ql = s4 * CPW + j;
             if ((mv >> ql) & 1u) {  // warp-uniform
               const int g = __shfl_sync(0xffffffffu, local, ql);
               const double v = __shfl_sync(0xffffffffu, val, ql);
@@ -388,13 +393,13 @@ k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, co
         }
         // advance the cursors and shift the queue: slot (cell, sub) takes what slot (cell, sub + c)
         // held, c = entries of the cell consumed in this round; vacated slots are loaded
-        if (lane < PT_CPW) cur += __popc((mc >> lane) & 0x01010101u);
-        const int c = __popc((mc >> j_of) & 0x01010101u);
+        if (lane < CPW) cur += __popc((mc >> lane) & CMASK);
+        const int c = __popc((mc >> j_of) & CMASK);
         const int src = sub + c;
-        const int kq_s = __shfl_sync(0xffffffffu, kq, ((src & 3) << 3) | j_of);
-        const double val_s = __shfl_sync(0xffffffffu, val, ((src & 3) << 3) | j_of);
+        const int kq_s = __shfl_sync(0xffffffffu, kq, (src & (NSUB - 1)) * CPW + j_of);
+        const double val_s = __shfl_sync(0xffffffffu, val, (src & (NSUB - 1)) * CPW + j_of);
         const long long k = __shfl_sync(0xffffffffu, cur, j_of) + sub, ej = __shfl_sync(0xffffffffu, end, j_of);
-        if (src < 4) {
+        if (src < NSUB) {
           kq = kq_s;
           val = val_s;
         } else if (k < ej) {
@@ -410,7 +415,7 @@ k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, co
     }
     // Y[c, col] = acc - b[col]
 #pragma unroll
-    for (int j = 0; j < PT_CPW; ++j) {
+    for (int j = 0; j < CPW; ++j) {
       const long long c = c0 + j;
       if (c < n_cells) {
         if (first) {
@@ -633,22 +638,32 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
       if (!attr) {
         if ((e = cudaFuncSetAttribute(k_project_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
         if ((e = cudaFuncSetAttribute(k_project_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
-        if ((e = cudaFuncSetAttribute(k_project_tiled2, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
+        if ((e = cudaFuncSetAttribute(k_project_tiled2<8, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
+        if ((e = cudaFuncSetAttribute(k_project_tiled2<4, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
+        if ((e = cudaFuncSetAttribute(k_project_tiled2<4, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
         attr = true;
       }
       const int tg = std::max(8, (int)(PT_SMEM_TILE / (nvp * sizeof(double))));
       const bool tma = !getenv("M3B_PROJECT_NO_TMA");
       const bool v1 = getenv("M3B_PROJECT_V1") != nullptr;  // first tiled version (block barrier per tile), for A/B runs
-      const int cells_per_cta = (tma && !v1) ? PT2_CELLS : PT_CELLS;
+      const bool wide = getenv("M3B_PROJECT_CPW8") != nullptr;  // 8 cells per warp, 16 warps (A/B runs); default 4 cells, 24 warps
+      const bool cw27 = getenv("M3B_PROJECT_CW27") != nullptr;  // 28 warps (A/B runs)
+      const int cells_per_cta = (tma && !v1) ? (wide ? 8 * 15 : (cw27 ? 4 * 27 : 4 * 23)) : PT_CELLS;
       const long long n_blocks = (rows + cells_per_cta - 1) / cells_per_cta;
       const int grid = (int)std::min<long long>(n_blocks, ctx->sm_count);
       cudaEventRecord(ctx->evk0, ctx->stream);
       for (int ps = 0; ps < n_pass; ++ps) {
         const int col0 = ps * pass_cols, ncols = std::min(pass_cols, nv - col0);
         const double* vs = dVs + (size_t)ps * n * nvp;
-        if (tma && !v1)
-          k_project_tiled2<<<grid, PT2_THREADS, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp, ncols,
-                                                                                tg, db + col0, dY + (size_t)col0 * rows, rows);
+        if (tma && !v1 && wide)
+          k_project_tiled2<8, 15><<<grid, 16 * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
+                                                                                   ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
+        else if (tma && !v1 && cw27)
+          k_project_tiled2<4, 27><<<grid, 28 * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
+                                                                                   ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
+        else if (tma && !v1)
+          k_project_tiled2<4, 23><<<grid, 24 * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
+                                                                                   ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
         else if (tma)
           k_project_tiled<true><<<grid, PT_WARPS * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
                                                                                   ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
