@@ -279,10 +279,11 @@ def run_reference(args, rank, world):
         return run_reference_project(args)
     gen_dev = "cuda" if torch.cuda.is_available() else "cpu"   # RNG engine only (the GPU arm's matrix needs the same stream)
     spec = SynthSpec(wl["n_genes"], wl["cells"], wl["density"], wl["n_types"], wl["seed"], device=gen_dev)
-    # a dgCMatrix holds < 2^31 nnz: cfg4 is sampled (first 1/8 of the cells = the cfg3 shape) and scaled
+    # a dgCMatrix holds < 2^31 nnz, and the whole arm has to end within minutes on the host cores: cfg4 is
+    # sampled (first 1/8 of the cells = the cfg3 shape, ~4e8 entries) and every component scaled linearly in nnz
     scale_cells = 1
     n_cells = wl["cells"]
-    while n_cells * wl["n_genes"] * wl["density"] > 1.5e9:
+    while n_cells * wl["n_genes"] * wl["density"] > 6e8:
         scale_cells *= 2
         n_cells = wl["cells"] // scale_cells
     indptr, indices, data = spec.cells(0, n_cells)

@@ -310,7 +310,7 @@ k_project_tiled2(const long long* __restrict__ p, const int* __restrict__ gi, co
   const size_t row_bytes = (size_t)nvp * sizeof(double);
   constexpr int CELLS = CPW * CW;            // cells per CTA
   constexpr int NSUB = 32 / CPW;             // queued entries per cell
-  constexpr unsigned CMASK = (CPW == 8) ? 0x01010101u : 0x11111111u;  // one bit per queue slot of a cell
+  constexpr unsigned CMASK = (CPW == 8) ? 0x01010101u : (CPW == 4 ? 0x11111111u : 0x55555555u);  // one bit per queue slot of a cell
   const long long n_blocks = (n_cells + CELLS - 1) / CELLS;
   if (warp == CW) {
     // ---- producer: one lane streams the tiles of every cell block this CTA owns
@@ -641,6 +641,7 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
         if ((e = cudaFuncSetAttribute(k_project_tiled2<8, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
         if ((e = cudaFuncSetAttribute(k_project_tiled2<4, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
         if ((e = cudaFuncSetAttribute(k_project_tiled2<4, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
+        if ((e = cudaFuncSetAttribute(k_project_tiled2<2, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PT_SMEM_TILE)) != cudaSuccess) break;
         attr = true;
       }
       const int tg = std::max(8, (int)(PT_SMEM_TILE / (nvp * sizeof(double))));
@@ -648,7 +649,8 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
       const bool v1 = getenv("M3B_PROJECT_V1") != nullptr;  // first tiled version (block barrier per tile), for A/B runs
       const bool wide = getenv("M3B_PROJECT_CPW8") != nullptr;  // 8 cells per warp, 16 warps (A/B runs); default 4 cells, 24 warps
       const bool cw27 = getenv("M3B_PROJECT_CW27") != nullptr;  // 28 warps (A/B runs)
-      const int cells_per_cta = (tma && !v1) ? (wide ? 8 * 15 : (cw27 ? 4 * 27 : 4 * 23)) : PT_CELLS;
+      const bool cpw2 = getenv("M3B_PROJECT_CPW2") != nullptr;  // 2 cells per warp, 32 warps (A/B runs)
+      const int cells_per_cta = (tma && !v1) ? (wide ? 8 * 15 : (cpw2 ? 2 * 31 : (cw27 ? 4 * 27 : 4 * 23))) : PT_CELLS;
       const long long n_blocks = (rows + cells_per_cta - 1) / cells_per_cta;
       const int grid = (int)std::min<long long>(n_blocks, ctx->sm_count);
       cudaEventRecord(ctx->evk0, ctx->stream);
@@ -657,6 +659,9 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
         const double* vs = dVs + (size_t)ps * n * nvp;
         if (tma && !v1 && wide)
           k_project_tiled2<8, 15><<<grid, 16 * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
+                                                                                   ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
+        else if (tma && !v1 && cpw2)
+          k_project_tiled2<2, 31><<<grid, 32 * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
                                                                                    ncols, tg, db + col0, dY + (size_t)col0 * rows, rows);
         else if (tma && !v1 && cw27)
           k_project_tiled2<4, 27><<<grid, 28 * 32, 2 * PT_SMEM_TILE, ctx->stream>>>(q->p, q->i, q->y, q->kept_of_gene, rows, n, vs, nvp,
