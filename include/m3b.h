@@ -208,7 +208,7 @@ int m3b_aggregate_expression(m3b_mat* mat, const int32_t* gene_group, int32_t n_
  * _monocle3_jaccard_coeff, src/RcppExports.cpp; called at R/cluster_cells.R:313 and
  * R/graph_test.R:429,506), same argument and result layout: idx is an n x k matrix of 1-based
  * neighbour ids as doubles, column-major (an R NumericMatrix); out is (n*k) x 3, column-major:
- * (from, to, weight), row r = i*k + j, weights divided by their maximum.  k <= 64. */
+ * (from, to, weight), row r = i*k + j, weights divided by their maximum.  k <= 2048 (the reference accepts any k; cluster_cells uses 20). */
 int m3b_jaccard_coeff(m3b_ctx* ctx, const double* idx, int64_t n, int32_t k, int weight, double* out);
 /* Exact k nearest neighbours (Euclidean) of every row of X among the rows of X: what
  * cluster_cells obtains from RANN::nn2(data, data, k, searchtype = "standard") with

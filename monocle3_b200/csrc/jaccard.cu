@@ -8,15 +8,16 @@
 //   finally the weight column is divided by its maximum.
 //
 // One warp per node i: its neighbour list sits in shared memory; for each neighbour kk the lanes
-// hold kk's list (two elements per lane, k <= 64), a value counts once (the first lane that holds
-// it, __match_any_sync) if it occurs in i's list.  Integer work; the two divisions are the same
+// walk kk's list 32 elements at a time (k <= 2048: the reference accepts any k, cluster_cells'
+// default is 20), a value counts once (the first lane that holds it, __match_any_sync, and not seen
+// in an earlier chunk) if it occurs in i's list.  Integer work; the two divisions are the same
 // IEEE operations as the reference's, so the result is bit-identical.
 #include <algorithm>
 
 #include "m3b_internal.h"
 
 #define JC_WARPS 8
-#define JC_KMAX 64
+#define JC_KMAX 2048
 
 // doubles, column-major, 1-based  ->  int32, row-major, 0-based
 __global__ void k_jc_pack(const double* __restrict__ idx, long long n, int k, int* __restrict__ out, int* __restrict__ bad) {
@@ -32,7 +33,8 @@ __global__ void k_jc_pack(const double* __restrict__ idx, long long n, int k, in
 
 __global__ void __launch_bounds__(32 * JC_WARPS) k_jaccard(const int* __restrict__ nb, long long n, int k, int weight,
                                                            double* __restrict__ out, unsigned long long* __restrict__ wmax) {
-  __shared__ int rows[JC_WARPS][JC_KMAX];
+  extern __shared__ int jc_rows[];  // [JC_WARPS][k]
+  int* const myrow = jc_rows + (size_t)(threadIdx.x >> 5) * k;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long total = n * (long long)k;
   double* o0 = out;
@@ -41,27 +43,26 @@ __global__ void __launch_bounds__(32 * JC_WARPS) k_jaccard(const int* __restrict
   double mx = 0.0;
   for (long long i = blockIdx.x * (long long)JC_WARPS + w; i < n; i += (long long)gridDim.x * JC_WARPS) {
     __syncwarp();
-    for (int t = lane; t < k; t += 32) rows[w][t] = nb[i * k + t];
+    for (int t = lane; t < k; t += 32) myrow[t] = nb[i * k + t];
     __syncwarp();
     for (int j = 0; j < k; ++j) {
-      const int kk = rows[w][j];
+      const int kk = myrow[j];
       double wt = 1.0;
       if (weight) {
         int u = 0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; 32 * half < k; ++half) {  // chunk of 32 elements of kk's list
           const int t = lane + 32 * half;
           const bool have = t < k;
           const int v = have ? nb[(long long)kk * k + t] : -1 - t;  // distinct dummies for idle lanes
-          // first occurrence inside kk's list: no lower lane of this half with the same value, and
-          // (second half) not present in the first half
+          // first occurrence inside kk's list: no lower lane of this chunk with the same value, and
+          // not present in an earlier chunk
           const unsigned peers = __match_any_sync(0xffffffffu, v);
           bool first = have && ((peers & ((1u << lane) - 1u)) == 0u);
-          if (half == 1 && first)
-            for (int q = 0; q < 32 && q < k; ++q) first = first && (nb[(long long)kk * k + q] != v);
+          if (half >= 1 && first)
+            for (int q = 0; q < 32 * half; ++q) first = first && (nb[(long long)kk * k + q] != v);
           bool in_i = false;
           if (first)
-            for (int q = 0; q < k; ++q) in_i = in_i || (rows[w][q] == v);
+            for (int q = 0; q < k; ++q) in_i = in_i || (myrow[q] == v);
           u += __popc(__ballot_sync(0xffffffffu, first && in_i));
         }
         if (u > 0) wt = (double)u / (double)(2 * k - u);
@@ -122,7 +123,11 @@ int run_jaccard(m3b_ctx* ctx, const double* idx, long long n, int k, int weight,
       break;
     }
     const int blocks = (int)std::min<long long>((n + JC_WARPS - 1) / JC_WARPS, (long long)ctx->sm_count * 8);
-    k_jaccard<<<blocks, 32 * JC_WARPS, 0, ctx->stream>>>(d_nb, n, k, weight ? 1 : 0, d_out, d_max);
+    const size_t jc_smem = (size_t)JC_WARPS * k * sizeof(int);
+    if (jc_smem > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(k_jaccard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jc_smem)) != cudaSuccess)
+      break;
+    k_jaccard<<<blocks, 32 * JC_WARPS, jc_smem, ctx->stream>>>(d_nb, n, k, weight ? 1 : 0, d_out, d_max);
     k_jc_scale<<<std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8), 256, 0, ctx->stream>>>(d_out + 2 * total, total, d_max);
     count_launch(ctx, 2);
     if ((e = cudaGetLastError()) != cudaSuccess) break;

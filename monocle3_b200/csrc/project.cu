@@ -648,7 +648,9 @@ int run_project(m3b_mat* q, const int* model_row, int n_model, const double* V, 
       const bool tma = !getenv("M3B_PROJECT_NO_TMA");
       const bool v1 = getenv("M3B_PROJECT_V1") != nullptr;  // first tiled version (block barrier per tile), for A/B runs
       const bool wide = getenv("M3B_PROJECT_CPW8") != nullptr;  // 8 cells per warp, 16 warps (A/B runs); default 4 cells, 24 warps
-      const bool cw27 = getenv("M3B_PROJECT_CW27") != nullptr;  // 28 warps (A/B runs)
+      // default: 4 cells per warp, 27 consumer warps + the producer = 28 warps (cfg5: 52.0 ms; 24 warps 55.6, 32 warps with
+      // 2 cells each 55.8, 16 warps with 8 cells each 68.3, first version 72.7); the others stay selectable for A/B runs
+      const bool cw27 = getenv("M3B_PROJECT_CW23") == nullptr;
       const bool cpw2 = getenv("M3B_PROJECT_CPW2") != nullptr;  // 2 cells per warp, 32 warps (A/B runs)
       const int cells_per_cta = (tma && !v1) ? (wide ? 8 * 15 : (cpw2 ? 2 * 31 : (cw27 ? 4 * 27 : 4 * 23))) : PT_CELLS;
       const long long n_blocks = (rows + cells_per_cta - 1) / cells_per_cta;

@@ -81,6 +81,36 @@ struct DeviceCounts {
     m3b_check(ctx, m3b_matrix_append_csc(m, dim[1], p.begin(), i.begin(), x.begin()));
     m3b_check(ctx, m3b_matrix_end(m));
   }
+  // A matrix beyond one dgCMatrix (2^31 stored entries): consecutive CELL BLOCKS, each a dgCMatrix with
+  // the same genes (what cbind() of them would be, if it could exist).  Appended in order, exactly
+  // like the chunks of one matrix; the Python mirror's monocle3_b200.CSCBlocks is the same thing.
+  explicit DeviceCounts(List blocks) : ctx(the_ctx()) {
+    if (blocks.size() == 0) Rcpp::stop("m3b: empty list of count blocks");
+    double nnz = 0;
+    long long cells = 0;
+    for (int b = 0; b < blocks.size(); ++b) {
+      S4 blk = blocks[b];
+      IntegerVector dim = blk.slot("Dim");
+      if (b == 0) n_genes = dim[0];
+      if (dim[0] != n_genes) Rcpp::stop("m3b: count blocks differ in their number of genes");
+      cells += dim[1];
+      nnz += (double)NumericVector(blk.slot("x")).size();
+    }
+    n_cells = (int)cells;  // (R-side bookkeeping only; the library counts cells in 64 bits)
+    m3b_check(ctx, m3b_matrix_begin(ctx, n_genes, cells, cells, (int64_t)nnz, &m));
+    for (int b = 0; b < blocks.size(); ++b) {
+      S4 blk = blocks[b];
+      IntegerVector p = blk.slot("p"), i = blk.slot("i"), dim = blk.slot("Dim");
+      NumericVector x = blk.slot("x");
+      const int st = m3b_matrix_append_csc(m, dim[1], p.begin(), i.begin(), x.begin());
+      if (st != M3B_OK) {
+        m3b_matrix_free(m);  // free before raising (the destructor does not run when the constructor throws)
+        m = nullptr;
+        m3b_check(ctx, st);
+      }
+    }
+    m3b_check(ctx, m3b_matrix_end(m));
+  }
   ~DeviceCounts() { m3b_matrix_free(m); }
   DeviceCounts(const DeviceCounts&) = delete;
   DeviceCounts& operator=(const DeviceCounts&) = delete;

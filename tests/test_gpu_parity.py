@@ -510,7 +510,7 @@ def test_invariant_subspace_random_restart(m3):
         dev.pca_irlba(6, v0, center=False, scale=False)
 
 
-@pytest.mark.parametrize("n,k", [(500, 20), (300, 33), (64, 64), (7, 1)])
+@pytest.mark.parametrize("n,k", [(500, 20), (300, 33), (64, 64), (7, 1), (300, 100), (40, 1500)])
 def test_jaccard_coeff_bit_exact(m3, n, k):
     """The reference's native kernel (src/clustering.cpp:13-58): bit-identical to the restatement,
     with repeated ids inside a row and asymmetric neighbourhoods."""
@@ -524,7 +524,7 @@ def test_jaccard_coeff_bit_exact(m3, n, k):
         m3.jaccard_coeff(np.array([[0.0, 2.0], [1.0, 2.0]]), True)
 
 
-@pytest.mark.parametrize("n,k", [(500, 20), (64, 64), (2000, 15)])
+@pytest.mark.parametrize("n,k", [(500, 20), (64, 64), (2000, 15), (200, 130)])
 def test_jaccard_coeff_vs_reference_native(m3, n, k):
     """m3b_jaccard_coeff against the REFERENCE'S OWN code: oracle/_ref/libm3ref.so is
     src/clustering.cpp compiled unmodified against a shim of the Rcpp containers (oracle/Makefile).
