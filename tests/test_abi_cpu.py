@@ -118,3 +118,21 @@ def test_product_rng_matches_r_and_oracle():
     from monocle3_b200.r_rng import RStream
     a, b = RStream(7), RRandom(7)
     assert np.array_equal(a.rnorm(11), b.rnorm(11)) and np.array_equal(a.rnorm(5), b.rnorm(5))
+
+
+def test_csc_blocks_host_logic():
+    """monocle3_b200.CSCBlocks (a matrix beyond the dgCMatrix limit as consecutive cell blocks): shape / nnz
+    bookkeeping and the argument checks need no device."""
+    import scipy.sparse as sp
+    import monocle3_b200 as m3
+    rng = np.random.default_rng(0)
+    a = sp.random(30, 7, density=0.3, format="csc", random_state=rng)
+    b = sp.random(30, 5, density=0.3, format="csc", random_state=rng)
+    blk = m3.CSCBlocks([a, b])
+    assert blk.shape == (30, 12) and blk.nnz == a.nnz + b.nnz
+    cds = m3.CellDataSet(blk)                       # accepted as it is (no coercion to one csc_matrix)
+    assert cds.counts is blk and cds.n_cells_total == 12 and len(cds.cell_names) == 12
+    with pytest.raises(ValueError, match="same number of genes"):
+        m3.CSCBlocks([a, sp.random(31, 5, density=0.3, format="csc", random_state=rng)])
+    with pytest.raises(ValueError, match="at least one block"):
+        m3.CSCBlocks([])
