@@ -1454,7 +1454,7 @@ struct BrSmem {
 template <bool HAS_VAL, int MAXE>
 __global__ void __launch_bounds__(256) k_bank_reorder(unsigned short* __restrict__ idx, double* __restrict__ val,
                                                       const ItemDesc* __restrict__ items, long long n_items,
-                                                      int S /* 2 or 8 */, int lgS) {
+                                                      int S /* 2 or 8 */, int lgS, int len_lo) {
   extern __shared__ __align__(16) unsigned char br_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   unsigned char* base = br_smem + (size_t)warp * BrSmem<HAS_VAL, MAXE>::bytes;
@@ -1469,7 +1469,7 @@ __global__ void __launch_bounds__(256) k_bank_reorder(unsigned short* __restrict
   for (long long it = (long long)blockIdx.x * nwarps + warp; it < n_items; it += (long long)gridDim.x * nwarps) {
     const ItemDesc d = items[it];
     const int len = d.len;
-    if (len < 64 || len > MAXE) continue;  // too short to matter (or unexpected)
+    if (len < len_lo || len > MAXE) continue;  // another size class's item, or too short to matter
     // items start on a multiple of 4 entries (general) / 8 entries (unit) and have such a length:
     // 8-byte / 16-byte accesses on idx, 16-byte accesses on val
     if (HAS_VAL) {
@@ -1552,24 +1552,39 @@ __global__ void __launch_bounds__(256) k_bank_reorder(unsigned short* __restrict
   }
 }
 
-static int bank_reorder(m3b_ctx* ctx, TiledLayout& L) {
-  if (L.n_items == 0 || getenv("M3B_NO_BANK_REORDER")) return M3B_OK;
-  static bool attr = false;
-  constexpr int SM_U = BrSmem<false, M3B_UITEM_MAX>::bytes, SM_G = BrSmem<true, M3B_ITEM_MAX>::bytes;
-  constexpr int W_U = 6, W_G = 4;  // warps per CTA: 6 x 33 KB / 4 x 48 KB of staging, one CTA per SM
-  if (!attr) {
-    CK(ctx, cudaFuncSetAttribute(k_bank_reorder<false, M3B_UITEM_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_U * SM_U));
-    CK(ctx, cudaFuncSetAttribute(k_bank_reorder<true, M3B_ITEM_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_G * SM_G));
-    attr = true;
-  }
-  const int w = L.is_unit ? W_U : W_G;
-  const unsigned grid = (unsigned)std::min<long long>((L.n_items + w - 1) / w, (long long)ctx->sm_count);
-  if (L.is_unit)
-    k_bank_reorder<false, M3B_UITEM_MAX><<<grid, 32 * w, W_U * SM_U, ctx->stream>>>(L.idx, nullptr, L.items, L.n_items, 8, 3);
-  else
-    k_bank_reorder<true, M3B_ITEM_MAX><<<grid, 32 * w, W_G * SM_G, ctx->stream>>>(L.idx, L.val, L.items, L.n_items, 2, 1);
+// Size classes.  The pass is latency-bound, so what counts is warps per SM, and the staging per warp
+// is sized for the LONGEST item the instantiation accepts: with one class (4096 unit / 2048 general
+// entries) 6 / 4 warps fit an SM although most items are a few hundred entries long (cfg4 on one GPU:
+// 35 + 15 ms per layout, 98 ms of a 250 ms m3b_select_genes).  Each class is its own launch over all
+// items with its own staging size; a launch skips the items of the other classes.
+template <bool HAS_VAL, int MAXE>
+static int bank_reorder_class(m3b_ctx* ctx, TiledLayout& L, int len_lo, int S, int lgS) {
+  constexpr int per_warp = BrSmem<HAS_VAL, MAXE>::bytes;
+  // CTAs of up to 8 warps, as many CTAs per SM as the shared memory holds
+  const int warps_per_sm = std::max(1, std::min(32, (int)((220 * 1024) / per_warp)));
+  int w = std::min(8, warps_per_sm);
+  for (int c = 4; c <= 8 && c <= warps_per_sm; ++c)  // CTA size (4..8 warps) that wastes the fewest warp slots
+    if ((warps_per_sm / c) * c > (warps_per_sm / w) * w) w = c;
+  const int ctas_per_sm = std::max(1, warps_per_sm / w);
+  const int smem = w * per_warp;
+  CK(ctx, cudaFuncSetAttribute(k_bank_reorder<HAS_VAL, MAXE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const unsigned grid = (unsigned)std::min<long long>((L.n_items + w - 1) / w, (long long)ctx->sm_count * ctas_per_sm);
+  k_bank_reorder<HAS_VAL, MAXE><<<grid, 32 * w, smem, ctx->stream>>>(L.idx, HAS_VAL ? L.val : nullptr, L.items, L.n_items, S, lgS, len_lo);
   count_launch(ctx);
   CK(ctx, cudaGetLastError());
+  return M3B_OK;
+}
+
+static int bank_reorder(m3b_ctx* ctx, TiledLayout& L) {
+  if (L.n_items == 0 || getenv("M3B_NO_BANK_REORDER")) return M3B_OK;
+  if (L.is_unit) {
+    RET((bank_reorder_class<false, 1024>(ctx, L, 64, 8, 3)));
+    RET((bank_reorder_class<false, 2048>(ctx, L, 1025, 8, 3)));
+    RET((bank_reorder_class<false, M3B_UITEM_MAX>(ctx, L, 2049, 8, 3)));
+  } else {
+    RET((bank_reorder_class<true, 512>(ctx, L, 64, 2, 1)));
+    RET((bank_reorder_class<true, M3B_ITEM_MAX>(ctx, L, 513, 2, 1)));
+  }
   return M3B_OK;
 }
 
