@@ -18,9 +18,12 @@
 // the driver for each one costs milliseconds and a device synchronisation per
 // call, which showed up as 50-150 ms of jitter per step.  Freed blocks are kept
 // in a size-ordered free list (per device) and handed out again when a request
-// fits within 12.5% slack; everything is stream-ordered on the context's single
-// stream, so reuse needs no extra synchronisation.  m3b_destroy() releases the
-// cache of its device.
+// fits within 12.5% slack.  Why reuse needs no extra synchronisation: the pool is per
+// device and process-wide, but a process drives one context per device, every kernel that
+// touches a pooled block is ordered on that context's main stream, and the one user of the
+// side stream (the pre-launched product inside run_irlba) works on blocks run_irlba owns
+// and is joined (both streams synchronised) before run_irlba gives them back.
+// m3b_destroy() releases the cache of its device.
 // ---------------------------------------------------------------------------
 #include <map>
 #include <mutex>
