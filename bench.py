@@ -651,11 +651,15 @@ def main():
                       wl["key"], ", oracle-checked at full size" if wl["key"] in ("cfg2", "cfg3") else
                       "; the oracle needs ~1 h per step at this size, cfg2 / cfg3 are the oracle-checked sizes"),
                   "iter": [res["iter"], expected["iter"]], "mprod": [res["mprod"], expected["mprod"]], "d_max_rel": rel,
-                  "ok": bool(res["iter"] == expected["iter"] and res["mprod"] == expected["mprod"] and rel < 1e-9)}
+                  "ok": bool(res["iter"] == expected["iter"] and res["mprod"] == expected["mprod"] and rel < 1e-9),
+                  "within_tolerance": bool(rel < 1e-6),
+                  "note": "ok = iter, mprod equal and singular values within 1e-9; within_tolerance = singular values within the "
+                          "north-star's 1e-6 (sums over a different number of ranks associate differently: the Ritz values agree "
+                          "to tol^2 and the last convergence test can fall one restart earlier or later)"}
         if rank == 0:
+            verdict = "OK" if parity["ok"] else ("WITHIN TOLERANCE (iter / mprod differ)" if parity["within_tolerance"] else "MISMATCH")
             print("PARITY vs stored 1-GPU run of the same matrix: iter %d/%d mprod %d/%d d_max_rel %.2e -> %s" % (
-                res["iter"], expected["iter"], res["mprod"], expected["mprod"], rel, "OK" if parity["ok"] else "MISMATCH"),
-                file=sys.stderr, flush=True)
+                res["iter"], expected["iter"], res["mprod"], expected["mprod"], rel, verdict), file=sys.stderr, flush=True)
             # hard failure only beyond the north-star tolerance; a different iter / mprod (the convergence
             # test sits on a rounding edge) is reported in the line, not hidden
             assert rel < 1e-6, "run differs from the stored single-GPU run of the same matrix (singular values, rel %.2e)" % rel
