@@ -385,8 +385,11 @@ __global__ void __launch_bounds__(NT) k_apply_orth(const double* __restrict__ X,
 // The separate kernels (k_combine_*, k_dots, k_reduce_dots, k_apply_orth, k_finish_*) each cost a
 // launch gap plus a ramp and a tail on vectors of 20-40 k elements: ~50 us per half step for
 // ~10 us of memory time.  Every CTA owns one contiguous chunk of rows for the whole kernel; all
-// reductions keep a fixed order (bit-reproducible).  The multi-rank path keeps the separate
-// kernels because its allreduces sit between the phases.
+// reductions keep a fixed order (bit-reproducible).  Cell-sharded runs use the same kernel with the
+// cross-rank sums inside it (flag-in-data pushes over peer memory, see ll_store / ll_wait below);
+// the separate kernels with NCCL calls between them remain as the fallback (no peer access, more
+// than M3B_LL_CAPF kept genes, M3B_NO_MR_FUSED=1) and as the careful path of the invariant-subspace
+// recovery.
 // --------------------------------------------------------------------------
 #define OF_THREADS 1024
 enum { OF_W = 0, OF_F = 1, OF_FLAST = 2 };
@@ -423,7 +426,7 @@ struct OrthArgs {
   int* ctl;
   unsigned long long* bar;
   unsigned long long bar_base;
-  // cell-sharded runs (world > 1): peer-memory exchange buffers (Comm::xchg of every rank), see xchg_wait
+  // cell-sharded runs (world > 1): peer-memory exchange buffers (Comm::xchg of every rank), see ll_area
   double* const* peers;
   int rank, world;
   unsigned long long seq;  // number of the first exchange of this launch (F side uses 1, W side 2)
@@ -435,53 +438,11 @@ struct OrthArgs {
 enum { XD_WAIT_F = 0, XD_WAIT_W1 = 1, XD_WAIT_W2 = 2, XD_KERNEL_F = 3, XD_KERNEL_W = 4, XD_N_F = 5, XD_N_W = 6, XD_COUNT = 8 };
 
 // ---- cross-rank exchange inside the fused kernel (one box, CUDA-IPC peer memory) ----
-// Every rank writes its contribution into its OWN buffer (slot seq & 1), one thread of the rank
-// then stores `seq` into its flag in EVERY rank's buffer (release, system scope); whoever needs the
-// sum spins on the world's flags in its own buffer (acquire) and reads the peers' slots directly.
-// Slots alternate, and a rank cannot start exchange s+2 before every peer has published s+1,
-// i.e. has finished reading s, so two slots suffice.  The spin is bounded (CT_FLAG bit 4).
-__device__ __forceinline__ double* xchg_slot(double* const* peers, int q, int world, unsigned long long seq) {
-  return peers[q] + (size_t)world * 2 * M3B_XCHG_FLAG_STRIDE + (size_t)(seq & 1ull) * M3B_XCHG_CAP;
-}
-// Publishing costs ONE system-scope fence: the first version issued a st.release.sys per peer, i.e. a
-// fence per peer (each waits for every outstanding write to be acknowledged over NVLink: 8 of them
-// in a row at 8 GPUs), and polled the world's flags with one ld.acquire.sys each.  Now: fence once,
-// then relaxed flag stores to all peers back to back; the waiter polls all flags with relaxed loads
-// and fences once when the last one has arrived.
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void xchg_publish(double* const* peers, int rank, int world, unsigned long long seq) {
-  __threadfence_system();
-  for (int q = 0; q < world; ++q)
-    st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(peers[q] + ((size_t)rank * 2 + (seq & 1ull)) * M3B_XCHG_FLAG_STRIDE), seq);
-}
-// called by ONE thread; returns false on time-out
-__device__ __forceinline__ bool xchg_wait(double* const* peers, int rank, int world, unsigned long long seq, int* ctl,
-                                          long long timeout) {
-  const long long t0 = clock64();
-  const unsigned long long* fl0 = reinterpret_cast<const unsigned long long*>(peers[rank] + (seq & 1ull) * M3B_XCHG_FLAG_STRIDE);
-  for (;;) {
-    int arrived = 0;
-    for (int q = 0; q < world; ++q)
-      arrived += ld_relaxed_sys_u64(fl0 + (size_t)q * 2 * M3B_XCHG_FLAG_STRIDE) == seq;
-    if (arrived == world) break;
-    if (clock64() - t0 > timeout) {
-      atomicOr(ctl + CT_FLAG, 4);
-      return false;
-    }
-  }
-  __threadfence_system();  // acquire: the peers' data published before their flags is visible from here on
-  return true;
-}
-
+// (Round 1 pulled: every rank wrote its contribution into its own slot, published a flag to every peer
+// behind a system-scope fence, and whoever needed the sum read the peers' slots over NVLink.  That
+// protocol survives in k_combine_xchg_fix_F, the non-fused fallback; the fused kernel pushes.)
 // ---- flag-in-data exchange ("LL": every 16-byte entry carries its own validity flag) ----
-// The pull protocol above costs, per exchange, a local grid barrier (the slot must be complete before
+// The pull protocol costs, per exchange, a local grid barrier (the slot must be complete before
 // it is published), a system-scope fence, a flag store, and then a dependent round trip over NVLink
 // for the data.  Here the data is PUSHED: a value travels as {lo32, flag, hi32, flag} in one 16-byte
 // store into the receiver's own memory (8-byte halves are single-copy atomic, so a half whose flag
@@ -1841,8 +1802,8 @@ int run_irlba(m3b_mat* m, int nv, int work, int maxit, double tol, double svtol,
     I.of_chunk_m = (int)((mloc + I.of_grid - 1) / I.of_grid);
     {
       const size_t smem = ((size_t)std::max(I.of_chunk_n, I.of_chunk_m) + work + 2 + 1024) * sizeof(double);
-      // sharded runs: only with the peer-memory exchange (verified on 2 and 4 GPUs; M3B_NO_MR_FUSED=1
-      // falls back to the separate kernels with NCCL between them)
+      // sharded runs: only with the peer-memory exchange (checked against the oracle at world 2 and 8,
+      // tests/test_gpu_multi.py; M3B_NO_MR_FUSED=1 falls back to the separate kernels with NCCL between them)
       const bool rank_ok = ctx->comm.world == 1 ||
                            (ctx->comm.p2p && n <= M3B_LL_CAPF && work <= M3B_LL_CAPW && I.of_grid <= M3B_LL_CAPG &&
                             !getenv("M3B_NO_MR_FUSED"));
