@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define M3B_ABI_VERSION 2
+#define M3B_ABI_VERSION 3  /* 3: m3b_stats gained xchg_diag[8] at its end; m3b_jaccard_coeff accepts k <= 2048 */
 
 /* status codes (negative = error; the first five mirror irlba's C path) */
 #define M3B_OK                0

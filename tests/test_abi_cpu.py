@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.m3b_abi_version() == 2
+    assert lib.m3b_abi_version() == 3
     # the first codes mirror irlba's C-path errors
     assert lib.m3b_status_string(-2) == b"didn't converge"
     assert lib.m3b_status_string(-4) == b"starting vector near the null space"
