@@ -136,3 +136,23 @@ def test_csc_blocks_host_logic():
         m3.CSCBlocks([a, sp.random(31, 5, density=0.3, format="csc", random_state=rng)])
     with pytest.raises(ValueError, match="at least one block"):
         m3.CSCBlocks([])
+
+
+@pytest.mark.parametrize("method", ["mean-geometric-mean-total", "mean-geometric-mean-log-total"])
+def test_size_factor_finish_threads_do_not_change_the_result(method):
+    """Above 65 536 cells the element-wise logs of m3b_size_factors_from_totals run on several host threads;
+    the mean stays R's sequential long-double loop, so the result must still equal the oracle's bit for bit
+    (600 000 cells: 8 threads)."""
+    import scipy.sparse as sp
+    from monocle3_b200 import engine, _lib as L
+    rng = np.random.default_rng(11)
+    tot = np.floor(rng.lognormal(7.5, 0.6, 600_000)) + 2.0
+    counts = sp.csc_matrix(tot[None, :])            # one gene: the column sums are the totals
+    sf_o, tot_o = ref.estimate_sf_sparse(counts, method=method)
+    assert np.array_equal(tot_o, tot)
+    code = L.SF_TOTAL if "log-total" not in method else L.SF_LOG_TOTAL
+    sf, any_zero = engine.size_factors_from_totals(tot, code)
+    assert not any_zero
+    assert np.array_equal(sf, sf_o)
+    tot[123_456] = 0.0
+    assert engine.size_factors_from_totals(tot, code)[1]       # the zero is seen whichever thread owns it
