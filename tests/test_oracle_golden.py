@@ -128,3 +128,19 @@ def test_lsi_goldens(cds):
     y = ref.preprocess_transform_lsi(counts, sf, r50, gidx)
     for (a, b) in ((0, 0), (1, 0), (0, 1)):
         assert y[a, b] == pytest.approx(r50["LSI"][a, b], abs=1e-6)
+
+
+def test_scale_without_center_is_root_mean_square_dense_check():
+    """sparse_prcomp_irlba(center=FALSE, scale.=TRUE) scales by sqrt(colSums(x^2) / (nrow - 1)) (R/utils.R:395-397):
+    the restatement against a dense SVD of the explicitly scaled matrix."""
+    rng = np.random.default_rng(3)
+    import scipy.sparse as sp
+    X = sp.random(300, 40, density=0.2, format="csc", random_state=rng)
+    X.data = np.round(X.data * 5) + 1
+    o = ref.sparse_prcomp_irlba(X, 5, center=False, scale=True)
+    D = X.toarray()
+    rms = np.sqrt((D ** 2).sum(axis=0) / (D.shape[0] - 1))
+    np.testing.assert_allclose(o["svd_scale"], rms, rtol=1e-14)
+    s = np.linalg.svd(D / rms[None, :], compute_uv=False)[:5]
+    np.testing.assert_allclose(o["d"], s, rtol=1e-6)
+    assert o["center"] is None
