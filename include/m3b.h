@@ -215,7 +215,8 @@ int m3b_jaccard_coeff(m3b_ctx* ctx, const double* idx, int64_t n, int32_t k, int
  * nn_control method "nn2" (R/cluster_cells.R:286-287; the caller passes k + 1 because the point
  * itself is its own first neighbour).  X: n x d, column-major doubles (an R matrix, e.g.
  * reducedDims(cds)[["PCA"]]).  nn_idx: n x k, column-major, 1-based ids sorted by distance (ties:
- * smaller id first); nn_dists: n x k distances (not squared).  k <= 64. */
+ * smaller id first); nn_dists: n x k distances (not squared).  k <= 1024 and 512 d + 768 k + 49 664 <= 225 280 bytes of
+ * shared memory per query block (d = 100: k <= 162; d = 50: k <= 195), else M3B_E_DIMS. */
 int m3b_knn_self(m3b_ctx* ctx, const double* X, int64_t n, int32_t d, int32_t k, int32_t* nn_idx, double* nn_dists);
 
 /* ---- align_cds residual regression ------------------- */

@@ -15,7 +15,7 @@
 #include "m3b_internal.h"
 
 #define KN_T 64       // tile edge
-#define KN_KMAX 64
+#define KN_KMAX 1024  // (what really bounds k is the shared memory of the sorted per-row lists, checked at launch)
 #define KN_DC 32      // dimensions staged per step for the candidate tile
 
 __global__ void __launch_bounds__(256) k_knn_self(const double* __restrict__ X, long long n, int d, int k,
@@ -110,7 +110,8 @@ int run_knn_self(m3b_ctx* ctx, const double* X, long long n, int d, int k, int* 
   const size_t smem = ((size_t)d * KN_T + (size_t)KN_DC * KN_T + (size_t)KN_T * (KN_T + 1) + (size_t)KN_T * k) * sizeof(double) +
                       (size_t)KN_T * k * sizeof(int);
   if (smem > 220 * 1024) {
-    m3b_set_error(ctx, "m3b_knn_self: d = %d is too large for the shared-memory query block", d);
+    m3b_set_error(ctx, "m3b_knn_self: d = %d with k = %d does not fit the shared memory of a query block (%zu KB > 220 KB)", d, k,
+                  smem / 1024);
     return M3B_E_DIMS;
   }
   double *d_X = nullptr, *d_dist = nullptr;

@@ -540,7 +540,7 @@ def test_jaccard_coeff_vs_reference_native(m3, n, k):
         assert np.array_equal(got, native_jaccard(idx, weight))
 
 
-@pytest.mark.parametrize("n,d,k", [(1000, 50, 21), (130, 7, 5), (64, 100, 64), (257, 3, 1)])
+@pytest.mark.parametrize("n,d,k", [(1000, 50, 21), (130, 7, 5), (64, 100, 64), (257, 3, 1), (400, 20, 150)])
 def test_knn_self_exact(m3, n, d, k):
     """Exact kNN (what RANN::nn2 returns for cluster_cells, R/cluster_cells.R:286-287) against the
     restatement: identical neighbour ids, distances to 1e-14 relative."""
